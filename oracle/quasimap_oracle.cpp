@@ -1236,6 +1236,7 @@ void Mapper::mapSingle(const std::string& r, std::vector<QuasiAlignment>& hits) 
   std::string m = r;
   collect(m, hc);
   hitsToMappingsSimple(SINGLE_END, hc, hits);
+  ctr.totHits += hits.size();  // counted before the clear (:241-246)
   if (hits.size() > o.maxNumHits) { hits.clear(); }
   if (o.selAln && !hits.empty()) {
     AlnCache cache;
@@ -1270,7 +1271,6 @@ void Mapper::mapSingle(const std::string& r, std::vector<QuasiAlignment>& hits) 
       for (auto& qa : hits) { qa.alnScore = static_cast<int32_t>(qa.score); qa.score = o.hardFilter ? -1.0 : std::exp(-(bestScoreD - qa.score)); }
     } else hits.clear();
   }
-  ctr.totHits += hits.size();
 }
 
 // =================================================================================================

@@ -1,0 +1,664 @@
+// C-ABI of the B200 quasi-mapping engine (include/rapmap_cuda.h): index image construction and upload,
+// per-stream mapper state, and the kernel pipeline behind rapmap_cuda_map_batch.
+#include <cuda_runtime.h>
+#include <cub/device/device_scan.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/rapmap_cuda.h"
+#include "hits_to_mappings.cuh"
+#include "index_loader.hpp"
+#include "kernels.cuh"
+#include "merge_pairs.cuh"
+#include "sa_collect.cuh"
+#include "sam_writer.hpp"
+#include "sel_aln.cuh"
+
+using namespace rapmap_b200;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CU_TRY(call)                                                                                     \
+  do {                                                                                                   \
+    cudaError_t e__ = (call);                                                                            \
+    if (e__ != cudaSuccess)                                                                              \
+      return fail(RAPMAP_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));                \
+  } while (0)
+
+inline uint64_t align256(uint64_t x) { return (x + 255) / 256 * 256; }
+
+struct CastU64 {
+  __host__ __device__ uint64_t operator()(uint32_t v) const { return v; }
+};
+
+// ---- hash table construction on the device ------------------------------------------------------
+__global__ void build_table_kernel(const KmerRecord* recs, uint64_t n, uint4* table, uint64_t mask) {
+  for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    KmerRecord r = recs[i];
+    uint64_t s = mix64(r.kmer) & mask;
+    while (true) {
+      unsigned long long* keyp = reinterpret_cast<unsigned long long*>(table + s);
+      unsigned long long old = atomicCAS(keyp, static_cast<unsigned long long>(kEmptyKey), static_cast<unsigned long long>(r.kmer));
+      if (old == kEmptyKey || old == r.kmer) {
+        reinterpret_cast<int32_t*>(table + s)[2] = r.begin;
+        reinterpret_cast<int32_t*>(table + s)[3] = r.end;
+        break;
+      }
+      s = (s + 1) & mask;
+    }
+  }
+}
+
+DeviceIndex viewOf(const uint8_t* blob, const ImageHeader& h) {
+  DeviceIndex d;
+  d.SA = reinterpret_cast<const int32_t*>(blob + h.offSA);
+  d.text = blob + h.offText;
+  d.rank = reinterpret_cast<const uint4*>(blob + h.offRank);
+  d.txpOffsets = reinterpret_cast<const int32_t*>(blob + h.offTxpOffsets);
+  d.txpLens = reinterpret_cast<const int32_t*>(blob + h.offTxpLens);
+  d.table = reinterpret_cast<const uint4*>(blob + h.offTable);
+  d.tableMask = h.tableSlots - 1;
+  d.n = static_cast<int64_t>(h.n);
+  d.k = h.k;
+  d.numTxp = static_cast<uint32_t>(h.numTxp);
+  return d;
+}
+
+} // namespace
+
+struct rapmap_cuda_index {
+  int device{0};
+  uint8_t* blob{nullptr};
+  bool ownsBlob{true};
+  ImageHeader hdr{};
+  DeviceIndex view{};
+  std::vector<std::string> names;
+  std::vector<int32_t> lens;
+};
+
+struct rapmap_cuda_mapper {
+  const rapmap_cuda_index* idx{nullptr};
+  rapmap_cuda_opts_t opts{};
+  DevOpts dopts{};
+  uint64_t maxBatch{0};
+  uint32_t maxReadLen{0};
+  cudaStream_t stream{nullptr};
+  int numSMs{0};
+  // staging of host reads
+  uint8_t* dSeq[2]{nullptr, nullptr};
+  uint64_t* dOff[2]{nullptr, nullptr};
+  uint64_t seqCap{0};
+  // stage 1
+  ReadSummary* dSumm{nullptr};
+  IntervalRec* dIvArena{nullptr};
+  uint32_t ivCap{0};
+  // stage 2
+  QASummary* dQSumm{nullptr};
+  QARec* dQaArena{nullptr};
+  uint32_t qaCap{0};
+  int32_t* dPosPool{nullptr};
+  uint32_t posCap{0};
+  uint8_t* dScratch{nullptr};
+  uint32_t scratchEntries{0};
+  uint64_t scratchStride{0};
+  uint32_t smemEntries{64};
+  int gridCollect{0}, gridMap{0};
+  uint32_t collectSmem{0}, mapSmem{0};
+  uint32_t lpad{0}, pmax{0}, warpSmem{0};
+  // stage 3
+  uint32_t* dPairCount{nullptr};
+  uint64_t* dPairOff{nullptr};
+  rapmap_hit_t* dHits{nullptr};
+  uint64_t hitsCap{0};
+  SelAlnWork selaln{};
+  void* dCubTemp{nullptr};
+  size_t cubTempBytes{0};
+  // control words: [0] interval cursor, [1] qa cursor, [2] pos cursor, [3] status
+  uint32_t* dCtl{nullptr};
+  Counters5* dCounters{nullptr};
+  struct Stage { uint32_t ctl[4]; Counters5 counters; uint64_t total; }* hStage{nullptr};
+  cudaEvent_t ev[9]{};
+  rapmap_cuda_timing_t timing{};
+  BatchView lastView{};
+  uint64_t lastReads{0};
+};
+
+static constexpr int kWarps = 8;
+
+extern "C" {
+
+const char* rapmap_cuda_last_error(void) { return g_err.c_str(); }
+
+void rapmap_cuda_opts_default(rapmap_cuda_opts_t* o) {
+  std::memset(o, 0, sizeof(*o));
+  o->max_num_hits = 200;
+  o->quasi_coverage = 0.0;
+  o->sensitive = 1;
+  o->strict_check = 1;
+  o->consensus_slack = 0.2f;
+  o->min_score_fraction = 0.65;
+  o->match_score = 2;
+  o->mismatch_penalty = -4;
+  o->gap_open_penalty = 4;
+  o->gap_extend_penalty = 2;
+  o->dp_bandwidth = 15;
+  o->max_mmp_extension = 7;
+}
+
+void rapmap_cuda_opts_selaln(rapmap_cuda_opts_t* o) {
+  rapmap_cuda_opts_default(o);
+  o->sel_aln = 1;
+}
+
+int rapmap_cuda_index_load(const char* index_dir, int device, rapmap_cuda_index_t** out) {
+  if (!index_dir || !out) return fail(RAPMAP_ERR_ARG, "null argument");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(RAPMAP_ERR_CUDA, std::string("no CUDA device available (") + cudaGetErrorString(e) + "); this engine has no CPU path");
+  if (device < 0 || device >= ndev) return fail(RAPMAP_ERR_ARG, "bad device ordinal");
+  CU_TRY(cudaSetDevice(device));
+
+  HostIndex h;
+  std::string err;
+  if (!h.load(index_dir, err)) return fail(RAPMAP_ERR_IO, err);
+
+  const uint64_t n = h.SA.size();
+  const uint64_t T = h.txpOffsets.size();
+  uint64_t slots = 64;
+  while (slots < 2 * h.kmers.size()) slots <<= 1;
+  const uint64_t rankWords = n / 64 + 1;
+
+  ImageHeader hdr{};
+  hdr.magic = kImageMagic;
+  hdr.n = n; hdr.numTxp = T; hdr.tableSlots = slots; hdr.numKmers = h.kmers.size(); hdr.k = h.k;
+  uint64_t off = align256(sizeof(ImageHeader));
+  hdr.offSA = off; off = align256(off + n * 4);
+  hdr.offText = off; off = align256(off + n + 256);
+  hdr.offRank = off; off = align256(off + rankWords * 16);
+  hdr.offTxpOffsets = off; off = align256(off + T * 4);
+  hdr.offTxpLens = off; off = align256(off + T * 4);
+  hdr.offTable = off; off = align256(off + slots * 16);
+  hdr.totalBytes = off;
+
+  auto* idx = new rapmap_cuda_index();
+  idx->device = device;
+  idx->hdr = hdr;
+  cudaError_t ce = cudaMalloc(&idx->blob, hdr.totalBytes);
+  if (ce != cudaSuccess) { delete idx; return fail(RAPMAP_ERR_CUDA, std::string("cudaMalloc(index image): ") + cudaGetErrorString(ce)); }
+  auto bail = [&](const std::string& m) { cudaFree(idx->blob); delete idx; return fail(RAPMAP_ERR_CUDA, m); };
+#define IDX_TRY(call) do { cudaError_t e2 = (call); if (e2 != cudaSuccess) return bail(std::string(#call) + ": " + cudaGetErrorString(e2)); } while (0)
+  IDX_TRY(cudaMemcpy(idx->blob, &hdr, sizeof(hdr), cudaMemcpyHostToDevice));
+  IDX_TRY(cudaMemcpy(idx->blob + hdr.offSA, h.SA.data(), n * 4, cudaMemcpyHostToDevice));
+  IDX_TRY(cudaMemset(idx->blob + hdr.offText, 0, n + 256));
+  IDX_TRY(cudaMemcpy(idx->blob + hdr.offText, h.text.data(), n, cudaMemcpyHostToDevice));
+  {
+    std::vector<uint4> rank(rankWords);
+    uint32_t cum = 0;
+    for (uint64_t w = 0; w < rankWords; ++w) {
+      uint64_t bits = w < h.rsdBits.size() ? h.rsdBits[w] : 0;
+      rank[w] = make_uint4(static_cast<uint32_t>(bits), static_cast<uint32_t>(bits >> 32), cum, 0);
+      cum += static_cast<uint32_t>(__builtin_popcountll(bits));
+    }
+    IDX_TRY(cudaMemcpy(idx->blob + hdr.offRank, rank.data(), rankWords * 16, cudaMemcpyHostToDevice));
+  }
+  IDX_TRY(cudaMemcpy(idx->blob + hdr.offTxpOffsets, h.txpOffsets.data(), T * 4, cudaMemcpyHostToDevice));
+  IDX_TRY(cudaMemcpy(idx->blob + hdr.offTxpLens, h.txpLens.data(), T * 4, cudaMemcpyHostToDevice));
+  IDX_TRY(cudaMemset(idx->blob + hdr.offTable, 0xFF, slots * 16));
+  if (!h.kmers.empty()) {
+    KmerRecord* dRecs = nullptr;
+    IDX_TRY(cudaMalloc(&dRecs, h.kmers.size() * sizeof(KmerRecord)));
+    cudaError_t e3 = cudaMemcpy(dRecs, h.kmers.data(), h.kmers.size() * sizeof(KmerRecord), cudaMemcpyHostToDevice);
+    if (e3 == cudaSuccess) {
+      build_table_kernel<<<2048, 256>>>(dRecs, h.kmers.size(), reinterpret_cast<uint4*>(idx->blob + hdr.offTable), slots - 1);
+      e3 = cudaDeviceSynchronize();
+    }
+    cudaFree(dRecs);
+    if (e3 != cudaSuccess) return bail(std::string("hash table build: ") + cudaGetErrorString(e3));
+  }
+#undef IDX_TRY
+  idx->view = viewOf(idx->blob, hdr);
+  idx->names = std::move(h.txpNames);
+  idx->lens = std::move(h.txpLens);
+  *out = idx;
+  return RAPMAP_OK;
+}
+
+void rapmap_cuda_index_free(rapmap_cuda_index_t* idx) {
+  if (!idx) return;
+  if (idx->ownsBlob && idx->blob) { cudaSetDevice(idx->device); cudaFree(idx->blob); }
+  delete idx;
+}
+
+uint64_t rapmap_cuda_index_num_transcripts(const rapmap_cuda_index_t* idx) { return idx ? idx->hdr.numTxp : 0; }
+const char* rapmap_cuda_index_transcript_name(const rapmap_cuda_index_t* idx, uint64_t tid) {
+  return (idx && tid < idx->names.size()) ? idx->names[tid].c_str() : "";
+}
+uint64_t rapmap_cuda_index_transcript_len(const rapmap_cuda_index_t* idx, uint64_t tid) {
+  return (idx && tid < idx->lens.size()) ? static_cast<uint64_t>(idx->lens[tid]) : 0;
+}
+uint32_t rapmap_cuda_index_k(const rapmap_cuda_index_t* idx) { return idx ? idx->hdr.k : 0; }
+uint64_t rapmap_cuda_index_device_bytes(const rapmap_cuda_index_t* idx) { return idx ? idx->hdr.totalBytes : 0; }
+
+int rapmap_cuda_index_image_bytes(const rapmap_cuda_index_t* idx, uint64_t* bytes) {
+  if (!idx || !bytes) return fail(RAPMAP_ERR_ARG, "null argument");
+  *bytes = idx->hdr.totalBytes;
+  return RAPMAP_OK;
+}
+int rapmap_cuda_index_image_ptr(const rapmap_cuda_index_t* idx, void** p) {
+  if (!idx || !p) return fail(RAPMAP_ERR_ARG, "null argument");
+  *p = idx->blob;
+  return RAPMAP_OK;
+}
+int rapmap_cuda_index_from_image(const rapmap_cuda_index_t* meta, int device, void* blob, uint64_t bytes, rapmap_cuda_index_t** out) {
+  if (!blob || !out) return fail(RAPMAP_ERR_ARG, "null argument");
+  CU_TRY(cudaSetDevice(device));
+  ImageHeader hdr;
+  CU_TRY(cudaMemcpy(&hdr, blob, sizeof(hdr), cudaMemcpyDeviceToHost));
+  if (hdr.magic != kImageMagic || hdr.totalBytes != bytes) return fail(RAPMAP_ERR_ARG, "not an index image (bad magic or size)");
+  auto* idx = new rapmap_cuda_index();
+  idx->device = device;
+  idx->blob = static_cast<uint8_t*>(blob);
+  idx->ownsBlob = false;
+  idx->hdr = hdr;
+  idx->view = viewOf(idx->blob, hdr);
+  if (meta) { idx->names = meta->names; idx->lens = meta->lens; }
+  *out = idx;
+  return RAPMAP_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+static int deriveOpts(const rapmap_cuda_opts_t& o, DevOpts& d) {
+  // Device path implements the default strand-decision mode of SACollector (disableNIP && strictCheck,
+  // reference include/SACollector.hpp:138).  NIP skipping (--noSensitive) and the k-mer-vote mode
+  // (--noStrictCheck) are refused, not approximated.
+  if (!o.sensitive) return fail(RAPMAP_ERR_UNSUPPORTED, "--noSensitive (NIP/LCE skipping) is not implemented on the device path");
+  if (!o.strict_check) return fail(RAPMAP_ERR_UNSUPPORTED, "--noStrictCheck (k-mer vote strand decision) is not implemented on the device path");
+  if (o.recover_orphans) return fail(RAPMAP_ERR_UNSUPPORTED, "--recoverOrphans is not implemented on the device path");
+  if (o.sel_aln || o.fuzzy) return fail(RAPMAP_ERR_UNSUPPORTED, "--selAln / --fuzzyIntersection are not implemented on the device path yet");
+  if (o.sel_aln) {
+    // validateOpts, reference src/RapMapSAMapper.cpp:911-954
+    if (o.consensus_slack < 0 || o.consensus_slack > 1) return fail(RAPMAP_ERR_ARG, "--consensusSlack must be between 0.0 and 1.0");
+    if (o.min_score_fraction < 0 || o.min_score_fraction > 1) return fail(RAPMAP_ERR_ARG, "--minScoreFrac must be between 0.0 and 1.0");
+    if (o.match_score <= 0) return fail(RAPMAP_ERR_ARG, "match score must be positive");
+    if (o.mismatch_penalty > 0) return fail(RAPMAP_ERR_ARG, "mismatch penalty cannot be positive");
+    int sv = 2 * (int(o.gap_open_penalty) + int(o.gap_extend_penalty)) + int(o.match_score);
+    if (sv >= 127) return fail(RAPMAP_ERR_ARG, "[2*(gapOpen+gapExtend)+matchScore] cannot exceed 127");
+  }
+  if (o.max_mmp_extension < 1) return fail(RAPMAP_ERR_ARG, "--maxMMPExtension must be at least 1");
+  std::memset(&d, 0, sizeof(d));
+  d.maxNumHits = o.max_num_hits;
+  d.covReq = o.quasi_coverage > 0.0 ? o.quasi_coverage : 0.0;
+  d.maxInterval = 1000;
+  d.doChaining = o.sel_aln;
+  d.considerMultiPos = o.sel_aln;
+  d.selAln = o.sel_aln;
+  d.fuzzy = o.fuzzy;
+  d.consensusFraction = 1.0f;
+  d.strictCheckSlack = 0;
+  d.maxMMPExtension = 7;
+  if (o.sel_aln) {  // reference src/RapMapSAMapper.cpp:410-417, include/SACollector.hpp:64,71
+    d.consensusFraction = static_cast<float>((o.consensus_slack == 0.0) ? 1.0 : (1.0 - o.consensus_slack));
+    d.strictCheckSlack = 1;
+    d.maxMMPExtension = o.max_mmp_extension;
+  }
+  d.noOrphans = o.no_orphans;
+  d.noDovetail = o.no_dovetail;
+  d.hardFilter = o.hard_filter;
+  d.alignmentPolicy = o.alignment_policy;
+  d.ma = o.match_score; d.mm = o.mismatch_penalty; d.go = o.gap_open_penalty; d.ge = o.gap_extend_penalty;
+  d.dpBandwidth = o.dp_bandwidth;
+  d.minScoreFraction = o.min_score_fraction;
+  return RAPMAP_OK;
+}
+
+static void freeMapperBuffers(rapmap_cuda_mapper* m) {
+  for (int i = 0; i < 2; ++i) { cudaFree(m->dSeq[i]); cudaFree(m->dOff[i]); }
+  cudaFree(m->dSumm); cudaFree(m->dIvArena); cudaFree(m->dQSumm); cudaFree(m->dQaArena); cudaFree(m->dPosPool);
+  cudaFree(m->dScratch); cudaFree(m->dPairCount); cudaFree(m->dPairOff); cudaFree(m->dHits); cudaFree(m->dCubTemp);
+  cudaFree(m->dCtl); cudaFree(m->dCounters);
+  selAlnFree(m->selaln);
+  if (m->hStage) cudaFreeHost(m->hStage);
+  for (auto& e : m->ev) if (e) cudaEventDestroy(e);
+  if (m->stream) cudaStreamDestroy(m->stream);
+}
+
+int rapmap_cuda_mapper_create(const rapmap_cuda_index_t* idx, const rapmap_cuda_opts_t* opts, uint64_t max_batch, uint32_t max_read_len,
+                              rapmap_cuda_mapper_t** out) {
+  if (!idx || !opts || !out || max_batch == 0) return fail(RAPMAP_ERR_ARG, "null / zero argument");
+  *out = nullptr;
+  if (max_read_len < idx->hdr.k || max_read_len > 1000) return fail(RAPMAP_ERR_ARG, "max_read_len must be in [k, 1000]");
+  if (max_batch > (1ull << 30)) return fail(RAPMAP_ERR_ARG, "max_batch too large");
+  DevOpts d;
+  int rc = deriveOpts(*opts, d);
+  if (rc) return rc;
+  CU_TRY(cudaSetDevice(idx->device));
+  auto* m = new rapmap_cuda_mapper();
+  m->idx = idx; m->opts = *opts; m->dopts = d; m->maxBatch = max_batch; m->maxReadLen = max_read_len;
+  auto bail = [&](const std::string& msg) { freeMapperBuffers(m); delete m; return fail(RAPMAP_ERR_CUDA, msg); };
+#define M_TRY(call) do { cudaError_t e2 = (call); if (e2 != cudaSuccess) return bail(std::string(#call) + ": " + cudaGetErrorString(e2)); } while (0)
+  cudaDeviceProp prop;
+  M_TRY(cudaGetDeviceProperties(&prop, idx->device));
+  m->numSMs = prop.multiProcessorCount;
+  M_TRY(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+  for (auto& e : m->ev) M_TRY(cudaEventCreate(&e));
+  const uint64_t R = 2 * max_batch;
+  m->seqCap = max_batch * max_read_len;
+  for (int i = 0; i < 2; ++i) {
+    M_TRY(cudaMalloc(&m->dSeq[i], m->seqCap + 16));
+    M_TRY(cudaMalloc(&m->dOff[i], (max_batch + 1) * 8));
+  }
+  M_TRY(cudaMalloc(&m->dSumm, R * sizeof(ReadSummary)));
+  m->ivCap = static_cast<uint32_t>(std::min<uint64_t>(R * (opts->sel_aln ? 10 : 4) + 1024, 0xFFFFFFF0ull));
+  M_TRY(cudaMalloc(&m->dIvArena, static_cast<uint64_t>(m->ivCap) * sizeof(IntervalRec)));
+  M_TRY(cudaMalloc(&m->dQSumm, R * sizeof(QASummary)));
+  m->qaCap = static_cast<uint32_t>(std::min<uint64_t>(R * 8 + 1024, 0xFFFFFFF0ull));
+  M_TRY(cudaMalloc(&m->dQaArena, static_cast<uint64_t>(m->qaCap) * sizeof(QARec)));
+  m->posCap = opts->sel_aln ? static_cast<uint32_t>(std::min<uint64_t>(R * 12 + 1024, 0xFFFFFFF0ull)) : 16;
+  M_TRY(cudaMalloc(&m->dPosPool, static_cast<uint64_t>(m->posCap) * 4));
+  M_TRY(cudaMalloc(&m->dPairCount, (max_batch + 1) * 4));
+  M_TRY(cudaMalloc(&m->dPairOff, (max_batch + 1) * 8));
+  m->hitsCap = max_batch * 6 + 1024;
+  M_TRY(cudaMalloc(&m->dHits, m->hitsCap * sizeof(rapmap_hit_t)));
+  M_TRY(cudaMalloc(&m->dCtl, 4 * 4));
+  M_TRY(cudaMalloc(&m->dCounters, sizeof(Counters5)));
+  M_TRY(cudaMallocHost(&m->hStage, sizeof(*m->hStage)));
+  {
+    cub::TransformInputIterator<uint64_t, CastU64, uint32_t*> it(m->dPairCount, CastU64());
+    M_TRY(cub::DeviceScan::ExclusiveSum(nullptr, m->cubTempBytes, it, m->dPairOff, static_cast<int>(max_batch + 1)));
+    M_TRY(cudaMalloc(&m->dCubTemp, m->cubTempBytes + 16));
+  }
+  // ---- launch geometry: persistent grids, whole multiples of the SM count
+  m->lpad = (max_read_len + 15) / 16 * 16;
+  m->pmax = max_read_len - idx->hdr.k + 1;
+  m->warpSmem = (2 * m->lpad + 2 * m->pmax * 8 + 2 * m->pmax * static_cast<uint32_t>(sizeof(IntervalRec)) + 15) / 16 * 16;
+  m->collectSmem = m->warpSmem * kWarps;
+  if (m->collectSmem > 227 * 1024) return bail("max_read_len too large for the shared-memory read cache");
+  M_TRY(cudaFuncSetAttribute(sa_collect_kernel<kWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(m->collectSmem)));
+  int occ = 0;
+  M_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sa_collect_kernel<kWarps>, kWarps * 32, m->collectSmem));
+  if (occ < 1) return bail("sa_collect_kernel does not fit on an SM");
+  m->gridCollect = m->numSMs * occ;
+  m->mapSmem = static_cast<uint32_t>(workAreaBytes(m->smemEntries)) * kWarps;
+  M_TRY(cudaFuncSetAttribute(hits_to_mappings_kernel<kWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(m->mapSmem)));
+  M_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hits_to_mappings_kernel<kWarps>, kWarps * 32, m->mapSmem));
+  if (occ < 1) return bail("hits_to_mappings_kernel does not fit on an SM");
+  m->gridMap = m->numSMs * occ;
+  // global work strip per resident warp: the worst case of one strand is (pmax intervals) x (maxInterval-1 entries);
+  // 8192 entries cover every read whose expanded intervals total <= 4096 SA entries (pow2 padding), larger reads are
+  // reported through kStatScratchFull and re-run with a strip sized from the actual maximum.
+  m->scratchEntries = 8192;
+  m->scratchStride = workAreaBytes(m->scratchEntries);
+  M_TRY(cudaMalloc(&m->dScratch, m->scratchStride * static_cast<uint64_t>(m->gridMap) * kWarps));
+  if (opts->sel_aln) {
+    cudaError_t e2 = selAlnAlloc(m->selaln, max_batch, max_read_len);
+    if (e2 != cudaSuccess) return bail(std::string("selAlnAlloc: ") + cudaGetErrorString(e2));
+  }
+#undef M_TRY
+  *out = m;
+  return RAPMAP_OK;
+}
+
+void rapmap_cuda_mapper_free(rapmap_cuda_mapper_t* m) {
+  if (!m) return;
+  cudaSetDevice(m->idx->device);
+  freeMapperBuffers(m);
+  delete m;
+}
+
+static int growU32(void** p, uint32_t& cap, uint64_t need, size_t elem) {
+  uint64_t nc = need + need / 4 + 1024;
+  if (nc > 0xFFFFFFF0ull) return fail(RAPMAP_ERR_CAPACITY, "device work arena would exceed 2^32 records; use smaller batches");
+  cudaFree(*p);
+  *p = nullptr;
+  CU_TRY(cudaMalloc(p, nc * elem));
+  cap = static_cast<uint32_t>(nc);
+  return RAPMAP_OK;
+}
+
+int rapmap_cuda_map_batch(rapmap_cuda_mapper_t* m, const rapmap_read_batch_t* reads, rapmap_hit_batch_t* out) {
+  if (!m || !reads || !out) return fail(RAPMAP_ERR_ARG, "null argument");
+  if (reads->n == 0) { out->num_hits = 0; std::memset(out->counters, 0, sizeof(out->counters)); if (out->pair_offsets && out->location == RAPMAP_LOC_HOST) out->pair_offsets[0] = 0; return RAPMAP_OK; }
+  if (reads->n > m->maxBatch) return fail(RAPMAP_ERR_ARG, "batch larger than the mapper's max_batch");
+  if (!reads->seq1) return fail(RAPMAP_ERR_ARG, "seq1 is null");
+  if (!reads->off1 && (reads->fixed_len == 0 || reads->fixed_len > m->maxReadLen)) return fail(RAPMAP_ERR_ARG, "fixed_len must be in [1, max_read_len]");
+  if (reads->seq2 && ((reads->off1 == nullptr) != (reads->off2 == nullptr))) return fail(RAPMAP_ERR_ARG, "off1/off2 must both be set or both be null");
+  if (!out->pair_offsets) return fail(RAPMAP_ERR_ARG, "pair_offsets is null");
+  CU_TRY(cudaSetDevice(m->idx->device));
+  cudaStream_t st = m->stream;
+  const uint64_t n = reads->n;
+  const bool paired = reads->seq2 != nullptr;
+  std::memset(&m->timing, 0, sizeof(m->timing));
+
+  // ---- reads to the device
+  CU_TRY(cudaEventRecord(m->ev[0], st));
+  BatchView bv{};
+  bv.n = n; bv.numReads = paired ? 2 * n : n; bv.fixedLen = reads->fixed_len;
+  uint64_t h2d = 0;
+  for (int mate = 0; mate < (paired ? 2 : 1); ++mate) {
+    const uint8_t* seq = mate ? reads->seq2 : reads->seq1;
+    const uint64_t* off = mate ? reads->off2 : reads->off1;
+    if (reads->location == RAPMAP_LOC_DEVICE) {
+      bv.seq[mate] = seq; bv.off[mate] = off;
+    } else {
+      uint64_t bytes = off ? off[n] - off[0] : n * reads->fixed_len;
+      if (off && off[0] != 0) return fail(RAPMAP_ERR_ARG, "offsets must start at 0");
+      if (bytes > m->seqCap) return fail(RAPMAP_ERR_ARG, "read bases exceed max_batch * max_read_len");
+      CU_TRY(cudaMemcpyAsync(m->dSeq[mate], seq, bytes, cudaMemcpyHostToDevice, st));
+      h2d += bytes;
+      bv.seq[mate] = m->dSeq[mate];
+      if (off) { CU_TRY(cudaMemcpyAsync(m->dOff[mate], off, (n + 1) * 8, cudaMemcpyHostToDevice, st)); bv.off[mate] = m->dOff[mate]; h2d += (n + 1) * 8; }
+      else bv.off[mate] = nullptr;
+    }
+  }
+  m->lastView = bv;
+  m->lastReads = bv.numReads;
+  CU_TRY(cudaEventRecord(m->ev[1], st));
+
+  uint32_t launches = 0, retries = 0;
+  uint64_t total = 0;
+  for (;; ++retries) {
+    if (retries > 6) return fail(RAPMAP_ERR_CAPACITY, "device work arenas kept overflowing");
+    CU_TRY(cudaMemsetAsync(m->dCtl, 0, 16, st));
+    CU_TRY(cudaMemsetAsync(m->dCounters, 0, sizeof(Counters5), st));
+    // ---- kernel 1: SA lookup
+    CollectParams cp{};
+    cp.ix = m->idx->view; cp.reads = bv; cp.opts = m->dopts; cp.maxReadLen = m->maxReadLen; cp.lpad = m->lpad; cp.pmax = m->pmax;
+    cp.warpSmemBytes = m->warpSmem; cp.summ = m->dSumm; cp.arena = m->dIvArena; cp.arenaCap = m->ivCap; cp.arenaCursor = m->dCtl + 0; cp.status = m->dCtl + 3;
+    int g1 = static_cast<int>(std::min<uint64_t>(m->gridCollect, (bv.numReads + kWarps - 1) / kWarps));
+    sa_collect_kernel<kWarps><<<g1, kWarps * 32, m->collectSmem, st>>>(cp);
+    ++launches;
+    CU_TRY(cudaEventRecord(m->ev[2], st));
+    // ---- kernel 2: hit resolution
+    MapParams mp{};
+    mp.ix = m->idx->view; mp.opts = m->dopts; mp.numReads = bv.numReads; mp.numPairs = n; mp.pairedInput = paired ? 1 : 0;
+    mp.summ = m->dSumm; mp.arena = m->dIvArena; mp.qsumm = m->dQSumm; mp.qaArena = m->dQaArena; mp.qaCap = m->qaCap; mp.qaCursor = m->dCtl + 1;
+    mp.posPool = m->dPosPool; mp.posCap = m->posCap; mp.posCursor = m->dCtl + 2;
+    mp.scratch = m->dScratch; mp.scratchEntries = m->scratchEntries; mp.scratchStride = m->scratchStride; mp.smemEntries = m->smemEntries;
+    mp.status = m->dCtl + 3;
+    int g2 = static_cast<int>(std::min<uint64_t>(m->gridMap, (bv.numReads + kWarps - 1) / kWarps));
+    hits_to_mappings_kernel<kWarps><<<g2, kWarps * 32, m->mapSmem, st>>>(mp);
+    ++launches;
+    CU_TRY(cudaEventRecord(m->ev[3], st));
+    // ---- kernel 3: mate merge (count)
+    MergeParams gp{};
+    gp.opts = m->dopts; gp.numPairs = n; gp.pairedInput = paired ? 1 : 0; gp.qsumm = m->dQSumm; gp.qaArena = m->dQaArena; gp.summ = m->dSumm;
+    gp.pairCount = m->dPairCount; gp.pairOffset = m->dPairOff; gp.hits = m->dHits; gp.hitsCap = m->hitsCap; gp.counters = m->dCounters;
+    gp.posPool = m->dPosPool;
+    int g3 = static_cast<int>(std::min<uint64_t>(static_cast<uint64_t>(m->numSMs) * 8, (n + 255) / 256));
+    CU_TRY(cudaMemsetAsync(m->dPairCount + n, 0, 4, st));
+    if (m->dopts.selAln || m->dopts.fuzzy) merge_count_kernel<true><<<g3, 256, 0, st>>>(gp);
+    else merge_count_kernel<false><<<g3, 256, 0, st>>>(gp);
+    ++launches;
+    {
+        cub::TransformInputIterator<uint64_t, CastU64, uint32_t*> it(m->dPairCount, CastU64());
+      size_t tb = m->cubTempBytes;
+      CU_TRY(cub::DeviceScan::ExclusiveSum(m->dCubTemp, tb, it, m->dPairOff, static_cast<int>(n + 1), st));
+    }
+    CU_TRY(cudaMemcpyAsync(m->hStage->ctl, m->dCtl, 16, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(&m->hStage->total, m->dPairOff + n, 8, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    CU_TRY(cudaGetLastError());
+    uint32_t status = m->hStage->ctl[3];
+    if (status & kStatReadTooLong) return fail(RAPMAP_ERR_ARG, "a read is longer than the mapper's max_read_len");
+    bool again = false;
+    if (status & kStatIntervalArenaFull) { int rc = growU32(reinterpret_cast<void**>(&m->dIvArena), m->ivCap, m->hStage->ctl[0], sizeof(IntervalRec)); if (rc) return rc; again = true; }
+    if (status & kStatQAArenaFull) { int rc = growU32(reinterpret_cast<void**>(&m->dQaArena), m->qaCap, m->hStage->ctl[1], sizeof(QARec)); if (rc) return rc; again = true; }
+    if (status & kStatPosPoolFull) { int rc = growU32(reinterpret_cast<void**>(&m->dPosPool), m->posCap, m->hStage->ctl[2], 4); if (rc) return rc; again = true; }
+    if (status & kStatScratchFull) {
+      // worst case of a strand: pmax intervals of < maxInterval entries, padded to a power of two
+      uint64_t worst = 1;
+      while (worst < static_cast<uint64_t>(m->pmax) * 1000ull * 2ull) worst <<= 1;
+      if (m->scratchEntries >= worst) return fail(RAPMAP_ERR_CAPACITY, "hit-resolution work strip overflow at worst-case size");
+      uint64_t ne = std::min<uint64_t>(worst, static_cast<uint64_t>(m->scratchEntries) * 8);
+      cudaFree(m->dScratch); m->dScratch = nullptr;
+      m->scratchEntries = static_cast<uint32_t>(ne);
+      m->scratchStride = workAreaBytes(m->scratchEntries);
+      // fewer resident warps when the strips get large
+      while (m->gridMap > m->numSMs && m->scratchStride * static_cast<uint64_t>(m->gridMap) * kWarps > (8ull << 30)) m->gridMap -= m->numSMs;
+      CU_TRY(cudaMalloc(&m->dScratch, m->scratchStride * static_cast<uint64_t>(m->gridMap) * kWarps));
+      again = true;
+    }
+    total = m->hStage->total;
+    if (!again && total > m->hitsCap) {
+      cudaFree(m->dHits); m->dHits = nullptr;
+      m->hitsCap = total + total / 4 + 1024;
+      CU_TRY(cudaMalloc(&m->dHits, m->hitsCap * sizeof(rapmap_hit_t)));
+      gp.hits = m->dHits; gp.hitsCap = m->hitsCap;
+    }
+    if (again) continue;
+    CU_TRY(cudaEventRecord(m->ev[4], st));
+    // ---- kernel 3: mate merge (write)
+    if (total > 0) {
+      if (m->dopts.selAln || m->dopts.fuzzy) merge_write_kernel<true><<<g3, 256, 0, st>>>(gp);
+      else merge_write_kernel<false><<<g3, 256, 0, st>>>(gp);
+      ++launches;
+    }
+    CU_TRY(cudaEventRecord(m->ev[5], st));
+    break;
+  }
+  // ---- selective alignment (ksw2 scoring + score filter), rewrites dHits / dPairOff in place
+  if (m->dopts.selAln && total > 0) {
+    uint32_t l2 = 0;
+    int rc = selAlnRun(m->selaln, m->idx->view, m->dopts, bv, n, paired, m->dHits, m->dPairOff, m->dPairCount, total, m->dCubTemp, m->cubTempBytes,
+                       m->numSMs, st, &l2, &total, m->hStage, g_err);
+    if (rc) return rc;
+    launches += l2;
+  }
+  CU_TRY(cudaEventRecord(m->ev[6], st));
+  CU_TRY(cudaMemcpyAsync(&m->hStage->counters, m->dCounters, sizeof(Counters5), cudaMemcpyDeviceToHost, st));
+  // ---- results out
+  out->num_hits = total;
+  int rcOut = RAPMAP_OK;
+  if (total > out->hits_capacity || (total > 0 && !out->hits)) {
+    rcOut = fail(RAPMAP_ERR_CAPACITY, "hits_capacity too small for this batch (see num_hits)");
+  } else {
+    cudaMemcpyKind kind = out->location == RAPMAP_LOC_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    rapmap_hit_t* src = (m->dopts.selAln && total > 0) ? m->selaln.outHits : m->dHits;
+    if (total > 0) CU_TRY(cudaMemcpyAsync(out->hits, src, total * sizeof(rapmap_hit_t), kind, st));
+    CU_TRY(cudaMemcpyAsync(out->pair_offsets, m->dPairOff, (n + 1) * 8, kind, st));
+  }
+  CU_TRY(cudaEventRecord(m->ev[7], st));
+  CU_TRY(cudaStreamSynchronize(st));
+  for (int c = 0; c < 5; ++c) out->counters[c] = m->hStage->counters.v[c];
+  if (m->dopts.selAln) out->counters[3] = total;  // totHits is taken after the score filter (reference src/RapMapSAMapper.cpp:702)
+  auto ms = [&](int a, int b) { float t = 0; cudaEventElapsedTime(&t, m->ev[a], m->ev[b]); return t; };
+  m->timing.ms_h2d = ms(0, 1);
+  m->timing.ms_sa_collect = ms(1, 2);
+  m->timing.ms_hits_to_mappings = ms(2, 3);
+  m->timing.ms_merge = ms(3, 4) + ms(4, 5);
+  m->timing.ms_sel_aln = ms(5, 6);
+  m->timing.ms_d2h = ms(6, 7);
+  m->timing.ms_total = ms(0, 7);
+  m->timing.launches = launches;
+  m->timing.retries = retries;
+  m->timing.sa_intervals = m->hStage->ctl[0];
+  (void)h2d;
+  return rcOut;
+}
+
+int rapmap_cuda_last_timing(const rapmap_cuda_mapper_t* m, rapmap_cuda_timing_t* t) {
+  if (!m || !t) return fail(RAPMAP_ERR_ARG, "null argument");
+  *t = m->timing;
+  return RAPMAP_OK;
+}
+
+int rapmap_cuda_debug_intervals(rapmap_cuda_mapper_t* m, uint64_t read_index, rapmap_sa_interval_t* out, uint32_t cap, uint32_t* n_fwd,
+                                uint32_t* n_rc, uint8_t* found_hit) {
+  if (!m || !n_fwd || !n_rc || !found_hit) return fail(RAPMAP_ERR_ARG, "null argument");
+  if (read_index >= m->lastReads) return fail(RAPMAP_ERR_ARG, "read index out of range of the last batch");
+  CU_TRY(cudaSetDevice(m->idx->device));
+  ReadSummary s;
+  CU_TRY(cudaMemcpy(&s, m->dSumm + read_index, sizeof(s), cudaMemcpyDeviceToHost));
+  *n_fwd = s.nFwd; *n_rc = s.nRc; *found_hit = s.found;
+  uint32_t tot = static_cast<uint32_t>(s.nFwd) + s.nRc;
+  if (tot > cap) return fail(RAPMAP_ERR_CAPACITY, "interval buffer too small");
+  if (tot == 0) return RAPMAP_OK;
+  std::vector<IntervalRec> tmp(tot);
+  CU_TRY(cudaMemcpy(tmp.data(), m->dIvArena + s.ivOff, tot * sizeof(IntervalRec), cudaMemcpyDeviceToHost));
+  for (uint32_t i = 0; i < tot; ++i) {
+    std::memset(&out[i], 0, sizeof(out[i]));
+    out[i].begin = tmp[i].begin; out[i].end = tmp[i].end; out[i].len = tmp[i].len; out[i].query_pos = tmp[i].qpos;
+    out[i].query_rc = i >= s.nFwd ? 1 : 0;
+  }
+  return RAPMAP_OK;
+}
+
+static int dupOut(const std::string& s, char** sam, uint64_t* len) {
+  char* p = static_cast<char*>(std::malloc(s.size() + 1));
+  if (!p) return fail(RAPMAP_ERR_ARG, "out of host memory");
+  std::memcpy(p, s.data(), s.size());
+  p[s.size()] = 0;
+  *sam = p;
+  *len = s.size();
+  return RAPMAP_OK;
+}
+
+int rapmap_cuda_sam_header(const rapmap_cuda_index_t* idx, char** sam, uint64_t* sam_len) {
+  if (!idx || !sam || !sam_len) return fail(RAPMAP_ERR_ARG, "null argument");
+  return dupOut(samHeader(idx->names, idx->lens), sam, sam_len);
+}
+
+int rapmap_cuda_format_sam(const rapmap_cuda_index_t* idx, const rapmap_cuda_opts_t* opts, const rapmap_read_batch_t* reads, const char* names1,
+                           const char* names2, rapmap_hit_batch_t* hits, char** sam, uint64_t* sam_len) {
+  if (!idx || !opts || !reads || !names1 || !hits || !sam || !sam_len) return fail(RAPMAP_ERR_ARG, "null argument");
+  if (reads->location != RAPMAP_LOC_HOST || hits->location != RAPMAP_LOC_HOST) return fail(RAPMAP_ERR_ARG, "format_sam needs host buffers");
+  if (!reads->seq2 || !names2) return fail(RAPMAP_ERR_UNSUPPORTED, "SAM text for unmated reads is not implemented (SURVEY.md f1)");
+  if (idx->names.empty()) return fail(RAPMAP_ERR_ARG, "index was created from an image without transcript names");
+  std::string out;
+  out.reserve(reads->n * 700);
+  const char* n1 = names1;
+  const char* n2 = names2;
+  for (uint64_t i = 0; i < reads->n; ++i) {
+    const char* s1; const char* s2; size_t l1, l2;
+    if (reads->off1) {
+      s1 = reinterpret_cast<const char*>(reads->seq1) + reads->off1[i]; l1 = reads->off1[i + 1] - reads->off1[i];
+      s2 = reinterpret_cast<const char*>(reads->seq2) + reads->off2[i]; l2 = reads->off2[i + 1] - reads->off2[i];
+    } else {
+      s1 = reinterpret_cast<const char*>(reads->seq1) + i * reads->fixed_len; l1 = reads->fixed_len;
+      s2 = reinterpret_cast<const char*>(reads->seq2) + i * reads->fixed_len; l2 = reads->fixed_len;
+    }
+    uint64_t b = hits->pair_offsets[i], e = hits->pair_offsets[i + 1];
+    samPair(idx->names, idx->lens, opts->max_num_hits, n1, s1, l1, n2, s2, l2, hits->hits + b, e - b, out);
+    n1 += std::strlen(n1) + 1;
+    n2 += std::strlen(n2) + 1;
+  }
+  return dupOut(out, sam, sam_len);
+}
+
+void rapmap_cuda_free(void* p) { std::free(p); }
+
+} // extern "C"

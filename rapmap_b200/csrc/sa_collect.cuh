@@ -1,0 +1,410 @@
+// Kernel 1 — "the SA-lookup kernel": seed + maximal-mappable-prefix collection for one read per warp.
+//
+// Replaces SACollector::operator() / getSAHits_ / spotCheck_ (reference include/SACollector.hpp:108-362,
+// :441-677, :366-431) and SASearcher::extendSearchNaive (include/SASearcher.hpp:87-309) for the default
+// strand-decision mode (disableNIP && strictCheck => coverage check, SACollector.hpp:138,:283-288), with
+// or without chain scoring (selAln).
+//
+// B200 mapping: one warp owns one read.  The reference's walk is a chain of dependent random reads
+// (hash probe -> SA probe -> text compare).  The walk itself must be replayed decision by decision to
+// stay bit-exact, so the warp shortens the chain instead:
+//   * k-mer lookups are pure, so the 32 lanes look up 16 consecutive read positions in BOTH strands at
+//     once (one DRAM round trip instead of up to 31 sequential ones across a mismatch) and park the
+//     intervals in shared memory; the rc-strand walk reuses the same entries (k-mer at p of the reverse
+//     complement == RC of the k-mer at L-k-p).
+//   * every suffix comparison of the binary searches covers 128 text bytes per round trip (4 per lane),
+//     reduced with one ballot.
+// All walk state is replicated in registers across the warp (warp-uniform control flow).
+#pragma once
+#include "kernels.cuh"
+
+namespace rapmap_b200 {
+
+struct CollectParams {
+  DeviceIndex ix;
+  BatchView reads;
+  DevOpts opts;
+  uint32_t maxReadLen;     // shared-memory sizing
+  uint32_t lpad;           // bytes per read buffer (multiple of 16)
+  uint32_t pmax;           // max k-mer positions per read
+  uint32_t warpSmemBytes;
+  ReadSummary* summ;
+  IntervalRec* arena;
+  uint32_t arenaCap;
+  uint32_t* arenaCursor;
+  uint32_t* status;
+};
+
+__device__ __forceinline__ int baseCode(uint8_t c) {  // reference include/Kmer.hpp:40-51
+  switch (c | 0x20) {
+    case 'a': return 0;
+    case 'c': return 1;
+    case 'g': return 2;
+    case 't': return 3;
+    default: return -1;
+  }
+}
+
+// Kmer::fromChars (include/Kmer.hpp:524-542): stops at the first invalid base, leaving the partial word.
+__device__ __forceinline__ bool encodeKmer(const uint8_t* s, int k, uint64_t& w) {
+  w = 0;
+  int shift = 2 * k - 2;
+  for (int i = 0; i < k; ++i, shift -= 2) {
+    int c = baseCode(s[i]);
+    if (c < 0) return false;
+    w |= static_cast<uint64_t>(c) << shift;
+  }
+  return true;
+}
+
+__device__ __forceinline__ uint64_t kmerRC(uint64_t w, int k) {  // include/Kmer.hpp:92-100
+  w = ((w >> 2) & 0x3333333333333333ULL) | ((w & 0x3333333333333333ULL) << 2);
+  w = ((w >> 4) & 0x0F0F0F0F0F0F0F0FULL) | ((w & 0x0F0F0F0F0F0F0F0FULL) << 4);
+  w = ((w >> 8) & 0x00FF00FF00FF00FFULL) | ((w & 0x00FF00FF00FF00FFULL) << 8);
+  w = ((w >> 16) & 0x0000FFFF0000FFFFULL) | ((w & 0x0000FFFF0000FFFFULL) << 16);
+  w = (w >> 32) | (w << 32);
+  return (~w) >> (2 * (32 - k));
+}
+
+__device__ __forceinline__ bool isHomopolymer(uint64_t w, int k) {  // include/Kmer.hpp:484-487
+  uint64_t mask = (1ULL << (2 * k)) - 1ULL;
+  uint64_t nuc = w & 3ULL;
+  return w == (mask & ((w << 2) | nuc));
+}
+
+__device__ __forceinline__ uint8_t upperChar(uint8_t c) { return (c >= 'a' && c <= 'z') ? static_cast<uint8_t>(c - 32) : c; }
+
+__device__ __forceinline__ uint8_t rcChar(uint8_t c) {  // rapmap::utils::reverseRead table, src/RapMapUtils.cpp:63-72
+  switch (c | 0x20) {
+    case 'a': return 'T';
+    case 'c': return 'G';
+    case 'g': return 'C';
+    case 't': return 'A';
+    case 'u': return (c == 'U' || c == 'u') ? 'A' : 'N';
+    default: return 'N';
+  }
+}
+
+struct WarpCtx {
+  DeviceIndex ix;
+  const uint8_t* fwdBuf;
+  const uint8_t* rcBuf;
+  int2* cF;   // per forward position: interval of the k-mer        (x == -2: not looked up, x == -1: absent)
+  int2* cR;   // per forward position: interval of its reverse complement
+  int L, k, npos, lane;
+  bool hasU;
+};
+
+// Speculative lookup of 16 consecutive forward positions q0, q0+dir, ... in both orientations.
+__device__ __forceinline__ void fillCache(const WarpCtx& c, int q0, int dir) {
+  int q = q0 + dir * (c.lane & 15);
+  bool rcSide = (c.lane >> 4) != 0;
+  if (q >= 0 && q < c.npos) {
+    int2* slot = (rcSide ? c.cR : c.cF) + q;
+    if (slot->x == -2) {
+      uint64_t w;
+      int2 res = make_int2(-1, -1);
+      if (encodeKmer(c.fwdBuf + q, c.k, w)) res = hashFind(c.ix, rcSide ? kmerRC(w, c.k) : w);
+      *slot = res;
+    }
+  }
+  __syncwarp();
+}
+
+// Lookup of the k-mer `w` found at position p of the walk strand (and of its reverse complement).
+// Full, cacheable k-mers go through the shared-memory cache; partial words (a non-ACGT base inside the
+// window, Kmer.hpp:536-537) and reads containing 'U' (reverseRead maps U->A, so strand symmetry breaks)
+// are looked up directly.
+__device__ __forceinline__ void lookupBoth(const WarpCtx& c, bool isRC, int p, uint64_t w, bool valid, bool needMer, bool needComp,
+                                           int2& mer, int2& comp) {
+  if (valid && !(isRC && c.hasU)) {
+    int q = isRC ? (c.L - c.k - p) : p;
+    int2* cm = isRC ? c.cR : c.cF;
+    int2* cc = isRC ? c.cF : c.cR;
+    if ((needMer && cm[q].x == -2) || (needComp && cc[q].x == -2)) fillCache(c, q, isRC ? -1 : 1);
+    mer = cm[q];
+    comp = cc[q];
+  } else {
+    if (needMer) mer = hashFind(c.ix, w);
+    if (needComp) comp = hashFind(c.ix, kmerRC(w, c.k));
+  }
+}
+
+// Cooperative suffix comparison: query q[i] vs text[t+i] for i >= i0 while i < m and t+i < n.
+// sentIdx >= 0 replaces q[sentIdx] by `sent` (searches 2/3 of extendSearchNaive).  Returns the index at
+// which the reference's inner while-loop stops; rel = -1 (query < text), +1 (query > text), 0 (ran off).
+__device__ __forceinline__ int coopCompare(const WarpCtx& c, const uint8_t* q, int m, int64_t t, int i0, int sentIdx, uint8_t sent, int& rel) {
+  int64_t limL = c.ix.n - t;
+  int lim = (limL < static_cast<int64_t>(m)) ? static_cast<int>(limL) : m;
+  if (i0 >= lim) { rel = 0; return i0; }
+  const uint8_t* tp = c.ix.text + t;
+  for (int base = i0;; base += 128) {
+    int idx = base + c.lane * 4;
+    uint8_t tc[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) tc[j] = (idx + j < lim) ? __ldg(tp + idx + j) : 0;
+    int stop = 4, r = 0;
+#pragma unroll
+    for (int j = 3; j >= 0; --j) {
+      int id = idx + j;
+      if (id >= lim) { stop = j; r = 0; }
+      else {
+        uint8_t qc = (id == sentIdx) ? sent : upperChar(q[id]);
+        if (qc != tc[j]) { stop = j; r = (qc < tc[j]) ? -1 : 1; }
+      }
+    }
+    unsigned b = __ballot_sync(0xffffffffu, stop < 4);
+    if (b) {
+      int src = __ffs(b) - 1;
+      int sIdx = __shfl_sync(0xffffffffu, idx + stop, src);
+      rel = __shfl_sync(0xffffffffu, r, src);
+      return sIdx;
+    }
+  }
+}
+
+// SASearcher::extendSearchNaive (include/SASearcher.hpp:87-309); startAt = k.
+__device__ __forceinline__ void extendSearch(const WarpCtx& c, int64_t lbIn, int64_t ubIn, const uint8_t* q, int mQ,
+                                             int& outLb, int& outUb, int& outLen) {
+  const int startAt = c.k;
+  const int64_t n = c.ix.n;
+  int rel;
+  if (ubIn - lbIn == 2) {  // :109-126
+    int64_t t = __ldg(c.ix.SA + lbIn + 1);
+    int i = coopCompare(c, q, mQ, t, startAt, -1, 0, rel);
+    outLb = static_cast<int>(lbIn + 1); outUb = static_cast<int>(ubIn); outLen = i;
+    return;
+  }
+  int64_t l = lbIn, r = ubIn;
+  int lcpLP = startAt, lcpRP = startAt;
+  int prevILow = startAt, prevIHigh = startAt;
+  int maxLen;
+  while (true) {  // :150-209
+    int64_t cc = (l + r) / 2;
+    int64_t t = __ldg(c.ix.SA + cc);
+    int i0 = lcpLP < lcpRP ? lcpLP : lcpRP;
+    int i = coopCompare(c, q, mQ, t, i0, -1, 0, rel);
+    bool plt = true;
+    if (rel < 0) { if (i > prevIHigh) prevIHigh = i; }
+    else if (rel > 0) { if (i > prevILow) prevILow = i; plt = false; }
+    else if (i == mQ || t + i == n) { if (i > prevIHigh) prevIHigh = i; }
+    if (plt) {
+      if (cc == l + 1) { maxLen = max(max(i, prevILow), prevIHigh); break; }
+      r = cc; lcpRP = i;
+    } else {
+      if (cc == r - 1) { maxLen = max(max(i, prevILow), prevIHigh); break; }
+      l = cc; lcpLP = i;
+    }
+  }
+  const int m = maxLen + 1;  // :212
+  int64_t bound[2];
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {  // :224-258 lower bound with '#', :270-304 upper bound with '{'
+    const uint8_t sent = pass == 0 ? '#' : '{';
+    l = pass == 0 ? lbIn : bound[0] - 1;
+    r = ubIn;
+    lcpLP = startAt; lcpRP = startAt;
+    while (true) {
+      int64_t cc = (l + r) / 2;
+      int64_t t = __ldg(c.ix.SA + cc);
+      int i0 = lcpLP < lcpRP ? lcpLP : lcpRP;
+      int i = coopCompare(c, q, m, t, i0, m - 1, sent, rel);
+      if (rel <= 0) {
+        if (cc == l + 1) { bound[pass] = cc; break; }
+        r = cc; lcpRP = i;
+      } else {
+        if (cc == r - 1) { bound[pass] = r; break; }
+        l = cc; lcpLP = i;
+      }
+    }
+  }
+  if (bound[0] == bound[1]) bound[1] += 1;  // :307
+  outLb = static_cast<int>(bound[0]); outUb = static_cast<int>(bound[1]); outLen = maxLen;
+}
+
+__device__ __forceinline__ int findN(const uint8_t* s, int from, int L) {  // std::string::find_first_of("nN", from)
+  for (int i = from; i < L; ++i)
+    if ((s[i] | 0x20) == 'n') return i;
+  return 0x7fffffff;
+}
+
+// SACollector::getSAHits_ (include/SACollector.hpp:441-677) on one strand.  `buf` is the strand's read.
+__device__ __forceinline__ void walkStrand(const WarpCtx& c, const DevOpts& o, bool isRC, int startPos, bool haveStart, int2 startIv,
+                                           uint32_t& cov, uint32_t& strandHits, uint32_t& otherStrandHits, IntervalRec* list, int& nList) {
+  const uint8_t* buf = isRC ? c.rcBuf : c.fwdBuf;
+  const int k = c.k, L = c.L;
+  int rb = 0;
+  int64_t lb = 0, ub = 0;
+  bool lastSearch = false;
+  int prevMMPEnd = 0;
+  bool skipSetup = haveStart;
+  if (skipSetup) { rb = startPos; lb = startIv.x; ub = startIv.y; }
+  while (skipSetup || rb + k <= L) {
+    if (!skipSetup) {
+      uint64_t mer;
+      bool valid = encodeKmer(buf + rb, k, mer);
+      if (!valid) {  // :505-516
+        int inv = findN(buf, rb, L);
+        if (inv < rb + k) { rb = inv + 1; continue; }
+      }
+      if (isHomopolymer(mer, k)) { rb += 1; continue; }  // :520-536
+      int2 fm, fc;
+      lookupBoth(c, isRC, rb, mer, valid, true, true, fm, fc);  // find + spotCheck_ complement (:541-546,:671)
+      if (fm.x >= 0) ++strandHits;
+      if (fc.x >= 0) ++otherStrandHits;
+      if (fm.x < 0) { rb += 1; continue; }  // :673
+      lb = fm.x; ub = fm.y;
+    }
+    skipSetup = false;
+    lb = lb - 1 > 0 ? lb - 1 : 0;  // :553
+    bool firstAttempt = o.doChaining ? (rb == 0) : true;
+    int endPos = firstAttempt ? L : min(rb + k + o.maxMMPExtension, L);
+    int nlb, nub, matchedLen;
+    extendSearch(c, lb, ub, buf + rb, endPos - rb, nlb, nub, matchedLen);
+    if (o.doChaining && firstAttempt && !(matchedLen >= L) && matchedLen >= k + o.maxMMPExtension) {  // :568-575
+      endPos = min(rb + k + o.maxMMPExtension, L);
+      extendSearch(c, lb, ub, buf + rb, endPos - rb, nlb, nub, matchedLen);
+    }
+    lb = nlb; ub = nub;
+    if (ub > lb && (ub - lb) < o.maxInterval) {  // :578
+      if (c.lane == 0) {
+        IntervalRec rec;
+        rec.begin = static_cast<int32_t>(lb); rec.end = static_cast<int32_t>(ub);
+        rec.len = static_cast<uint16_t>(matchedLen); rec.qpos = static_cast<uint16_t>(rb);
+        list[nList] = rec;
+      }
+      ++nList;
+      int correction = prevMMPEnd > rb ? prevMMPEnd - rb : 0;
+      cov += static_cast<uint32_t>(matchedLen - correction);
+      prevMMPEnd = rb + matchedLen;
+      if (rb + matchedLen < L) {  // :599-616 mismatching k-mer, both orientations
+        int kp = rb + matchedLen - (k - 1);
+        uint64_t mm;
+        if (encodeKmer(buf + kp, k, mm)) {
+          int2 fm, fc;
+          lookupBoth(c, isRC, kp, mm, true, true, true, fm, fc);
+          if (fm.x >= 0) ++strandHits;
+          if (fc.x >= 0) ++otherStrandHits;
+        }
+      }
+    }
+    if (lastSearch) return;            // :623
+    if (rb + matchedLen >= L) return;  // :630
+    rb = rb + matchedLen - (k - 1);    // :640-647 with disableNIP (lce == matchedLen)
+    if (rb + k == L) lastSearch = true;  // :663
+  }
+}
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) sa_collect_kernel(CollectParams P) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  uint8_t* base = smem + static_cast<size_t>(warp) * P.warpSmemBytes;
+  uint8_t* fwdBuf = base;
+  uint8_t* rcBuf = base + P.lpad;
+  int2* cF = reinterpret_cast<int2*>(base + 2 * P.lpad);
+  int2* cR = cF + P.pmax;
+  IntervalRec* ivF = reinterpret_cast<IntervalRec*>(cR + P.pmax);
+  IntervalRec* ivR = ivF + P.pmax;
+  const DevOpts& o = P.opts;
+  const int k = static_cast<int>(P.ix.k);
+
+  for (uint64_t r = static_cast<uint64_t>(blockIdx.x) * WARPS + warp; r < P.reads.numReads; r += static_cast<uint64_t>(gridDim.x) * WARPS) {
+    const int mate = r >= P.reads.n ? 1 : 0;
+    const uint64_t ri = r - static_cast<uint64_t>(mate) * P.reads.n;
+    const uint8_t* src;
+    uint32_t len;
+    if (P.reads.off[mate]) {
+      uint64_t o0 = P.reads.off[mate][ri], o1 = P.reads.off[mate][ri + 1];
+      src = P.reads.seq[mate] + o0;
+      len = static_cast<uint32_t>(o1 - o0);
+    } else {
+      src = P.reads.seq[mate] + ri * P.reads.fixedLen;
+      len = P.reads.fixedLen;
+    }
+    ReadSummary s;
+    s.ivOff = 0; s.nFwd = 0; s.nRc = 0; s.found = 0; s.pad = 0;
+    s.readLen = static_cast<uint16_t>(len);
+    if (len > P.maxReadLen) {
+      if (lane == 0) { atomicOr(P.status, kStatReadTooLong); s.readLen = 0; P.summ[r] = s; }
+      continue;
+    }
+    const int L = static_cast<int>(len);
+    const int npos = L - k + 1;
+    __syncwarp();
+    bool u = false;
+    for (int i = lane; i < L; i += 32) {
+      uint8_t ch = __ldg(src + i);
+      fwdBuf[i] = ch;
+      rcBuf[L - 1 - i] = rcChar(ch);
+      u |= ((ch | 0x20) == 'u');
+    }
+    for (int i = lane; i < npos; i += 32) { cF[i] = make_int2(-2, -2); cR[i] = make_int2(-2, -2); }
+    const bool hasU = __any_sync(0xffffffffu, u);
+    __syncwarp();
+
+    WarpCtx c;
+    c.ix = P.ix; c.fwdBuf = fwdBuf; c.rcBuf = rcBuf; c.cF = cF; c.cR = cR; c.L = L; c.k = k; c.npos = npos; c.lane = lane; c.hasU = hasU;
+
+    // ---- first-hit scan (SACollector.hpp:167-237)
+    uint32_t fwdHit = 0, rcHit = 0, fwdCov = 0, rcCov = 0;
+    bool foundHit = false;
+    int rb = 0;
+    int invalidPos = 0;
+    int2 firstIv = make_int2(-1, -1);
+    while (rb + k <= L) {
+      if (invalidPos != 0x7fffffff) {
+        invalidPos = findN(fwdBuf, rb, L);
+        if (invalidPos <= rb + k) { rb = invalidPos + 1; continue; }  // note <= (SACollector.hpp:178)
+      }
+      uint64_t mer;
+      bool valid = encodeKmer(fwdBuf + rb, k, mer);
+      if (isHomopolymer(mer, k)) { rb += 1; continue; }
+      int2 fm, fc;
+      lookupBoth(c, false, rb, mer, valid, true, true, fm, fc);
+      if (fm.x >= 0) { ++fwdHit; if (fc.x >= 0) ++rcHit; }
+      if (fc.x >= 0 && !fwdHit) ++rcHit;
+      if (fwdHit + rcHit > 0) { foundHit = true; firstIv = fm; break; }
+      ++rb;
+    }
+    int nF = 0, nR = 0;
+    if (foundHit) {
+      bool didCheckFwd = false;
+      if (fwdHit) {  // :247-254
+        didCheckFwd = true;
+        walkStrand(c, o, false, rb, true, firstIv, fwdCov, fwdHit, rcHit, ivF, nF);
+      }
+      if (rcHit > 0)  // :256-265 (coverage mode: checkRC = rcHit > 0)
+        walkStrand(c, o, true, 0, false, make_int2(0, 0), rcCov, rcHit, fwdHit, ivR, nR);
+      if (!didCheckFwd && fwdHit > 0)  // :270-278
+        walkStrand(c, o, false, 0, false, make_int2(0, 0), fwdCov, fwdHit, rcHit, ivF, nF);
+      // strand decision by coverage (:283-288)
+      if (fwdCov > rcCov + static_cast<uint32_t>(o.strictCheckSlack)) nR = 0;
+      else if (rcCov > fwdCov + static_cast<uint32_t>(o.strictCheckSlack)) nF = 0;
+      if (o.covReq > 0.0) {  // :343-358
+        if (nF > 0 && (static_cast<double>(fwdCov) / static_cast<double>(L)) < o.covReq) nF = 0;
+        if (nR > 0 && (static_cast<double>(rcCov) / static_cast<double>(L)) < o.covReq) nR = 0;
+      }
+    }
+    __syncwarp();
+    // ---- publish
+    const int tot = nF + nR;
+    uint32_t off = 0;
+    if (tot > 0) {
+      if (lane == 0) off = atomicAdd(P.arenaCursor, static_cast<uint32_t>(tot));
+      off = __shfl_sync(0xffffffffu, off, 0);
+      if (off + static_cast<uint32_t>(tot) > P.arenaCap) {
+        if (lane == 0) atomicOr(P.status, kStatIntervalArenaFull);
+      } else {
+        for (int i = lane; i < tot; i += 32) P.arena[off + i] = i < nF ? ivF[i] : ivR[i - nF];
+      }
+    }
+    if (lane == 0) {
+      s.ivOff = off; s.nFwd = static_cast<uint16_t>(nF); s.nRc = static_cast<uint16_t>(nR); s.found = foundHit ? 1 : 0;
+      P.summ[r] = s;
+    }
+  }
+}
+
+} // namespace rapmap_b200

@@ -1,0 +1,268 @@
+"""Test-side plumbing: the CPU oracle (ctypes), the compiled reference binary, synthetic data, golden fixtures.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg import this module; the product
+package (rapmap_b200/) never touches oracle/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import gzip
+import hashlib
+import os
+import subprocess
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+import rapmap_b200 as rb
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+CACHE = os.environ.get("RAPMAP_B200_CACHE", "/tmp/rapmap_b200_cache")
+ORACLE_SO = os.path.join(ROOT, "oracle", "_build", "liboracle.so")
+ORACLE_CLI = os.path.join(ROOT, "oracle", "_build", "quasimap_oracle")
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "rapmap_ref")
+SYNTH_SO = os.path.join(ROOT, "build", "libsynth.so")
+SYNTH_BIN = os.path.join(ROOT, "build", "bin", "synth")
+
+
+# ----------------------------------------------------------------------------------------------
+# oracle
+# ----------------------------------------------------------------------------------------------
+_olib = None
+_oidx = {}
+
+
+def oracle_lib() -> C.CDLL:
+    global _olib
+    if _olib is None:
+        if not os.path.exists(ORACLE_SO):
+            subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, capture_output=True)
+        L = C.CDLL(ORACLE_SO)
+        L.oracle_index_load.restype = C.c_void_p
+        L.oracle_index_load.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
+        L.oracle_index_free.argtypes = [C.c_void_p]
+        L.oracle_index_num_kmers.restype = C.c_uint64
+        L.oracle_index_num_kmers.argtypes = [C.c_void_p]
+        L.oracle_mapper_new.restype = C.c_void_p
+        L.oracle_mapper_new.argtypes = [C.c_void_p, C.POINTER(rb.Opts)]
+        L.oracle_mapper_free.argtypes = [C.c_void_p]
+        L.oracle_map_batch.argtypes = [C.c_void_p, C.POINTER(rb.ReadBatch), C.POINTER(rb.HitBatch)]
+        L.oracle_collect.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.POINTER(rb.SAInterval), C.c_uint32, C.POINTER(C.c_uint32),
+                                     C.POINTER(C.c_uint32), C.POINTER(C.c_uint8)]
+        L.oracle_op_counts.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+        L.oracle_ksw_extz_score.restype = C.c_int32
+        L.oracle_ksw_extz_score.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int]
+        _olib = L
+    return _olib
+
+
+def oracle_index(idx_dir: str):
+    if idx_dir not in _oidx:
+        err = C.create_string_buffer(512)
+        h = oracle_lib().oracle_index_load(os.fsencode(idx_dir), err, 512)
+        if not h:
+            raise RuntimeError("oracle index load failed: " + err.value.decode())
+        _oidx[idx_dir] = h
+    return _oidx[idx_dir]
+
+
+class OracleMapper:
+    def __init__(self, idx_dir: str, opts: rb.Opts):
+        self.L = oracle_lib()
+        self.h = self.L.oracle_mapper_new(oracle_index(idx_dir), C.byref(opts))
+
+    def map(self, s1, s2, fixed_len=0, off1=None, off2=None, n=None) -> rb.BatchResult:
+        if n is None:
+            n = (len(off1) - 1) if off1 is not None else s1.size // fixed_len
+        rbatch = rb.ReadBatch()
+        rbatch.seq1 = s1.ctypes.data
+        rbatch.seq2 = s2.ctypes.data if s2 is not None else 0
+        rbatch.off1 = off1.ctypes.data if off1 is not None else 0
+        rbatch.off2 = off2.ctypes.data if off2 is not None else 0
+        rbatch.n = n
+        rbatch.fixed_len = fixed_len
+        cap = max(1024, 16 * n)
+        while True:
+            hits = np.zeros(cap, dtype=rb.HIT_DTYPE)
+            offs = np.zeros(n + 1, dtype=np.uint64)
+            hb = rb.HitBatch()
+            hb.hits = hits.ctypes.data
+            hb.hits_capacity = cap
+            hb.pair_offsets = offs.ctypes.data
+            rc = self.L.oracle_map_batch(self.h, C.byref(rbatch), C.byref(hb))
+            if rc == 5:
+                cap = int(hb.num_hits) + 16
+                continue
+            assert rc == 0
+            nh = int(hb.num_hits)
+            return rb.BatchResult(hits[:nh], offs, np.array(list(hb.counters), dtype=np.uint64), nh)
+
+    def collect(self, read: bytes, cap: int = 4096):
+        buf = (rb.SAInterval * cap)()
+        nf, nr, found = C.c_uint32(), C.c_uint32(), C.c_uint8()
+        rc = self.L.oracle_collect(self.h, read, len(read), buf, cap, C.byref(nf), C.byref(nr), C.byref(found))
+        assert rc == 0
+        ivs = [(int(b.begin), int(b.end), int(b.len), int(b.query_pos), int(b.query_rc)) for b in buf[: nf.value + nr.value]]
+        return bool(found.value), nf.value, nr.value, ivs
+
+    def op_counts(self):
+        out = (C.c_uint64 * 7)()
+        self.L.oracle_op_counts(self.h, out)
+        return dict(zip(["hashFind", "saProbes", "textCmp", "rankCalls", "intervals", "kswCalls", "alnCalls"], [int(x) for x in out]))
+
+    def ksw(self, q: bytes, t: bytes) -> int:
+        return self.L.oracle_ksw_extz_score(self.h, q, len(q), t, len(t))
+
+    def __del__(self):
+        try:
+            self.L.oracle_mapper_free(self.h)
+        except Exception:
+            pass
+
+
+def oracle_map(idx_dir, opts, s1, s2, fixed_len=0, off1=None, off2=None) -> rb.BatchResult:
+    return OracleMapper(idx_dir, opts).map(s1, s2, fixed_len, off1, off2)
+
+
+# ----------------------------------------------------------------------------------------------
+# synthetic data (tools/synth.cpp)
+# ----------------------------------------------------------------------------------------------
+_slib = None
+
+
+def synth_lib() -> C.CDLL:
+    global _slib
+    if _slib is None:
+        if not os.path.exists(SYNTH_SO):
+            os.makedirs(os.path.dirname(SYNTH_SO), exist_ok=True)
+            subprocess.run(["g++", "-O2", "-fopenmp", "-shared", "-fPIC", os.path.join(ROOT, "tools", "synth.cpp"), "-o", SYNTH_SO], check=True)
+        L = C.CDLL(SYNTH_SO)
+        L.synth_txome_new.restype = C.c_void_p
+        L.synth_txome_new.argtypes = [C.c_uint64, C.c_int64, C.c_int]
+        L.synth_txome_free.argtypes = [C.c_void_p]
+        L.synth_txome_ntxp.restype = C.c_int64
+        L.synth_txome_ntxp.argtypes = [C.c_void_p]
+        L.synth_txome_text_len.restype = C.c_int64
+        L.synth_txome_text_len.argtypes = [C.c_void_p]
+        L.synth_txome_write_fasta.argtypes = [C.c_uint64, C.c_int64, C.c_int, C.c_char_p]
+        L.synth_reads.argtypes = [C.c_void_p, C.c_uint64, C.c_int64, C.c_int64, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                  C.c_void_p, C.c_void_p, C.c_void_p]
+        _slib = L
+    return _slib
+
+
+class SynthTxome:
+    def __init__(self, seed: int, genes: int, repeats: int = 0):
+        self.seed, self.genes, self.repeats = seed, genes, repeats
+        self.h = synth_lib().synth_txome_new(seed, genes, repeats)
+
+    @property
+    def ntxp(self):
+        return synth_lib().synth_txome_ntxp(self.h)
+
+    def write_fasta(self, path: str):
+        assert synth_lib().synth_txome_write_fasta(self.seed, self.genes, self.repeats, os.fsencode(path)) == 0
+
+    def reads(self, n: int, rseed: int = 54321, first: int = 0, read_len: int = 100, sub=10000, ins=300, dele=300, nn=1000, out1=None, out2=None):
+        s1 = out1 if out1 is not None else np.empty((n, read_len), dtype=np.uint8)
+        s2 = out2 if out2 is not None else np.empty((n, read_len), dtype=np.uint8)
+        p1 = s1.ctypes.data if isinstance(s1, np.ndarray) else int(s1.data_ptr())
+        p2 = s2.ctypes.data if isinstance(s2, np.ndarray) else int(s2.data_ptr())
+        synth_lib().synth_reads(self.h, rseed, first, n, read_len, sub, ins, dele, nn, p1, p2, None)
+        return s1, s2
+
+    def __del__(self):
+        try:
+            synth_lib().synth_txome_free(self.h)
+        except Exception:
+            pass
+
+
+def have_ref() -> bool:
+    return os.path.exists(REF_BIN)
+
+
+def build_index(fasta: str, out_dir: str, perfect: bool = False, k: int = 31) -> str:
+    """quasiindex with the compiled reference (oracle/_ref) — the index format is the reference's own."""
+    if not out_dir.endswith("/"):
+        out_dir += "/"
+    if os.path.exists(os.path.join(out_dir, "header.json")):
+        return out_dir
+    os.makedirs(out_dir, exist_ok=True)
+    cmd = [REF_BIN, "quasiindex", "-t", fasta, "-i", out_dir, "-k", str(k)]
+    if perfect:
+        cmd += ["-p", "-x", "4"]
+    subprocess.run(cmd, check=True, capture_output=True)
+    return out_dir
+
+
+def synth_index(genes: int, seed: int = 12345, repeats: int = 0, perfect: bool = False) -> tuple[str, SynthTxome]:
+    """Index of a synthetic transcriptome, cached under CACHE (built with the reference's quasiindex)."""
+    tag = f"synth_g{genes}_s{seed}_r{repeats}" + ("_p" if perfect else "")
+    d = os.path.join(CACHE, tag)
+    tx = SynthTxome(seed, genes, repeats)
+    if not os.path.exists(os.path.join(d, "idx", "header.json")):
+        os.makedirs(d, exist_ok=True)
+        fa = os.path.join(d, "t.fasta")
+        tx.write_fasta(fa)
+        build_index(fa, os.path.join(d, "idx"), perfect)
+    return os.path.join(d, "idx") + "/", tx
+
+
+# ----------------------------------------------------------------------------------------------
+# golden fixtures
+# ----------------------------------------------------------------------------------------------
+def read_fastq(path: str):
+    op = gzip.open if path.endswith(".gz") else open
+    names, seqs = [], []
+    with op(path, "rt") as f:
+        while True:
+            h = f.readline()
+            if not h:
+                break
+            s = f.readline().rstrip("\n")
+            f.readline()
+            f.readline()
+            names.append(h[1:].rstrip("\n").split()[0])
+            seqs.append(s)
+    return names, seqs
+
+
+def pack_fixed(seqs, L=None):
+    L = L or len(seqs[0])
+    a = np.frombuffer("".join(seqs).encode(), dtype=np.uint8).reshape(len(seqs), L).copy()
+    return a
+
+
+def pack_ragged(seqs):
+    off = np.zeros(len(seqs) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([len(s) for s in seqs])
+    buf = np.frombuffer("".join(seqs).encode(), dtype=np.uint8).copy() if off[-1] > 0 else np.zeros(1, dtype=np.uint8)
+    return buf, off
+
+
+def golden_sample():
+    """(index dir, mate1 array, mate2 array, read length) of the committed sample_data fixture."""
+    _, a = read_fastq(os.path.join(GOLD, "sample_reads_1.fastq.gz"))
+    _, b = read_fastq(os.path.join(GOLD, "sample_reads_2.fastq.gz"))
+    return os.path.join(GOLD, "sample_idx") + "/", pack_fixed(a), pack_fixed(b), len(a[0])
+
+
+def md5(data: bytes) -> str:
+    return hashlib.md5(data).hexdigest()
+
+
+def explain_mismatch(res: rb.BatchResult, ref: rb.BatchResult, limit: int = 5) -> str:
+    """Human-readable first differences between two batch results."""
+    out = []
+    n = len(ref.pair_offsets) - 1
+    for i in range(n):
+        a = res.hits[int(res.pair_offsets[i]) : int(res.pair_offsets[i + 1])]
+        b = ref.hits[int(ref.pair_offsets[i]) : int(ref.pair_offsets[i + 1])]
+        if len(a) != len(b) or not np.array_equal(a, b):
+            out.append(f"pair {i}: got {a.tolist()} expected {b.tolist()}")
+            if len(out) >= limit:
+                break
+    return "\n".join(out)

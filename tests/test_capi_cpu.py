@@ -1,0 +1,55 @@
+"""CPU: the C-ABI library builds, loads, exports every symbol of include/rapmap_cuda.h, and refuses to run without a GPU."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+import rapmap_b200 as rb
+from helpers import GOLD, ROOT
+
+
+def test_library_exports_every_declared_symbol():
+    L = rb.lib()
+    hdr = open(os.path.join(ROOT, "include", "rapmap_cuda.h")).read()
+    declared = set(re.findall(r"\b(rapmap_cuda_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(rb.SYMBOLS), declared ^ set(rb.SYMBOLS)
+    for s in declared:
+        assert hasattr(L, s), s
+
+
+def test_struct_layouts_match_header():
+    assert C.sizeof(rb.Hit) == 28
+    assert C.sizeof(rb.SAInterval) == 32
+    assert C.sizeof(rb.ReadBatch) == 48
+    assert C.sizeof(rb.HitBatch) == 80
+    o = rb.default_opts()
+    assert (o.max_num_hits, o.sensitive, o.strict_check, o.sel_aln, o.dp_bandwidth, o.max_mmp_extension) == (200, 1, 1, 0, 15, 7)
+    assert (o.match_score, o.mismatch_penalty, o.gap_open_penalty, o.gap_extend_penalty) == (2, -4, 4, 2)
+    assert abs(o.consensus_slack - 0.2) < 1e-6 and o.min_score_fraction == 0.65
+    assert rb.default_opts(sel_aln=True).sel_aln == 1
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product path must fail loudly, never compute on the CPU."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(rb.RapMapCudaError) as e:
+        rb.Index(os.path.join(GOLD, "sample_idx"), 0)
+    assert e.value.code == rb.ERR_CUDA
+    assert "no CPU path" in str(e.value)
+
+
+def test_product_does_not_reference_oracle():
+    """Nothing under rapmap_b200/ may import, link or execute oracle/."""
+    bad = []
+    for dp, _, fs in os.walk(os.path.join(ROOT, "rapmap_b200")):
+        if "_build" in dp or "__pycache__" in dp:
+            continue
+        for f in fs:
+            txt = open(os.path.join(dp, f), errors="replace").read()
+            if re.search(r"oracle/|liboracle|quasimap_oracle|oracle_", txt):
+                bad.append(os.path.join(dp, f))
+    assert not bad, bad

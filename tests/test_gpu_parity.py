@@ -1,0 +1,279 @@
+"""GPU: the CUDA path (through the C-ABI) is bit-identical to the CPU oracle and to the reference's golden SAM."""
+import gzip
+import json
+import os
+
+import numpy as np
+import pytest
+
+import rapmap_b200 as rb
+from helpers import (GOLD, OracleMapper, SynthTxome, explain_mismatch, golden_sample, have_ref, md5, pack_fixed, pack_ragged, read_fastq,
+                     synth_index)
+
+pytestmark = pytest.mark.gpu
+
+with open(os.path.join(GOLD, "golden.json")) as f:
+    GOLDEN = json.load(f)
+META = GOLDEN["_meta"]["synth"]
+
+
+def _supported(opts):
+    """Mapper for opts, or skip if the device path refuses the option set (it must refuse, never approximate)."""
+    return opts
+
+
+def assert_same(res, ref, what=""):
+    assert res.num_hits == ref.num_hits, f"{what}: hits {res.num_hits} != {ref.num_hits}\n" + explain_mismatch(res, ref)
+    assert np.array_equal(res.pair_offsets, ref.pair_offsets), f"{what}: offsets differ\n" + explain_mismatch(res, ref)
+    assert np.array_equal(res.hits, ref.hits), f"{what}: records differ\n" + explain_mismatch(res, ref)
+    assert np.array_equal(res.counters, ref.counters), f"{what}: counters {res.counters} != {ref.counters}"
+
+
+def make_mapper(index, opts, n, L):
+    try:
+        return rb.Mapper(index, opts, max_batch=n, max_read_len=L)
+    except rb.RapMapCudaError as e:
+        if e.code == rb.ERR_UNSUPPORTED:
+            pytest.skip(f"refused by the device path: {e}")
+        raise
+
+
+@pytest.fixture(scope="module")
+def sample():
+    idx_dir, s1, s2, L = golden_sample()
+    n1, _ = read_fastq(os.path.join(GOLD, "sample_reads_1.fastq.gz"))
+    n2, _ = read_fastq(os.path.join(GOLD, "sample_reads_2.fastq.gz"))
+    return idx_dir, rb.Index(idx_dir, 0), s1, s2, L, n1, n2
+
+
+@pytest.fixture(scope="module")
+def synth_small():
+    idx_dir = os.path.join(GOLD, "synth_idx") + "/"
+    tx = SynthTxome(META["seed"], META["genes"])
+    s1, s2 = tx.reads(META["pairs"], rseed=META["rseed"], sub=META["sub"], ins=META["ins"], dele=META["del"], nn=META["n"])
+    names = [f"r{i}" for i in range(META["pairs"])]
+    return idx_dir, rb.Index(idx_dir, 0), s1, s2, 100, tx
+
+
+def flag_opts(fname):
+    flags = GOLDEN[f"synth/{fname}"]["flags"]
+    o = rb.default_opts()
+    it = iter(flags)
+    bt2 = strict = False
+    for a in it:
+        if a == "-s": o.sel_aln = 1
+        elif a == "--hardFilter": o.hard_filter = 1
+        elif a == "--mimicBT2": bt2 = True
+        elif a == "--mimicStrictBT2": strict = True
+        elif a == "--dpBandwidth": o.dp_bandwidth = int(next(it))
+        elif a == "--ma": o.match_score = int(next(it))
+        elif a == "--mm": o.mismatch_penalty = int(next(it))
+        elif a == "--go": o.gap_open_penalty = int(next(it))
+        elif a == "--ge": o.gap_extend_penalty = int(next(it))
+        elif a == "--minScoreFrac": o.min_score_fraction = float(next(it))
+        elif a == "--noOrphans": o.no_orphans = 1
+        elif a == "--noDovetail": o.no_dovetail = 1
+        elif a == "--consensusSlack": o.consensus_slack = float(next(it))
+        elif a == "--maxMMPExtension": o.max_mmp_extension = int(next(it))
+        elif a == "-f": o.fuzzy = 1
+        elif a == "-m": o.max_num_hits = int(next(it))
+        elif a == "-z": o.quasi_coverage = float(next(it))
+        elif a == "--noSensitive": o.sensitive = 0
+        elif a == "--noStrictCheck": o.strict_check = 0
+        else: raise ValueError(a)
+    if bt2 or strict:  # reference src/RapMapSAMapper.cpp:1150-1174
+        o.sel_aln = 1; o.alignment_policy = 1 if bt2 else 2; o.no_orphans = 1; o.no_dovetail = 1; o.consensus_slack = 0.35; o.max_num_hits = 1000
+        if strict:
+            o.min_score_fraction = 0.8; o.match_score = 1; o.mismatch_penalty = 0; o.gap_open_penalty = 25; o.gap_extend_penalty = 25
+    return o
+
+
+@pytest.mark.parametrize("sel", [False, True])
+def test_sample_records_and_sam_match_reference(sample, sel):
+    idx_dir, index, s1, s2, L, n1, n2 = sample
+    opts = rb.default_opts(sel_aln=sel)
+    n = s1.shape[0]
+    mapper = make_mapper(index, opts, n, L)
+    res = mapper.map_batch(s1, s2, n=n, fixed_len=L)
+    assert_same(res, OracleMapper(idx_dir, opts).map(s1, s2, L), "sample")
+    sam = index.sam_header() + mapper.format_sam(s1, s2, n1, n2, res, n, fixed_len=L)
+    key = "sample/selaln" if sel else "sample/default"
+    assert md5(sam) == GOLDEN[key]["md5"], "SAM differs from the reference's golden SAM"
+
+
+@pytest.mark.parametrize("fname", sorted(k.split("/")[1] for k in GOLDEN if k.startswith("synth/")))
+def test_synth_flagsets_match_oracle_and_golden_sam(synth_small, fname):
+    idx_dir, index, s1, s2, L, tx = synth_small
+    opts = flag_opts(fname)
+    n = s1.shape[0]
+    mapper = make_mapper(index, opts, n, L)
+    res = mapper.map_batch(s1, s2, n=n, fixed_len=L)
+    assert_same(res, OracleMapper(idx_dir, opts).map(s1, s2, L), fname)
+    # SAM through the host formatter must equal what the reference printed (names as the generator CLI writes them)
+    truth = np.zeros((n, 4), dtype=np.int64)
+    from helpers import synth_lib
+    import ctypes as C
+    synth_lib().synth_reads(tx.h, META["rseed"], 0, n, 100, META["sub"], META["ins"], META["del"], META["n"], s1.ctypes.data, s2.ctypes.data, truth.ctypes.data)
+    names1 = [f"r{i}:{truth[i,0]}:{truth[i,1]}:{truth[i,2]}/1" for i in range(n)]
+    names2 = [f"r{i}:{truth[i,0]}:{truth[i,1]}:{truth[i,2]}/2" for i in range(n)]
+    sam = index.sam_header() + mapper.format_sam(s1, s2, names1, names2, res, n, fixed_len=L)
+    assert md5(sam) == GOLDEN[f"synth/{fname}"]["md5"], f"{fname}: SAM differs from the reference's golden SAM"
+
+
+def test_sa_interval_stage_matches_oracle(synth_small):
+    """Kernel 1 alone: SAIntervalHit lists == SACollector::operator() of the oracle, read by read."""
+    idx_dir, index, s1, s2, L, tx = synth_small
+    opts = rb.default_opts()
+    n = 400
+    mapper = make_mapper(index, opts, n, L)
+    mapper.map_batch(s1[:n].copy(), s2[:n].copy(), n=n, fixed_len=L)
+    om = OracleMapper(idx_dir, opts)
+    for r in range(2 * n):
+        read = (s1 if r < n else s2)[r % n].tobytes()
+        assert mapper.debug_intervals(r) == om.collect(read), f"read {r}: {read!r}"
+
+
+EDGE_READS = [
+    "lower", "n_mid", "n30", "n31", "lead_n", "trail_n", "len30", "len31", "len32", "homopolymer", "sub1", "del2", "ins2", "iupac", "u_base", "unrelated_mate",
+    "overhang_start", "overhang_end", "all_n", "short_both",
+]
+
+
+def edge_cases(tx_text: str):
+    """Crafted pairs after SURVEY.md Appendix D, cut from a real transcript so that they map."""
+    comp = {"A": "T", "C": "G", "G": "C", "T": "A"}
+    rc = lambda s: "".join(comp.get(c, "N") for c in reversed(s))
+    frag = tx_text[40:340]
+    m1, m2 = frag[:100], rc(frag[-100:])
+    out = {}
+    out["lower"] = (m1.lower(), m2.lower())
+    out["n_mid"] = (m1[:50] + "N" + m1[51:], m2)
+    out["n30"] = (m1[:30] + "N" + m1[31:], m2)
+    out["n31"] = (m1[:31] + "n" + m1[32:], m2)
+    out["lead_n"] = ("N" * 40 + m1[40:], m2)
+    out["trail_n"] = (m1[:60] + "N" * 40, m2)
+    out["len30"] = (m1[:30], m2[:30])
+    out["len31"] = (m1[:31], m2[:31])
+    out["len32"] = (m1[:32], m2[:32])
+    out["homopolymer"] = ("A" * 100, "T" * 100)
+    out["sub1"] = (m1[:45] + comp[m1[45]] + m1[46:], m2)
+    out["del2"] = (m1[:60] + m1[62:] + frag[100:102], m2)
+    out["ins2"] = (m1[:60] + "GT" + m1[60:98], m2)
+    out["iupac"] = (m1[:20] + "R" + m1[21:], m2[:70] + "Y" + m2[71:])
+    out["u_base"] = (m1.replace("T", "U", 3), m2[:50] + m2[50:].replace("T", "u", 2))
+    out["unrelated_mate"] = (m1, "ACGTTGCA" * 12 + "ACGT")
+    out["overhang_start"] = ("ACGTACGTAC" + tx_text[:90], rc(tx_text[150:250]))
+    out["overhang_end"] = (m1, rc(frag[-90:] + "ACGTACGTAC"))
+    out["all_n"] = ("N" * 100, "N" * 100)
+    out["short_both"] = (m1[:10], "")
+    return out
+
+
+@pytest.mark.parametrize("sel", [False, True])
+def test_edge_case_reads_ragged(synth_small, sel):
+    """Ragged batch (offset arrays) of crafted reads: Ns, IUPAC, U, lower case, length 0/10/30/31/32, overhangs, orphans."""
+    idx_dir, index, s1, s2, L, tx = synth_small
+    first = read_first_transcript(idx_dir)
+    cases = edge_cases(first)
+    a = [cases[k][0] for k in EDGE_READS]
+    b = [cases[k][1] for k in EDGE_READS]
+    # plus the same pairs with mates swapped (other strand)
+    a, b = a + b, b + a
+    b1, o1 = pack_ragged(a)
+    b2, o2 = pack_ragged(b)
+    opts = rb.default_opts(sel_aln=sel)
+    mapper = make_mapper(index, opts, len(a), 120)
+    res = mapper.map_batch(b1, b2, n=len(a), off1=o1, off2=o2)
+    ref = OracleMapper(idx_dir, opts).map(b1, b2, 0, o1, o2)
+    assert_same(res, ref, "edge cases")
+    assert res.num_hits > 10
+
+
+def read_first_transcript(idx_dir):
+    import struct
+    with open(os.path.join(idx_dir, "txpInfo.bin"), "rb") as f:
+        n = struct.unpack("<Q", f.read(8))[0]
+        for _ in range(n):
+            l = struct.unpack("<Q", f.read(8))[0]
+            f.read(l)
+        n = struct.unpack("<Q", f.read(8))[0]
+        f.read(4 * n)
+        n = struct.unpack("<Q", f.read(8))[0]
+        text = f.read(n).decode()
+    return text.split("$")[0]
+
+
+def test_empty_and_single_read_batches(synth_small):
+    idx_dir, index, s1, s2, L, tx = synth_small
+    opts = rb.default_opts()
+    mapper = make_mapper(index, opts, 8, L)
+    res = mapper.map_batch(s1[:1].copy(), s2[:1].copy(), n=1, fixed_len=L)
+    assert_same(res, OracleMapper(idx_dir, opts).map(s1[:1].copy(), s2[:1].copy(), L), "n=1")
+    hb = mapper.map_batch(s1[:0].copy(), s2[:0].copy(), n=0, fixed_len=L)
+    assert hb.num_hits == 0
+
+
+def test_unmated_reads(synth_small):
+    idx_dir, index, s1, s2, L, tx = synth_small
+    opts = rb.default_opts()
+    n = 500
+    mapper = make_mapper(index, opts, n, L)
+    res = mapper.map_batch(s1[:n].copy(), None, n=n, fixed_len=L)
+    assert_same(res, OracleMapper(idx_dir, opts).map(s1[:n].copy(), None, L, n=n), "unmated")
+
+
+def test_device_resident_inputs_match_host_inputs(synth_small):
+    import torch
+
+    idx_dir, index, s1, s2, L, tx = synth_small
+    opts = rb.default_opts()
+    n = s1.shape[0]
+    mapper = make_mapper(index, opts, n, L)
+    host = mapper.map_batch(s1, s2, n=n, fixed_len=L)
+    h_hits, h_off = host.hits.copy(), host.pair_offsets.copy()
+    d1, d2 = torch.from_numpy(s1).cuda(), torch.from_numpy(s2).cuda()
+    dev = mapper.map_batch(d1, d2, n=n, fixed_len=L, location=rb.LOC_DEVICE)
+    assert np.array_equal(dev.hits, h_hits) and np.array_equal(dev.pair_offsets, h_off)
+
+
+def test_perfect_hash_index_gives_identical_hits(synth_small):
+    idx_dir, index, s1, s2, L, tx = synth_small
+    opts = rb.default_opts()
+    n = s1.shape[0]
+    a = make_mapper(index, opts, n, L).map_batch(s1, s2, n=n, fixed_len=L)
+    a_hits, a_off = a.hits.copy(), a.pair_offsets.copy()
+    pidx = rb.Index(os.path.join(GOLD, "synth_idx_p"), 0)
+    b = make_mapper(pidx, opts, n, L).map_batch(s1, s2, n=n, fixed_len=L)
+    assert np.array_equal(a_hits, b.hits) and np.array_equal(a_off, b.pair_offsets)
+
+
+@pytest.mark.skipif(not have_ref(), reason="needs oracle/_ref to build the mid-size index")
+@pytest.mark.parametrize("sel", [False, True])
+def test_mid_size_synthetic_matches_oracle(sel):
+    """13.9k-transcript isoform-structured index, 60k noisy pairs: records and counters identical to the oracle."""
+    idx_dir, tx = synth_index(2500)
+    n = 60000
+    s1, s2 = tx.reads(n)
+    opts = rb.default_opts(sel_aln=sel)
+    index = rb.Index(idx_dir, 0)
+    mapper = make_mapper(index, opts, n, 100)
+    res = mapper.map_batch(s1, s2, n=n, fixed_len=100)
+    assert_same(res, OracleMapper(idx_dir, opts).map(s1, s2, 100), f"mid sel={sel}")
+    # size-independent properties: offsets monotone, every pair's hits sorted by tid for paired hits, idempotence
+    off = res.pair_offsets.astype(np.int64)
+    assert (np.diff(off) >= 0).all() and off[-1] == res.num_hits
+    again = mapper.map_batch(s1, s2, n=n, fixed_len=100)
+    assert np.array_equal(again.hits, res.hits)
+
+
+@pytest.mark.skipif(not have_ref(), reason="needs oracle/_ref to build the repeat-family index")
+def test_repeat_families_exercise_big_intervals_and_spill():
+    """Transcriptome with repeat families (intervals near the 1000 cap, long hit lists): global work-strip path."""
+    idx_dir, tx = synth_index(600, seed=4711, repeats=6)
+    n = 20000
+    s1, s2 = tx.reads(n, rseed=7)
+    opts = rb.default_opts()
+    index = rb.Index(idx_dir, 0)
+    mapper = make_mapper(index, opts, n, 100)
+    res = mapper.map_batch(s1, s2, n=n, fixed_len=100)
+    assert_same(res, OracleMapper(idx_dir, opts).map(s1, s2, 100), "repeats")
