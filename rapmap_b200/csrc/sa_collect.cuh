@@ -178,8 +178,9 @@ __device__ __forceinline__ void extendSearch(const WarpCtx& c, int64_t lbIn, int
   int64_t l = lbIn, r = ubIn;
   int lcpLP = startAt, lcpRP = startAt;
   int prevILow = startAt, prevIHigh = startAt;
-  int maxLen;
-  while (true) {  // :150-209
+  int maxLen = startAt;
+  // Each search halves [l, r]; 80 rounds can only be exceeded on a malformed index (guards the GPU against a hang).
+  for (int guard = 0; guard < 80; ++guard) {  // :150-209
     int64_t cc = (l + r) / 2;
     int64_t t = __ldg(c.ix.SA + cc);
     int i0 = lcpLP < lcpRP ? lcpLP : lcpRP;
@@ -204,7 +205,8 @@ __device__ __forceinline__ void extendSearch(const WarpCtx& c, int64_t lbIn, int
     l = pass == 0 ? lbIn : bound[0] - 1;
     r = ubIn;
     lcpLP = startAt; lcpRP = startAt;
-    while (true) {
+    bound[pass] = r;
+    for (int guard = 0; guard < 80; ++guard) {
       int64_t cc = (l + r) / 2;
       int64_t t = __ldg(c.ix.SA + cc);
       int i0 = lcpLP < lcpRP ? lcpLP : lcpRP;

@@ -1,0 +1,10 @@
+#!/bin/bash
+# first GPU bring-up: parity tests, then a memcheck pass on the small cases
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
+timeout 1500 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1
+echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
+tail -5 gpurun_out/pytest_gpu.log
+timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -q -x -k "sample or edge or interval_stage" -p no:cacheprovider > gpurun_out/memcheck.log 2>&1
+echo "memcheck exit $?" >> gpurun_out/memcheck.log
+tail -3 gpurun_out/memcheck.log
