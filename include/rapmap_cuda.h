@@ -149,6 +149,9 @@ void rapmap_cuda_mapper_free(rapmap_cuda_mapper_t* m);
  * (src/RapMapSAMapper.cpp:461-711), up to and excluding SAM formatting. */
 int rapmap_cuda_map_batch(rapmap_cuda_mapper_t* m, const rapmap_read_batch_t* reads, rapmap_hit_batch_t* out);
 int rapmap_cuda_last_timing(const rapmap_cuda_mapper_t* m, rapmap_cuda_timing_t* t);
+/* The mapper's CUDA stream (cudaStream_t as void*): every kernel and copy of map_batch is issued on it, so a caller
+ * can bracket calls with its own CUDA events. */
+void* rapmap_cuda_mapper_stream(const rapmap_cuda_mapper_t* m);
 
 /* Stage taps for parity tests: SAIntervalHit lists exactly as SACollector::operator() leaves them in
  * HitCollectorInfo (include/SACollector.hpp:108-362, include/HitManager.hpp:59-72) for the reads of the

@@ -117,7 +117,7 @@ SYMBOLS = [
     "rapmap_cuda_last_error", "rapmap_cuda_opts_default", "rapmap_cuda_opts_selaln", "rapmap_cuda_index_load", "rapmap_cuda_index_free",
     "rapmap_cuda_index_num_transcripts", "rapmap_cuda_index_transcript_name", "rapmap_cuda_index_transcript_len", "rapmap_cuda_index_k",
     "rapmap_cuda_index_device_bytes", "rapmap_cuda_index_image_bytes", "rapmap_cuda_index_image_ptr", "rapmap_cuda_index_from_image",
-    "rapmap_cuda_mapper_create", "rapmap_cuda_mapper_free", "rapmap_cuda_map_batch", "rapmap_cuda_last_timing", "rapmap_cuda_debug_intervals",
+    "rapmap_cuda_mapper_create", "rapmap_cuda_mapper_free", "rapmap_cuda_map_batch", "rapmap_cuda_last_timing", "rapmap_cuda_mapper_stream", "rapmap_cuda_debug_intervals",
     "rapmap_cuda_format_sam", "rapmap_cuda_sam_header", "rapmap_cuda_free",
 ]
 
@@ -154,6 +154,8 @@ def lib() -> C.CDLL:
     L.rapmap_cuda_mapper_free.argtypes = [C.c_void_p]
     L.rapmap_cuda_map_batch.argtypes = [C.c_void_p, C.POINTER(ReadBatch), C.POINTER(HitBatch)]
     L.rapmap_cuda_last_timing.argtypes = [C.c_void_p, C.POINTER(Timing)]
+    L.rapmap_cuda_mapper_stream.argtypes = [C.c_void_p]
+    L.rapmap_cuda_mapper_stream.restype = C.c_void_p
     L.rapmap_cuda_debug_intervals.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(SAInterval), C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint8)]
     L.rapmap_cuda_format_sam.argtypes = [C.c_void_p, C.POINTER(Opts), C.POINTER(ReadBatch), C.c_char_p, C.c_char_p, C.POINTER(HitBatch), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
     L.rapmap_cuda_sam_header.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
@@ -313,6 +315,11 @@ class Mapper:
         t = Timing()
         _check(lib().rapmap_cuda_last_timing(self._h, C.byref(t)))
         return t
+
+    @property
+    def stream_ptr(self) -> int:
+        """cudaStream_t of this mapper (all of map_batch is issued on it)."""
+        return int(lib().rapmap_cuda_mapper_stream(self._h) or 0)
 
     def debug_intervals(self, read_index: int, cap: int = 2048):
         """SAIntervalHit lists of read `read_index` of the last batch (mate-1 reads first, then mate-2)."""

@@ -596,6 +596,8 @@ int rapmap_cuda_last_timing(const rapmap_cuda_mapper_t* m, rapmap_cuda_timing_t*
   return RAPMAP_OK;
 }
 
+void* rapmap_cuda_mapper_stream(const rapmap_cuda_mapper_t* m) { return m ? static_cast<void*>(m->stream) : nullptr; }
+
 int rapmap_cuda_debug_intervals(rapmap_cuda_mapper_t* m, uint64_t read_index, rapmap_sa_interval_t* out, uint32_t cap, uint32_t* n_fwd,
                                 uint32_t* n_rc, uint8_t* found_hit) {
   if (!m || !n_fwd || !n_rc || !found_hit) return fail(RAPMAP_ERR_ARG, "null argument");

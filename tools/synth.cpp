@@ -304,3 +304,107 @@ int main(int argc, char** argv) {
   return 1;
 }
 #endif
+
+// =================================================================================================
+// hash.bin writer: lays a (k-mer -> SA interval) set out exactly as the reference's dense index file
+// (sparsepp sparse_hash_map serialisation: magic 0x24687531, table_size, num_buckets as 4-byte
+// big-endian words, one little-endian u32 occupancy bitmap per group of 32 buckets, then the records
+// {u64 kmer, i32 begin, i32 end} in bucket order).  Bucket of a key = XXH64(key bytes, seed 0) & mask with
+// triangular probing — the placement the reference's own find() walks.  Used by tools/build_index.py so
+// that bench-scale indexes can be produced in seconds and still be read by the UNMODIFIED reference.
+// =================================================================================================
+namespace {
+inline uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+// XXH64 (public xxHash specification) specialised to an 8-byte input, seed 0.
+inline uint64_t xxh64_u64(uint64_t v) {
+  const uint64_t P1 = 0x9E3779B185EBCA87ULL, P2 = 0xC2B2AE3D27D4EB4FULL, P3 = 0x165667B19E3779F9ULL, P4 = 0x85EBCA77C2B2AE63ULL,
+                 P5 = 0x27D4EB2F165667C5ULL;
+  uint64_t h = P5 + 8;
+  uint64_t k1 = v * P2;
+  k1 = rotl64(k1, 31);
+  k1 *= P1;
+  h ^= k1;
+  h = rotl64(h, 27) * P1 + P4;
+  h ^= h >> 33;
+  h *= P2;
+  h ^= h >> 29;
+  h *= P3;
+  h ^= h >> 32;
+  return h;
+}
+void put_be32(FILE* f, uint32_t v) {
+  unsigned char b[4] = {static_cast<unsigned char>(v >> 24), static_cast<unsigned char>(v >> 16), static_cast<unsigned char>(v >> 8),
+                        static_cast<unsigned char>(v)};
+  fwrite(b, 1, 4, f);
+}
+} // namespace
+
+extern "C" int synth_write_dense_hash(const uint64_t* keys, const int32_t* begin, const int32_t* end, uint64_t n, const char* path) {
+  uint64_t table = 32;
+  while (table < 2 * n) table <<= 1;
+  if (table >= 0xFFFFFFFFULL) return -2;
+  const uint64_t mask = table - 1;
+  std::vector<uint32_t> bitmap(table / 32, 0);
+  std::vector<uint32_t> slotOf(n);
+  for (uint64_t i = 0; i < n; ++i) {
+    uint64_t b = xxh64_u64(keys[i]) & mask;
+    uint64_t probes = 0;
+    while (bitmap[b >> 5] >> (b & 31) & 1u) { ++probes; b = (b + probes) & mask; }
+    bitmap[b >> 5] |= 1u << (b & 31);
+    slotOf[i] = static_cast<uint32_t>(b);
+  }
+  // rank of each occupied bucket = position of its record in the file
+  std::vector<uint32_t> groupBase(table / 32 + 1, 0);
+  for (uint64_t g = 0; g < table / 32; ++g) groupBase[g + 1] = groupBase[g] + static_cast<uint32_t>(__builtin_popcount(bitmap[g]));
+  struct Rec { uint64_t k; int32_t b, e; };
+  std::vector<Rec> recs(n);
+  for (uint64_t i = 0; i < n; ++i) {
+    uint32_t s = slotOf[i];
+    uint32_t r = groupBase[s >> 5] + static_cast<uint32_t>(__builtin_popcount(bitmap[s >> 5] & ((1u << (s & 31)) - 1u)));
+    recs[r] = {keys[i], begin[i], end[i]};
+  }
+  FILE* f = fopen(path, "wb");
+  if (!f) return -1;
+  put_be32(f, 0x24687531u);
+  put_be32(f, static_cast<uint32_t>(table));
+  put_be32(f, static_cast<uint32_t>(n));
+  fwrite(bitmap.data(), 4, bitmap.size(), f);
+  fwrite(recs.data(), sizeof(Rec), recs.size(), f);
+  fclose(f);
+  return 0;
+}
+
+// Transcript text with separators, as the reference indexer lays it out (src/RapMapSAIndexer.cpp:536-635):
+// upper-case, poly-A tails of >= 10 clipped, '$' after every transcript.  Returns total length; fills
+// out_text (caller-sized text_len + ntxp), starts (ntxp), complete lengths (ntxp).
+extern "C" int64_t synth_txome_concat(const SynthTxome* s, char* out_text, int64_t* starts, uint32_t* complete_lens) {
+  int64_t w = 0;
+  for (int64_t t = 0; t < s->ntxp; ++t) {
+    int64_t L = s->len[t];
+    const char* p = s->text + s->off[t];
+    complete_lens[t] = static_cast<uint32_t>(L);
+    if (L > 10) {
+      bool polyA = true;
+      for (int i = 1; i <= 10; ++i) if (p[L - i] != 'A') { polyA = false; break; }
+      if (polyA) { while (L > 0 && p[L - 1] == 'A') --L; }
+    }
+    if (L == 0) return -1;  // the reference would drop the entry; the generator never produces this
+    starts[t] = w;
+    memcpy(out_text + w, p, static_cast<size_t>(L));
+    w += L;
+    out_text[w++] = '$';
+  }
+  return w;
+}
+extern "C" void synth_txome_name(uint64_t seed, int64_t genes, int repeat_families, char* out, int64_t cap) {
+  // names joined by '\n' (regenerated; cheap relative to indexing)
+  Txome tx = gen_txome(seed, genes, repeat_families);
+  int64_t w = 0;
+  for (auto& nm : tx.names) {
+    if (w + static_cast<int64_t>(nm.size()) + 1 >= cap) break;
+    memcpy(out + w, nm.data(), nm.size());
+    w += static_cast<int64_t>(nm.size());
+    out[w++] = '\n';
+  }
+  out[w] = 0;
+}
