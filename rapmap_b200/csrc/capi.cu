@@ -116,7 +116,7 @@ struct rapmap_cuda_mapper {
   uint32_t smemEntries{64};
   int gridCollect{0}, gridMap{0};
   uint32_t collectSmem{0}, mapSmem{0};
-  uint32_t lpad{0}, pmax{0}, warpSmem{0};
+  uint32_t lpad{0}, pmax{0}, warpSmem{0}, packOff{0}, ctxOff{0};
   // stage 3
   uint32_t* dPairCount{nullptr};
   uint64_t* dPairOff{nullptr};
@@ -288,7 +288,6 @@ static int deriveOpts(const rapmap_cuda_opts_t& o, DevOpts& d) {
   if (!o.sensitive) return fail(RAPMAP_ERR_UNSUPPORTED, "--noSensitive (NIP/LCE skipping) is not implemented on the device path");
   if (!o.strict_check) return fail(RAPMAP_ERR_UNSUPPORTED, "--noStrictCheck (k-mer vote strand decision) is not implemented on the device path");
   if (o.recover_orphans) return fail(RAPMAP_ERR_UNSUPPORTED, "--recoverOrphans is not implemented on the device path");
-  if (o.sel_aln || o.fuzzy) return fail(RAPMAP_ERR_UNSUPPORTED, "--selAln / --fuzzyIntersection are not implemented on the device path yet");
   if (o.sel_aln) {
     // validateOpts, reference src/RapMapSAMapper.cpp:911-954
     if (o.consensus_slack < 0 || o.consensus_slack > 1) return fail(RAPMAP_ERR_ARG, "--consensusSlack must be between 0.0 and 1.0");
@@ -384,7 +383,9 @@ int rapmap_cuda_mapper_create(const rapmap_cuda_index_t* idx, const rapmap_cuda_
   // ---- launch geometry: persistent grids, whole multiples of the SM count
   m->lpad = (max_read_len + 15) / 16 * 16;
   m->pmax = max_read_len - idx->hdr.k + 1;
-  m->warpSmem = (2 * m->lpad + 2 * m->pmax * 8 + 2 * m->pmax * static_cast<uint32_t>(sizeof(IntervalRec)) + 15) / 16 * 16;
+  m->packOff = (2 * m->lpad + 2 * m->pmax * 8 + 2 * m->pmax * static_cast<uint32_t>(sizeof(IntervalRec)) + 15) / 16 * 16;
+  m->ctxOff = (m->packOff + (m->lpad / 32 + 2) * (2 * 8 + 4 * 4) + 15) / 16 * 16;
+  m->warpSmem = (m->ctxOff + static_cast<uint32_t>(sizeof(WarpCtx)) + 15) / 16 * 16;
   m->collectSmem = m->warpSmem * kWarps;
   if (m->collectSmem > 227 * 1024) return bail("max_read_len too large for the shared-memory read cache");
   M_TRY(cudaFuncSetAttribute(sa_collect_kernel<kWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(m->collectSmem)));
@@ -477,7 +478,7 @@ int rapmap_cuda_map_batch(rapmap_cuda_mapper_t* m, const rapmap_read_batch_t* re
     // ---- kernel 1: SA lookup
     CollectParams cp{};
     cp.ix = m->idx->view; cp.reads = bv; cp.opts = m->dopts; cp.maxReadLen = m->maxReadLen; cp.lpad = m->lpad; cp.pmax = m->pmax;
-    cp.warpSmemBytes = m->warpSmem; cp.summ = m->dSumm; cp.arena = m->dIvArena; cp.arenaCap = m->ivCap; cp.arenaCursor = m->dCtl + 0; cp.status = m->dCtl + 3;
+    cp.warpSmemBytes = m->warpSmem; cp.packOff = m->packOff; cp.ctxOff = m->ctxOff; cp.summ = m->dSumm; cp.arena = m->dIvArena; cp.arenaCap = m->ivCap; cp.arenaCursor = m->dCtl + 0; cp.status = m->dCtl + 3;
     int g1 = static_cast<int>(std::min<uint64_t>(m->gridCollect, (bv.numReads + kWarps - 1) / kWarps));
     sa_collect_kernel<kWarps><<<g1, kWarps * 32, m->collectSmem, st>>>(cp);
     ++launches;
@@ -553,8 +554,8 @@ int rapmap_cuda_map_batch(rapmap_cuda_mapper_t* m, const rapmap_read_batch_t* re
   // ---- selective alignment (ksw2 scoring + score filter), rewrites dHits / dPairOff in place
   if (m->dopts.selAln && total > 0) {
     uint32_t l2 = 0;
-    int rc = selAlnRun(m->selaln, m->idx->view, m->dopts, bv, n, paired, m->dHits, m->dPairOff, m->dPairCount, total, m->dCubTemp, m->cubTempBytes,
-                       m->numSMs, st, &l2, &total, m->hStage, g_err);
+    int rc = selAlnRun(m->selaln, m->idx->view, m->dopts, bv, n, paired, m->dHits, m->dPairOff, total, m->dCubTemp, m->cubTempBytes, m->numSMs, st,
+                       &l2, &total, g_err);
     if (rc) return rc;
     launches += l2;
   }

@@ -2,13 +2,15 @@
 //
 // Replaces hit_manager::hitsToMappingsSimple (reference src/HitManager.cpp:691-882): the single-interval
 // expansion (:716-807), intersectSAHits + intersectSAIntervalWithOutput (:587-689, :449-493),
-// collectHitsSimpleSA (:84-326, leftmost anchor or chain DP) and the fwd/rc merge (:834-881).
+// collectHitsSimpleSA (:84-326, leftmost anchor or minimap2-style chain DP) and the fwd/rc merge (:834-881).
 //
 // B200 mapping: the reference walks SA entries one by one into a std::map<tid, ProcessedSAHit>.  Here the
 // warp expands all SA entries of a strand at once (lane = entry: SA[i] -> rank record -> txpOffsets, three
 // dependent loads per lane, 32 in flight), sorts the (tid, interval order, entry) keys with a warp bitonic
-// network (shared memory for the common <= 64 entries, an L2-resident global scratch strip otherwise) and
-// resolves each transcript segment with one lane.  Map iteration order == ascending tid == sorted order.
+// network (shared memory for the common <= 64 entries, an L2-resident global work strip otherwise) and
+// resolves each transcript segment with one lane (map iteration order == ascending tid == sorted order).
+// Chain scoring keeps the reference's double/float arithmetic with explicit round-to-nearest intrinsics so
+// that no FMA contraction can change a tie.
 #pragma once
 #include "kernels.cuh"
 
@@ -29,35 +31,43 @@ struct MapParams {
   int32_t* posPool;
   uint32_t posCap;
   uint32_t* posCursor;
-  // per-warp work strip (global): keys u64[cap] | vals u64[cap] | segs u32[cap+1] | qa QARec[cap] | dbl double[cap] ...
-  uint8_t* scratch;
-  uint32_t scratchEntries;   // entries per warp in the global strip
-  uint64_t scratchStride;    // bytes per warp
-  uint32_t smemEntries;      // entries per warp in shared memory
+  uint8_t* scratch;          // per-warp global work strips
+  uint32_t scratchEntries;
+  uint64_t scratchStride;
+  uint32_t smemEntries;
   uint32_t* status;
 };
 
-// Work-area view (either shared memory or the warp's global strip).
+// Work-area view (either shared memory or the warp's global strip); every array has `cap` entries.
 struct WorkArea {
-  uint64_t* keys;   // tid << 32 | ord << 16 | entry
-  uint64_t* vals;   // pos << 32 | qpos << 16 | len
-  uint32_t* segs;   // segment starts
-  QARec* qa;        // resolved hits of this read (fwd list then rc list)
+  uint64_t* keys;    // tid << 32 | ord << 16 | entry ; reused as double f[] by the chain DP
+  uint64_t* vals;    // pos << 32 | qpos << 16 | len
+  double* qaScore;   // chain score per resolved hit
+  QARec* qa;         // resolved hits of this read (fwd list then rc list)
+  uint32_t* segs;    // segment starts (bit 31: active)   [cap + 1]
+  int32_t* p;        // chain predecessor
+  int32_t* aux;      // best chain ends / chain starts
+  int32_t* posTmp;   // staged allPositions
+  uint8_t* seen;
   uint32_t cap;
 };
 
 __host__ __device__ inline uint64_t workAreaBytes(uint32_t entries) {
-  // keys + vals + segs(+1) + qa, 16-byte aligned
-  uint64_t b = static_cast<uint64_t>(entries) * (8 + 8 + 4 + sizeof(QARec)) + 16;
+  uint64_t b = static_cast<uint64_t>(entries) * (8 + 8 + 8 + sizeof(QARec) + 4 + 4 + 4 + 4 + 1) + 32;
   return (b + 15) / 16 * 16;
 }
 
-__device__ __forceinline__ WorkArea carve(uint8_t* p, uint32_t entries) {
+__device__ __forceinline__ WorkArea carve(uint8_t* base, uint32_t entries) {
   WorkArea w;
-  w.keys = reinterpret_cast<uint64_t*>(p);
+  w.keys = reinterpret_cast<uint64_t*>(base);
   w.vals = w.keys + entries;
-  w.qa = reinterpret_cast<QARec*>(w.vals + entries);
+  w.qaScore = reinterpret_cast<double*>(w.vals + entries);
+  w.qa = reinterpret_cast<QARec*>(w.qaScore + entries);
   w.segs = reinterpret_cast<uint32_t*>(w.qa + entries);
+  w.p = reinterpret_cast<int32_t*>(w.segs + entries + 1);
+  w.aux = w.p + entries;
+  w.posTmp = w.aux + entries;
+  w.seen = reinterpret_cast<uint8_t*>(w.posTmp + entries);
   w.cap = entries;
   return w;
 }
@@ -80,13 +90,145 @@ __device__ __forceinline__ void warpBitonicSort(uint64_t* keys, uint64_t* vals, 
   }
 }
 
-// Resolves one strand: appends QARecs (ascending tid) to w.qa[nOut...].  Returns false on work-area overflow.
-// No chaining (doChaining == false): leftmost anchor per active transcript (HitManager.cpp:308-322) or per
-// transcript of the single interval (:716-807).
-__device__ __forceinline__ bool resolveStrand(const MapParams& P, WorkArea& w, const IntervalRec* ivs, int nIv, bool isFw, uint32_t readLen,
-                                              uint8_t mateStatus, int lane, uint32_t& nOut, bool& overflow) {
+__device__ __forceinline__ uint32_t vPos(uint64_t v) { return static_cast<uint32_t>(v >> 32); }
+__device__ __forceinline__ uint32_t vQpos(uint64_t v) { return static_cast<uint32_t>(v >> 16) & 0xffffu; }
+__device__ __forceinline__ int32_t vLen(uint64_t v) { return static_cast<int32_t>(v & 0xffffu); }
+
+// fastlog2 (reference src/HitManager.cpp:33-42), float ops in source order, never contracted.
+__device__ __forceinline__ float fastlog2Ref(float x) {
+  uint32_t vi = __float_as_uint(x);
+  float mx = __uint_as_float((vi & 0x007FFFFFu) | 0x3f000000u);
+  float y = __uint2float_rn(vi);
+  y = __fmul_rn(y, 1.1920928955078125e-7f);
+  float t = __fsub_rn(y, 124.22551499f);
+  t = __fsub_rn(t, __fmul_rn(1.498030302f, mx));
+  t = __fsub_rn(t, __fdiv_rn(1.72587999f, __fadd_rn(0.3520887068f, mx)));
+  return t;
+}
+
+// alpha / beta of collectHitsSimpleSA (:126-139); returns f[j] + alpha - beta.
+__device__ __forceinline__ double extensionScore(double fj, int32_t qdiff, int32_t rdiff, int32_t ilen, int32_t maxDist) {
+  double score = static_cast<double>(ilen);
+  double mindiff = static_cast<double>((qdiff < rdiff) ? qdiff : rdiff);
+  double alpha = (score < mindiff) ? score : mindiff;
+  double beta;
+  if (qdiff < 0 || ((qdiff > rdiff ? qdiff : rdiff) > maxDist)) {
+    beta = __longlong_as_double(0x7ff0000000000000LL);
+  } else {
+    double l = static_cast<double>(qdiff - rdiff);
+    int32_t al = static_cast<int32_t>(fabs(l));
+    if (l == 0.0) beta = 0.0;
+    else beta = __dadd_rn(__dmul_rn(__dmul_rn(0.01, 31.0), static_cast<double>(al)), __dmul_rn(0.5, static_cast<double>(fastlog2Ref(static_cast<float>(al)))));
+  }
+  return __dsub_rn(__dadd_rn(fj, alpha), beta);
+}
+
+// One transcript segment [b, e) of sorted entries, chain mode (collectHitsSimpleSA :107-306).  Executed by one lane.
+// Writes the hit positions (allPositions) to w.posTmp[b ...] and returns their count; q gets pos / chain status.
+__device__ __forceinline__ uint32_t chainSegment(WorkArea& w, uint32_t b, uint32_t e, uint32_t readLen, int32_t maxDist, bool considerMultiPos,
+                                                 QARec& q, double& bestScoreOut) {
+  const int32_t m = static_cast<int32_t>(e - b);
+  uint64_t* v = w.vals + b;
+  double* f = reinterpret_cast<double*>(w.keys + b);
+  int32_t* p = w.p + b;
+  int32_t* ends = w.aux + b;
+  uint8_t* seen = w.seen + b;
+  // sort by (ref end, query end) — keys are unique within a transcript (:111-121), insertion sort of a short list
+  for (int32_t i = 1; i < m; ++i) {
+    uint64_t x = v[i];
+    uint32_t xr = vPos(x) + static_cast<uint32_t>(vLen(x)), xq = vQpos(x) + static_cast<uint32_t>(vLen(x));
+    int32_t j = i - 1;
+    while (j >= 0) {
+      uint64_t y = v[j];
+      uint32_t yr = vPos(y) + static_cast<uint32_t>(vLen(y)), yq = vQpos(y) + static_cast<uint32_t>(vLen(y));
+      bool less = (xr < yr) || (xr == yr && xq < yq);
+      if (!less) break;
+      v[j + 1] = y;
+      --j;
+    }
+    v[j + 1] = x;
+  }
+  double bestScore = -1.7976931348623157e308;  // numeric_limits<double>::lowest()
+  int32_t bestChainEnd = -1;
+  int32_t nEnds = 0;
+  for (int32_t i = 0; i < m; ++i) {
+    uint64_t hi = v[i];
+    const int32_t len = vLen(hi);
+    const uint32_t qposi = vQpos(hi) + static_cast<uint32_t>(len), rposi = vPos(hi) + static_cast<uint32_t>(len);
+    int32_t pi = i;
+    double fi = static_cast<double>(len);
+    int32_t numRounds = 2;
+    for (int32_t j = i - 1; j >= 0; --j) {
+      uint64_t hj = v[j];
+      const uint32_t qposj = vQpos(hj) + static_cast<uint32_t>(vLen(hj)), rposj = vPos(hj) + static_cast<uint32_t>(vLen(hj));
+      const int32_t qdiff = static_cast<int32_t>(qposi - qposj), rdiff = static_cast<int32_t>(rposi - rposj);
+      double ext = extensionScore(f[j], qdiff, rdiff, len, maxDist);
+      bool extendWithJ = ext > fi;
+      pi = extendWithJ ? j : pi;
+      fi = extendWithJ ? ext : fi;
+      if (pi < i) { numRounds--; if (numRounds <= 0) break; }
+    }
+    p[i] = pi;
+    f[i] = fi;
+    seen[i] = 0;
+    if (fi > bestScore) {
+      bestScore = fi; bestChainEnd = i;
+      if (considerMultiPos) { nEnds = 0; ends[nEnds++] = i; }
+    } else if (considerMultiPos && fi == bestScore) {
+      ends[nEnds++] = i;
+    }
+  }
+  if (!considerMultiPos) { nEnds = 0; ends[nEnds++] = bestChainEnd; }
+  // backtracking with the seen[] de-duplication (:220-257); chain starts overwrite ends[] in place
+  int32_t nStarts = 0;
+  uint32_t numDistinctOpt = 0;
+  for (int32_t k = 0; k < nEnds; ++k) {
+    int32_t cur = ends[k];
+    bool valid = true;
+    int32_t lastPtr = p[cur];
+    while (lastPtr < cur) {
+      if (seen[cur]) { valid = false; break; }
+      seen[cur] = 1;
+      cur = lastPtr;
+      lastPtr = p[cur];
+    }
+    if (seen[cur]) valid = false;
+    if (valid) { ++numDistinctOpt; ends[nStarts++] = lastPtr; }
+  }
+  // hit record (:259-280)
+  int32_t* out = w.posTmp + b;
+  for (int32_t k = 0; k < nStarts; ++k) {
+    uint64_t s = v[ends[k]];
+    out[k] = static_cast<int32_t>(vPos(s) - vQpos(s));
+  }
+  q.pos = out[0];
+  if (nStarts > 1) {  // std::sort(allPositions)
+    for (int32_t i = 1; i < nStarts; ++i) {
+      int32_t x = out[i];
+      int32_t j = i - 1;
+      while (j >= 0 && out[j] > x) { out[j + 1] = out[j]; --j; }
+      out[j + 1] = x;
+    }
+  }
+  // gapless chain spanning the read => UNGAPPED (:283-306)
+  q.chain = 4;
+  if (m > 1 && numDistinctOpt == 1 && bestChainEnd == m - 1) {
+    uint64_t last = v[m - 1], first = v[0];
+    int64_t queryRange = static_cast<int64_t>(vQpos(last) + static_cast<uint32_t>(vLen(last))) - static_cast<int64_t>(vQpos(first));
+    int64_t refRange = static_cast<int64_t>(vPos(last) + static_cast<uint32_t>(vLen(last))) - static_cast<int64_t>(vPos(first));
+    if (queryRange == refRange && queryRange == static_cast<int64_t>(readLen)) q.chain = 1;
+  }
+  bestScoreOut = bestScore;
+  return static_cast<uint32_t>(nStarts);
+}
+
+// Resolves one strand: appends QARecs (ascending tid) to w.qa[nOut...], their positions to w.posTmp.
+__device__ __forceinline__ void resolveStrand(const MapParams& P, WorkArea& w, const IntervalRec* ivs, int nIv, bool isFw, uint32_t readLen,
+                                              int lane, uint32_t& nOut, uint32_t& posBase) {
   const DeviceIndex& ix = P.ix;
-  // ---- order of processing: smallest-span interval first (first wins on ties, :636-641), others in original order
+  const DevOpts& o = P.opts;
+  const bool needPos = o.selAln || o.fuzzy;
+  // ---- processing order: smallest-span interval first (first wins on ties, :636-641), others in original order
   int minIdx = 0;
   uint32_t total = 0;
   {
@@ -97,8 +239,9 @@ __device__ __forceinline__ bool resolveStrand(const MapParams& P, WorkArea& w, c
       if (nIv > 1 && span < bestSpan) { bestSpan = span; minIdx = j; }
     }
   }
-  if (total + nOut > w.cap) { overflow = true; return false; }
-  // ---- expand: lane = SA entry
+  // ---- expand: lane = SA entry.  Entries of this strand occupy [posBase, posBase + total) of the work arrays.
+  uint64_t* keys = w.keys + posBase;
+  uint64_t* vals = w.vals + posBase;
   uint32_t base = 0;
   for (int j = 0; j < nIv; ++j) {
     IntervalRec iv = ivs[j];
@@ -108,8 +251,8 @@ __device__ __forceinline__ bool resolveStrand(const MapParams& P, WorkArea& w, c
       int32_t g = __ldg(ix.SA + iv.begin + e);
       uint32_t tid = transcriptAt(ix, g);
       int32_t pos = g - __ldg(ix.txpOffsets + tid);
-      w.keys[base + e] = (static_cast<uint64_t>(tid) << 32) | (static_cast<uint64_t>(ord) << 16) | static_cast<uint64_t>(e);
-      w.vals[base + e] = (static_cast<uint64_t>(static_cast<uint32_t>(pos)) << 32) | (static_cast<uint64_t>(iv.qpos) << 16) | iv.len;
+      keys[base + e] = (static_cast<uint64_t>(tid) << 32) | (static_cast<uint64_t>(ord) << 16) | static_cast<uint64_t>(e);
+      vals[base + e] = (static_cast<uint64_t>(static_cast<uint32_t>(pos)) << 32) | (static_cast<uint64_t>(iv.qpos) << 16) | iv.len;
     }
     base += static_cast<uint32_t>(span);
   }
@@ -118,57 +261,118 @@ __device__ __forceinline__ bool resolveStrand(const MapParams& P, WorkArea& w, c
   if (total > 1) {
     int n2 = 1;
     while (n2 < static_cast<int>(total)) n2 <<= 1;
-    if (static_cast<uint32_t>(n2) > w.cap) { overflow = true; return false; }
-    for (int i = total + lane; i < n2; i += 32) { w.keys[i] = ~0ULL; w.vals[i] = 0; }
+    for (int i = total + lane; i < n2; i += 32) { keys[i] = ~0ULL; vals[i] = 0; }
     __syncwarp();
-    warpBitonicSort(w.keys, w.vals, n2, lane);
+    warpBitonicSort(keys, vals, n2, lane);
   }
   // ---- segment heads
+  uint32_t* segs = w.segs;
   uint32_t nSeg = 0;
   for (uint32_t b0 = 0; b0 < total; b0 += 32) {
     uint32_t i = b0 + lane;
     bool head = false;
-    if (i < total) head = (i == 0) || ((w.keys[i] >> 32) != (w.keys[i - 1] >> 32));
-    unsigned m = __ballot_sync(0xffffffffu, head);
-    if (head) w.segs[nSeg + __popc(m & ((1u << lane) - 1u))] = i;
-    nSeg += __popc(m);
+    if (i < total) head = (i == 0) || ((keys[i] >> 32) != (keys[i - 1] >> 32));
+    unsigned mk = __ballot_sync(0xffffffffu, head);
+    if (head) segs[nSeg + __popc(mk & ((1u << lane) - 1u))] = i;
+    nSeg += __popc(mk);
   }
-  if (lane == 0) w.segs[nSeg] = total;
+  if (lane == 0) segs[nSeg] = total;
   __syncwarp();
+  // ---- which transcripts are active (:613-628, :667-686)
+  int32_t required = nIv, maxSlack = 0;
+  if (nIv > 1 && o.consensusFraction < 1.0f) {
+    float requiredFrac = __fmul_rn(static_cast<float>(nIv), o.consensusFraction);
+    int32_t fl = static_cast<int32_t>(floorf(requiredFrac));
+    required = fl > 1 ? fl : 1;
+    maxSlack = nIv - required;
+  }
+  if (nIv > 1) {
+    bool anyActive = false;
+    for (uint32_t s0 = 0; s0 < nSeg; s0 += 32) {
+      uint32_t s = s0 + lane;
+      bool act = false;
+      if (s < nSeg) {
+        uint32_t b = segs[s], e = segs[s + 1] & 0x7fffffffu;
+        int32_t distinct = 0;
+        uint32_t lastOrd = 0xffffffffu;
+        for (uint32_t i = b; i < e; ++i) {
+          uint32_t ord = static_cast<uint32_t>(keys[i] >> 16) & 0xffffu;
+          if (ord != lastOrd) { ++distinct; lastOrd = ord; }
+        }
+        // strict intersection (maxSlack == 0): a transcript survives only if present in every interval; with slack
+        // every entry is recorded and numActive is the number of distinct intervals (:460,:473-490)
+        act = distinct >= required;
+      }
+      anyActive |= __any_sync(0xffffffffu, act);
+      __syncwarp();
+      if (s < nSeg && act) segs[s] |= 0x80000000u;
+      __syncwarp();
+    }
+    if (maxSlack > 0 && !anyActive) {
+      for (uint32_t s = lane; s < nSeg; s += 32) segs[s] |= 0x80000000u;
+      __syncwarp();
+    }
+  }
   // ---- one lane per transcript segment
-  const uint32_t required = static_cast<uint32_t>(nIv);  // strict intersection: present in every interval (:613-628 with consensusFraction == 1)
+  const bool chain = o.doChaining && nIv > 1;
   for (uint32_t s0 = 0; s0 < nSeg; s0 += 32) {
     uint32_t s = s0 + lane;
     bool active = false;
     QARec q;
+    double score = -1.7976931348623157e308;
     if (s < nSeg) {
-      uint32_t b = w.segs[s], e = w.segs[s + 1];
-      uint32_t tid = static_cast<uint32_t>(w.keys[b] >> 32);
-      uint32_t distinct = 0, lastOrd = 0xffffffffu;
-      uint32_t bestPos = 0xffffffffu;
-      int32_t bestHit = 0;
-      for (uint32_t i = b; i < e; ++i) {
-        uint32_t ord = static_cast<uint32_t>(w.keys[i] >> 16) & 0xffffu;
-        if (ord != lastOrd) { ++distinct; lastOrd = ord; }
-        uint64_t v = w.vals[i];
-        uint32_t pos = static_cast<uint32_t>(v >> 32);
-        if (pos < bestPos) {  // std::min_element keeps the first minimum in tqvec order == sorted (ord, entry) order
-          bestPos = pos;
-          bestHit = static_cast<int32_t>(pos) - static_cast<int32_t>((v >> 16) & 0xffffu);
+      uint32_t sb = segs[s];
+      uint32_t b = sb & 0x7fffffffu, e = segs[s + 1] & 0x7fffffffu;
+      active = (nIv == 1) || (sb & 0x80000000u);
+      if (active) {
+        q.tid = static_cast<uint32_t>(keys[b] >> 32);
+        q.fwd = isFw ? 1 : 0; q.pad = 0; q.oppOff = 0; q.nOpp = 0; q.posOff = posBase + b; q.nAll = 1; q.chain = 4;
+        if (chain) {
+          q.nAll = chainSegment(w, posBase + b, posBase + e, readLen, static_cast<int32_t>(readLen), o.considerMultiPos, q, score);
+        } else if (nIv == 1) {
+          // collectFromSingleInterval (:716-807): sorted by (tid, pos); first position is the hit, the rest are allPositions
+          q.chain = (ivs[0].len == readLen) ? 0 : 4;  // PERFECT iff the single MMP spans the read (:741-746)
+          const int32_t qp = static_cast<int32_t>(ivs[0].qpos);
+          if (o.considerMultiPos) {
+            int32_t* out = w.posTmp + posBase + b;
+            uint32_t cnt = 0;
+            for (uint32_t i = b; i < e; ++i) {
+              int32_t hp = static_cast<int32_t>(vPos(vals[i])) - qp;
+              int32_t j = static_cast<int32_t>(cnt) - 1;
+              while (j >= 0 && out[j] > hp) { out[j + 1] = out[j]; --j; }
+              out[j + 1] = hp;
+              ++cnt;
+            }
+            q.pos = out[0]; q.nAll = cnt;
+          } else {
+            int32_t best = 0x7fffffff;
+            for (uint32_t i = b; i < e; ++i) { int32_t hp = static_cast<int32_t>(vPos(vals[i])) - qp; best = hp < best ? hp : best; }
+            q.pos = best;
+            if (needPos) w.posTmp[posBase + b] = best;
+          }
+        } else {
+          // leftmost anchor (:308-322): std::min_element keeps the first minimum in tqvec order == (ord, entry) order
+          uint32_t bestPos = 0xffffffffu;
+          int32_t bestHit = 0;
+          for (uint32_t i = b; i < e; ++i) {
+            uint64_t v = vals[i];
+            if (vPos(v) < bestPos) { bestPos = vPos(v); bestHit = static_cast<int32_t>(vPos(v) - vQpos(v)); }
+          }
+          q.pos = bestHit;
+          if (needPos) w.posTmp[posBase + b] = bestHit;
         }
       }
-      active = (nIv == 1) || (distinct >= required);
-      q.tid = tid; q.pos = bestHit; q.posOff = 0; q.nAll = 1; q.nOpp = 0; q.fwd = isFw ? 1 : 0; q.pad = 0;
-      uint8_t cs = 4;  // REGULAR
-      if (nIv == 1) cs = (ivs[0].len == readLen) ? 0 : 4;  // PERFECT iff the single MMP spans the read (:741-746)
-      q.chain = cs;
     }
-    unsigned m = __ballot_sync(0xffffffffu, active);
-    if (active) w.qa[nOut + __popc(m & ((1u << lane) - 1u))] = q;
-    nOut += __popc(m);
+    unsigned mk = __ballot_sync(0xffffffffu, active);
+    if (active) {
+      uint32_t slot = nOut + __popc(mk & ((1u << lane) - 1u));
+      w.qa[slot] = q;
+      w.qaScore[slot] = score;
+    }
+    nOut += __popc(mk);
   }
+  posBase += total;
   __syncwarp();
-  return true;
 }
 
 template <int WARPS>
@@ -179,6 +383,7 @@ __global__ void __launch_bounds__(WARPS * 32) hits_to_mappings_kernel(MapParams 
   const uint64_t gw = static_cast<uint64_t>(blockIdx.x) * WARPS + warp;
   uint8_t* smemBase = smem + static_cast<size_t>(warp) * workAreaBytes(P.smemEntries);
   uint8_t* globBase = P.scratch + gw * P.scratchStride;
+  const bool needPos = P.opts.selAln || P.opts.fuzzy;
 
   for (uint64_t r = gw; r < P.numReads; r += static_cast<uint64_t>(gridDim.x) * WARPS) {
     ReadSummary s = P.summ[r];
@@ -190,63 +395,95 @@ __global__ void __launch_bounds__(WARPS * 32) hits_to_mappings_kernel(MapParams 
       continue;
     }
     const IntervalRec* ivs = P.arena + s.ivOff;
-    uint32_t total = 0;
-    for (int j = 0; j < nF + nR; ++j) total += static_cast<uint32_t>(ivs[j].end - ivs[j].begin);
-    // pow2 padding of the larger strand must fit as well
-    uint32_t need = 1;
-    while (need < total) need <<= 1;
-    need = need > total ? need : total;
-    WorkArea w = (need <= P.smemEntries) ? carve(smemBase, P.smemEntries) : carve(globBase, P.scratchEntries);
-    const uint8_t mateStatus = P.pairedInput ? (r >= P.numPairs ? 2 : 1) : 0;
-    uint32_t nOut = 0;
-    bool overflow = false;
-    uint32_t nFwdOut = 0;
-    if (nF > 0) resolveStrand(P, w, ivs, nF, true, s.readLen, mateStatus, lane, nOut, overflow);
-    nFwdOut = nOut;
-    if (!overflow && nR > 0) resolveStrand(P, w, ivs + nF, nR, false, s.readLen, mateStatus, lane, nOut, overflow);
-    if (overflow) {
+    // work-area demand: the two strands sit side by side; each is padded to a power of two for the sort, and the
+    // fwd/rc merge writes its result behind the two hit lists (<= 2 * entries)
+    uint32_t totF = 0, totR = 0;
+    for (int j = 0; j < nF; ++j) totF += static_cast<uint32_t>(ivs[j].end - ivs[j].begin);
+    for (int j = nF; j < nF + nR; ++j) totR += static_cast<uint32_t>(ivs[j].end - ivs[j].begin);
+    uint32_t padR = 1;
+    while (padR < totR) padR <<= 1;
+    uint32_t padF = 1;
+    while (padF < totF) padF <<= 1;
+    uint32_t need = totF + (padR > padF ? padR : padF);
+    if (nF > 0 && nR > 0) need = need > 2 * (totF + totR) ? need : 2 * (totF + totR);
+    WorkArea w;
+    if (need <= P.smemEntries) w = carve(smemBase, P.smemEntries);
+    else if (need <= P.scratchEntries) w = carve(globBase, P.scratchEntries);
+    else {
       if (lane == 0) { atomicOr(P.status, kStatScratchFull); P.qsumm[r] = out; }
       continue;
     }
+    uint32_t nOut = 0, posBase = 0;
+    if (nF > 0) resolveStrand(P, w, ivs, nF, true, s.readLen, lane, nOut, posBase);
+    const uint32_t nFwdOut = nOut;
+    if (nR > 0) resolveStrand(P, w, ivs + nF, nR, false, s.readLen, lane, nOut, posBase);
     uint32_t nFinal = nOut;
-    // ---- merge forward and reverse-complement lists (HitManager.cpp:834-881); rare, done by lane 0.
-    // Without chain scores every tie keeps the forward hit (stable inplace_merge, equal chainScore).
+    // ---- merge forward and reverse-complement lists (:834-881).  Rare (both strands kept), done by lane 0:
+    // stable merge on tid, equal tid => higher chain score first (forward first on a tie); the survivor takes the
+    // loser's allPositions as oppositeStrandPositions.
     if (nFwdOut > 0 && nOut > nFwdOut) {
       if (lane == 0) {
-        // merged order written behind the two lists, then moved to the front
-        uint32_t a = 0, b = nFwdOut, o = nOut;
-        if (2 * nOut <= w.cap) {
-          while (a < nFwdOut || b < nOut) {
-            if (b >= nOut || (a < nFwdOut && w.qa[a].tid <= w.qa[b].tid)) {
-              if (a < nFwdOut && b < nOut && w.qa[a].tid == w.qa[b].tid) ++b;  // drop the rc duplicate
-              w.qa[o++] = w.qa[a++];
-            } else {
-              w.qa[o++] = w.qa[b++];
-            }
+        uint32_t a = 0, b = nFwdOut, oo = nOut;
+        while (a < nFwdOut || b < nOut) {
+          bool takeA;
+          if (b >= nOut) takeA = true;
+          else if (a >= nFwdOut) takeA = false;
+          else if (w.qa[a].tid != w.qa[b].tid) takeA = w.qa[a].tid < w.qa[b].tid;
+          else {
+            // same transcript on both strands
+            bool rcFirst = w.qaScore[b] > w.qaScore[a];
+            QARec win = rcFirst ? w.qa[b] : w.qa[a];
+            const QARec& lose = rcFirst ? w.qa[a] : w.qa[b];
+            win.oppOff = lose.posOff; win.nOpp = lose.nAll;
+            w.qaScore[oo] = rcFirst ? w.qaScore[b] : w.qaScore[a];
+            w.qa[oo++] = win;
+            ++a; ++b;
+            continue;
           }
-          nFinal = o - nOut;
-          for (uint32_t i = 0; i < nFinal; ++i) w.qa[i] = w.qa[nOut + i];
-        } else {
-          nFinal = 0xffffffffu;
+          if (takeA) { w.qaScore[oo] = w.qaScore[a]; w.qa[oo++] = w.qa[a++]; }
+          else { w.qaScore[oo] = w.qaScore[b]; w.qa[oo++] = w.qa[b++]; }
         }
+        nFinal = oo - nOut;
+        for (uint32_t i = 0; i < nFinal; ++i) w.qa[i] = w.qa[nOut + i];
       }
       nFinal = __shfl_sync(0xffffffffu, nFinal, 0);
-      if (nFinal == 0xffffffffu) {
-        if (lane == 0) { atomicOr(P.status, kStatScratchFull); P.qsumm[r] = out; }
-        continue;
-      }
       __syncwarp();
     }
-    // ---- publish
+    // ---- publish hits (+ position lists)
     uint32_t off = 0;
+    bool ok = true;
     if (nFinal > 0) {
       if (lane == 0) off = atomicAdd(P.qaCursor, nFinal);
       off = __shfl_sync(0xffffffffu, off, 0);
       if (off + nFinal > P.qaCap) {
         if (lane == 0) atomicOr(P.status, kStatQAArenaFull);
-        nFinal = 0;
+        ok = false;
+      }
+      uint32_t poolOff = 0, nPosTot = 0;
+      if (needPos) {
+        for (uint32_t i = lane; i < nFinal; i += 32) nPosTot += w.qa[i].nAll + w.qa[i].nOpp;
+        for (int d = 16; d > 0; d >>= 1) nPosTot += __shfl_xor_sync(0xffffffffu, nPosTot, d);
+        if (lane == 0) poolOff = atomicAdd(P.posCursor, nPosTot);
+        poolOff = __shfl_sync(0xffffffffu, poolOff, 0);
+        if (poolOff + nPosTot > P.posCap) {
+          if (lane == 0) atomicOr(P.status, kStatPosPoolFull);
+          ok = false;
+        }
+      }
+      if (ok) {
+        uint32_t run = poolOff;
+        for (uint32_t i = 0; i < nFinal; ++i) {  // warp walks the hits, lanes copy the position lists
+          QARec q = w.qa[i];
+          if (needPos) {
+            for (uint32_t j = lane; j < q.nAll; j += 32) P.posPool[run + j] = w.posTmp[q.posOff + j];
+            for (uint32_t j = lane; j < q.nOpp; j += 32) P.posPool[run + q.nAll + j] = w.posTmp[q.oppOff + j];
+            q.posOff = run; q.oppOff = run + q.nAll;
+            run += q.nAll + q.nOpp;
+          }
+          if (lane == 0) P.qaArena[off + i] = q;
+        }
       } else {
-        for (uint32_t i = lane; i < nFinal; i += 32) P.qaArena[off + i] = w.qa[i];
+        nFinal = 0;
       }
     }
     if (lane == 0) { out.qaOff = off; out.nQA = nFinal; P.qsumm[r] = out; }

@@ -34,8 +34,10 @@ struct ReadSummary {
 struct QARec {
   uint32_t tid;
   int32_t pos;
-  uint32_t posOff;       // allPositions then oppositeStrandPositions in the position pool (only when considerMultiPos)
-  uint16_t nAll, nOpp;
+  uint32_t posOff;       // allPositions in the position pool (only when fuzzy / selAln)
+  uint32_t nAll;
+  uint32_t oppOff;       // oppositeStrandPositions
+  uint32_t nOpp;
   uint8_t fwd;
   uint8_t chain;         // ChainStatus of this read end
   uint16_t pad;

@@ -141,11 +141,156 @@ __device__ __forceinline__ uint32_t mergeSimple(const MergeParams& P, uint64_t p
   return nOut;
 }
 
+// findBestHitFWRC (include/RapMapUtils.hpp:903-975): closest "rc read downstream of fwd read" pair of positions.
+__device__ __forceinline__ bool bestFwRc(const int32_t* fw, uint32_t nFw, const int32_t* rc, uint32_t nRc, int32_t fwdReadLen, int32_t& fwPos,
+                                         int32_t& rcPos, int32_t& gapOut) {
+  if (nFw == 0 || nRc == 0) return false;
+  const int32_t maxGap = 0x7fffffff;
+  int32_t bestGap = maxGap;
+  uint32_t bf = 0, br = 0;
+  for (uint32_t fi = 0; fi < nFw; ++fi) {
+    const int32_t p1 = fw[fi];
+    uint32_t lo = 0, hi = nRc;  // std::lower_bound
+    while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (rc[mid] < p1) lo = mid + 1; else hi = mid; }
+    uint32_t cand[2];
+    int nc = 0;
+    if (lo == nRc) cand[nc++] = lo - 1;
+    else if (lo == 0) cand[nc++] = lo;
+    else { cand[nc++] = lo; cand[nc++] = lo - 1; }
+    for (int c = 0; c < nc; ++c) {
+      const int32_t r = rc[cand[c]];
+      int32_t d = r - (p1 + fwdReadLen);
+      int32_t gap = (r >= p1) ? (d < 0 ? -d : d) : maxGap;
+      if (gap < bestGap) { bestGap = gap; bf = fi; br = cand[c]; }
+    }
+  }
+  if (bestGap == maxGap) return false;
+  fwPos = fw[bf]; rcPos = rc[br]; gapOut = bestGap;
+  return true;
+}
+
+// mergeLeftRightHitsFuzzy (include/RapMapUtils.hpp:864-1183) + the post-merge steps of src/RapMapSAMapper.cpp:533-551.
+// With selAln the hits are scored and filtered afterwards (sel_aln.cuh); --noDovetail is applied there.
+template <bool WRITE>
+__device__ __forceinline__ uint32_t mergeFuzzy(const MergeParams& P, uint64_t pi, unsigned long long* ctr) {
+  const DevOpts& o = P.opts;
+  const QASummary ls = P.qsumm[pi], rs = P.qsumm[P.numPairs + pi];
+  const QARec* L = P.qaArena + ls.qaOff;
+  const QARec* R = P.qaArena + rs.qaOff;
+  const ReadSummary lsum = P.summ[pi], rsum = P.summ[P.numPairs + pi];
+  const uint16_t lLen = lsum.readLen, rLen = rsum.readLen;
+  const uint32_t nl = ls.nQA, nr = rs.nQA;
+  rapmap_hit_t* out = nullptr;
+  uint64_t room = 0;
+  if (WRITE) {
+    uint64_t off = P.pairOffset[pi];
+    room = P.pairOffset[pi + 1] - off;
+    out = P.hits + off;
+    if (off + room > P.hitsCap) return 0;
+  }
+  uint32_t nOut = 0;
+  auto emit = [&](const rapmap_hit_t& h) {
+    if (WRITE) { if (nOut < room) out[nOut] = h; }
+    ++nOut;
+  };
+  auto orphan = [&](const QARec& q, int side) {
+    rapmap_hit_t h;
+    h.tid = q.tid; h.pos = q.pos; h.mate_pos = 0; h.frag_len = 0; h.read_len = side ? rLen : lLen; h.mate_len = 0; h.aln_score = 0;
+    h.fwd = q.fwd; h.mate_fwd = 1; h.mate_status = side ? 2 : 1;
+    h.chain_status = side ? static_cast<uint8_t>(4 | (q.chain << 4)) : static_cast<uint8_t>(q.chain | (4 << 4));
+    return h;
+  };
+  bool tooManyHits = false;
+  int mode = 0;  // 0 nothing, 1 only right, 2 only left, 3 paired
+  uint32_t numHits = 0;
+  if (nl == 0) {
+    if (!lsum.found && nr > 0) mode = 1;   // orphans only if the other end had no k-mer hit at all (:880-899)
+  } else if (nr == 0) {
+    if (!rsum.found) mode = 2;
+  } else {
+    mode = 3;
+  }
+  if (!WRITE) ctr[0] += 1;
+  if (mode == 1 || mode == 2) {
+    const uint32_t n = mode == 1 ? nr : nl;
+    if (!WRITE) { ctr[2] += n; ctr[1] += n; }  // seHits, and peHits counts every non-empty jointHits (:1176-1179)
+    uint32_t size = n;
+    if (size > o.maxNumHits) size = 0;
+    if (o.noOrphans) size = 0;
+    if (size == 0) return 0;
+    const QARec* Q = mode == 1 ? R : L;
+    for (uint32_t i = 0; i < n; ++i) {
+      rapmap_hit_t h = orphan(Q[i], mode == 1 ? 1 : 0);
+      if (!o.selAln && o.noDovetail && dovetailDrop(h)) continue;
+      emit(h);
+    }
+    if (!WRITE && !o.selAln) ctr[3] += nOut;
+    return nOut;
+  }
+  if (mode == 0) return 0;
+  // paired: the walk is run twice in count mode (once to learn tooManyHits), once more to write
+  for (int pass = 0; pass < 2; ++pass) {
+    uint32_t li = 0, ri = 0;
+    numHits = 0;
+    const bool writing = pass == 1;
+    while (li < nl && ri < nr) {
+      const uint32_t lt = L[li].tid, rt = R[ri].tid;
+      if (lt < rt) { ++li; }
+      else {
+        if (!(rt < lt)) {
+          const QARec& l = L[li];
+          const QARec& r = R[ri];
+          const int32_t* lAll = P.posPool + l.posOff; const int32_t* lOpp = P.posPool + l.oppOff;
+          const int32_t* rAll = P.posPool + r.posOff; const int32_t* rOpp = P.posPool + r.oppOff;
+          const int32_t* leftFwd = l.fwd ? lAll : lOpp;   const uint32_t nLeftFwd = l.fwd ? l.nAll : l.nOpp;
+          const int32_t* leftRC = l.fwd ? lOpp : lAll;    const uint32_t nLeftRC = l.fwd ? l.nOpp : l.nAll;
+          const int32_t* rightFwd = r.fwd ? rAll : rOpp;  const uint32_t nRightFwd = r.fwd ? r.nAll : r.nOpp;
+          const int32_t* rightRC = r.fwd ? rOpp : rAll;   const uint32_t nRightRC = r.fwd ? r.nOpp : r.nAll;
+          int32_t a1 = 0, a2 = 0, ag = 0, b1 = 0, b2 = 0, bg = 0;
+          const bool haveFWRC = bestFwRc(leftFwd, nLeftFwd, rightRC, nRightRC, static_cast<int32_t>(lLen), a1, a2, ag);
+          const bool haveRCFW = bestFwRc(rightFwd, nRightFwd, leftRC, nLeftRC, static_cast<int32_t>(rLen), b1, b2, bg);
+          bool found = false, leftFwdFlag = false, rightFwdFlag = false;
+          int32_t bestGap = 0x7fffffff, leftPos = -1, rightPos = -1;
+          if (haveFWRC) { leftPos = a1; rightPos = a2; bestGap = ag; leftFwdFlag = true; rightFwdFlag = false; found = true; }
+          if (haveRCFW) {
+            if (bg < bestGap) { leftPos = b2; rightPos = b1; leftFwdFlag = false; rightFwdFlag = true; }
+            found = true;
+          }
+          if (found) {
+            ++numHits;
+            if (writing) {
+              const int32_t s1 = leftPos > 0 ? leftPos : 0, s2 = rightPos > 0 ? rightPos : 0;
+              const bool read1First = s1 < s2;
+              const int32_t fragStart = read1First ? s1 : s2;
+              const int32_t fragEnd = read1First ? (s2 + static_cast<int32_t>(rLen)) : (s1 + static_cast<int32_t>(lLen));
+              rapmap_hit_t h;
+              h.tid = lt; h.pos = leftPos; h.mate_pos = rightPos; h.frag_len = static_cast<uint32_t>(fragEnd - fragStart);
+              h.read_len = lLen; h.mate_len = rLen; h.aln_score = 0; h.fwd = leftFwdFlag; h.mate_fwd = rightFwdFlag; h.mate_status = 3;
+              h.chain_status = static_cast<uint8_t>(l.chain | (r.chain << 4));
+              if (!(!o.selAln && o.noDovetail && dovetailDrop(h))) emit(h);
+            }
+            if (numHits > o.maxNumHits) { tooManyHits = true; break; }
+          }
+          ++li;
+        }
+        ++ri;
+      }
+    }
+    if (pass == 0) {
+      uint32_t nJoint = tooManyHits ? 0 : numHits;
+      if (!WRITE) { if (tooManyHits) ctr[4] += 1; ctr[1] += nJoint; }
+      if (nJoint == 0 || nJoint > o.maxNumHits) return 0;
+    }
+  }
+  if (!WRITE && !o.selAln) ctr[3] += nOut;
+  return nOut;
+}
+
 template <bool FUZZY>
 __global__ void __launch_bounds__(256) merge_count_kernel(MergeParams P) {
   unsigned long long ctr[5] = {0, 0, 0, 0, 0};
   for (uint64_t pi = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; pi < P.numPairs; pi += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
-    P.pairCount[pi] = mergeSimple<false>(P, pi, ctr);
+    P.pairCount[pi] = FUZZY ? mergeFuzzy<false>(P, pi, ctr) : mergeSimple<false>(P, pi, ctr);
   }
   // block reduction of the five HitCounters, one atomic per warp
 #pragma unroll
@@ -159,7 +304,7 @@ __global__ void __launch_bounds__(256) merge_count_kernel(MergeParams P) {
 template <bool FUZZY>
 __global__ void __launch_bounds__(256) merge_write_kernel(MergeParams P) {
   for (uint64_t pi = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; pi < P.numPairs; pi += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
-    mergeSimple<true>(P, pi, nullptr);
+    if (FUZZY) mergeFuzzy<true>(P, pi, nullptr); else mergeSimple<true>(P, pi, nullptr);
   }
 }
 

@@ -28,6 +28,8 @@ struct CollectParams {
   uint32_t lpad;           // bytes per read buffer (multiple of 16)
   uint32_t pmax;           // max k-mer positions per read
   uint32_t warpSmemBytes;
+  uint32_t packOff;        // offset of the packed-read area inside a warp's shared-memory slice
+  uint32_t ctxOff;         // offset of the per-warp WarpCtx
   ReadSummary* summ;
   IntervalRec* arena;
   uint32_t arenaCap;
@@ -91,20 +93,53 @@ struct WarpCtx {
   const uint8_t* rcBuf;
   int2* cF;   // per forward position: interval of the k-mer        (x == -2: not looked up, x == -1: absent)
   int2* cR;   // per forward position: interval of its reverse complement
+  const uint64_t* packF;  // 2-bit packed read, base i at bits (63-2(i%32), 62-2(i%32)) of word i/32 (forward strand)
+  const uint64_t* packR;  // same for the reverse complement
+  const uint32_t* invF;   // bit i%32 of word i/32: base i is not A/C/G/T (either case)
+  const uint32_t* invR;
+  const uint32_t* nmF;    // bit set: base is N/n
+  const uint32_t* nmR;
   int L, k, npos, lane;
+  int maxMMPExtension, maxInterval;
+  bool doChaining;
   bool hasU;
 };
 
+// k-mer at position p of a packed strand in O(1): funnel shift of two packed words; valid == no non-ACGT base in
+// the window.  Invalid windows fall back to encodeKmer (partial-word semantics of Kmer::fromChars).
+__device__ __forceinline__ bool packedKmer(const uint64_t* pack, const uint32_t* inv, const uint8_t* buf, int p, int k, uint64_t& w) {
+  const int wi = p >> 5, sh = p & 31;
+  const uint32_t m0 = inv[wi], m1 = inv[wi + 1];
+  const uint32_t win = sh ? ((m0 >> sh) | (m1 << (32 - sh))) : m0;
+  if ((win & ((1u << k) - 1u)) != 0u) return encodeKmer(buf + p, k, w);
+  const uint64_t w0 = pack[wi], w1 = pack[wi + 1];
+  const uint64_t val = sh ? ((w0 << (2 * sh)) | (w1 >> (64 - 2 * sh))) : w0;
+  w = val >> (64 - 2 * k);
+  return true;
+}
+
+__device__ __forceinline__ int findNMask(const uint32_t* nm, int from, int L) {  // std::string::find_first_of("nN", from)
+  if (from >= L) return 0x7fffffff;
+  int wi = from >> 5;
+  uint32_t m = nm[wi] & (0xffffffffu << (from & 31));
+  while (true) {
+    if (m) return wi * 32 + __ffs(m) - 1;
+    ++wi;
+    if (wi * 32 >= L) return 0x7fffffff;
+    m = nm[wi];
+  }
+}
+
 // Speculative lookup of 16 consecutive forward positions q0, q0+dir, ... in both orientations.
 __device__ __forceinline__ void fillCache(const WarpCtx& c, int q0, int dir) {
-  int q = q0 + dir * (c.lane & 15);
-  bool rcSide = (c.lane >> 4) != 0;
+  int q = q0 + dir * ((static_cast<int>(threadIdx.x) & 31) & 15);
+  bool rcSide = ((static_cast<int>(threadIdx.x) & 31) >> 4) != 0;
   if (q >= 0 && q < c.npos) {
     int2* slot = (rcSide ? c.cR : c.cF) + q;
     if (slot->x == -2) {
       uint64_t w;
       int2 res = make_int2(-1, -1);
-      if (encodeKmer(c.fwdBuf + q, c.k, w)) res = hashFind(c.ix, rcSide ? kmerRC(w, c.k) : w);
+      if (packedKmer(c.packF, c.invF, c.fwdBuf, q, c.k, w)) res = hashFind(c.ix, rcSide ? kmerRC(w, c.k) : w);
       *slot = res;
     }
   }
@@ -133,13 +168,13 @@ __device__ __forceinline__ void lookupBoth(const WarpCtx& c, bool isRC, int p, u
 // Cooperative suffix comparison: query q[i] vs text[t+i] for i >= i0 while i < m and t+i < n.
 // sentIdx >= 0 replaces q[sentIdx] by `sent` (searches 2/3 of extendSearchNaive).  Returns the index at
 // which the reference's inner while-loop stops; rel = -1 (query < text), +1 (query > text), 0 (ran off).
-__device__ __forceinline__ int coopCompare(const WarpCtx& c, const uint8_t* q, int m, int64_t t, int i0, int sentIdx, uint8_t sent, int& rel) {
+__device__ __noinline__ int coopCompare(const WarpCtx& c, const uint8_t* q, int m, int64_t t, int i0, int sentIdx, uint8_t sent, int& rel) {
   int64_t limL = c.ix.n - t;
   int lim = (limL < static_cast<int64_t>(m)) ? static_cast<int>(limL) : m;
   if (i0 >= lim) { rel = 0; return i0; }
   const uint8_t* tp = c.ix.text + t;
   for (int base = i0;; base += 128) {
-    int idx = base + c.lane * 4;
+    int idx = base + (static_cast<int>(threadIdx.x) & 31) * 4;
     uint8_t tc[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) tc[j] = (idx + j < lim) ? __ldg(tp + idx + j) : 0;
@@ -164,7 +199,7 @@ __device__ __forceinline__ int coopCompare(const WarpCtx& c, const uint8_t* q, i
 }
 
 // SASearcher::extendSearchNaive (include/SASearcher.hpp:87-309); startAt = k.
-__device__ __forceinline__ void extendSearch(const WarpCtx& c, int64_t lbIn, int64_t ubIn, const uint8_t* q, int mQ,
+__device__ __noinline__ void extendSearch(const WarpCtx& c, int64_t lbIn, int64_t ubIn, const uint8_t* q, int mQ,
                                              int& outLb, int& outUb, int& outLen) {
   const int startAt = c.k;
   const int64_t n = c.ix.n;
@@ -231,9 +266,12 @@ __device__ __forceinline__ int findN(const uint8_t* s, int from, int L) {  // st
 }
 
 // SACollector::getSAHits_ (include/SACollector.hpp:441-677) on one strand.  `buf` is the strand's read.
-__device__ __forceinline__ void walkStrand(const WarpCtx& c, const DevOpts& o, bool isRC, int startPos, bool haveStart, int2 startIv,
+__device__ __noinline__ void walkStrand(const WarpCtx& c, bool isRC, int startPos, bool haveStart, int2 startIv,
                                            uint32_t& cov, uint32_t& strandHits, uint32_t& otherStrandHits, IntervalRec* list, int& nList) {
   const uint8_t* buf = isRC ? c.rcBuf : c.fwdBuf;
+  const uint64_t* pack = isRC ? c.packR : c.packF;
+  const uint32_t* inv = isRC ? c.invR : c.invF;
+  const uint32_t* nm = isRC ? c.nmR : c.nmF;
   const int k = c.k, L = c.L;
   int rb = 0;
   int64_t lb = 0, ub = 0;
@@ -244,10 +282,10 @@ __device__ __forceinline__ void walkStrand(const WarpCtx& c, const DevOpts& o, b
   while (skipSetup || rb + k <= L) {
     if (!skipSetup) {
       uint64_t mer;
-      bool valid = encodeKmer(buf + rb, k, mer);
+      bool valid = packedKmer(pack, inv, buf, rb, k, mer);
       if (!valid) {  // :505-516
-        int inv = findN(buf, rb, L);
-        if (inv < rb + k) { rb = inv + 1; continue; }
+        int ip = findNMask(nm, rb, L);
+        if (ip < rb + k) { rb = ip + 1; continue; }
       }
       if (isHomopolymer(mer, k)) { rb += 1; continue; }  // :520-536
       int2 fm, fc;
@@ -259,17 +297,17 @@ __device__ __forceinline__ void walkStrand(const WarpCtx& c, const DevOpts& o, b
     }
     skipSetup = false;
     lb = lb - 1 > 0 ? lb - 1 : 0;  // :553
-    bool firstAttempt = o.doChaining ? (rb == 0) : true;
-    int endPos = firstAttempt ? L : min(rb + k + o.maxMMPExtension, L);
+    bool firstAttempt = c.doChaining ? (rb == 0) : true;
+    int endPos = firstAttempt ? L : min(rb + k + c.maxMMPExtension, L);
     int nlb, nub, matchedLen;
     extendSearch(c, lb, ub, buf + rb, endPos - rb, nlb, nub, matchedLen);
-    if (o.doChaining && firstAttempt && !(matchedLen >= L) && matchedLen >= k + o.maxMMPExtension) {  // :568-575
-      endPos = min(rb + k + o.maxMMPExtension, L);
+    if (c.doChaining && firstAttempt && !(matchedLen >= L) && matchedLen >= k + c.maxMMPExtension) {  // :568-575
+      endPos = min(rb + k + c.maxMMPExtension, L);
       extendSearch(c, lb, ub, buf + rb, endPos - rb, nlb, nub, matchedLen);
     }
     lb = nlb; ub = nub;
-    if (ub > lb && (ub - lb) < o.maxInterval) {  // :578
-      if (c.lane == 0) {
+    if (ub > lb && (ub - lb) < c.maxInterval) {  // :578
+      if ((static_cast<int>(threadIdx.x) & 31) == 0) {
         IntervalRec rec;
         rec.begin = static_cast<int32_t>(lb); rec.end = static_cast<int32_t>(ub);
         rec.len = static_cast<uint16_t>(matchedLen); rec.qpos = static_cast<uint16_t>(rb);
@@ -282,7 +320,7 @@ __device__ __forceinline__ void walkStrand(const WarpCtx& c, const DevOpts& o, b
       if (rb + matchedLen < L) {  // :599-616 mismatching k-mer, both orientations
         int kp = rb + matchedLen - (k - 1);
         uint64_t mm;
-        if (encodeKmer(buf + kp, k, mm)) {
+        if (packedKmer(pack, inv, buf, kp, k, mm)) {
           int2 fm, fc;
           lookupBoth(c, isRC, kp, mm, true, true, true, fm, fc);
           if (fm.x >= 0) ++strandHits;
@@ -298,7 +336,7 @@ __device__ __forceinline__ void walkStrand(const WarpCtx& c, const DevOpts& o, b
 }
 
 template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) sa_collect_kernel(CollectParams P) {
+__global__ void __launch_bounds__(WARPS * 32, 4) sa_collect_kernel(CollectParams P) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -309,6 +347,13 @@ __global__ void __launch_bounds__(WARPS * 32) sa_collect_kernel(CollectParams P)
   int2* cR = cF + P.pmax;
   IntervalRec* ivF = reinterpret_cast<IntervalRec*>(cR + P.pmax);
   IntervalRec* ivR = ivF + P.pmax;
+  const uint32_t pw = P.lpad / 32 + 2;  // packed words / mask words per strand (one spare word for the funnel shift)
+  uint64_t* packF = reinterpret_cast<uint64_t*>(base + P.packOff);
+  uint64_t* packR = packF + pw;
+  uint32_t* invF = reinterpret_cast<uint32_t*>(packR + pw);
+  uint32_t* invR = invF + pw;
+  uint32_t* nmF = invR + pw;
+  uint32_t* nmR = nmF + pw;
   const DevOpts& o = P.opts;
   const int k = static_cast<int>(P.ix.k);
 
@@ -345,9 +390,35 @@ __global__ void __launch_bounds__(WARPS * 32) sa_collect_kernel(CollectParams P)
     for (int i = lane; i < npos; i += 32) { cF[i] = make_int2(-2, -2); cR[i] = make_int2(-2, -2); }
     const bool hasU = __any_sync(0xffffffffu, u);
     __syncwarp();
+    // 2-bit pack both strands + invalid / N masks (32 bases per step: two OR-reductions and two ballots)
+    for (uint32_t j = 0; j < pw; ++j) {
+      const int i = static_cast<int>(j) * 32 + lane;
+#pragma unroll
+      for (int strand = 0; strand < 2; ++strand) {
+        const uint8_t ch = i < L ? (strand ? rcBuf[i] : fwdBuf[i]) : 0;
+        const int cd = baseCode(ch);
+        const uint32_t c2 = cd < 0 ? 0u : static_cast<uint32_t>(cd);
+        const uint32_t hi = __reduce_or_sync(0xffffffffu, lane < 16 ? (c2 << (30 - 2 * lane)) : 0u);
+        const uint32_t lo = __reduce_or_sync(0xffffffffu, lane >= 16 ? (c2 << (30 - 2 * (lane - 16))) : 0u);
+        const uint32_t im = __ballot_sync(0xffffffffu, cd < 0);
+        const uint32_t nn = __ballot_sync(0xffffffffu, i < L && (ch | 0x20) == 'n');
+        if (lane == 0) {
+          (strand ? packR : packF)[j] = (static_cast<uint64_t>(hi) << 32) | lo;
+          (strand ? invR : invF)[j] = im;
+          (strand ? nmR : nmF)[j] = nn;
+        }
+      }
+    }
+    __syncwarp();
 
-    WarpCtx c;
-    c.ix = P.ix; c.fwdBuf = fwdBuf; c.rcBuf = rcBuf; c.cF = cF; c.cR = cR; c.L = L; c.k = k; c.npos = npos; c.lane = lane; c.hasU = hasU;
+    WarpCtx& c = *reinterpret_cast<WarpCtx*>(base + P.ctxOff);
+    __syncwarp();
+    if (lane == 0) {
+    c.ix = P.ix; c.fwdBuf = fwdBuf; c.rcBuf = rcBuf; c.cF = cF; c.cR = cR; c.L = L; c.k = k; c.npos = npos; c.hasU = hasU;
+    c.packF = packF; c.packR = packR; c.invF = invF; c.invR = invR; c.nmF = nmF; c.nmR = nmR;
+    c.maxMMPExtension = o.maxMMPExtension; c.maxInterval = o.maxInterval; c.doChaining = o.doChaining != 0;
+    }
+    __syncwarp();
 
     // ---- first-hit scan (SACollector.hpp:167-237)
     uint32_t fwdHit = 0, rcHit = 0, fwdCov = 0, rcCov = 0;
@@ -357,11 +428,11 @@ __global__ void __launch_bounds__(WARPS * 32) sa_collect_kernel(CollectParams P)
     int2 firstIv = make_int2(-1, -1);
     while (rb + k <= L) {
       if (invalidPos != 0x7fffffff) {
-        invalidPos = findN(fwdBuf, rb, L);
+        invalidPos = findNMask(nmF, rb, L);
         if (invalidPos <= rb + k) { rb = invalidPos + 1; continue; }  // note <= (SACollector.hpp:178)
       }
       uint64_t mer;
-      bool valid = encodeKmer(fwdBuf + rb, k, mer);
+      bool valid = packedKmer(packF, invF, fwdBuf, rb, k, mer);
       if (isHomopolymer(mer, k)) { rb += 1; continue; }
       int2 fm, fc;
       lookupBoth(c, false, rb, mer, valid, true, true, fm, fc);
@@ -375,12 +446,12 @@ __global__ void __launch_bounds__(WARPS * 32) sa_collect_kernel(CollectParams P)
       bool didCheckFwd = false;
       if (fwdHit) {  // :247-254
         didCheckFwd = true;
-        walkStrand(c, o, false, rb, true, firstIv, fwdCov, fwdHit, rcHit, ivF, nF);
+        walkStrand(c, false, rb, true, firstIv, fwdCov, fwdHit, rcHit, ivF, nF);
       }
       if (rcHit > 0)  // :256-265 (coverage mode: checkRC = rcHit > 0)
-        walkStrand(c, o, true, 0, false, make_int2(0, 0), rcCov, rcHit, fwdHit, ivR, nR);
+        walkStrand(c, true, 0, false, make_int2(0, 0), rcCov, rcHit, fwdHit, ivR, nR);
       if (!didCheckFwd && fwdHit > 0)  // :270-278
-        walkStrand(c, o, false, 0, false, make_int2(0, 0), fwdCov, fwdHit, rcHit, ivF, nF);
+        walkStrand(c, false, 0, false, make_int2(0, 0), fwdCov, fwdHit, rcHit, ivF, nF);
       // strand decision by coverage (:283-288)
       if (fwdCov > rcCov + static_cast<uint32_t>(o.strictCheckSlack)) nR = 0;
       else if (rcCov > fwdCov + static_cast<uint32_t>(o.strictCheckSlack)) nF = 0;

@@ -1,21 +1,561 @@
-// Kernel 4 — selective alignment (getAlnScore + ksw_extz2_sse restatement + score filter).
-// Placeholder until the device implementation lands: selecting -s fails loudly (no CPU fallback).
+// Kernel 4 — selective alignment: scoring of the surviving candidates and the score filter.
+//
+// Replaces, for a whole chunk, the `-s` block of processReadsPairSA / processReadsSingleSA (reference
+// src/RapMapSAMapper.cpp:553-683, :248-330): selective_alignment::utils::getAlnScore
+// (include/SelectiveAlignmentUtils.hpp:260-373: PERFECT shortcut, overhang trim, BT2 policy, UNGAPPED linear
+// score, per-read alignment cache), KSW2Aligner::operator()(EXTENSION) (src/ksw2pp/KSW2Aligner.cpp:205-234) and
+// ksw_extz2_sse41 in score-only mode (src/ksw2pp/ksw2_extz2_sse.c:18-304), then the minScoreFrac threshold, the
+// dovetail veto, the soft / hard filter and alnScore_.
+//
+// Stages (all on the mapper's stream):
+//   selaln_prepare_kernel  warp per pair: classifies every (hit, read end) task, emulates the alignment cache
+//                          ("first earlier hit of this read end with a byte-identical reference window wins", which
+//                          is what a MetroHash64-keyed map gives up to 2^-64 collisions), scores UNGAPPED tasks
+//                          inline and queues the remaining ones as DP jobs.
+//   ksw_extz_kernel        warp per DP job: lane-for-lane restatement of the SSE kernel — int8 wrapping lanes with
+//                          unsigned max/min clamps, the 16-lane block rounding that widens the band, stale
+//                          out-of-band lanes, the separate int32 H[] track — in shared memory laid out exactly as
+//                          the reference's kcalloc block (u|v|x|y|s|sf|qr) because its 16-byte loads and stores run
+//                          past tlen/qlen into the neighbouring arrays.  Integer-ALU bound; no HBM traffic beyond
+//                          the <= 120-byte window.
+//   selaln_score_kernel    thread per pair: per-hit score, best score, survivor count.
+//   selaln_write_kernel    thread per pair: compacts the survivors (after an exclusive scan) with aln_score set.
 #pragma once
 #include <string>
+
+#include <cub/device/device_scan.cuh>
+
 #include "kernels.cuh"
+#include "sa_collect.cuh"
 
 namespace rapmap_b200 {
 
-struct SelAlnWork {
-  rapmap_hit_t* outHits{nullptr};
+static constexpr int32_t kKswNegInf = -0x40000000;
+static constexpr int32_t kIntMin = static_cast<int32_t>(0x80000000u);
+
+struct DPJob {
+  int64_t tpos;       // global text position of the target window
+  uint32_t slot;      // task slot (2 * hit + end) receiving the score
+  uint32_t read;      // read index in the batch view (mate 2 reads follow mate 1 reads)
+  int32_t tlen1;      // target window length
+  int32_t rlen;       // query length after overhang trimming
+  int32_t rskip;      // bases trimmed from the query start (pos < 0)
+  uint8_t rc;         // query is the reverse complement of the read
+  uint8_t pad[3];
 };
 
-inline cudaError_t selAlnAlloc(SelAlnWork&, uint64_t, uint32_t) { return cudaSuccess; }
-inline void selAlnFree(SelAlnWork&) {}
-inline int selAlnRun(SelAlnWork&, const DeviceIndex&, const DevOpts&, const BatchView&, uint64_t, bool, rapmap_hit_t*, uint64_t*, uint32_t*, uint64_t,
-                     void*, size_t, int, cudaStream_t, uint32_t*, uint64_t*, void*, std::string& err) {
-  err = "selective alignment is not implemented on the device path yet";
-  return RAPMAP_ERR_UNSUPPORTED;
+struct SelAlnWork {
+  int32_t* taskScore{nullptr};   // [2 * hitsCap]
+  int32_t* taskRef{nullptr};     // -1: own score, >= 0: copy of that slot (alignment cache hit)
+  uint64_t* taskHash{nullptr};   // window hash, 0 = task never reaches the cache stage
+  DPJob* jobs{nullptr};
+  uint32_t* jobCursor{nullptr};
+  int32_t* hitScore{nullptr};    // [hitsCap] final per-hit score (INT_MIN = dropped)
+  int32_t* pairBest{nullptr};    // [maxBatch]
+  uint32_t* outCount{nullptr};   // [maxBatch + 1]
+  uint64_t* outOff{nullptr};     // [maxBatch + 1]
+  rapmap_hit_t* outHits{nullptr};
+  uint64_t hitsCap{0};
+  uint64_t maxBatch{0};
+  uint32_t maxReadLen{0};
+  uint64_t* hTotal{nullptr};     // pinned
+};
+
+inline void selAlnFree(SelAlnWork& w) {
+  cudaFree(w.taskScore); cudaFree(w.taskRef); cudaFree(w.taskHash); cudaFree(w.jobs); cudaFree(w.jobCursor); cudaFree(w.hitScore);
+  cudaFree(w.pairBest); cudaFree(w.outCount); cudaFree(w.outOff); cudaFree(w.outHits);
+  if (w.hTotal) cudaFreeHost(w.hTotal);
+  w = SelAlnWork();
+}
+
+inline cudaError_t selAlnReserve(SelAlnWork& w, uint64_t hits) {
+  if (hits <= w.hitsCap) return cudaSuccess;
+  cudaFree(w.taskScore); cudaFree(w.taskRef); cudaFree(w.taskHash); cudaFree(w.jobs); cudaFree(w.hitScore); cudaFree(w.outHits);
+  w.taskScore = nullptr; w.taskRef = nullptr; w.taskHash = nullptr; w.jobs = nullptr; w.hitScore = nullptr; w.outHits = nullptr;
+  uint64_t cap = hits + hits / 4 + 1024;
+  cudaError_t e;
+  if ((e = cudaMalloc(&w.taskScore, cap * 2 * 4)) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&w.taskRef, cap * 2 * 4)) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&w.taskHash, cap * 2 * 8)) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&w.jobs, cap * 2 * sizeof(DPJob))) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&w.hitScore, cap * 4)) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&w.outHits, cap * sizeof(rapmap_hit_t))) != cudaSuccess) return e;
+  w.hitsCap = cap;
+  return cudaSuccess;
+}
+
+inline cudaError_t selAlnAlloc(SelAlnWork& w, uint64_t maxBatch, uint32_t maxReadLen) {
+  w.maxBatch = maxBatch;
+  w.maxReadLen = maxReadLen;
+  cudaError_t e;
+  if ((e = cudaMalloc(&w.jobCursor, 4)) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&w.pairBest, maxBatch * 4)) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&w.outCount, (maxBatch + 1) * 4)) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&w.outOff, (maxBatch + 1) * 8)) != cudaSuccess) return e;
+  if ((e = cudaMallocHost(&w.hTotal, 16)) != cudaSuccess) return e;
+  return selAlnReserve(w, maxBatch * 6 + 1024);
+}
+
+struct SelAlnParams {
+  DeviceIndex ix;
+  DevOpts opts;
+  BatchView reads;
+  uint64_t numPairs;
+  uint8_t pairedInput;
+  const rapmap_hit_t* hits;
+  const uint64_t* pairOff;
+  int32_t* taskScore;
+  int32_t* taskRef;
+  uint64_t* taskHash;
+  DPJob* jobs;
+  uint32_t* jobCursor;
+  int32_t* hitScore;
+  int32_t* pairBest;
+  uint32_t* outCount;
+  const uint64_t* outOff;
+  rapmap_hit_t* outHits;
+  uint32_t maxReadLen;
+};
+
+__device__ __forceinline__ void readSpan(const BatchView& b, uint64_t r, const uint8_t*& p, uint32_t& len) {
+  const int mate = r >= b.n ? 1 : 0;
+  const uint64_t i = r - static_cast<uint64_t>(mate) * b.n;
+  if (b.off[mate]) { uint64_t o0 = b.off[mate][i]; p = b.seq[mate] + o0; len = static_cast<uint32_t>(b.off[mate][i + 1] - o0); }
+  else { p = b.seq[mate] + i * b.fixedLen; len = b.fixedLen; }
+}
+
+// Query character i of the (possibly reverse-complemented) read, as the reference passes it to getAlnScore:
+// raw bytes for the forward read, reverseRead() output for the reverse complement.
+__device__ __forceinline__ uint8_t queryChar(const uint8_t* read, uint32_t len, bool rc, int32_t i) {
+  return rc ? rcChar(__ldg(read + (len - 1 - i))) : __ldg(read + i);
+}
+
+struct TaskGeom {
+  int64_t tpos;
+  int32_t tlen1, rlen, rskip, keyLen;
+  bool ungapped;
+};
+
+// Front half of getAlnScore (:268-312).  Returns 0 = needs a score (geometry in g), 1 = final score in `done`.
+__device__ __forceinline__ int classifyTask(const DeviceIndex& ix, const DevOpts& o, uint32_t tid, int32_t pos, int32_t rlenFull, uint8_t chainStat,
+                                            int32_t maxScore, TaskGeom& g, int32_t& done) {
+  if (chainStat == 0) { done = maxScore; return 1; }  // PERFECT
+  const int32_t tlen = __ldg(ix.txpLens + tid);
+  int32_t rlen = rlenFull, rskip = 0;
+  const bool invalidStart = pos < 0;
+  const bool invalidEnd = (pos + rlen >= tlen);
+  if (invalidStart) { rskip = -pos; rlen += pos; pos = 0; }
+  if ((invalidStart || invalidEnd) && (o.alignmentPolicy == 1 || o.alignmentPolicy == 2)) { done = kIntMin; return 1; }
+  if (!(pos < tlen)) { done = kIntMin; return 1; }
+  const bool doUngapped = (!invalidStart) && (chainStat == 1);
+  const uint32_t buf = doUngapped ? 0u : 20u;
+  const uint32_t lnobuf = static_cast<uint32_t>(tlen - pos);
+  const uint32_t lbuf = static_cast<uint32_t>(rlen) + buf;   // NB: unsigned, like the reference (rlen may be <= 0 after trimming)
+  const bool useBuf = lbuf < lnobuf;
+  const uint32_t tlen1 = lbuf < lnobuf ? lbuf : lnobuf;
+  g.tpos = static_cast<int64_t>(__ldg(ix.txpOffsets + tid)) + pos;
+  g.tlen1 = static_cast<int32_t>(tlen1);
+  g.rlen = rlen;
+  g.rskip = rskip;
+  g.keyLen = static_cast<int32_t>(useBuf ? tlen1 - buf : tlen1);
+  g.ungapped = doUngapped;
+  return 0;
+}
+
+__device__ __forceinline__ uint64_t windowHash(const uint8_t* t, int32_t n) {
+  uint64_t h = 0x9E3779B97F4A7C15ULL ^ static_cast<uint64_t>(static_cast<uint32_t>(n));
+  for (int32_t i = 0; i < n; ++i) h = mix64(h ^ (static_cast<uint64_t>(__ldg(t + i)) + 0x100ULL * static_cast<uint64_t>(i & 7)));
+  return h | 1ULL;  // never 0
+}
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) selaln_prepare_kernel(SelAlnParams P) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t gw = static_cast<uint64_t>(blockIdx.x) * WARPS + (threadIdx.x >> 5);
+  const DevOpts& o = P.opts;
+  const int32_t a = static_cast<int8_t>(o.ma), b = static_cast<int8_t>(o.mm);
+  for (uint64_t pi = gw; pi < P.numPairs; pi += static_cast<uint64_t>(gridDim.x) * WARPS) {
+    const uint64_t h0 = P.pairOff[pi], h1 = P.pairOff[pi + 1];
+    const uint32_t cnt = static_cast<uint32_t>(h1 - h0);
+    if (cnt == 0) continue;
+    const bool multiMapping = cnt > 1;
+    for (int end = 0; end < 2; ++end) {
+      const uint64_t r = end ? P.numPairs + pi : pi;
+      if (end == 1 && !P.pairedInput) break;
+      const uint8_t* read;
+      uint32_t rl;
+      readSpan(P.reads, r, read, rl);
+      const int32_t maxScore = a * static_cast<int32_t>(rl);
+      // ---- pass 1: classify + hash the window
+      for (uint32_t i = lane; i < cnt; i += 32) {
+        const rapmap_hit_t h = P.hits[h0 + i];
+        const uint64_t slot = 2 * (h0 + i) + end;
+        const bool paired = h.mate_status == 3;
+        const bool mine = paired || (end == 0 ? (h.mate_status == 1 || h.mate_status == 0) : h.mate_status == 2);
+        int32_t score = kIntMin;
+        uint64_t hash = 0;
+        if (mine) {
+          const int32_t pos = (end == 0 || !paired) ? h.pos : h.mate_pos;
+          const uint8_t cs = end == 0 ? (h.chain_status & 15) : (h.chain_status >> 4);
+          TaskGeom g;
+          if (classifyTask(P.ix, o, h.tid, pos, static_cast<int32_t>(rl), cs, maxScore, g, score) == 0) hash = windowHash(P.ix.text + g.tpos, g.keyLen);
+        }
+        P.taskScore[slot] = score;
+        P.taskHash[slot] = hash;
+        P.taskRef[slot] = -1;
+      }
+      __syncwarp();
+      // ---- pass 2: alignment cache = first earlier task of this read end with an identical window (:320-333,:362-368);
+      //      the cache only fills for multi-mapping reads.  Then score or queue the tasks that own their result.
+      for (uint32_t i = lane; i < cnt; i += 32) {
+        const uint64_t slot = 2 * (h0 + i) + end;
+        const uint64_t hash = P.taskHash[slot];
+        if (hash == 0) continue;
+        const rapmap_hit_t h = P.hits[h0 + i];
+        const bool paired = h.mate_status == 3;
+        const int32_t pos = (end == 0 || !paired) ? h.pos : h.mate_pos;
+        const bool fwd = (end == 0 || !paired) ? h.fwd : h.mate_fwd;
+        const uint8_t cs = end == 0 ? (h.chain_status & 15) : (h.chain_status >> 4);
+        TaskGeom g;
+        int32_t dummy;
+        classifyTask(P.ix, o, h.tid, pos, static_cast<int32_t>(rl), cs, maxScore, g, dummy);
+        int32_t ref = -1;
+        if (multiMapping) {
+          for (uint32_t j = 0; j < i && ref < 0; ++j) {
+            const uint64_t sj = 2 * (h0 + j) + end;
+            if (P.taskHash[sj] != hash) continue;
+            const rapmap_hit_t hj = P.hits[h0 + j];
+            const bool pj = hj.mate_status == 3;
+            const int32_t posj = (end == 0 || !pj) ? hj.pos : hj.mate_pos;
+            const uint8_t csj = end == 0 ? (hj.chain_status & 15) : (hj.chain_status >> 4);
+            TaskGeom gj;
+            classifyTask(P.ix, o, hj.tid, posj, static_cast<int32_t>(rl), csj, maxScore, gj, dummy);
+            if (gj.keyLen != g.keyLen) continue;
+            bool same = true;
+            for (int32_t c = 0; c < g.keyLen && same; ++c) same = __ldg(P.ix.text + g.tpos + c) == __ldg(P.ix.text + gj.tpos + c);
+            if (same) ref = static_cast<int32_t>(sj);
+          }
+        }
+        if (ref >= 0) { P.taskRef[slot] = ref; continue; }
+        if (g.ungapped) {  // ungappedAln (:273-283): raw character compare, N on either side counts as a match
+          const int32_t alnLen = g.rlen < g.tlen1 ? g.rlen : g.tlen1;
+          int32_t sc = 0;
+          for (int32_t c = 0; c < alnLen; ++c) {
+            uint8_t c1 = __ldg(P.ix.text + g.tpos + c);
+            const uint8_t c2 = queryChar(read, rl, !fwd, c);
+            c1 = (c1 == 'N' || c2 == 'N') ? c2 : c1;
+            sc += (c1 == c2) ? a : b;
+          }
+          P.taskScore[slot] = sc;
+        } else {
+          const uint32_t jx = atomicAdd(P.jobCursor, 1u);
+          DPJob jb;
+          jb.tpos = g.tpos; jb.slot = static_cast<uint32_t>(slot); jb.read = static_cast<uint32_t>(r); jb.tlen1 = g.tlen1; jb.rlen = g.rlen; jb.rskip = g.rskip;
+          jb.rc = fwd ? 0 : 1; jb.pad[0] = jb.pad[1] = jb.pad[2] = 0;
+          P.jobs[jx] = jb;
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+__device__ __forceinline__ uint8_t nt4(uint8_t c) {  // seq_nt4_table_loc, src/ksw2pp/KSW2Aligner.cpp:61-72
+  if (c < 4) return c;
+  switch (c | 0x20) {
+    case 'a': return 0;
+    case 'c': return 1;
+    case 'g': return 2;
+    case 't': return 3;
+    default: return 4;
+  }
+}
+
+struct KswParams {
+  DeviceIndex ix;
+  BatchView reads;
+  const DPJob* jobs;
+  const uint32_t* jobCount;
+  int32_t* taskScore;
+  uint32_t warpSmemBytes;
+  int32_t tl16max;      // bytes per DP byte array (multiple of 16) for the largest window
+  int8_t mat0, mat1, matN;  // match, mismatch, wildcard scores of the 5x5 matrix (KSW2Aligner.cpp:74-96)
+  int8_t q, e;
+  int32_t w;
+};
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) ksw_extz_kernel(KswParams P) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  uint8_t* mem = smem + static_cast<size_t>(warp) * P.warpSmemBytes;
+  const uint32_t nJobs = *P.jobCount;
+  const int8_t q = P.q, e = P.e;
+  const int qe = q + e;
+  const int8_t qe2 = static_cast<int8_t>((q + e) * 2);
+  const uint8_t maxSc = static_cast<uint8_t>(static_cast<int8_t>(P.mat0 + (q + e) * 2));
+  for (uint32_t j = blockIdx.x * WARPS + warp; j < nJobs; j += gridDim.x * WARPS) {
+    const DPJob jb = P.jobs[j];
+    const int qlen = jb.rlen, tlen = jb.tlen1;
+    int32_t mqe = kKswNegInf, mte = kKswNegInf;
+    // early returns of ksw_extz2_sse (:60,:83): empty input, or mismatch penalty beyond 2(q+e)
+    int minSc = P.mat1 < P.matN ? P.mat1 : P.matN;
+    minSc = minSc < P.mat0 ? minSc : P.mat0;
+    if (qlen <= 0 || tlen <= 0 || -minSc > 2 * (q + e)) {
+      if (lane == 0) P.taskScore[jb.slot] = kKswNegInf;
+      continue;
+    }
+    const int tlen_ = (tlen + 15) / 16, qlen_ = (qlen + 15) / 16;
+    const int tl16 = tlen_ * 16;
+    uint8_t* u = mem;
+    uint8_t* v = u + tl16;
+    uint8_t* x = v + tl16;
+    uint8_t* y = x + tl16;
+    uint8_t* s = y + tl16;
+    uint8_t* sf = s + tl16;
+    uint8_t* qr = sf + tl16;
+    const int memBytes = (tlen_ * 6 + qlen_ + 1) * 16;
+    int32_t* H = reinterpret_cast<int32_t*>(mem + P.warpSmemBytes - static_cast<uint32_t>(P.tl16max) * 4);
+    __syncwarp();
+    for (int i = lane; i < memBytes; i += 32) mem[i] = 0;   // kcalloc
+    for (int i = lane; i < tl16; i += 32) H[i] = kKswNegInf;
+    __syncwarp();
+    const uint8_t* read;
+    uint32_t rl;
+    readSpan(P.reads, jb.read, read, rl);
+    // query of the alignment = (rc ? reverseRead(read) : read)[rskip ...]; qr holds it reversed (:97)
+    for (int t = lane; t < qlen; t += 32) qr[t] = nt4(queryChar(read, rl, jb.rc != 0, jb.rskip + (qlen - 1 - t)));
+    for (int t = lane; t < tlen; t += 32) sf[t] = nt4(__ldg(P.ix.text + jb.tpos + t));
+    __syncwarp();
+    int w = P.w;
+    if (w < 0) w = tlen > qlen ? tlen : qlen;
+    int last_st = -1, last_en = -1;
+    for (int r = 0; r < qlen + tlen - 1; ++r) {
+      int st = 0, en = tlen - 1;
+      if (st < r - qlen + 1) st = r - qlen + 1;
+      if (en > r) en = r;
+      if (st < ((r - w + 1) >> 1)) st = (r - w + 1) >> 1;
+      if (en > ((r + w) >> 1)) en = (r + w) >> 1;
+      if (st > en) break;  // zdropped (:111-114)
+      const int st0 = st, en0 = en;
+      st = st / 16 * 16; en = (en + 16) / 16 * 16 - 1;
+      int8_t x1, v1;
+      if (st > 0) {
+        if (st - 1 >= last_st && st - 1 <= last_en) { x1 = static_cast<int8_t>(x[st - 1]); v1 = static_cast<int8_t>(v[st - 1]); }
+        else { x1 = 0; v1 = 0; }
+      } else { x1 = 0; v1 = r ? q : 0; }
+      __syncwarp();
+      if (en >= r && lane == 0) { y[r] = 0; u[r] = static_cast<uint8_t>(r ? q : 0); }
+      __syncwarp();
+      // scores, whole 16-lane blocks from st0 (:126-140); two blocks per step, reads before writes
+      const uint8_t* qrr = qr + (qlen - 1 - r);
+      const int sEnd = st0 + ((en0 - st0) / 16 + 1) * 16;
+      for (int t0 = st0; t0 < sEnd; t0 += 32) {
+        const int t = t0 + lane;
+        uint8_t sc = 0;
+        const bool on = t < sEnd;
+        if (on) {
+          const uint8_t a1 = sf[t], a2 = qrr[t];
+          int8_t z = (a1 == a2) ? P.mat0 : P.mat1;
+          if (a1 == 4 || a2 == 4) z = P.matN;
+          sc = static_cast<uint8_t>(z);
+        }
+        __syncwarp();
+        if (on) s[t] = sc;
+        __syncwarp();
+      }
+      // core loop (:147-164): every lane reads previous-row state, then all write
+      int8_t carryX = x1, carryV = v1;
+      for (int t0 = st; t0 <= en; t0 += 32) {
+        const int t = t0 + lane;
+        const bool on = t <= en;
+        int8_t xt1 = 0, vt1 = 0, ut = 0, yt = 0, sv = 0, xo = 0, vo = 0;
+        if (on) {
+          xo = static_cast<int8_t>(x[t]); vo = static_cast<int8_t>(v[t]);
+          ut = static_cast<int8_t>(u[t]); yt = static_cast<int8_t>(y[t]); sv = static_cast<int8_t>(s[t]);
+        }
+        xt1 = static_cast<int8_t>(__shfl_up_sync(0xffffffffu, static_cast<int>(xo), 1));
+        vt1 = static_cast<int8_t>(__shfl_up_sync(0xffffffffu, static_cast<int>(vo), 1));
+        if (lane == 0) { xt1 = carryX; vt1 = carryV; }
+        carryX = static_cast<int8_t>(__shfl_sync(0xffffffffu, static_cast<int>(xo), 31));
+        carryV = static_cast<int8_t>(__shfl_sync(0xffffffffu, static_cast<int>(vo), 31));
+        __syncwarp();
+        if (on) {
+          int8_t z = static_cast<int8_t>(sv + qe2);
+          int8_t aa = static_cast<int8_t>(xt1 + vt1);
+          int8_t bb = static_cast<int8_t>(yt + ut);
+          z = z > aa ? z : aa;                                    // _mm_max_epi8
+          uint8_t zu = static_cast<uint8_t>(z), bu = static_cast<uint8_t>(bb);
+          zu = zu > bu ? zu : bu;                                 // _mm_max_epu8
+          zu = zu < maxSc ? zu : maxSc;                           // _mm_min_epu8
+          z = static_cast<int8_t>(zu);
+          u[t] = static_cast<uint8_t>(static_cast<int8_t>(z - vt1));
+          v[t] = static_cast<uint8_t>(static_cast<int8_t>(z - ut));
+          z = static_cast<int8_t>(z - q);
+          aa = static_cast<int8_t>(aa - z);
+          bb = static_cast<int8_t>(bb - z);
+          x[t] = static_cast<uint8_t>(aa > 0 ? aa : 0);
+          y[t] = static_cast<uint8_t>(bb > 0 ? bb : 0);
+        }
+        __syncwarp();
+      }
+      // exact max track (:228-272)
+      if (r > 0) {
+        const int32_t hPrev = en0 > 0 ? H[en0 - 1] : 0;
+        const int32_t hSelf = H[en0];
+        __syncwarp();
+        for (int t0 = st0; t0 < en0; t0 += 32) {
+          const int t = t0 + lane;
+          if (t < en0) H[t] += static_cast<int32_t>(v[t]) - qe;
+        }
+        if (lane == 0) H[en0] = en0 > 0 ? hPrev + static_cast<int32_t>(u[en0]) - qe : hSelf + static_cast<int32_t>(v[en0]) - qe;
+      } else {
+        if (lane == 0) H[0] = static_cast<int32_t>(v[0]) - qe - qe;
+      }
+      __syncwarp();
+      if (en0 == tlen - 1 && H[en0] > mte) mte = H[en0];
+      if (r - st0 == qlen - 1 && H[st0] > mqe) mqe = H[st0];
+      last_st = st; last_en = en;
+    }
+    if (lane == 0) P.taskScore[jb.slot] = mqe > mte ? mqe : mte;
+    __syncwarp();
+  }
+}
+
+__device__ __forceinline__ int32_t taskValue(const SelAlnParams& P, uint64_t slot) {
+  const int32_t ref = P.taskRef[slot];
+  return ref >= 0 ? P.taskScore[ref] : P.taskScore[slot];
+}
+
+// Per-hit score, best score and survivor count of one pair (src/RapMapSAMapper.cpp:567-683).
+__global__ void __launch_bounds__(256) selaln_score_kernel(SelAlnParams P) {
+  const DevOpts& o = P.opts;
+  const int32_t a = static_cast<int8_t>(o.ma);
+  for (uint64_t pi = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; pi < P.numPairs; pi += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    const uint64_t h0 = P.pairOff[pi], h1 = P.pairOff[pi + 1];
+    if (h0 == h1) { P.outCount[pi] = 0; continue; }
+    const uint8_t* rd;
+    uint32_t l1 = 0, l2 = 0;
+    readSpan(P.reads, pi, rd, l1);
+    if (P.pairedInput) readSpan(P.reads, P.numPairs + pi, rd, l2);
+    const int32_t maxLeft = a * static_cast<int32_t>(l1), maxRight = a * static_cast<int32_t>(l2);
+    const double optFrac = o.minScoreFraction;
+    int32_t best = kIntMin;
+    for (uint64_t h = h0; h < h1; ++h) {
+      const rapmap_hit_t hit = P.hits[h];
+      int32_t score = kIntMin;
+      if (hit.mate_status == 3) {
+        int32_t s1 = taskValue(P, 2 * h), s2 = taskValue(P, 2 * h + 1);
+        if (hit.fwd != hit.mate_fwd && o.noDovetail) {
+          if (hit.fwd && (hit.pos > hit.mate_pos)) { s1 = kIntMin; s2 = kIntMin; }
+          else if (hit.mate_fwd && (hit.mate_pos > hit.pos)) { s1 = kIntMin; s2 = kIntMin; }
+        }
+        if ((static_cast<double>(s1) < __dmul_rn(optFrac, static_cast<double>(maxLeft))) || (static_cast<double>(s2) < __dmul_rn(optFrac, static_cast<double>(maxRight)))) score = kIntMin;
+        else score = s1 + s2;
+      } else if (hit.mate_status == 2) {
+        const int32_t s = taskValue(P, 2 * h + 1);
+        score = (static_cast<double>(s) < __dmul_rn(optFrac, static_cast<double>(maxRight))) ? kIntMin : s;
+      } else {  // PAIRED_END_LEFT or SINGLE_END
+        const int32_t s = taskValue(P, 2 * h);
+        score = (static_cast<double>(s) < __dmul_rn(optFrac, static_cast<double>(maxLeft))) ? kIntMin : s;
+      }
+      P.hitScore[h] = score;
+      best = score > best ? score : best;
+    }
+    uint32_t keep = 0;
+    if (best > kIntMin) {
+      for (uint64_t h = h0; h < h1; ++h) {
+        const int32_t sc = P.hitScore[h];
+        const bool rem = o.hardFilter ? (sc < best) : (sc == kIntMin);
+        keep += rem ? 0u : 1u;
+      }
+    }
+    P.pairBest[pi] = best;
+    P.outCount[pi] = keep;
+  }
+}
+
+__global__ void __launch_bounds__(256) selaln_write_kernel(SelAlnParams P) {
+  const DevOpts& o = P.opts;
+  for (uint64_t pi = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; pi < P.numPairs; pi += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    const uint64_t h0 = P.pairOff[pi], h1 = P.pairOff[pi + 1];
+    const int32_t best = P.pairBest[pi];
+    if (h0 == h1 || !(best > kIntMin)) continue;
+    uint64_t w = P.outOff[pi];
+    for (uint64_t h = h0; h < h1; ++h) {
+      const int32_t sc = P.hitScore[h];
+      const bool rem = o.hardFilter ? (sc < best) : (sc == kIntMin);
+      if (rem) continue;
+      rapmap_hit_t hit = P.hits[h];
+      hit.aln_score = sc;
+      P.outHits[w++] = hit;
+    }
+  }
+}
+
+struct CastU64b {
+  __host__ __device__ uint64_t operator()(uint32_t v) const { return v; }
+};
+
+// Runs the four stages; on return dPairOff holds the post-filter offsets, w.outHits the surviving hits.
+inline int selAlnRun(SelAlnWork& w, const DeviceIndex& ix, const DevOpts& opts, const BatchView& bv, uint64_t n, bool paired, rapmap_hit_t* dHits,
+                     uint64_t* dPairOff, uint64_t total, void* dCubTemp, size_t cubTempBytes, int numSMs, cudaStream_t st, uint32_t* launches,
+                     uint64_t* totalOut, std::string& err) {
+  auto cuFail = [&](const char* what, cudaError_t e) { err = std::string(what) + ": " + cudaGetErrorString(e); return RAPMAP_ERR_CUDA; };
+  cudaError_t e = selAlnReserve(w, total);
+  if (e != cudaSuccess) return cuFail("selAlnReserve", e);
+  SelAlnParams sp{};
+  sp.ix = ix; sp.opts = opts; sp.reads = bv; sp.numPairs = n; sp.pairedInput = paired ? 1 : 0; sp.hits = dHits; sp.pairOff = dPairOff;
+  sp.taskScore = w.taskScore; sp.taskRef = w.taskRef; sp.taskHash = w.taskHash; sp.jobs = w.jobs; sp.jobCursor = w.jobCursor; sp.hitScore = w.hitScore;
+  sp.pairBest = w.pairBest; sp.outCount = w.outCount; sp.outOff = w.outOff; sp.outHits = w.outHits; sp.maxReadLen = w.maxReadLen;
+  if ((e = cudaMemsetAsync(w.jobCursor, 0, 4, st)) != cudaSuccess) return cuFail("memset", e);
+  constexpr int W = 8;
+  int g = static_cast<int>(std::min<uint64_t>(static_cast<uint64_t>(numSMs) * 8, (n + W - 1) / W));
+  selaln_prepare_kernel<W><<<g, W * 32, 0, st>>>(sp);
+  ++*launches;
+  // DP kernel: shared memory per warp = the reference's kcalloc block for the largest window + the int32 H track
+  KswParams kp{};
+  kp.ix = ix; kp.reads = bv; kp.jobs = w.jobs; kp.jobCount = w.jobCursor; kp.taskScore = w.taskScore;
+  const int tlenMax = static_cast<int>(w.maxReadLen) + 20;
+  const int tl16 = (tlenMax + 15) / 16 * 16;
+  const int qlen_ = (static_cast<int>(w.maxReadLen) + 15) / 16;
+  kp.tl16max = tl16;
+  kp.warpSmemBytes = static_cast<uint32_t>((tl16 / 16 * 6 + qlen_ + 1) * 16 + tl16 * 4);
+  {
+    int a = opts.ma, b = opts.mm;  // KSW2Aligner ctor (:74-96)
+    a = a < 0 ? -a : a;
+    b = b > 0 ? -b : b;
+    kp.mat0 = static_cast<int8_t>(a); kp.mat1 = static_cast<int8_t>(b); kp.matN = 0;
+  }
+  kp.q = static_cast<int8_t>(opts.go); kp.e = static_cast<int8_t>(opts.ge); kp.w = opts.dpBandwidth;
+  constexpr int KW = 4;
+  const uint32_t smemK = kp.warpSmemBytes * KW;
+  if (smemK > 200 * 1024) { err = "max_read_len too large for the ksw2 shared-memory layout"; return RAPMAP_ERR_ARG; }
+  if ((e = cudaFuncSetAttribute(ksw_extz_kernel<KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smemK))) != cudaSuccess)
+    return cuFail("cudaFuncSetAttribute(ksw)", e);
+  int occ = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ksw_extz_kernel<KW>, KW * 32, smemK);
+  if (occ < 1) occ = 1;
+  ksw_extz_kernel<KW><<<numSMs * occ, KW * 32, smemK, st>>>(kp);
+  ++*launches;
+  int g3 = static_cast<int>(std::min<uint64_t>(static_cast<uint64_t>(numSMs) * 8, (n + 255) / 256));
+  if ((e = cudaMemsetAsync(w.outCount + n, 0, 4, st)) != cudaSuccess) return cuFail("memset", e);
+  selaln_score_kernel<<<g3, 256, 0, st>>>(sp);
+  ++*launches;
+  {
+    cub::TransformInputIterator<uint64_t, CastU64b, uint32_t*> it(w.outCount, CastU64b());
+    size_t tb = cubTempBytes;
+    if ((e = cub::DeviceScan::ExclusiveSum(dCubTemp, tb, it, w.outOff, static_cast<int>(n + 1), st)) != cudaSuccess) return cuFail("scan", e);
+  }
+  selaln_write_kernel<<<g3, 256, 0, st>>>(sp);
+  ++*launches;
+  if ((e = cudaMemcpyAsync(w.hTotal, w.outOff + n, 8, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuFail("memcpy", e);
+  if ((e = cudaMemcpyAsync(dPairOff, w.outOff, (n + 1) * 8, cudaMemcpyDeviceToDevice, st)) != cudaSuccess) return cuFail("memcpy", e);
+  if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return cuFail("selAln sync", e);
+  if ((e = cudaGetLastError()) != cudaSuccess) return cuFail("selAln kernels", e);
+  *totalOut = *w.hTotal;
+  return RAPMAP_OK;
 }
 
 } // namespace rapmap_b200
