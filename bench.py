@@ -168,7 +168,7 @@ def run_reference(args) -> None:
     value = total / mapping_s
     line.update({
         "value": value, "ms_per_step": 1e3 * mapping_s / args.steps,
-        "config": {"workload": f"GENCODE-like {args.genes}-gene (~200k txp) synthetic index, 2x100bp synthetic pairs, quasimap{' -s' if args.selaln else ''} -n -t {cores}",
+        "config": {"workload": f"GENCODE-like {args.genes}-gene synthetic index, 2x100bp synthetic pairs, quasimap{' -s' if args.selaln else ''} -n -t {cores}",
                    "pairs_per_step": sample, "timed": "reference ScopedTimer 'Elapsed time' around mapReads (index load excluded)", "wall_s_incl_index_load": wall},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": f"{total} pairs (first pairs of the benchmark read stream)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -222,23 +222,10 @@ def main():
     barrier()
     idx_dir = index_dir(args.genes) + "/"
     t0 = time.time()
-    if rank == 0 or world == 1:
-        index = rb.Index(idx_dir, local)
-        ptr, nbytes = index.image()
-    if world > 1:
-        nb = torch.tensor([nbytes if rank == 0 else 0], dtype=torch.int64, device="cuda")
-        dist.broadcast(nb, 0)
-        nbytes = int(nb.item())
-        if rank == 0:
-            class _Ext:  # zero-copy torch view of the image blob
-                __cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
-            blob = torch.as_tensor(_Ext(), device="cuda")
-        else:
-            blob = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
-        dist.broadcast(blob, 0)
-        torch.cuda.synchronize()
-        if rank != 0:
-            index = rb.Index.from_image(local, blob.data_ptr(), nbytes)
+    from rapmap_b200.sharding import replicate_index
+
+    index = rb.Index(idx_dir, local) if rank == 0 else None
+    index, _image_keepalive = replicate_index(index, rank, local)
     log(f"rank {rank}: index ready in {time.time() - t0:.1f}s ({index.device_bytes / 2**30:.2f} GiB in HBM, {index.num_transcripts} transcripts)")
 
     # ---- reads: rank-sharded contiguous ranges of the counter-based stream; pinned host copies + device copies
