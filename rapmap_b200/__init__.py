@@ -21,7 +21,7 @@ from typing import Optional
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_build", "librapmap_cuda.so")
+LIB_PATH = os.environ.get("RAPMAP_B200_LIB") or os.path.join(_HERE, "_build", "librapmap_cuda.so")  # env override: A/B builds of the same ABI
 
 OK, ERR_IO, ERR_CUDA, ERR_UNSUPPORTED, ERR_ARG, ERR_CAPACITY = range(6)
 LOC_HOST, LOC_DEVICE = 0, 1

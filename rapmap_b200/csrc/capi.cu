@@ -73,6 +73,15 @@ DeviceIndex viewOf(const uint8_t* blob, const ImageHeader& h) {
   d.n = static_cast<int64_t>(h.n);
   d.k = h.k;
   d.numTxp = static_cast<uint32_t>(h.numTxp);
+  d.hashKind = h.hashKind; d.phfLevels = h.phfLevels; d.phfNumFinal = static_cast<uint32_t>(h.phfNumFinal);
+  d.phfNumOverflow = static_cast<uint32_t>(h.phfNumOverflow); d.phfLastRank = h.phfLastRank; d.phfNumData = h.phfNumData;
+  d.phfLv = reinterpret_cast<const PhfLevelDev*>(blob + h.offPhfLevels);
+  d.phfBits = reinterpret_cast<const uint64_t*>(blob + h.offPhfBits);
+  d.phfRanks = reinterpret_cast<const uint64_t*>(blob + h.offPhfRanks);
+  d.phfFinal = reinterpret_cast<const ulonglong2*>(blob + h.offPhfFinal);
+  d.phfData = reinterpret_cast<const int32_t*>(blob + h.offPhfData);
+  d.phfLens = blob + h.offPhfLens;
+  d.phfOverflow = reinterpret_cast<const int2*>(blob + h.offPhfOverflow);
   return d;
 }
 
@@ -116,7 +125,7 @@ struct rapmap_cuda_mapper {
   uint32_t smemEntries{64};
   int gridCollect{0}, gridMap{0};
   uint32_t collectSmem{0}, mapSmem{0};
-  uint32_t lpad{0}, pmax{0}, warpSmem{0}, packOff{0}, ctxOff{0};
+  uint32_t lpad{0}, pmax{0}, warpSmem{0}, packOff{0}, ctxOff{0}, voteOff{0};
   // stage 3
   uint32_t* dPairCount{nullptr};
   uint64_t* dPairOff{nullptr};
@@ -180,6 +189,7 @@ int rapmap_cuda_index_load(const char* index_dir, int device, rapmap_cuda_index_
   const uint64_t T = h.txpOffsets.size();
   uint64_t slots = 64;
   while (slots < 2 * h.kmers.size()) slots <<= 1;
+  if (h.perfectHash) slots = 16;  // -p index: no dense table, the BooPHF arrays are used as they are
   const uint64_t rankWords = n / 64 + 1;
 
   ImageHeader hdr{};
@@ -192,6 +202,28 @@ int rapmap_cuda_index_load(const char* index_dir, int device, rapmap_cuda_index_
   hdr.offTxpOffsets = off; off = align256(off + T * 4);
   hdr.offTxpLens = off; off = align256(off + T * 4);
   hdr.offTable = off; off = align256(off + slots * 16);
+  // -p index: level table, concatenated bitsets and rank samples, _final_hash, data_, lens_, overflow_
+  uint64_t phfWords = 0, phfRanks = 0;
+  std::vector<PhfLevelDev> lvDev;
+  if (h.perfectHash) {
+    hdr.hashKind = 1;
+    hdr.phfLevels = static_cast<uint32_t>(h.phf.nbLevels);
+    hdr.phfLastRank = h.phf.lastBitsetRank; hdr.phfNumData = h.phf.data.size(); hdr.phfNumFinal = h.phf.finalHash.size();
+    hdr.phfNumOverflow = h.phf.overflow.size();
+    for (auto& lv : h.phf.levels) {
+      PhfLevelDev d{lv.hashDomain, phfWords, phfRanks, 0};
+      lvDev.push_back(d);
+      phfWords += lv.bits.size() + 1;   // one spare word: rank() may read bits[word_idx] for word_idx == nchar - 1
+      phfRanks += lv.ranks.size() + 1;
+    }
+    hdr.offPhfLevels = off; off = align256(off + lvDev.size() * sizeof(PhfLevelDev));
+    hdr.offPhfBits = off; off = align256(off + phfWords * 8);
+    hdr.offPhfRanks = off; off = align256(off + phfRanks * 8);
+    hdr.offPhfFinal = off; off = align256(off + (h.phf.finalHash.size() + 1) * 16);
+    hdr.offPhfData = off; off = align256(off + (h.phf.data.size() + 1) * 4);
+    hdr.offPhfLens = off; off = align256(off + h.phf.lens.size() + 1);
+    hdr.offPhfOverflow = off; off = align256(off + (h.phf.overflow.size() + 1) * 8);
+  }
   hdr.totalBytes = off;
 
   auto* idx = new rapmap_cuda_index();
@@ -218,6 +250,19 @@ int rapmap_cuda_index_load(const char* index_dir, int device, rapmap_cuda_index_
   IDX_TRY(cudaMemcpy(idx->blob + hdr.offTxpOffsets, h.txpOffsets.data(), T * 4, cudaMemcpyHostToDevice));
   IDX_TRY(cudaMemcpy(idx->blob + hdr.offTxpLens, h.txpLens.data(), T * 4, cudaMemcpyHostToDevice));
   IDX_TRY(cudaMemset(idx->blob + hdr.offTable, 0xFF, slots * 16));
+  if (h.perfectHash) {
+    IDX_TRY(cudaMemset(idx->blob + hdr.offPhfLevels, 0, hdr.totalBytes - hdr.offPhfLevels));
+    IDX_TRY(cudaMemcpy(idx->blob + hdr.offPhfLevels, lvDev.data(), lvDev.size() * sizeof(PhfLevelDev), cudaMemcpyHostToDevice));
+    for (size_t i = 0; i < lvDev.size(); ++i) {
+      const auto& lv = h.phf.levels[i];
+      if (!lv.bits.empty()) IDX_TRY(cudaMemcpy(idx->blob + hdr.offPhfBits + lvDev[i].bitsOff * 8, lv.bits.data(), lv.bits.size() * 8, cudaMemcpyHostToDevice));
+      if (!lv.ranks.empty()) IDX_TRY(cudaMemcpy(idx->blob + hdr.offPhfRanks + lvDev[i].ranksOff * 8, lv.ranks.data(), lv.ranks.size() * 8, cudaMemcpyHostToDevice));
+    }
+    if (!h.phf.finalHash.empty()) IDX_TRY(cudaMemcpy(idx->blob + hdr.offPhfFinal, h.phf.finalHash.data(), h.phf.finalHash.size() * 16, cudaMemcpyHostToDevice));
+    if (!h.phf.data.empty()) IDX_TRY(cudaMemcpy(idx->blob + hdr.offPhfData, h.phf.data.data(), h.phf.data.size() * 4, cudaMemcpyHostToDevice));
+    if (!h.phf.lens.empty()) IDX_TRY(cudaMemcpy(idx->blob + hdr.offPhfLens, h.phf.lens.data(), h.phf.lens.size(), cudaMemcpyHostToDevice));
+    if (!h.phf.overflow.empty()) IDX_TRY(cudaMemcpy(idx->blob + hdr.offPhfOverflow, h.phf.overflow.data(), h.phf.overflow.size() * 8, cudaMemcpyHostToDevice));
+  }
   if (!h.kmers.empty()) {
     KmerRecord* dRecs = nullptr;
     IDX_TRY(cudaMalloc(&dRecs, h.kmers.size() * sizeof(KmerRecord)));
@@ -282,11 +327,6 @@ int rapmap_cuda_index_from_image(const rapmap_cuda_index_t* meta, int device, vo
 
 // -------------------------------------------------------------------------------------------------
 static int deriveOpts(const rapmap_cuda_opts_t& o, DevOpts& d) {
-  // Device path implements the default strand-decision mode of SACollector (disableNIP && strictCheck,
-  // reference include/SACollector.hpp:138).  NIP skipping (--noSensitive) and the k-mer-vote mode
-  // (--noStrictCheck) are refused, not approximated.
-  if (!o.sensitive) return fail(RAPMAP_ERR_UNSUPPORTED, "--noSensitive (NIP/LCE skipping) is not implemented on the device path");
-  if (!o.strict_check) return fail(RAPMAP_ERR_UNSUPPORTED, "--noStrictCheck (k-mer vote strand decision) is not implemented on the device path");
   if (o.recover_orphans) return fail(RAPMAP_ERR_UNSUPPORTED, "--recoverOrphans is not implemented on the device path");
   if (o.sel_aln) {
     // validateOpts, reference src/RapMapSAMapper.cpp:911-954
@@ -303,6 +343,8 @@ static int deriveOpts(const rapmap_cuda_opts_t& o, DevOpts& d) {
   d.covReq = o.quasi_coverage > 0.0 ? o.quasi_coverage : 0.0;
   d.maxInterval = 1000;
   d.doChaining = o.sel_aln;
+  d.disableNIP = o.sensitive ? 1 : 0;      // reference src/RapMapSAMapper.cpp:386-388
+  d.strictCheck = o.strict_check ? 1 : 0;  // :389
   d.considerMultiPos = o.sel_aln;
   d.selAln = o.sel_aln;
   d.fuzzy = o.fuzzy;
@@ -385,10 +427,13 @@ int rapmap_cuda_mapper_create(const rapmap_cuda_index_t* idx, const rapmap_cuda_
   m->pmax = max_read_len - idx->hdr.k + 1;
   m->packOff = (2 * m->lpad + 2 * m->pmax * 8 + 2 * m->pmax * static_cast<uint32_t>(sizeof(IntervalRec)) + 15) / 16 * 16;
   m->ctxOff = (m->packOff + (m->lpad / 32 + 2) * (2 * 8 + 4 * 4) + 15) / 16 * 16;
-  m->warpSmem = (m->ctxOff + static_cast<uint32_t>(sizeof(WarpCtx)) + 15) / 16 * 16;
+  m->voteOff = (m->ctxOff + static_cast<uint32_t>(sizeof(WarpCtx)) + 15) / 16 * 16;
+  m->warpSmem = (m->voteOff + 2 * m->pmax + 15) / 16 * 16;
   m->collectSmem = m->warpSmem * kWarps;
   if (m->collectSmem > 227 * 1024) return bail("max_read_len too large for the shared-memory read cache");
   M_TRY(cudaFuncSetAttribute(sa_collect_kernel<kWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(m->collectSmem)));
+  M_TRY(cudaFuncSetAttribute(sa_collect_kernel<kWarps>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  M_TRY(cudaFuncSetAttribute(hits_to_mappings_kernel<kWarps>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   int occ = 0;
   M_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sa_collect_kernel<kWarps>, kWarps * 32, m->collectSmem));
   if (occ < 1) return bail("sa_collect_kernel does not fit on an SM");
@@ -478,7 +523,7 @@ int rapmap_cuda_map_batch(rapmap_cuda_mapper_t* m, const rapmap_read_batch_t* re
     // ---- kernel 1: SA lookup
     CollectParams cp{};
     cp.ix = m->idx->view; cp.reads = bv; cp.opts = m->dopts; cp.maxReadLen = m->maxReadLen; cp.lpad = m->lpad; cp.pmax = m->pmax;
-    cp.warpSmemBytes = m->warpSmem; cp.packOff = m->packOff; cp.ctxOff = m->ctxOff; cp.summ = m->dSumm; cp.arena = m->dIvArena; cp.arenaCap = m->ivCap; cp.arenaCursor = m->dCtl + 0; cp.status = m->dCtl + 3;
+    cp.warpSmemBytes = m->warpSmem; cp.packOff = m->packOff; cp.ctxOff = m->ctxOff; cp.voteOff = m->voteOff; cp.summ = m->dSumm; cp.arena = m->dIvArena; cp.arenaCap = m->ivCap; cp.arenaCursor = m->dCtl + 0; cp.status = m->dCtl + 3;
     int g1 = static_cast<int>(std::min<uint64_t>(m->gridCollect, (bv.numReads + kWarps - 1) / kWarps));
     sa_collect_kernel<kWarps><<<g1, kWarps * 32, m->collectSmem, st>>>(cp);
     ++launches;

@@ -24,8 +24,21 @@ struct ImageHeader {
   uint64_t tableSlots;     // power of two
   uint64_t numKmers;
   uint32_t k;
-  uint32_t pad;
+  uint32_t hashKind;       // 0: dense open-addressing table, 1: BooPHF + FrugalBooMap arrays (-p index)
   uint64_t offSA, offText, offRank, offTxpOffsets, offTxpLens, offTable;
+  // -p index only
+  uint32_t phfLevels, phfPad;
+  uint64_t phfLastRank, phfNumData, phfNumFinal, phfNumOverflow;
+  uint64_t offPhfLevels, offPhfBits, offPhfRanks, offPhfFinal, offPhfData, offPhfLens, offPhfOverflow;
+};
+
+// One level of the MPHF (boomphf::level, reference include/BooPHF.hpp:820-842): bitset of `domain` bits with a rank
+// sample every 512 bits (bitVector::rank, :756-769).
+struct PhfLevelDev {
+  uint64_t domain;
+  uint64_t bitsOff;    // first 64-bit word of this level in the shared bits array
+  uint64_t ranksOff;   // first rank sample of this level
+  uint64_t pad;
 };
 static constexpr uint64_t kImageMagic = 0x31474D4932424D52ULL;
 
@@ -40,6 +53,16 @@ struct DeviceIndex {
   int64_t n;
   uint32_t k;
   uint32_t numTxp;
+  // perfect-hash flavour
+  uint32_t hashKind, phfLevels, phfNumFinal, phfNumOverflow;
+  uint64_t phfLastRank, phfNumData;
+  const PhfLevelDev* phfLv;
+  const uint64_t* phfBits;
+  const uint64_t* phfRanks;
+  const ulonglong2* phfFinal;    // sorted (key, value)
+  const int32_t* phfData;        // FrugalBooMap::data_  : interval start per MPHF slot
+  const uint8_t* phfLens;        // FrugalBooMap::lens_  : interval length, 255 => overflow
+  const int2* phfOverflow;       // sorted (start, length)
 };
 
 static constexpr uint64_t kEmptyKey = ~0ULL;
@@ -54,8 +77,80 @@ __host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
 }
 
 #ifdef __CUDACC__
+// boomphf hash of a key (HashFunctors::hash64, reference include/BooPHF.hpp:394-407)
+__device__ __forceinline__ uint64_t phfHash64(uint64_t key, uint64_t seed) {
+  uint64_t hash = seed;
+  hash ^= (hash << 7) ^ key * (hash >> 3) ^ (~((hash << 11) + (key ^ (hash >> 5))));
+  hash = (~hash) + (hash << 21);
+  hash = hash ^ (hash >> 24);
+  hash = (hash + (hash << 3)) + (hash << 8);
+  hash = hash ^ (hash >> 14);
+  hash = (hash + (hash << 2)) + (hash << 4);
+  hash = hash ^ (hash >> 28);
+  hash = hash + (hash << 31);
+  return hash;
+}
+
+// FrugalBooMap::find (reference include/FrugalBooMap.hpp:149-167) over boomphf::mphf::lookup (include/BooPHF.hpp:971-1009,
+// getLevel :1318-1351, xorshift128* next :493-499, fastrange64 :815-820, bitVector::rank :756-769): level walk -> rank ->
+// data_[slot] -> SA -> verify the 31-mer in the text against the key -> length from lens_ / overflow_.
+__device__ __noinline__ int2 phfFind(const DeviceIndex& ix, uint64_t key) {
+  uint64_t s0 = 0, s1 = 0, h = 0, hashi = 0;
+  uint32_t level = 0;
+  const uint32_t last = ix.phfLevels - 1;
+  for (uint32_t ii = 0; ii < last; ++ii) {
+    if (ii == 0) { s0 = phfHash64(key, 0xAAAAAAAA55555555ULL); h = s0; }
+    else if (ii == 1) { s1 = phfHash64(key, 0x33333333CCCCCCCCULL); h = s1; }
+    else {
+      uint64_t a = s0;
+      const uint64_t b = s1;
+      s0 = b;
+      a ^= a << 23;
+      s1 = a ^ b ^ (a >> 17) ^ (b >> 26);
+      h = s1 + b;
+    }
+    const PhfLevelDev lv = ix.phfLv[ii];
+    hashi = __umul64hi(h, lv.domain);
+    if ((__ldg(ix.phfBits + lv.bitsOff + (hashi >> 6)) >> (hashi & 63)) & 1ULL) break;
+    ++level;
+  }
+  uint64_t slot;
+  if (level == last) {  // _final_hash
+    uint32_t lo = 0, hi = ix.phfNumFinal;
+    while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (ix.phfFinal[mid].x < key) lo = mid + 1; else hi = mid; }
+    if (lo >= ix.phfNumFinal || ix.phfFinal[lo].x != key) return make_int2(-1, -1);
+    slot = ix.phfFinal[lo].y + ix.phfLastRank;
+  } else {
+    const PhfLevelDev lv = ix.phfLv[level];
+    const uint64_t wordIdx = hashi >> 6, block = hashi >> 9;
+    uint64_t r = __ldg(ix.phfRanks + lv.ranksOff + block);
+    for (uint64_t w = block * 8; w < wordIdx; ++w) r += __popcll(__ldg(ix.phfBits + lv.bitsOff + w));
+    r += __popcll(__ldg(ix.phfBits + lv.bitsOff + wordIdx) & ((1ULL << (hashi & 63)) - 1ULL));
+    slot = r;
+  }
+  if (slot >= ix.phfNumData) return make_int2(-1, -1);
+  const int32_t ind = __ldg(ix.phfData + slot);
+  const int64_t textInd = __ldg(ix.SA + ind);
+  uint64_t w = 0;
+  for (uint32_t j = 0; j < ix.k; ++j) {  // Kmer::fromChars on the text; the text holds upper-case ACGT and '$'
+    const uint8_t ch = __ldg(ix.text + textInd + j);
+    uint32_t cd;
+    if (ch == 'A') cd = 0; else if (ch == 'C') cd = 1; else if (ch == 'G') cd = 2; else if (ch == 'T') cd = 3; else break;
+    w |= static_cast<uint64_t>(cd) << (2 * (ix.k - 1 - j));
+  }
+  if (w != key) return make_int2(-1, -1);
+  int32_t len = __ldg(ix.phfLens + slot);
+  if (len == 255) {
+    uint32_t lo = 0, hi = ix.phfNumOverflow;
+    while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (ix.phfOverflow[mid].x < ind) lo = mid + 1; else hi = mid; }
+    len = (lo < ix.phfNumOverflow && ix.phfOverflow[lo].x == ind) ? ix.phfOverflow[lo].y : 0;
+  }
+  return make_int2(ind, ind + len);
+}
+
 // k-mer -> SA interval; {-1,-1} when absent.  (RegHashT::find, reference include/SACollector.hpp:196,541)
 __device__ __forceinline__ int2 hashFind(const DeviceIndex& ix, uint64_t key) {
+  if (ix.hashKind) return phfFind(ix, key);
   uint64_t s = mix64(key) & ix.tableMask;
   while (true) {
     uint4 e = __ldg(ix.table + s);

@@ -75,8 +75,9 @@ __device__ __forceinline__ WorkArea carve(uint8_t* base, uint32_t entries) {
 __device__ __forceinline__ void warpBitonicSort(uint64_t* keys, uint64_t* vals, int n2, int lane) {
   for (int kk = 2; kk <= n2; kk <<= 1) {
     for (int j = kk >> 1; j > 0; j >>= 1) {
+      const int lj = __ffs(j) - 1;  // j is a power of two
       for (int t = lane; t < (n2 >> 1); t += 32) {
-        int i = ((t / j) * (j << 1)) + (t % j);
+        int i = ((t >> lj) << (lj + 1)) + (t & (j - 1));
         int l = i + j;
         bool up = ((i & kk) == 0);
         uint64_t a = keys[i], b = keys[l];
@@ -258,7 +259,20 @@ __device__ __forceinline__ void resolveStrand(const MapParams& P, WorkArea& w, c
   }
   __syncwarp();
   // ---- sort by (tid, ord, entry)
-  if (total > 1) {
+  if (total > 1 && total <= 32) {
+    // rank by counting: every lane holds one key, its rank is the number of smaller keys (keys are unique)
+    const bool mine = static_cast<uint32_t>(lane) < total;
+    const uint64_t kx = mine ? keys[lane] : ~0ULL;
+    const uint64_t vx = mine ? vals[lane] : 0ULL;
+    uint32_t rank = 0;
+    for (uint32_t j = 0; j < total; ++j) {
+      const uint64_t kj = __shfl_sync(0xffffffffu, kx, j);
+      rank += kj < kx ? 1u : 0u;
+    }
+    __syncwarp();
+    if (mine) { keys[rank] = kx; vals[rank] = vx; }
+    __syncwarp();
+  } else if (total > 1) {
     int n2 = 1;
     while (n2 < static_cast<int>(total)) n2 <<= 1;
     for (int i = total + lane; i < n2; i += 32) { keys[i] = ~0ULL; vals[i] = 0; }
@@ -470,7 +484,9 @@ __global__ void __launch_bounds__(WARPS * 32) hits_to_mappings_kernel(MapParams 
           ok = false;
         }
       }
-      if (ok) {
+      if (ok && !needPos) {
+        for (uint32_t i = lane; i < nFinal; i += 32) P.qaArena[off + i] = w.qa[i];
+      } else if (ok) {
         uint32_t run = poolOff;
         for (uint32_t i = 0; i < nFinal; ++i) {  // warp walks the hits, lanes copy the position lists
           QARec q = w.qa[i];

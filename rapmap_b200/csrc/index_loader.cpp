@@ -1,5 +1,7 @@
 #include "index_loader.hpp"
 
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -156,30 +158,59 @@ bool HostIndex::load(const std::string& dirIn, std::string& err) {
     kmers.resize(numBuckets);
     if (!f.read(kmers.data(), numBuckets * rec)) { err = "hash.bin: truncated"; return false; }
   } else {
-    // -p indexes: FrugalBooMap::find (include/FrugalBooMap.hpp:149-167) can only ever return
-    // "k-mer of the text -> its SA range" (it verifies the key against the text at SA[start]).  The same
-    // (k-mer, [begin,end)) set is recovered here by one scan of SA + text, and served by the device hash
-    // table.  hash_info.bph / hash_info.val are not read.  (On-device BooPHF probing: next round, DESIGN.md.)
-    const int64_t n = static_cast<int64_t>(SA.size());
-    const int kk = static_cast<int>(k);
-    bool have = false;
-    uint64_t prev = 0;
-    int32_t start = 0;
-    for (int64_t i = 0; i <= n; ++i) {
-      uint64_t w = 0;
-      bool valid = false;
-      if (i < n && static_cast<int64_t>(SA[i]) + kk <= n) {
-        valid = true;
-        const char* s = text.data() + SA[i];
-        for (int j = 0; j < kk; ++j) {
-          int c = code(s[j]);
-          if (c < 0) { valid = false; break; }
-          w = (w << 2) | static_cast<uint64_t>(c);
-        }
-      }
-      if (have && (!valid || w != prev)) { kmers.push_back({prev, start, static_cast<int32_t>(i)}); have = false; }
-      if (valid && !have) { prev = w; start = static_cast<int32_t>(i); have = true; }
+    // ---- hash_info.bph: boomphf::mphf::save (include/BooPHF.hpp:1172-1197)
+    File f(dir + "hash_info.bph");
+    if (!f.ok()) { err = "cannot open hash_info.bph"; return false; }
+    if (!f.get(phf.gamma) || !f.get(phf.nbLevels) || !f.get(phf.lastBitsetRank) || !f.get(phf.nelem)) { err = "hash_info.bph: truncated"; return false; }
+    if (phf.nbLevels < 2 || phf.nbLevels > 64) { err = "hash_info.bph: implausible level count"; return false; }
+    phf.levels.resize(static_cast<size_t>(phf.nbLevels));
+    for (auto& lv : phf.levels) {
+      uint64_t nchar = 0, nranks = 0;
+      if (!f.get(lv.sizeBits) || !f.get(nchar)) { err = "hash_info.bph: truncated"; return false; }
+      lv.bits.resize(nchar);
+      if (!f.read(lv.bits.data(), nchar * 8) || !f.get(nranks)) { err = "hash_info.bph: truncated"; return false; }
+      lv.ranks.resize(nranks);
+      if (!f.read(lv.ranks.data(), nranks * 8)) { err = "hash_info.bph: truncated"; return false; }
     }
+    {  // level domains are not stored: mphf::load recomputes them with pow() (:1219-1230); same libm here
+      const double nelemD = static_cast<double>(phf.nelem);
+      const double proba = 1.0 - std::pow(((phf.gamma * nelemD - 1) / (phf.gamma * nelemD)), static_cast<double>(phf.nelem - 1));
+      const uint64_t hashDomain = static_cast<uint64_t>(std::ceil(nelemD * phf.gamma));
+      for (int ii = 0; ii < phf.nbLevels; ++ii) {
+        uint64_t d = ((static_cast<uint64_t>(static_cast<double>(hashDomain) * std::pow(proba, ii)) + 63) / 64) * 64;
+        if (d == 0) d = 64;
+        phf.levels[static_cast<size_t>(ii)].hashDomain = d;
+      }
+    }
+    uint64_t nfinal = 0;
+    if (!f.get(nfinal)) { err = "hash_info.bph: truncated"; return false; }
+    phf.finalHash.resize(nfinal);
+    for (auto& kv : phf.finalHash)
+      if (!f.get(kv.first) || !f.get(kv.second)) { err = "hash_info.bph: truncated"; return false; }
+    std::sort(phf.finalHash.begin(), phf.finalHash.end());
+    // ---- hash_info.val: FrugalBooMap::save (include/FrugalBooMap.hpp:199-213)
+    File v(dir + "hash_info.val");
+    if (!v.ok()) { err = "cannot open hash_info.val"; return false; }
+    uint64_t n = 0;
+    if (!v.get(n)) { err = "hash_info.val: truncated"; return false; }
+    phf.data.resize(n);
+    if (!v.read(phf.data.data(), n * 4) || !v.get(n)) { err = "hash_info.val: truncated"; return false; }
+    phf.lens.resize(n);
+    if (!v.read(phf.lens.data(), n)) { err = "hash_info.val: truncated"; return false; }
+    if (phf.lens.size() != phf.data.size()) { err = "hash_info.val: data_/lens_ size mismatch"; return false; }
+    uint64_t hdr = 0, magic = 0, tableSize = 0, numBuckets = 0;
+    if (!read32or64(v, magic, hdr) || !read32or64(v, tableSize, hdr) || !read32or64(v, numBuckets, hdr) || magic != 0x24687531ULL) {
+      err = "hash_info.val: bad overflow table";
+      return false;
+    }
+    long here = std::ftell(v.f);
+    uint64_t remaining = v.size() - static_cast<uint64_t>(here);
+    if (remaining < numBuckets * 8) { err = "hash_info.val: truncated overflow table"; return false; }
+    std::fseek(v.f, static_cast<long>(static_cast<uint64_t>(here) + (remaining - numBuckets * 8)), SEEK_SET);
+    phf.overflow.resize(numBuckets);
+    for (auto& kv : phf.overflow)
+      if (!v.get(kv.first) || !v.get(kv.second)) { err = "hash_info.val: truncated"; return false; }
+    std::sort(phf.overflow.begin(), phf.overflow.end());
   }
   return true;
 }

@@ -16,6 +16,25 @@ struct KmerRecord {  // one dense hash.bin record for a 32-bit index
   int32_t begin, end;
 };
 
+// Perfect-hash flavour (-p): boomphf::mphf levels (reference include/BooPHF.hpp:1172-1245) + FrugalBooMap values
+// (include/FrugalBooMap.hpp:199-247), parsed from hash_info.bph / hash_info.val unchanged.
+struct PhfLevel {
+  uint64_t sizeBits{0};            // bitVector::_size
+  uint64_t hashDomain{0};          // recomputed at load exactly as mphf::load does (pow on the host)
+  std::vector<uint64_t> bits;      // _nchar words
+  std::vector<uint64_t> ranks;     // one sample per 512 bits, offset by the keys of the previous levels
+};
+struct HostPhf {
+  double gamma{0};
+  int32_t nbLevels{0};
+  uint64_t lastBitsetRank{0}, nelem{0};
+  std::vector<PhfLevel> levels;
+  std::vector<std::pair<uint64_t, uint64_t>> finalHash;   // sorted by key
+  std::vector<int32_t> data;                               // interval start per MPHF slot
+  std::vector<uint8_t> lens;                               // interval length, 255 => overflow
+  std::vector<std::pair<int32_t, int32_t>> overflow;       // sorted by start: start -> length
+};
+
 struct HostIndex {
   uint32_t k{31};
   bool bigSA{false};
@@ -28,7 +47,8 @@ struct HostIndex {
   std::vector<uint32_t> txpCompleteLens;
   uint64_t numBits{0};
   std::vector<uint64_t> rsdBits;      // '$' positions
-  std::vector<KmerRecord> kmers;      // dense: parsed from hash.bin; perfect: rebuilt from SA+text (see .cpp)
+  std::vector<KmerRecord> kmers;      // dense index: records of hash.bin
+  HostPhf phf;                        // -p index: BooPHF + FrugalBooMap arrays
   // Returns false and fills err on failure.
   bool load(const std::string& dir, std::string& err);
 };

@@ -57,6 +57,7 @@ struct DevOpts {
   int32_t strictCheckSlack;
   int32_t maxInterval;
   uint8_t doChaining, considerMultiPos, fuzzy, selAln;
+  uint8_t disableNIP, strictCheck;   // SACollector::disableNIP_ / strictCheck_ (coverage mode when both are set)
   uint8_t noOrphans, noDovetail, hardFilter, alignmentPolicy;
   int16_t ma, mm, go, ge;
   int32_t dpBandwidth;

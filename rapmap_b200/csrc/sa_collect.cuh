@@ -30,6 +30,7 @@ struct CollectParams {
   uint32_t warpSmemBytes;
   uint32_t packOff;        // offset of the packed-read area inside a warp's shared-memory slice
   uint32_t ctxOff;         // offset of the per-warp WarpCtx
+  uint32_t voteOff;        // offset of the per-position k-mer vote arrays (strand decision without coverage)
   ReadSummary* summ;
   IntervalRec* arena;
   uint32_t arenaCap;
@@ -48,7 +49,7 @@ __device__ __forceinline__ int baseCode(uint8_t c) {  // reference include/Kmer.
 }
 
 // Kmer::fromChars (include/Kmer.hpp:524-542): stops at the first invalid base, leaving the partial word.
-__device__ __forceinline__ bool encodeKmer(const uint8_t* s, int k, uint64_t& w) {
+__device__ __noinline__ bool encodeKmer(const uint8_t* s, int k, uint64_t& w) {
   w = 0;
   int shift = 2 * k - 2;
   for (int i = 0; i < k; ++i, shift -= 2) {
@@ -101,8 +102,11 @@ struct WarpCtx {
   const uint32_t* nmR;
   int L, k, npos, lane;
   int maxMMPExtension, maxInterval;
+  int8_t* voteF;   // per forward position: +1 present / -1 absent / 0 untested, forward orientation (KmerDirScore::fwdScore)
+  int8_t* voteR;   // same for the reverse-complement orientation
   bool doChaining;
   bool hasU;
+  bool disableNIP, voteMode;
 };
 
 // k-mer at position p of a packed strand in O(1): funnel shift of two packed words; valid == no non-ACGT base in
@@ -131,7 +135,7 @@ __device__ __forceinline__ int findNMask(const uint32_t* nm, int from, int L) { 
 }
 
 // Speculative lookup of 16 consecutive forward positions q0, q0+dir, ... in both orientations.
-__device__ __forceinline__ void fillCache(const WarpCtx& c, int q0, int dir) {
+__device__ __noinline__ void fillCache(const WarpCtx& c, int q0, int dir) {
   int q = q0 + dir * ((static_cast<int>(threadIdx.x) & 31) & 15);
   bool rcSide = ((static_cast<int>(threadIdx.x) & 31) >> 4) != 0;
   if (q >= 0 && q < c.npos) {
@@ -150,7 +154,7 @@ __device__ __forceinline__ void fillCache(const WarpCtx& c, int q0, int dir) {
 // Full, cacheable k-mers go through the shared-memory cache; partial words (a non-ACGT base inside the
 // window, Kmer.hpp:536-537) and reads containing 'U' (reverseRead maps U->A, so strand symmetry breaks)
 // are looked up directly.
-__device__ __forceinline__ void lookupBoth(const WarpCtx& c, bool isRC, int p, uint64_t w, bool valid, bool needMer, bool needComp,
+__device__ __noinline__ void lookupBoth(const WarpCtx& c, bool isRC, int p, uint64_t w, bool valid, bool needMer, bool needComp,
                                            int2& mer, int2& comp) {
   if (valid && !(isRC && c.hasU)) {
     int q = isRC ? (c.L - c.k - p) : p;
@@ -198,15 +202,23 @@ __device__ __noinline__ int coopCompare(const WarpCtx& c, const uint8_t* q, int 
   }
 }
 
+// One suffix comparison of extendSearchNaive.  (A variant that pre-fetched all suffixes of the range into a table
+// and replayed the searches from it halved the dependent round trips but ran 1.6x slower on the B200: the kernel is
+// bound by instruction issue / instruction fetch, not by memory latency — profiles/r01_notes.md.)
+__device__ __forceinline__ int probeSuffix(const WarpCtx& c, int64_t cc, const uint8_t* q, int m, int i0, int sentIdx, uint8_t sent, int& rel, int64_t& t) {
+  t = __ldg(c.ix.SA + cc);
+  return coopCompare(c, q, m, t, i0, sentIdx, sent, rel);
+}
+
 // SASearcher::extendSearchNaive (include/SASearcher.hpp:87-309); startAt = k.
 __device__ __noinline__ void extendSearch(const WarpCtx& c, int64_t lbIn, int64_t ubIn, const uint8_t* q, int mQ,
                                              int& outLb, int& outUb, int& outLen) {
   const int startAt = c.k;
   const int64_t n = c.ix.n;
   int rel;
+  int64_t t;
   if (ubIn - lbIn == 2) {  // :109-126
-    int64_t t = __ldg(c.ix.SA + lbIn + 1);
-    int i = coopCompare(c, q, mQ, t, startAt, -1, 0, rel);
+    int i = probeSuffix(c, lbIn + 1, q, mQ, startAt, -1, 0, rel, t);
     outLb = static_cast<int>(lbIn + 1); outUb = static_cast<int>(ubIn); outLen = i;
     return;
   }
@@ -217,9 +229,8 @@ __device__ __noinline__ void extendSearch(const WarpCtx& c, int64_t lbIn, int64_
   // Each search halves [l, r]; 80 rounds can only be exceeded on a malformed index (guards the GPU against a hang).
   for (int guard = 0; guard < 80; ++guard) {  // :150-209
     int64_t cc = (l + r) / 2;
-    int64_t t = __ldg(c.ix.SA + cc);
     int i0 = lcpLP < lcpRP ? lcpLP : lcpRP;
-    int i = coopCompare(c, q, mQ, t, i0, -1, 0, rel);
+    int i = probeSuffix(c, cc, q, mQ, i0, -1, 0, rel, t);
     bool plt = true;
     if (rel < 0) { if (i > prevIHigh) prevIHigh = i; }
     else if (rel > 0) { if (i > prevILow) prevILow = i; plt = false; }
@@ -243,9 +254,8 @@ __device__ __noinline__ void extendSearch(const WarpCtx& c, int64_t lbIn, int64_
     bound[pass] = r;
     for (int guard = 0; guard < 80; ++guard) {
       int64_t cc = (l + r) / 2;
-      int64_t t = __ldg(c.ix.SA + cc);
       int i0 = lcpLP < lcpRP ? lcpLP : lcpRP;
-      int i = coopCompare(c, q, m, t, i0, m - 1, sent, rel);
+      int i = probeSuffix(c, cc, q, m, i0, m - 1, sent, rel, t);
       if (rel <= 0) {
         if (cc == l + 1) { bound[pass] = cc; break; }
         r = cc; lcpRP = i;
@@ -263,6 +273,37 @@ __device__ __forceinline__ int findN(const uint8_t* s, int from, int L) {  // st
   for (int i = from; i < L; ++i)
     if ((s[i] | 0x20) == 'n') return i;
   return 0x7fffffff;
+}
+
+// kmerScores.emplace_back of spotCheck_ / the first-hit scan (include/SACollector.hpp:200-227,:417-430): statuses in
+// forward orientation at the forward position; duplicates of a position carry the same statuses, the first one is kept.
+__device__ __forceinline__ void recordVote(const WarpCtx& c, bool isRC, int p, bool merPresent, bool compPresent) {
+  if (!c.voteMode) return;
+  const int q = isRC ? (c.L - c.k - p) : p;
+  if ((static_cast<int>(threadIdx.x) & 31) == 0 && c.voteF[q] == 0) {
+    c.voteF[q] = (isRC ? compPresent : merPresent) ? 1 : -1;
+    c.voteR[q] = (isRC ? merPresent : compPresent) ? 1 : -1;
+  }
+}
+
+// SASearcher::lce (include/SASearcher.hpp:318-334) including its doubled start offset: the comparison runs at
+// SA[p] + startAt + len with len starting at startAt.  32 positions per round trip.
+__device__ __noinline__ int lceCoop(const WarpCtx& c, int64_t p1, int64_t p2, int startAt, int stopAt) {
+  const int lane = static_cast<int>(threadIdx.x) & 31;
+  const int64_t n = c.ix.n;
+  p1 = p1 < 0 ? 0 : (p1 >= n ? n - 1 : p1);
+  p2 = p2 < 0 ? 0 : (p2 >= n ? n - 1 : p2);
+  const int64_t o1 = static_cast<int64_t>(__ldg(c.ix.SA + p1)) + startAt, o2 = static_cast<int64_t>(__ldg(c.ix.SA + p2)) + startAt;
+  const int64_t maxIndex = o1 > o2 ? o1 : o2;
+  for (int len = startAt;; len += 32) {
+    const int idx = len + lane;
+    const bool inRange = maxIndex + idx < n;
+    const uint8_t a = inRange ? __ldg(c.ix.text + o1 + idx) : 0;
+    const uint8_t b = inRange ? __ldg(c.ix.text + o2 + idx) : 1;
+    const bool stop = !inRange || a != b || a == '$' || idx >= stopAt;
+    const unsigned m = __ballot_sync(0xffffffffu, stop);
+    if (m) return len + __ffs(m) - 1;
+  }
 }
 
 // SACollector::getSAHits_ (include/SACollector.hpp:441-677) on one strand.  `buf` is the strand's read.
@@ -292,6 +333,7 @@ __device__ __noinline__ void walkStrand(const WarpCtx& c, bool isRC, int startPo
       lookupBoth(c, isRC, rb, mer, valid, true, true, fm, fc);  // find + spotCheck_ complement (:541-546,:671)
       if (fm.x >= 0) ++strandHits;
       if (fc.x >= 0) ++otherStrandHits;
+      recordVote(c, isRC, rb, fm.x >= 0, fc.x >= 0);
       if (fm.x < 0) { rb += 1; continue; }  // :673
       lb = fm.x; ub = fm.y;
     }
@@ -325,18 +367,28 @@ __device__ __noinline__ void walkStrand(const WarpCtx& c, bool isRC, int startPo
           lookupBoth(c, isRC, kp, mm, true, true, true, fm, fc);
           if (fm.x >= 0) ++strandHits;
           if (fc.x >= 0) ++otherStrandHits;
+          recordVote(c, isRC, kp, fm.x >= 0, fc.x >= 0);
         }
       }
     }
     if (lastSearch) return;            // :623
     if (rb + matchedLen >= L) return;  // :630
-    rb = rb + matchedLen - (k - 1);    // :640-647 with disableNIP (lce == matchedLen)
+    {  // :634-657 next start: MMP skip, or the NIP skip when --noSensitive
+      const int mismatchPos = rb + matchedLen;
+      const int lce = c.disableNIP ? matchedLen : lceCoop(c, lb, ub - 1, matchedLen, L - mismatchPos);
+      const int skipMatch = mismatchPos - (k - 1), skipLCE = rb + lce - (k - 1);
+      rb = skipMatch > skipLCE ? skipMatch : skipLCE;
+      if (!c.disableNIP && lce > matchedLen && L > k) rb = rb < L - k ? rb : L - k;
+    }
     if (rb + k == L) lastSearch = true;  // :663
   }
 }
 
+#ifndef RAPMAP_K1_MIN_BLOCKS
+#define RAPMAP_K1_MIN_BLOCKS 4  // 64 registers per thread: 32 resident warps per SM
+#endif
 template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 4) sa_collect_kernel(CollectParams P) {
+__global__ void __launch_bounds__(WARPS * 32, RAPMAP_K1_MIN_BLOCKS) sa_collect_kernel(CollectParams P) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -356,6 +408,10 @@ __global__ void __launch_bounds__(WARPS * 32, 4) sa_collect_kernel(CollectParams
   uint32_t* nmR = nmF + pw;
   const DevOpts& o = P.opts;
   const int k = static_cast<int>(P.ix.k);
+  int8_t* voteF = reinterpret_cast<int8_t*>(base + P.voteOff);
+  int8_t* voteR = voteF + P.pmax;
+  const bool useCoverageCheck = o.disableNIP && o.strictCheck;   // include/SACollector.hpp:138
+  const bool voteMode = o.strictCheck && !useCoverageCheck;
 
   for (uint64_t r = static_cast<uint64_t>(blockIdx.x) * WARPS + warp; r < P.reads.numReads; r += static_cast<uint64_t>(gridDim.x) * WARPS) {
     const int mate = r >= P.reads.n ? 1 : 0;
@@ -417,7 +473,9 @@ __global__ void __launch_bounds__(WARPS * 32, 4) sa_collect_kernel(CollectParams
     c.ix = P.ix; c.fwdBuf = fwdBuf; c.rcBuf = rcBuf; c.cF = cF; c.cR = cR; c.L = L; c.k = k; c.npos = npos; c.hasU = hasU;
     c.packF = packF; c.packR = packR; c.invF = invF; c.invR = invR; c.nmF = nmF; c.nmR = nmR;
     c.maxMMPExtension = o.maxMMPExtension; c.maxInterval = o.maxInterval; c.doChaining = o.doChaining != 0;
+    c.disableNIP = o.disableNIP != 0; c.voteMode = voteMode; c.voteF = voteF; c.voteR = voteR;
     }
+    if (voteMode) for (int i = lane; i < npos; i += 32) { voteF[i] = 0; voteR[i] = 0; }
     __syncwarp();
 
     // ---- first-hit scan (SACollector.hpp:167-237)
@@ -438,7 +496,7 @@ __global__ void __launch_bounds__(WARPS * 32, 4) sa_collect_kernel(CollectParams
       lookupBoth(c, false, rb, mer, valid, true, true, fm, fc);
       if (fm.x >= 0) { ++fwdHit; if (fc.x >= 0) ++rcHit; }
       if (fc.x >= 0 && !fwdHit) ++rcHit;
-      if (fwdHit + rcHit > 0) { foundHit = true; firstIv = fm; break; }
+      if (fwdHit + rcHit > 0) { recordVote(c, false, rb, fm.x >= 0, fc.x >= 0); foundHit = true; firstIv = fm; break; }
       ++rb;
     }
     int nF = 0, nR = 0;
@@ -448,14 +506,26 @@ __global__ void __launch_bounds__(WARPS * 32, 4) sa_collect_kernel(CollectParams
         didCheckFwd = true;
         walkStrand(c, false, rb, true, firstIv, fwdCov, fwdHit, rcHit, ivF, nF);
       }
-      if (rcHit > 0)  // :256-265 (coverage mode: checkRC = rcHit > 0)
-        walkStrand(c, true, 0, false, make_int2(0, 0), rcCov, rcHit, fwdHit, ivR, nR);
-      if (!didCheckFwd && fwdHit > 0)  // :270-278
-        walkStrand(c, false, 0, false, make_int2(0, 0), fwdCov, fwdHit, rcHit, ivF, nF);
-      // strand decision by coverage (:283-288)
-      if (fwdCov > rcCov + static_cast<uint32_t>(o.strictCheckSlack)) nR = 0;
-      else if (rcCov > fwdCov + static_cast<uint32_t>(o.strictCheckSlack)) nF = 0;
-      if (o.covReq > 0.0) {  // :343-358
+      const bool checkRC = useCoverageCheck ? (rcHit > 0) : (rcHit >= fwdHit);  // :256
+      if (checkRC) walkStrand(c, true, 0, false, make_int2(0, 0), rcCov, rcHit, fwdHit, ivR, nR);
+      const bool checkFwd = useCoverageCheck ? (fwdHit > 0) : (fwdHit >= rcHit);  // :270
+      if (!didCheckFwd && checkFwd) walkStrand(c, false, 0, false, make_int2(0, 0), fwdCov, fwdHit, rcHit, ivF, nF);
+      if (useCoverageCheck) {  // strand decision by coverage (:283-288)
+        if (fwdCov > rcCov + static_cast<uint32_t>(o.strictCheckSlack)) nR = 0;
+        else if (rcCov > fwdCov + static_cast<uint32_t>(o.strictCheckSlack)) nF = 0;
+      } else if (o.strictCheck) {  // k-mer "spot check" vote (:289-337)
+        if (fwdHit > 0 && rcHit == 0) nR = 0;
+        else if (rcHit > 0 && fwdHit == 0) nF = 0;
+        else {
+          __syncwarp();
+          int fs = 0, rs = 0;
+          for (int i = lane; i < npos; i += 32) { fs += voteF[i]; rs += voteR[i]; }
+          for (int d = 16; d > 0; d >>= 1) { fs += __shfl_xor_sync(0xffffffffu, fs, d); rs += __shfl_xor_sync(0xffffffffu, rs, d); }
+          if (fs > rs) nR = 0;
+          else if (rs > fs) nF = 0;
+        }
+      }
+      if (o.covReq > 0.0 && o.disableNIP) {  // :343-358
         if (nF > 0 && (static_cast<double>(fwdCov) / static_cast<double>(L)) < o.covReq) nF = 0;
         if (nR > 0 && (static_cast<double>(rcCov) / static_cast<double>(L)) < o.covReq) nR = 0;
       }

@@ -247,6 +247,40 @@ def test_perfect_hash_index_gives_identical_hits(synth_small):
     assert np.array_equal(a_hits, b.hits) and np.array_equal(a_off, b.pair_offsets)
 
 
+@pytest.mark.parametrize("sel", [False, True])
+def test_perfect_hash_index_matches_reference_golden_sam(synth_small, sel):
+    """-p index through the on-device BooPHF + FrugalBooMap lookup: SAM identical to `rapmap_ref quasimap` on its own -p index."""
+    idx_dir, index, s1, s2, L, tx = synth_small
+    n = s1.shape[0]
+    opts = rb.default_opts(sel_aln=sel)
+    pidx = rb.Index(os.path.join(GOLD, "synth_idx_p"), 0)
+    mapper = make_mapper(pidx, opts, n, L)
+    res = mapper.map_batch(s1, s2, n=n, fixed_len=L)
+    assert_same(res, OracleMapper(os.path.join(GOLD, "synth_idx_p") + "/", opts).map(s1, s2, L), "perfect hash")
+    from helpers import synth_lib
+    truth = np.zeros((n, 4), dtype=np.int64)
+    a, b = s1.copy(), s2.copy()
+    synth_lib().synth_reads(tx.h, META["rseed"], 0, n, 100, META["sub"], META["ins"], META["del"], META["n"], a.ctypes.data, b.ctypes.data, truth.ctypes.data)
+    names1 = [f"r{i}:{truth[i,0]}:{truth[i,1]}:{truth[i,2]}/1" for i in range(n)]
+    names2 = [f"r{i}:{truth[i,0]}:{truth[i,1]}:{truth[i,2]}/2" for i in range(n)]
+    sam = pidx.sam_header() + mapper.format_sam(s1, s2, names1, names2, res, n, fixed_len=L)
+    assert md5(sam) == GOLDEN["synth_p/selaln" if sel else "synth_p/default"]["md5"]
+
+
+@pytest.mark.skipif(not have_ref(), reason="needs oracle/_ref to build the mid-size index")
+def test_mid_size_perfect_hash_index_matches_dense():
+    """13.9k-transcript -p index (6.1 M keys over 25 BooPHF levels) gives the hits of the dense index."""
+    d_dir, tx = synth_index(2500)
+    p_dir, _ = synth_index(2500, perfect=True)
+    n = 30000
+    s1, s2 = tx.reads(n, rseed=11)
+    opts = rb.default_opts()
+    a = make_mapper(rb.Index(d_dir, 0), opts, n, 100).map_batch(s1, s2, n=n, fixed_len=100)
+    a_hits, a_off = a.hits.copy(), a.pair_offsets.copy()
+    b = make_mapper(rb.Index(p_dir, 0), opts, n, 100).map_batch(s1, s2, n=n, fixed_len=100)
+    assert np.array_equal(a_hits, b.hits) and np.array_equal(a_off, b.pair_offsets)
+
+
 @pytest.mark.skipif(not have_ref(), reason="needs oracle/_ref to build the mid-size index")
 @pytest.mark.parametrize("sel", [False, True])
 def test_mid_size_synthetic_matches_oracle(sel):
