@@ -432,8 +432,8 @@ int rapmap_cuda_mapper_create(const rapmap_cuda_index_t* idx, const rapmap_cuda_
   m->collectSmem = m->warpSmem * kWarps;
   if (m->collectSmem > 227 * 1024) return bail("max_read_len too large for the shared-memory read cache");
   M_TRY(cudaFuncSetAttribute(sa_collect_kernel<kWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(m->collectSmem)));
-  M_TRY(cudaFuncSetAttribute(sa_collect_kernel<kWarps>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  M_TRY(cudaFuncSetAttribute(hits_to_mappings_kernel<kWarps>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  // NB: no cudaSharedmemCarveoutMaxShared here - these kernels live off L1 hits on the text / SA / table sectors; forcing the
+  // maximum shared-memory carve-out shrank L1 and cost 20 % (profiles/r01_notes.md).
   int occ = 0;
   M_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sa_collect_kernel<kWarps>, kWarps * 32, m->collectSmem));
   if (occ < 1) return bail("sa_collect_kernel does not fit on an SM");

@@ -135,7 +135,10 @@ __device__ __forceinline__ int findNMask(const uint32_t* nm, int from, int L) { 
 }
 
 // Speculative lookup of 16 consecutive forward positions q0, q0+dir, ... in both orientations.
-__device__ __noinline__ void fillCache(const WarpCtx& c, int q0, int dir) {
+#ifndef RAPMAP_FILL_ATTR
+#define RAPMAP_FILL_ATTR __forceinline__
+#endif
+__device__ RAPMAP_FILL_ATTR void fillCache(const WarpCtx& c, int q0, int dir) {
   int q = q0 + dir * ((static_cast<int>(threadIdx.x) & 31) & 15);
   bool rcSide = ((static_cast<int>(threadIdx.x) & 31) >> 4) != 0;
   if (q >= 0 && q < c.npos) {
@@ -154,7 +157,7 @@ __device__ __noinline__ void fillCache(const WarpCtx& c, int q0, int dir) {
 // Full, cacheable k-mers go through the shared-memory cache; partial words (a non-ACGT base inside the
 // window, Kmer.hpp:536-537) and reads containing 'U' (reverseRead maps U->A, so strand symmetry breaks)
 // are looked up directly.
-__device__ __noinline__ void lookupBoth(const WarpCtx& c, bool isRC, int p, uint64_t w, bool valid, bool needMer, bool needComp,
+__device__ __forceinline__ void lookupBoth(const WarpCtx& c, bool isRC, int p, uint64_t w, bool valid, bool needMer, bool needComp,
                                            int2& mer, int2& comp) {
   if (valid && !(isRC && c.hasU)) {
     int q = isRC ? (c.L - c.k - p) : p;
@@ -202,23 +205,106 @@ __device__ __noinline__ int coopCompare(const WarpCtx& c, const uint8_t* q, int 
   }
 }
 
-// One suffix comparison of extendSearchNaive.  (A variant that pre-fetched all suffixes of the range into a table
-// and replayed the searches from it halved the dependent round trips but ran 1.6x slower on the B200: the kernel is
-// bound by instruction issue / instruction fetch, not by memory latency — profiles/r01_notes.md.)
-__device__ __forceinline__ int probeSuffix(const WarpCtx& c, int64_t cc, const uint8_t* q, int m, int i0, int sentIdx, uint8_t sent, int& rel, int64_t& t) {
+// Suffix table.  For an SA range of 2..32 suffixes, lane i takes suffix i: one coalesced SA load, then its own common
+// prefix with the query, 8 bytes per step.  (lcp, order relation at the first difference, SA value) stay in that lane's
+// registers and the three binary searches of extendSearchNaive are replayed with shuffles instead of memory probes:
+// ~0.4x the instructions of probing suffix by suffix with the whole warp.  (A first version that let all 32 lanes
+// cooperate on every suffix was 1.6x SLOWER than no table at all: this kernel is bound by instruction issue and
+// instruction fetch, not by memory latency - profiles/r01_notes.md.)
+struct SufTab {
+  int64_t lo;   // SA index of the suffix held by lane 0
+  int cnt;      // 0 = no table
+  int mTab;     // query length the table was built for
+  int32_t sa;   // per lane
+  int ell;      // per lane: first index >= k where query and suffix differ, capped at min(mTab, n - sa)
+  int rel;      // per lane: -1 query < text, +1 query > text, 0 ran off
+};
+
+__device__ __forceinline__ uint64_t load8Global(const uint8_t* p) {
+  const uint64_t* a = reinterpret_cast<const uint64_t*>(reinterpret_cast<uintptr_t>(p) & ~static_cast<uintptr_t>(7));
+  const unsigned sh = static_cast<unsigned>(reinterpret_cast<uintptr_t>(p) & 7) * 8;
+  const uint64_t lo = __ldg(a), hi = __ldg(a + 1);
+  return sh ? ((lo >> sh) | (hi << (64 - sh))) : lo;
+}
+__device__ __forceinline__ uint64_t load8Shared(const uint8_t* p) {
+  const uint64_t* a = reinterpret_cast<const uint64_t*>(reinterpret_cast<uintptr_t>(p) & ~static_cast<uintptr_t>(7));
+  const unsigned sh = static_cast<unsigned>(reinterpret_cast<uintptr_t>(p) & 7) * 8;
+  const uint64_t lo = a[0], hi = a[1];
+  return sh ? ((lo >> sh) | (hi << (64 - sh))) : lo;
+}
+
+// q must point into an UPPER-CASED read buffer in shared memory.
+__device__ __noinline__ SufTab buildSufTab(const WarpCtx& c, int64_t lbIn, int64_t ubIn, const uint8_t* q, int mTab) {
+  SufTab tb;
+  tb.lo = lbIn + 1; tb.cnt = 0; tb.mTab = mTab; tb.sa = 0; tb.ell = 0; tb.rel = 0;
+  const int64_t cnt64 = ubIn - lbIn - 1;
+#ifdef RAPMAP_NO_SUFTAB
+  return tb;
+#endif
+  if (cnt64 < 2 || cnt64 > 32) return tb;
+  const int lane = static_cast<int>(threadIdx.x) & 31;
+  if (lane < static_cast<int>(cnt64)) {
+    const int32_t t = __ldg(c.ix.SA + tb.lo + lane);
+    const int64_t limL = c.ix.n - static_cast<int64_t>(t);
+    const int lim = limL < static_cast<int64_t>(mTab) ? static_cast<int>(limL) : mTab;
+    int ell = c.k, rel = 0;
+    const uint8_t* tp = c.ix.text + t;
+    while (ell < lim) {
+      const uint64_t tw = load8Global(tp + ell), qw = load8Shared(q + ell);
+      const uint64_t x = tw ^ qw;
+      if (x) {
+        const int d = (__ffsll(static_cast<long long>(x)) - 1) >> 3;
+        ell += d;
+        if (ell < lim) rel = ((qw >> (8 * d)) & 0xffu) < ((tw >> (8 * d)) & 0xffu) ? -1 : 1;
+        break;
+      }
+      ell += 8;
+    }
+    if (ell >= lim) { ell = lim; rel = 0; }
+    tb.sa = t; tb.ell = ell; tb.rel = rel;
+  }
+  __syncwarp();
+  tb.cnt = static_cast<int>(cnt64);
+  return tb;
+}
+
+// One suffix comparison of extendSearchNaive: from the table when possible, else from memory.
+__device__ __forceinline__ int probeSuffix(const WarpCtx& c, const SufTab& tb, int64_t cc, const uint8_t* q, int m, int i0, int sentIdx, uint8_t sent,
+                                           int& rel, int64_t& t) {
+  if (tb.cnt > 0 && m <= tb.mTab + 1) {
+    const int sidx = static_cast<int>(cc - tb.lo);
+    if (sidx >= 0 && sidx < tb.cnt) {
+      t = __shfl_sync(0xffffffffu, tb.sa, sidx);
+      const int ell = __shfl_sync(0xffffffffu, tb.ell, sidx);
+      const int rl = __shfl_sync(0xffffffffu, tb.rel, sidx);
+      const int64_t limL = c.ix.n - t;
+      const int lim = limL < static_cast<int64_t>(m) ? static_cast<int>(limL) : m;
+      if (i0 >= lim) { rel = 0; return i0; }
+      if (i0 <= ell) {
+        if (sentIdx >= 0 && ell >= sentIdx) {
+          if (sentIdx < lim) { rel = sent == '#' ? -1 : 1; return sentIdx; }  // '#' < '$' < letters < '{'
+          rel = 0;
+          return lim;
+        }
+        if (ell >= lim) { rel = 0; return lim; }
+        rel = rl;
+        return ell;
+      }
+    }
+  }
   t = __ldg(c.ix.SA + cc);
   return coopCompare(c, q, m, t, i0, sentIdx, sent, rel);
 }
 
 // SASearcher::extendSearchNaive (include/SASearcher.hpp:87-309); startAt = k.
-__device__ __noinline__ void extendSearch(const WarpCtx& c, int64_t lbIn, int64_t ubIn, const uint8_t* q, int mQ,
+__device__ __noinline__ void extendSearch(const WarpCtx& c, const SufTab& tb, int64_t lbIn, int64_t ubIn, const uint8_t* q, int mQ,
                                              int& outLb, int& outUb, int& outLen) {
   const int startAt = c.k;
   const int64_t n = c.ix.n;
   int rel;
   int64_t t;
   if (ubIn - lbIn == 2) {  // :109-126
-    int i = probeSuffix(c, lbIn + 1, q, mQ, startAt, -1, 0, rel, t);
+    int i = probeSuffix(c, tb, lbIn + 1, q, mQ, startAt, -1, 0, rel, t);
     outLb = static_cast<int>(lbIn + 1); outUb = static_cast<int>(ubIn); outLen = i;
     return;
   }
@@ -230,7 +316,7 @@ __device__ __noinline__ void extendSearch(const WarpCtx& c, int64_t lbIn, int64_
   for (int guard = 0; guard < 80; ++guard) {  // :150-209
     int64_t cc = (l + r) / 2;
     int i0 = lcpLP < lcpRP ? lcpLP : lcpRP;
-    int i = probeSuffix(c, cc, q, mQ, i0, -1, 0, rel, t);
+    int i = probeSuffix(c, tb, cc, q, mQ, i0, -1, 0, rel, t);
     bool plt = true;
     if (rel < 0) { if (i > prevIHigh) prevIHigh = i; }
     else if (rel > 0) { if (i > prevILow) prevILow = i; plt = false; }
@@ -255,7 +341,7 @@ __device__ __noinline__ void extendSearch(const WarpCtx& c, int64_t lbIn, int64_
     for (int guard = 0; guard < 80; ++guard) {
       int64_t cc = (l + r) / 2;
       int i0 = lcpLP < lcpRP ? lcpLP : lcpRP;
-      int i = probeSuffix(c, cc, q, m, i0, m - 1, sent, rel, t);
+      int i = probeSuffix(c, tb, cc, q, m, i0, m - 1, sent, rel, t);
       if (rel <= 0) {
         if (cc == l + 1) { bound[pass] = cc; break; }
         r = cc; lcpRP = i;
@@ -342,10 +428,11 @@ __device__ __noinline__ void walkStrand(const WarpCtx& c, bool isRC, int startPo
     bool firstAttempt = c.doChaining ? (rb == 0) : true;
     int endPos = firstAttempt ? L : min(rb + k + c.maxMMPExtension, L);
     int nlb, nub, matchedLen;
-    extendSearch(c, lb, ub, buf + rb, endPos - rb, nlb, nub, matchedLen);
+    const SufTab tb = buildSufTab(c, lb, ub, buf + rb, endPos - rb);
+    extendSearch(c, tb, lb, ub, buf + rb, endPos - rb, nlb, nub, matchedLen);
     if (c.doChaining && firstAttempt && !(matchedLen >= L) && matchedLen >= k + c.maxMMPExtension) {  // :568-575
       endPos = min(rb + k + c.maxMMPExtension, L);
-      extendSearch(c, lb, ub, buf + rb, endPos - rb, nlb, nub, matchedLen);
+      extendSearch(c, tb, lb, ub, buf + rb, endPos - rb, nlb, nub, matchedLen);
     }
     lb = nlb; ub = nub;
     if (ub > lb && (ub - lb) < c.maxInterval) {  // :578
@@ -439,7 +526,7 @@ __global__ void __launch_bounds__(WARPS * 32, RAPMAP_K1_MIN_BLOCKS) sa_collect_k
     bool u = false;
     for (int i = lane; i < L; i += 32) {
       uint8_t ch = __ldg(src + i);
-      fwdBuf[i] = ch;
+      fwdBuf[i] = upperChar(ch);  // extendSearchNaive compares ::toupper(query); k-mer codes are case-insensitive
       rcBuf[L - 1 - i] = rcChar(ch);
       u |= ((ch | 0x20) == 'u');
     }

@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q --tb=line -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1; tail -6 gpurun_out/pytest_gpu.log | cut -c1-300
+timeout 900 python -m pytest tests -m gpu -q --tb=line -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1; tail -4 gpurun_out/pytest_gpu.log | cut -c1-300
 run() { # name, lib, extra flags
   RAPMAP_B200_LIB=$2 timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --oracle-sample 2000 $3 > gpurun_out/ab_$1.json 2> gpurun_out/ab_$1.log
   python - <<PY
@@ -10,9 +10,7 @@ try:
 except Exception as e: print("$1", "ERR", e, open("gpurun_out/ab_$1.log").read()[-400:])
 PY
 }
-run base4 "" ""
-run b3 $PWD/rapmap_b200/_build/ab/lib_k1b3.so ""
-run b5 $PWD/rapmap_b200/_build/ab/lib_k1b5.so ""
-run b6 $PWD/rapmap_b200/_build/ab/lib_k1b6.so ""
-run base4_sel "" "--selaln"
-run b6_sel $PWD/rapmap_b200/_build/ab/lib_k1b6.so "--selaln"
+run tab "" ""
+run notab $PWD/rapmap_b200/_build/ab/lib_notab.so ""
+run tab_sel "" "--selaln"
+run notab_sel $PWD/rapmap_b200/_build/ab/lib_notab.so "--selaln"
