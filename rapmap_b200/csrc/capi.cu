@@ -16,6 +16,7 @@
 #include "kernels.cuh"
 #include "merge_pairs.cuh"
 #include "sa_collect.cuh"
+#include "sa_collect_lane.cuh"
 #include "sam_writer.hpp"
 #include "sel_aln.cuh"
 
@@ -126,6 +127,14 @@ struct rapmap_cuda_mapper {
   int gridCollect{0}, gridMap{0};
   uint32_t collectSmem{0}, mapSmem{0};
   uint32_t lpad{0}, pmax{0}, warpSmem{0}, packOff{0}, ctxOff{0}, voteOff{0};
+  // stage 1, lane-per-read form
+  bool laneKernel{true};
+  uint4* dPacked{nullptr};
+  IntervalRec* dIvScratch{nullptr};
+  uint32_t ivStride{0};
+  uint32_t* dVoteScratch{nullptr};
+  uint32_t voteWords{0}, laneWords{0}, laneSmem{0};
+  int gridLane{0};
   // stage 3
   uint32_t* dPairCount{nullptr};
   uint64_t* dPairOff{nullptr};
@@ -134,7 +143,7 @@ struct rapmap_cuda_mapper {
   SelAlnWork selaln{};
   void* dCubTemp{nullptr};
   size_t cubTempBytes{0};
-  // control words: [0] interval cursor, [1] qa cursor, [2] pos cursor, [3] status
+  // control words: [0] interval cursor, [1] qa cursor, [2] pos cursor, [3] status, [4] read cursor of the lane kernel
   uint32_t* dCtl{nullptr};
   Counters5* dCounters{nullptr};
   struct Stage { uint32_t ctl[4]; Counters5 counters; uint64_t total; }* hStage{nullptr};
@@ -145,6 +154,8 @@ struct rapmap_cuda_mapper {
 };
 
 static constexpr int kWarps = 8;
+static constexpr int kLaneThreads = 256;  // lane-per-read SA-lookup kernel: threads per block
+static constexpr int kLaneMinBlocks = 4;   // 64 registers per thread
 
 extern "C" {
 
@@ -371,6 +382,7 @@ static void freeMapperBuffers(rapmap_cuda_mapper* m) {
   cudaFree(m->dSumm); cudaFree(m->dIvArena); cudaFree(m->dQSumm); cudaFree(m->dQaArena); cudaFree(m->dPosPool);
   cudaFree(m->dScratch); cudaFree(m->dPairCount); cudaFree(m->dPairOff); cudaFree(m->dHits); cudaFree(m->dCubTemp);
   cudaFree(m->dCtl); cudaFree(m->dCounters);
+  cudaFree(m->dPacked); cudaFree(m->dIvScratch); cudaFree(m->dVoteScratch);
   selAlnFree(m->selaln);
   if (m->hStage) cudaFreeHost(m->hStage);
   for (auto& e : m->ev) if (e) cudaEventDestroy(e);
@@ -414,7 +426,7 @@ int rapmap_cuda_mapper_create(const rapmap_cuda_index_t* idx, const rapmap_cuda_
   M_TRY(cudaMalloc(&m->dPairOff, (max_batch + 1) * 8));
   m->hitsCap = max_batch * 6 + 1024;
   M_TRY(cudaMalloc(&m->dHits, m->hitsCap * sizeof(rapmap_hit_t)));
-  M_TRY(cudaMalloc(&m->dCtl, 4 * 4));
+  M_TRY(cudaMalloc(&m->dCtl, 8 * 4));
   M_TRY(cudaMalloc(&m->dCounters, sizeof(Counters5)));
   M_TRY(cudaMallocHost(&m->hStage, sizeof(*m->hStage)));
   {
@@ -438,6 +450,34 @@ int rapmap_cuda_mapper_create(const rapmap_cuda_index_t* idx, const rapmap_cuda_
   M_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sa_collect_kernel<kWarps>, kWarps * 32, m->collectSmem));
   if (occ < 1) return bail("sa_collect_kernel does not fit on an SM");
   m->gridCollect = m->numSMs * occ;
+  // lane-per-read form of kernel 1 (default); RAPMAP_B200_K1=warp selects the warp-per-read form for A/B runs
+  {
+    const char* sel = std::getenv("RAPMAP_B200_K1");
+    m->laneKernel = !(sel && std::string(sel) == "warp");
+  }
+  if (m->laneKernel) {
+    m->laneWords = (max_read_len + 31) / 32;
+    m->laneSmem = m->laneWords * 16u * kLaneThreads;
+    if (m->laneSmem > 227 * 1024) return bail("max_read_len too large for the shared-memory read words");
+    M_TRY(cudaFuncSetAttribute(sa_collect_lane_kernel<kLaneThreads, kLaneMinBlocks>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(m->laneSmem)));
+    M_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sa_collect_lane_kernel<kLaneThreads, kLaneMinBlocks>, kLaneThreads, m->laneSmem));
+    if (occ < 1) return bail("sa_collect_lane_kernel does not fit on an SM");
+    m->gridLane = m->numSMs * occ;
+    M_TRY(cudaMalloc(&m->dPacked, R * m->laneWords * sizeof(uint4)));
+    {  // every resident warp reserves arena records RAPMAP_LANE_CHUNK at a time: allow for the unused tails
+      const uint64_t want = static_cast<uint64_t>(m->ivCap) + static_cast<uint64_t>(m->gridLane) * (kLaneThreads / 32) * RAPMAP_LANE_CHUNK;
+      cudaFree(m->dIvArena); m->dIvArena = nullptr;
+      m->ivCap = static_cast<uint32_t>(std::min<uint64_t>(want, 0xFFFFFFF0ull));
+      M_TRY(cudaMalloc(&m->dIvArena, static_cast<uint64_t>(m->ivCap) * sizeof(IntervalRec)));
+    }
+    m->ivStride = std::min<uint32_t>(m->pmax, 24);
+    M_TRY(cudaMalloc(&m->dIvScratch, static_cast<uint64_t>(m->gridLane) * kLaneThreads * 2 * m->ivStride * sizeof(IntervalRec)));
+    const bool voteMode = d.strictCheck && !(d.disableNIP && d.strictCheck);
+    if (voteMode) {
+      m->voteWords = (m->pmax + 31) / 32;
+      M_TRY(cudaMalloc(&m->dVoteScratch, static_cast<uint64_t>(m->gridLane) * kLaneThreads * 3 * m->voteWords * 4));
+    }
+  }
   m->mapSmem = static_cast<uint32_t>(workAreaBytes(m->smemEntries)) * kWarps;
   M_TRY(cudaFuncSetAttribute(hits_to_mappings_kernel<kWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(m->mapSmem)));
   M_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hits_to_mappings_kernel<kWarps>, kWarps * 32, m->mapSmem));
@@ -518,15 +558,27 @@ int rapmap_cuda_map_batch(rapmap_cuda_mapper_t* m, const rapmap_read_batch_t* re
   uint64_t total = 0;
   for (;; ++retries) {
     if (retries > 6) return fail(RAPMAP_ERR_CAPACITY, "device work arenas kept overflowing");
-    CU_TRY(cudaMemsetAsync(m->dCtl, 0, 16, st));
+    CU_TRY(cudaMemsetAsync(m->dCtl, 0, 32, st));
     CU_TRY(cudaMemsetAsync(m->dCounters, 0, sizeof(Counters5), st));
     // ---- kernel 1: SA lookup
     CollectParams cp{};
     cp.ix = m->idx->view; cp.reads = bv; cp.opts = m->dopts; cp.maxReadLen = m->maxReadLen; cp.lpad = m->lpad; cp.pmax = m->pmax;
     cp.warpSmemBytes = m->warpSmem; cp.packOff = m->packOff; cp.ctxOff = m->ctxOff; cp.voteOff = m->voteOff; cp.summ = m->dSumm; cp.arena = m->dIvArena; cp.arenaCap = m->ivCap; cp.arenaCursor = m->dCtl + 0; cp.status = m->dCtl + 3;
-    int g1 = static_cast<int>(std::min<uint64_t>(m->gridCollect, (bv.numReads + kWarps - 1) / kWarps));
-    sa_collect_kernel<kWarps><<<g1, kWarps * 32, m->collectSmem, st>>>(cp);
-    ++launches;
+    if (m->laneKernel) {
+      LaneParams lp{};
+      lp.ix = m->idx->view; lp.reads = bv; lp.opts = m->dopts; lp.maxReadLen = m->maxReadLen; lp.nw = m->laneWords; lp.packed = m->dPacked;
+      lp.summ = m->dSumm; lp.arena = m->dIvArena; lp.arenaCap = m->ivCap; lp.arenaCursor = m->dCtl + 0; lp.status = m->dCtl + 3;
+      lp.ivScratch = m->dIvScratch; lp.ivStride = m->ivStride; lp.voteScratch = m->dVoteScratch; lp.voteWords = m->voteWords; lp.readCursor = m->dCtl + 4;
+      const int g0 = static_cast<int>(std::min<uint64_t>(static_cast<uint64_t>(m->numSMs) * 8, (bv.numReads + 7) / 8));
+      pack_reads_kernel<<<g0, 256, 0, st>>>(lp);
+      const int g1 = static_cast<int>(std::min<uint64_t>(m->gridLane, (bv.numReads + kLaneThreads - 1) / kLaneThreads));
+      sa_collect_lane_kernel<kLaneThreads, kLaneMinBlocks><<<g1, kLaneThreads, m->laneSmem, st>>>(lp);
+      launches += 2;
+    } else {
+      int g1 = static_cast<int>(std::min<uint64_t>(m->gridCollect, (bv.numReads + kWarps - 1) / kWarps));
+      sa_collect_kernel<kWarps><<<g1, kWarps * 32, m->collectSmem, st>>>(cp);
+      ++launches;
+    }
     CU_TRY(cudaEventRecord(m->ev[2], st));
     // ---- kernel 2: hit resolution
     MapParams mp{};
@@ -562,6 +614,13 @@ int rapmap_cuda_map_batch(rapmap_cuda_mapper_t* m, const rapmap_read_batch_t* re
     if (status & kStatReadTooLong) return fail(RAPMAP_ERR_ARG, "a read is longer than the mapper's max_read_len");
     bool again = false;
     if (status & kStatIntervalArenaFull) { int rc = growU32(reinterpret_cast<void**>(&m->dIvArena), m->ivCap, m->hStage->ctl[0], sizeof(IntervalRec)); if (rc) return rc; again = true; }
+    if (status & kStatIvScratchFull) {  // a read produced more intervals per strand than the per-thread list holds: size it for the worst case
+      if (m->ivStride >= m->pmax) return fail(RAPMAP_ERR_CAPACITY, "interval scratch overflow at worst-case size");
+      cudaFree(m->dIvScratch); m->dIvScratch = nullptr;
+      m->ivStride = m->pmax;
+      CU_TRY(cudaMalloc(&m->dIvScratch, static_cast<uint64_t>(m->gridLane) * kLaneThreads * 2 * m->ivStride * sizeof(IntervalRec)));
+      again = true;
+    }
     if (status & kStatQAArenaFull) { int rc = growU32(reinterpret_cast<void**>(&m->dQaArena), m->qaCap, m->hStage->ctl[1], sizeof(QARec)); if (rc) return rc; again = true; }
     if (status & kStatPosPoolFull) { int rc = growU32(reinterpret_cast<void**>(&m->dPosPool), m->posCap, m->hStage->ctl[2], 4); if (rc) return rc; again = true; }
     if (status & kStatScratchFull) {

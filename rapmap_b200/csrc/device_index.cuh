@@ -94,7 +94,7 @@ __device__ __forceinline__ uint64_t phfHash64(uint64_t key, uint64_t seed) {
 // FrugalBooMap::find (reference include/FrugalBooMap.hpp:149-167) over boomphf::mphf::lookup (include/BooPHF.hpp:971-1009,
 // getLevel :1318-1351, xorshift128* next :493-499, fastrange64 :815-820, bitVector::rank :756-769): level walk -> rank ->
 // data_[slot] -> SA -> verify the 31-mer in the text against the key -> length from lens_ / overflow_.
-__device__ __noinline__ int2 phfFind(const DeviceIndex& ix, uint64_t key) {
+__device__ __forceinline__ int2 phfFindImpl(const DeviceIndex& ix, uint64_t key) {
   uint64_t s0 = 0, s1 = 0, h = 0, hashi = 0;
   uint32_t level = 0;
   const uint32_t last = ix.phfLevels - 1;
@@ -147,6 +147,8 @@ __device__ __noinline__ int2 phfFind(const DeviceIndex& ix, uint64_t key) {
   }
   return make_int2(ind, ind + len);
 }
+
+__device__ __noinline__ int2 phfFind(const DeviceIndex& ix, uint64_t key) { return phfFindImpl(ix, key); }
 
 // k-mer -> SA interval; {-1,-1} when absent.  (RegHashT::find, reference include/SACollector.hpp:196,541)
 __device__ __forceinline__ int2 hashFind(const DeviceIndex& ix, uint64_t key) {

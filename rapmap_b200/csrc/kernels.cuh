@@ -73,6 +73,7 @@ enum : uint32_t {
   kStatScratchFull = 4u,
   kStatReadTooLong = 8u,
   kStatPosPoolFull = 16u,
+  kStatIvScratchFull = 32u,
 };
 
 } // namespace rapmap_b200

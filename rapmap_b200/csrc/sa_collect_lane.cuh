@@ -1,0 +1,624 @@
+// Kernel 1, lane-per-read form — "the SA-lookup kernel": seed + maximal-mappable-prefix collection, ONE THREAD PER READ.
+//
+// Replaces SACollector::operator() / getSAHits_ / spotCheck_ (reference include/SACollector.hpp:108-362, :441-677,
+// :366-431), SASearcher::extendSearchNaive and ::lce (include/SASearcher.hpp:87-334), Kmer encode / RC / homopolymer
+// (include/Kmer.hpp:92-100,484-542) and the khash / FrugalBooMap find (include/RapMapUtils.hpp:65-67).
+//
+// Why a thread per read.  The walk of one read is a chain of dependent random reads (hash probe -> SA probe -> text
+// compare) whose decision sequence has to be replayed exactly; a warp that owns one read spends 31/32 of its issue
+// slots replicating scalar state and has one read's worth of memory parallelism (profiles/r01c: 5.9k warp instructions
+// per read, 26 % issue utilisation, DRAM 4 % of peak).  Here every lane walks its own read, so a resident warp has 32
+// independent chains in flight and an SM ~1000; HBM latency is covered by reads, not by speculation.
+//
+// Divergence is handled by writing the walk as a state machine with a fixed phase order per loop trip:
+//   refill -> (A) advance to the next k-mer that needs a lookup -> (B) ONE pair of hash lookups (k-mer and its reverse
+//   complement, loads issued together) -> (C) set up a suffix search -> (D) ONE binary-search probe (SA load + text
+//   compare, 8 bytes per step) -> (E) bookkeeping / interval record / strand sequencing -> publish.
+// Lanes meet again at every phase, so the two expensive phases are executed once per trip for all lanes that need them.
+// A lane that finishes its read fetches a new one (warp-aggregated atomic on a read cursor) as soon as enough lanes are
+// idle, so a warp's 32 chains stay occupied until the batch runs dry.
+//
+// The read lives in shared memory as 16-byte words of 32 bases {2-bit codes (u64), non-ACGT mask, N mask}, written by
+// pack_reads_kernel (coalesced, one warp per read) and interleaved across the block (word j of thread t at
+// [j * NT + t]) so a warp's accesses are conflict-free.  A k-mer at any position of either strand is two LDS.128 and a
+// funnel shift; 8 query characters for the text compare are rebuilt from the codes with two PRMTs.  Windows that
+// contain a non-ACGT base take exact slow paths (partial k-mer words of Kmer::fromChars, original bytes re-read).
+#pragma once
+#include <climits>
+#include "sa_collect.cuh"
+
+namespace rapmap_b200 {
+
+struct LaneParams {
+  DeviceIndex ix;
+  BatchView reads;
+  DevOpts opts;
+  uint32_t maxReadLen;
+  uint32_t nw;             // 32-base words per read (ceil(maxReadLen / 32))
+  uint4* packed;           // [numReads][nw] {codes_lo, codes_hi, invalid mask, N mask}
+  ReadSummary* summ;
+  IntervalRec* arena;
+  uint32_t arenaCap;
+  uint32_t* arenaCursor;
+  uint32_t* status;
+  IntervalRec* ivScratch;  // per resident thread: forward list [0, ivStride), reverse-complement list [ivStride, 2 ivStride)
+  uint32_t ivStride;
+  uint32_t* voteScratch;   // per resident thread: 3 x voteWords (tested, fwd present, rc present); k-mer vote mode only
+  uint32_t voteWords;
+  uint32_t* readCursor;
+};
+
+// ---- K0: pack reads.  One warp per read; 32 bases per step (two OR-reductions, two ballots).
+// Codes: A C G T = 0..3 (either case); 'U' = 3 with the invalid bit set (reverseRead turns U into A, so on the
+// reverse-complement strand it is a valid base, src/RapMapUtils.cpp:63-72); N = 1 + invalid; anything else 0 + invalid.
+__global__ void __launch_bounds__(256) pack_reads_kernel(LaneParams P) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t gw = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = (static_cast<uint64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (uint64_t r = gw; r < P.reads.numReads; r += nwarps) {
+    const int mate = r >= P.reads.n ? 1 : 0;
+    const uint64_t ri = r - static_cast<uint64_t>(mate) * P.reads.n;
+    const uint8_t* src;
+    uint32_t len;
+    if (P.reads.off[mate]) {
+      const uint64_t o0 = P.reads.off[mate][ri], o1 = P.reads.off[mate][ri + 1];
+      src = P.reads.seq[mate] + o0;
+      len = static_cast<uint32_t>(o1 - o0);
+    } else {
+      src = P.reads.seq[mate] + ri * P.reads.fixedLen;
+      len = P.reads.fixedLen;
+    }
+    uint4* dst = P.packed + r * P.nw;
+    if (len > P.maxReadLen) len = 0;  // reported by the lane kernel
+    const int L = static_cast<int>(len);
+    for (uint32_t j = 0; j < P.nw; ++j) {
+      const int i = static_cast<int>(j) * 32 + lane;
+      const bool inb = i < L;
+      const uint8_t ch = inb ? __ldg(src + i) : 0;
+      const int cd = baseCode(ch);
+      const bool isN = (ch | 0x20) == 'n', isU = (ch | 0x20) == 'u';
+      const uint32_t code = !inb ? 0u : (cd >= 0 ? static_cast<uint32_t>(cd) : (isU ? 3u : (isN ? 1u : 0u)));
+      const uint32_t hi = __reduce_or_sync(0xffffffffu, lane < 16 ? (code << (30 - 2 * lane)) : 0u);
+      const uint32_t lo = __reduce_or_sync(0xffffffffu, lane >= 16 ? (code << (30 - 2 * (lane - 16))) : 0u);
+      const uint32_t inv = __ballot_sync(0xffffffffu, inb && cd < 0);
+      const uint32_t nn = __ballot_sync(0xffffffffu, inb && isN);
+      if (lane == 0) dst[j] = make_uint4(lo, hi, inv, nn);
+    }
+  }
+}
+
+// 32 bases (base q in bits 63:62) and 32 invalid bits (base q in bit 0) starting at forward position q >= 0.
+template <int NT>
+__device__ __forceinline__ void loadWin(const uint4* sm, int nw, int q, uint64_t& val, uint32_t& invw) {
+  const int wi = q >> 5, sh = q & 31;
+  const uint4 a = sm[wi * NT];
+  uint4 b = make_uint4(0u, 0u, 0u, 0u);
+  if (sh != 0 && wi + 1 < nw) b = sm[(wi + 1) * NT];
+  const uint64_t p0 = (static_cast<uint64_t>(a.y) << 32) | a.x, p1 = (static_cast<uint64_t>(b.y) << 32) | b.x;
+  val = sh ? ((p0 << (2 * sh)) | (p1 >> (64 - 2 * sh))) : p0;
+  invw = __funnelshift_r(a.z, b.z, sh);
+}
+
+// k-mer at position p of a strand (Kmer::fromChars, include/Kmer.hpp:524-542): returns false and the PARTIAL word
+// (codes before the first invalid base, the rest zero) when the window holds a non-ACGT base.
+template <int NT>
+__device__ __forceinline__ bool kmerAt(const uint4* sm, int nw, int L, int k, bool rc, int p, uint64_t& w) {
+  const int q = rc ? L - k - p : p;
+  uint64_t val;
+  uint32_t invw;
+  loadWin<NT>(sm, nw, q, val, invw);
+  const uint64_t wf = val >> (64 - 2 * k);
+  invw &= (k >= 32) ? 0xffffffffu : ((1u << k) - 1u);
+  if (!rc) {
+    w = wf;
+    if (invw == 0u) return true;
+    const int j = __ffs(invw) - 1;
+    w = j == 0 ? 0ULL : (wf & ~((1ULL << (2 * (k - j))) - 1ULL));
+    return false;
+  }
+  if (invw != 0u) {  // 'U' is a valid base on the reverse-complement strand
+    uint32_t m = invw;
+    while (m) {
+      const int b = __ffs(m) - 1;
+      m &= m - 1u;
+      if (((wf >> (2 * (k - 1 - b))) & 3ULL) == 3ULL) invw &= ~(1u << b);
+    }
+  }
+  w = kmerRC(wf, k);
+  if (invw == 0u) return true;
+  const int j = (k - 1) - (31 - __clz(invw));  // first invalid base in reverse-complement order
+  w = j == 0 ? 0ULL : (w & ~((1ULL << (2 * (k - j))) - 1ULL));
+  return false;
+}
+
+// std::string::find_first_of("nN", from) on a strand.  On the reverse-complement strand every non-ACGTU base reads 'N'.
+template <int NT>
+__device__ __noinline__ int findNLane(const uint4* sm, int L, bool rc, int from) {
+  if (from >= L) return INT_MAX;
+  if (!rc) {
+    int wi = from >> 5;
+    uint32_t m = sm[wi * NT].w & (0xffffffffu << (from & 31));
+    while (true) {
+      if (m) return wi * 32 + __ffs(m) - 1;
+      ++wi;
+      if (wi * 32 >= L) return INT_MAX;
+      m = sm[wi * NT].w;
+    }
+  }
+  const int f0 = L - 1 - from;
+  int wi = f0 >> 5;
+  uint4 a = sm[wi * NT];
+  uint32_t m = a.z & (0xffffffffu >> (31 - (f0 & 31)));
+  while (true) {
+    while (m) {
+      const int b = 31 - __clz(m);
+      m &= ~(1u << b);
+      const uint64_t p0 = (static_cast<uint64_t>(a.y) << 32) | a.x;
+      if (((p0 >> (62 - 2 * b)) & 3ULL) != 3ULL) return L - 1 - (wi * 32 + b);
+    }
+    if (--wi < 0) return INT_MAX;
+    a = sm[wi * NT];
+    m = a.z;
+  }
+}
+
+__device__ __noinline__ uint64_t query8Bytes(const uint8_t* src, int L, bool rc, int p) {
+  uint64_t out = 0;
+  for (int j = 0; j < 8; ++j) {
+    const int pos = p + j;
+    if (pos < L) {
+      const uint8_t ch = rc ? rcChar(__ldg(src + (L - 1 - pos))) : upperChar(__ldg(src + pos));
+      out |= static_cast<uint64_t>(ch) << (8 * j);
+    }
+  }
+  return out;
+}
+
+// 8 upper-cased characters of a strand at p .. p+7 (byte j = position p + j; positions >= L unspecified).
+template <int NT>
+__device__ __forceinline__ uint64_t query8(const LaneParams& P, const uint4* sm, uint32_t r, int L, bool rc, int p) {
+  const int q = rc ? L - 8 - p : p;
+  const int qs = q < 0 ? 0 : q;
+  uint64_t val;
+  uint32_t invw;
+  loadWin<NT>(sm, static_cast<int>(P.nw), qs, val, invw);
+  uint32_t v = static_cast<uint32_t>(val >> 48);  // 8 bases, base qs in bits 15:14
+  invw &= 0xffu;
+  if (q < 0) { v >>= 2 * (-q); invw &= (1u << (8 + q)) - 1u; }
+  if (invw != 0u) {  // a non-ACGT base in the window: exact characters from the original read
+    const int mate = r >= P.reads.n ? 1 : 0;
+    const uint64_t ri = r - static_cast<uint64_t>(mate) * P.reads.n;
+    const uint8_t* src = P.reads.off[mate] ? P.reads.seq[mate] + P.reads.off[mate][ri] : P.reads.seq[mate] + ri * P.reads.fixedLen;
+    return query8Bytes(src, L, rc, p);
+  }
+  uint32_t lo, hi;
+  if (!rc) {
+    const uint32_t a = v >> 8, b = v & 0xffu;
+    const uint32_t sa = ((a >> 6) & 3u) | (((a >> 4) & 3u) << 4) | (((a >> 2) & 3u) << 8) | ((a & 3u) << 12);
+    const uint32_t sb = ((b >> 6) & 3u) | (((b >> 4) & 3u) << 4) | (((b >> 2) & 3u) << 8) | ((b & 3u) << 12);
+    lo = __byte_perm(0x54474341u, 0u, sa);  // "ACGT"
+    hi = __byte_perm(0x54474341u, 0u, sb);
+  } else {
+    const uint32_t a = v & 0xffu, b = v >> 8;
+    const uint32_t sa = (a & 3u) | ((a & 0xCu) << 2) | ((a & 0x30u) << 4) | ((a & 0xC0u) << 6);
+    const uint32_t sb = (b & 3u) | ((b & 0xCu) << 2) | ((b & 0x30u) << 4) | ((b & 0xC0u) << 6);
+    lo = __byte_perm(0x41434754u, 0u, sa);  // complement: "TGCA"
+    hi = __byte_perm(0x41434754u, 0u, sb);
+  }
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+
+// One suffix comparison of extendSearchNaive (include/SASearcher.hpp:160-176 and the two sentinel searches): query
+// q[i] vs text[t + i] for i >= i0 while i < m and t + i < n; q[sentIdx] reads `sent` when sentIdx >= 0.  Returns the
+// index at which the reference's inner loop stops; rel = -1 (query < text), +1 (query > text), 0 (ran off).
+template <int NT>
+__device__ __forceinline__ int cmpSuffix(const LaneParams& P, const uint4* sm, uint32_t r, int L, bool rc, int rb, int m, int32_t t, int i0,
+                                         int sentIdx, uint32_t sent, int& rel) {
+  const int64_t limL = P.ix.n - static_cast<int64_t>(t);
+  const int lim = limL < static_cast<int64_t>(m) ? static_cast<int>(limL) : m;
+  rel = 0;
+  if (i0 >= lim) return i0;
+  int i = i0;
+  const uint8_t* tp = P.ix.text + t + i;
+  const uint64_t* a = reinterpret_cast<const uint64_t*>(reinterpret_cast<uintptr_t>(tp) & ~static_cast<uintptr_t>(7));
+  const unsigned sh = static_cast<unsigned>(reinterpret_cast<uintptr_t>(tp) & 7) * 8;
+  uint64_t lo = __ldg(a);
+  for (;;) {
+    const uint64_t hi = __ldg(a + 1);  // the text section is padded: reads past n are in bounds
+    const uint64_t tw = sh ? ((lo >> sh) | (hi << (64 - sh))) : lo;
+    uint64_t qw = query8<NT>(P, sm, r, L, rc, rb + i);
+    const unsigned sd = static_cast<unsigned>(sentIdx - i);
+    if (sd < 8u) qw = (qw & ~(0xffULL << (8 * sd))) | (static_cast<uint64_t>(sent) << (8 * sd));
+    uint64_t x = tw ^ qw;
+    const int nv = lim - i;
+    if (nv < 8) x &= (1ULL << (8 * nv)) - 1ULL;
+    if (x) {
+      const int d = (__ffsll(static_cast<long long>(x)) - 1) >> 3;
+      rel = ((qw >> (8 * d)) & 0xffULL) < ((tw >> (8 * d)) & 0xffULL) ? -1 : 1;
+      return i + d;
+    }
+    i += 8;
+    if (i >= lim) return lim;
+    lo = hi;
+    ++a;
+  }
+}
+
+// k-mer and its reverse complement -> SA intervals; both table probes are in flight together.
+__device__ __forceinline__ void hashFind2(const DeviceIndex& ix, uint64_t ka, uint64_t kb, int2& ra, int2& rb) {
+  if (ix.hashKind) {  // -p index: the two BooPHF walks run one after the other (one inlined copy of the walk)
+#pragma unroll 1
+    for (int which = 0; which < 2; ++which) {
+      const int2 res = phfFindImpl(ix, which ? kb : ka);
+      if (which) rb = res; else ra = res;
+    }
+    return;
+  }
+  uint64_t sa = mix64(ka) & ix.tableMask, sb = mix64(kb) & ix.tableMask;
+  uint4 ea = __ldg(ix.table + sa), eb = __ldg(ix.table + sb);
+  bool da = false, db = false;
+  ra = make_int2(-1, -1); rb = make_int2(-1, -1);
+  for (;;) {
+    if (!da) {
+      const uint64_t kk = (static_cast<uint64_t>(ea.y) << 32) | ea.x;
+      if (kk == ka) { ra = make_int2(static_cast<int>(ea.z), static_cast<int>(ea.w)); da = true; }
+      else if (kk == kEmptyKey) da = true;
+      else sa = (sa + 1) & ix.tableMask;
+    }
+    if (!db) {
+      const uint64_t kk = (static_cast<uint64_t>(eb.y) << 32) | eb.x;
+      if (kk == kb) { rb = make_int2(static_cast<int>(eb.z), static_cast<int>(eb.w)); db = true; }
+      else if (kk == kEmptyKey) db = true;
+      else sb = (sb + 1) & ix.tableMask;
+    }
+    if (da && db) return;
+    if (!da) ea = __ldg(ix.table + sa);
+    if (!db) eb = __ldg(ix.table + sb);
+  }
+}
+
+// SASearcher::lce (include/SASearcher.hpp:318-334) incl. its doubled start offset; --noSensitive only.
+__device__ __noinline__ int lceLane(const int32_t* SA, const uint8_t* text, int64_t n, int64_t p1, int64_t p2, int startAt, int stopAt) {
+  p1 = p1 < 0 ? 0 : (p1 >= n ? n - 1 : p1);
+  p2 = p2 < 0 ? 0 : (p2 >= n ? n - 1 : p2);
+  const int64_t o1 = static_cast<int64_t>(__ldg(SA + p1)) + startAt, o2 = static_cast<int64_t>(__ldg(SA + p2)) + startAt;
+  const int64_t maxIndex = o1 > o2 ? o1 : o2;
+  for (int len = startAt;; ++len) {
+    if (!(maxIndex + len < n)) return len;
+    const uint8_t a = __ldg(text + o1 + len), b = __ldg(text + o2 + len);
+    if (a != b || a == '$' || len >= stopAt) return len;
+  }
+}
+
+// kmerScores.emplace_back of spotCheck_ / the first-hit scan (include/SACollector.hpp:200-227,:417-430) as three bit
+// sets over forward positions: tested, present in forward orientation, present in reverse-complement orientation.
+__device__ __noinline__ void voteLane(uint32_t* votes, uint32_t vw, bool isRC, int p, int L, int k, bool mer, bool comp) {
+  const int q = isRC ? (L - k - p) : p;
+  const uint32_t word = static_cast<uint32_t>(q) >> 5, bit = 1u << (q & 31);
+  if (votes[word] & bit) return;
+  votes[word] |= bit;
+  if (isRC ? comp : mer) votes[vw + word] |= bit;
+  if (isRC ? mer : comp) votes[2 * vw + word] |= bit;
+}
+
+enum : int { LST_IDLE = 0, LST_SCAN, LST_WSTART, LST_MM, LST_EXTINIT, LST_EXT, LST_EXTDONE, LST_POSTMM, LST_WALKEND, LST_FINAL, LST_EXIT };
+enum : uint32_t {
+  LF_RC = 1u, LF_LAST = 2u, LF_DIDFWD = 4u, LF_FOUND = 8u, LF_NOMOREN = 16u, LF_FIRST = 32u, LF_SECOND = 64u, LF_OVF = 128u,
+  LF_STAGE_SHIFT = 8u, LF_STAGE_MASK = 3u << 8,
+};
+
+#ifndef RAPMAP_LANE_REFILL
+#define RAPMAP_LANE_REFILL 8   // fetch new reads once this many lanes of a warp are idle
+#endif
+#ifndef RAPMAP_LANE_CHUNK
+#define RAPMAP_LANE_CHUNK 256  // interval-arena records a warp reserves per atomic
+#endif
+
+template <int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) sa_collect_lane_kernel(LaneParams P) {
+  extern __shared__ __align__(16) uint8_t smemRaw[];
+  uint4* smw = reinterpret_cast<uint4*>(smemRaw) + threadIdx.x;
+  const uint4* sm = smw;
+  const int lane = threadIdx.x & 31;
+  const int k = static_cast<int>(P.ix.k);
+  const int nw = static_cast<int>(P.nw);
+  const DevOpts& o = P.opts;
+  const bool useCov = o.disableNIP && o.strictCheck;  // include/SACollector.hpp:138
+  const bool voteMode = o.strictCheck && !useCov;
+  const uint32_t slot = blockIdx.x * NT + threadIdx.x;
+  IntervalRec* scr = P.ivScratch + static_cast<size_t>(slot) * 2 * P.ivStride;
+  uint32_t* votes = voteMode ? P.voteScratch + static_cast<size_t>(slot) * 3 * P.voteWords : nullptr;
+
+  uint32_t chunkBase = 0, chunkLeft = 0;  // warp-uniform: reserved slice of the interval arena
+
+  int st = LST_IDLE;
+  uint32_t r = 0, flags = 0;
+  int L = 0, rb = 0, lbIn = 0, ubIn = 0, l = 0, rr = 0, lcpLP = 0, lcpRP = 0, prevILow = 0, prevIHigh = 0;
+  int mlen = 0, b0 = 0, b1 = 0, mQ = 0, pass = 0, guard = 0, prevMMPEnd = 0, nF = 0, nR = 0;
+  uint32_t fwdHit = 0, rcHit = 0, fwdCov = 0, rcCov = 0;
+
+  for (;;) {
+    // ---------------- refill: idle lanes take the next reads of the batch
+    {
+      const unsigned idle = __ballot_sync(0xffffffffu, st == LST_IDLE);
+      if (idle) {
+        const unsigned busy = __ballot_sync(0xffffffffu, st != LST_IDLE && st != LST_EXIT);
+        if (__popc(idle) >= RAPMAP_LANE_REFILL || busy == 0u) {
+          const int leader = __ffs(idle) - 1;
+          uint32_t base = 0;
+          if (lane == leader) base = atomicAdd(P.readCursor, static_cast<uint32_t>(__popc(idle)));
+          base = __shfl_sync(0xffffffffu, base, leader);
+          if (st == LST_IDLE) {
+            const uint64_t nr = static_cast<uint64_t>(base) + __popc(idle & ((1u << lane) - 1u));
+            if (nr >= P.reads.numReads) st = LST_EXIT;
+            else {
+              r = static_cast<uint32_t>(nr);
+              const int mate = nr >= P.reads.n ? 1 : 0;
+              const uint64_t ri = nr - static_cast<uint64_t>(mate) * P.reads.n;
+              uint32_t len = P.reads.fixedLen;
+              if (P.reads.off[mate]) len = static_cast<uint32_t>(P.reads.off[mate][ri + 1] - P.reads.off[mate][ri]);
+              if (len > P.maxReadLen) {
+                atomicOr(P.status, kStatReadTooLong);
+                ReadSummary s;
+                s.ivOff = 0; s.nFwd = 0; s.nRc = 0; s.readLen = 0; s.found = 0; s.pad = 0;
+                P.summ[r] = s;
+              } else {
+                const uint4* src = P.packed + static_cast<size_t>(nr) * P.nw;
+                for (int j = 0; j < nw; ++j) smw[j * NT] = __ldg(src + j);
+                if (voteMode) for (uint32_t j = 0; j < 3 * P.voteWords; ++j) votes[j] = 0u;
+                L = static_cast<int>(len);
+                rb = 0; flags = 0; nF = 0; nR = 0; fwdHit = 0; rcHit = 0; fwdCov = 0; rcCov = 0;
+                st = LST_SCAN;
+              }
+            }
+          }
+        }
+      }
+      if (__ballot_sync(0xffffffffu, st != LST_EXIT) == 0u) break;
+    }
+
+    // ---------------- A: advance to the next k-mer that needs a lookup
+    bool ready = false;
+    uint64_t w = 0;
+    int lookPos = 0;
+    if (st == LST_SCAN || st == LST_WSTART || st == LST_MM) {
+      const bool rc = (flags & LF_RC) != 0u;
+      for (;;) {
+        if (st == LST_MM) {  // mismatching k-mer after an interval, :599-616
+          lookPos = rb + mlen - (k - 1);
+          if (kmerAt<NT>(sm, nw, L, k, rc, lookPos, w)) ready = true; else st = LST_POSTMM;
+          break;
+        }
+        if (rb + k > L) { st = (st == LST_SCAN) ? LST_FINAL : LST_WALKEND; break; }
+        lookPos = rb;
+        if (st == LST_SCAN) {  // first-hit scan, include/SACollector.hpp:167-237
+          if (!(flags & LF_NOMOREN)) {
+            const int ip = findNLane<NT>(sm, L, false, rb);
+            if (ip == INT_MAX) flags |= LF_NOMOREN;
+            else if (ip <= rb + k) { rb = ip + 1; continue; }  // note <= (SACollector.hpp:178)
+          }
+          kmerAt<NT>(sm, nw, L, k, false, rb, w);
+          if (isHomopolymer(w, k)) { ++rb; continue; }
+          ready = true;
+          break;
+        }
+        const bool valid = kmerAt<NT>(sm, nw, L, k, rc, rb, w);  // getSAHits_ loop head, :505-536
+        if (!valid) {
+          const int ip = findNLane<NT>(sm, L, rc, rb);
+          if (ip < rb + k) { rb = ip + 1; continue; }
+        }
+        if (isHomopolymer(w, k)) { ++rb; continue; }
+        ready = true;
+        break;
+      }
+    }
+
+    // ---------------- B: one pair of lookups (k-mer, reverse complement)
+    if (ready) {
+      int2 fm, fc;
+      hashFind2(P.ix, w, kmerRC(w, k), fm, fc);
+      const bool hm = fm.x >= 0, hc = fc.x >= 0;
+      const bool rc = (flags & LF_RC) != 0u;
+      if (st == LST_SCAN) {
+        if (hm) { ++fwdHit; if (hc) ++rcHit; }
+        if (hc && !fwdHit) ++rcHit;
+        if (fwdHit + rcHit > 0u) {
+          if (voteMode) voteLane(votes, P.voteWords, false, lookPos, L, k, hm, hc);
+          flags |= LF_FOUND;
+          lbIn = fm.x; ubIn = fm.y;  // start interval of the forward walk (used only when fwdHit > 0)
+          st = LST_WALKEND;
+        } else ++rb;
+      } else {
+        if (rc) { rcHit += hm ? 1u : 0u; fwdHit += hc ? 1u : 0u; } else { fwdHit += hm ? 1u : 0u; rcHit += hc ? 1u : 0u; }
+        if (voteMode) voteLane(votes, P.voteWords, rc, lookPos, L, k, hm, hc);
+        if (st == LST_WSTART) {
+          if (!hm) ++rb;  // :673
+          else { lbIn = fm.x; ubIn = fm.y; st = LST_EXTINIT; }
+        } else st = LST_POSTMM;
+      }
+    }
+
+    // ---------------- C: set up extendSearchNaive for the interval [lbIn, ubIn)
+    if (st == LST_EXTINIT) {
+      lbIn = lbIn - 1 > 0 ? lbIn - 1 : 0;  // :553
+      const bool firstAttempt = o.doChaining ? (rb == 0) : true;
+      const int endPos = firstAttempt ? L : min(rb + k + o.maxMMPExtension, L);
+      mQ = endPos - rb;
+      flags = (flags & ~(LF_FIRST | LF_SECOND)) | (firstAttempt ? LF_FIRST : 0u);
+      pass = (ubIn - lbIn == 2) ? 3 : 0;
+      l = lbIn; rr = ubIn; lcpLP = k; lcpRP = k; prevILow = k; prevIHigh = k; mlen = k; guard = 0;
+      st = LST_EXT;
+    }
+
+    // ---------------- D: one probe of the three binary searches (include/SASearcher.hpp:87-309)
+    if (st == LST_EXT) {
+      int cc, i0, m, sentIdx = -1;
+      uint32_t sent = 0;
+      if (pass == 3) { cc = lbIn + 1; i0 = k; }
+      else { cc = static_cast<int>((static_cast<int64_t>(l) + rr) >> 1); i0 = lcpLP < lcpRP ? lcpLP : lcpRP; }
+      if (pass == 1 || pass == 2) { m = mlen + 1; sentIdx = m - 1; sent = pass == 1 ? '#' : '{'; }
+      else m = mQ;
+      const int32_t t = __ldg(P.ix.SA + cc);
+      int rel;
+      const int i = cmpSuffix<NT>(P, sm, r, L, (flags & LF_RC) != 0u, rb, m, t, i0, sentIdx, sent, rel);
+      if (pass == 3) {  // :109-126
+        b0 = lbIn + 1; b1 = ubIn; mlen = i;
+        st = LST_EXTDONE;
+      } else if (pass == 0) {  // :150-209
+        bool plt = true;
+        if (rel < 0) { if (i > prevIHigh) prevIHigh = i; }
+        else if (rel > 0) { if (i > prevILow) prevILow = i; plt = false; }
+        else if (i == m || static_cast<int64_t>(t) + i == P.ix.n) { if (i > prevIHigh) prevIHigh = i; }
+        bool fin = false;
+        if (plt) { if (cc == l + 1) fin = true; else { rr = cc; lcpRP = i; } }
+        else { if (cc == rr - 1) fin = true; else { l = cc; lcpLP = i; } }
+        if (fin) mlen = max(max(i, prevILow), prevIHigh);
+        else if (++guard >= 80) fin = true;  // only a malformed index gets here; protects the GPU from a hang
+        if (fin) { pass = 1; l = lbIn; rr = ubIn; lcpLP = k; lcpRP = k; guard = 0; }
+      } else {  // :224-258 lower bound with '#', :270-304 upper bound with '{'
+        bool fin = false;
+        int bnd = ubIn;
+        if (rel <= 0) { if (cc == l + 1) { bnd = cc; fin = true; } else { rr = cc; lcpRP = i; } }
+        else { if (cc == rr - 1) { bnd = rr; fin = true; } else { l = cc; lcpLP = i; } }
+        if (!fin && ++guard >= 80) { fin = true; bnd = ubIn; }
+        if (fin) {
+          if (pass == 1) { b0 = bnd; pass = 2; l = b0 - 1; rr = ubIn; lcpLP = k; lcpRP = k; guard = 0; }
+          else { b1 = bnd; if (b0 == b1) ++b1; st = LST_EXTDONE; }  // :307
+        }
+      }
+    }
+
+    // ---------------- E: bookkeeping
+    if (st == LST_EXTDONE) {
+      if (o.doChaining && (flags & LF_FIRST) && !(flags & LF_SECOND) && !(mlen >= L) && mlen >= k + o.maxMMPExtension) {  // :568-575
+        mQ = min(rb + k + o.maxMMPExtension, L) - rb;
+        flags |= LF_SECOND;
+        pass = (ubIn - lbIn == 2) ? 3 : 0;
+        l = lbIn; rr = ubIn; lcpLP = k; lcpRP = k; prevILow = k; prevIHigh = k; mlen = k; guard = 0;
+        st = LST_EXT;
+      } else {
+        st = LST_POSTMM;
+        const bool rc = (flags & LF_RC) != 0u;
+        if (b1 > b0 && (b1 - b0) < o.maxInterval) {  // :578
+          const int idx = rc ? nR : nF;
+          if (static_cast<uint32_t>(idx) < P.ivStride) {
+            IntervalRec rec;
+            rec.begin = b0; rec.end = b1; rec.len = static_cast<uint16_t>(mlen); rec.qpos = static_cast<uint16_t>(rb);
+            scr[(rc ? P.ivStride : 0u) + idx] = rec;
+          } else flags |= LF_OVF;
+          if (rc) ++nR; else ++nF;
+          const int correction = prevMMPEnd > rb ? prevMMPEnd - rb : 0;
+          if (rc) rcCov += static_cast<uint32_t>(mlen - correction); else fwdCov += static_cast<uint32_t>(mlen - correction);
+          prevMMPEnd = rb + mlen;
+          if (rb + mlen < L) st = LST_MM;
+        }
+        lbIn = b0; ubIn = b1;
+      }
+    }
+    if (st == LST_POSTMM) {
+      if ((flags & LF_LAST) || rb + mlen >= L) st = LST_WALKEND;  // :623, :630
+      else {  // :634-657 next start: MMP skip, or the NIP skip when --noSensitive
+        const int mismatchPos = rb + mlen;
+        const int lce = o.disableNIP ? mlen : lceLane(P.ix.SA, P.ix.text, P.ix.n, lbIn, static_cast<int64_t>(ubIn) - 1, mlen, L - mismatchPos);
+        const int skipMatch = mismatchPos - (k - 1), skipLCE = rb + lce - (k - 1);
+        rb = skipMatch > skipLCE ? skipMatch : skipLCE;
+        if (!o.disableNIP && lce > mlen && L > k) rb = rb < L - k ? rb : L - k;
+        if (rb + k == L) flags |= LF_LAST;  // :663
+        st = LST_WSTART;
+      }
+    }
+    if (st == LST_WALKEND) {  // strand sequencing of SACollector::operator(), :247-281
+      uint32_t stage = (flags & LF_STAGE_MASK) >> LF_STAGE_SHIFT;
+      st = LST_FINAL;
+      if (stage == 0u) {
+        stage = 1u;
+        if (fwdHit) {  // walk forward from the first hit with its interval (:247-254)
+          flags = (flags | LF_DIDFWD) & ~(LF_RC | LF_LAST);
+          prevMMPEnd = 0;
+          st = LST_EXTINIT;
+        }
+      }
+      if (st == LST_FINAL && stage == 1u) {
+        stage = 2u;
+        const bool checkRC = useCov ? (rcHit > 0u) : (rcHit >= fwdHit);  // :256
+        if (checkRC) { flags = (flags | LF_RC) & ~LF_LAST; rb = 0; prevMMPEnd = 0; st = LST_WSTART; }
+      }
+      if (st == LST_FINAL && stage == 2u) {
+        stage = 3u;
+        const bool checkFwd = useCov ? (fwdHit > 0u) : (fwdHit >= rcHit);  // :270
+        if (!(flags & LF_DIDFWD) && checkFwd) { flags &= ~(LF_RC | LF_LAST); rb = 0; prevMMPEnd = 0; st = LST_WSTART; }
+      }
+      flags = (flags & ~LF_STAGE_MASK) | (stage << LF_STAGE_SHIFT);
+    }
+
+    // ---------------- publish finished reads
+    {
+      const bool fin = st == LST_FINAL;
+      int tot = 0;
+      if (fin) {
+        if (flags & LF_FOUND) {
+          if (useCov) {  // strand decision by coverage (:283-288)
+            if (fwdCov > rcCov + static_cast<uint32_t>(o.strictCheckSlack)) nR = 0;
+            else if (rcCov > fwdCov + static_cast<uint32_t>(o.strictCheckSlack)) nF = 0;
+          } else if (o.strictCheck) {  // k-mer "spot check" vote (:289-337)
+            if (fwdHit > 0u && rcHit == 0u) nR = 0;
+            else if (rcHit > 0u && fwdHit == 0u) nF = 0;
+            else {
+              int fs = 0, rs = 0;
+              for (uint32_t j = 0; j < P.voteWords; ++j) {
+                const int tested = __popc(votes[j]);
+                fs += 2 * __popc(votes[P.voteWords + j]) - tested;
+                rs += 2 * __popc(votes[2 * P.voteWords + j]) - tested;
+              }
+              if (fs > rs) nR = 0;
+              else if (rs > fs) nF = 0;
+            }
+          }
+          if (o.covReq > 0.0 && o.disableNIP) {  // :343-358
+            if (nF > 0 && (static_cast<double>(fwdCov) / static_cast<double>(L)) < o.covReq) nF = 0;
+            if (nR > 0 && (static_cast<double>(rcCov) / static_cast<double>(L)) < o.covReq) nR = 0;
+          }
+        } else { nF = 0; nR = 0; }
+        tot = nF + nR;
+      }
+      const unsigned pm = __ballot_sync(0xffffffffu, fin && tot > 0);
+      uint32_t off = 0;
+      if (pm) {  // warp-aggregated reservation out of the warp's arena slice
+        int incl = fin ? tot : 0;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, incl, d);
+          if (lane >= d) incl += v;
+        }
+        const uint32_t total = static_cast<uint32_t>(__shfl_sync(0xffffffffu, incl, 31));
+        if (total > chunkLeft) {
+          const uint32_t grab = total > RAPMAP_LANE_CHUNK ? total : RAPMAP_LANE_CHUNK;
+          uint32_t base = 0;
+          if (lane == 0) base = atomicAdd(P.arenaCursor, grab);
+          chunkBase = __shfl_sync(0xffffffffu, base, 0);
+          chunkLeft = grab;
+        }
+        off = chunkBase + static_cast<uint32_t>(incl - tot);
+        chunkBase += total;
+        chunkLeft -= total;
+      }
+      if (fin) {
+        if (tot > 0) {
+          if (flags & LF_OVF) atomicOr(P.status, kStatIvScratchFull);
+          else if (static_cast<uint64_t>(off) + static_cast<uint64_t>(tot) > P.arenaCap) atomicOr(P.status, kStatIntervalArenaFull);
+          else {
+            for (int i = 0; i < nF; ++i) P.arena[off + i] = scr[i];
+            for (int i = 0; i < nR; ++i) P.arena[off + nF + i] = scr[P.ivStride + i];
+          }
+        }
+        ReadSummary s;
+        s.ivOff = off; s.nFwd = static_cast<uint16_t>(nF); s.nRc = static_cast<uint16_t>(nR);
+        s.readLen = static_cast<uint16_t>(L); s.found = (flags & LF_FOUND) ? 1 : 0; s.pad = 0;
+        P.summ[r] = s;
+        st = LST_IDLE;
+      }
+    }
+  }
+}
+
+} // namespace rapmap_b200
