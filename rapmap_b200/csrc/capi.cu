@@ -48,7 +48,7 @@ struct CastU64 {
 __global__ void build_table_kernel(const KmerRecord* recs, uint64_t n, uint4* table, uint64_t mask) {
   for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
     KmerRecord r = recs[i];
-    uint64_t s = mix64(r.kmer) & mask;
+    uint64_t s = mix64(r.kmer) & mask & ~1ULL;
     while (true) {
       unsigned long long* keyp = reinterpret_cast<unsigned long long*>(table + s);
       unsigned long long old = atomicCAS(keyp, static_cast<unsigned long long>(kEmptyKey), static_cast<unsigned long long>(r.kmer));
@@ -154,8 +154,14 @@ struct rapmap_cuda_mapper {
 };
 
 static constexpr int kWarps = 8;
-static constexpr int kLaneThreads = 256;  // lane-per-read SA-lookup kernel: threads per block
-static constexpr int kLaneMinBlocks = 4;   // 64 registers per thread
+#ifndef RAPMAP_LANE_THREADS
+#define RAPMAP_LANE_THREADS 256
+#endif
+#ifndef RAPMAP_LANE_MINB
+#define RAPMAP_LANE_MINB 4
+#endif
+static constexpr int kLaneThreads = RAPMAP_LANE_THREADS;  // lane-per-read SA-lookup kernel: threads per block
+static constexpr int kLaneMinBlocks = RAPMAP_LANE_MINB;   // 4 x 256 threads: 64 registers per thread
 
 extern "C" {
 

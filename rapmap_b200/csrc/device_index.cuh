@@ -7,8 +7,8 @@
 // * rank: one 16-byte record per 64 text positions {bits_lo, bits_hi, #'$' before this word, 0}: a
 //   transcript id is ONE 16-byte load + popcount (replaces rank9b::rank, reference src/rank9b.cpp:55-60,
 //   which needs three loads; same value: number of set bits strictly before p).
-// * hash table: open addressing, linear probing, 16-byte slots {kmer_lo, kmer_hi, begin, end}, capacity a
-//   power of two >= 2 x #k-mers; two slots share a 32-byte DRAM sector.  Replaces the sparsepp
+// * hash table: open addressing, linear probing from the even slot of the key's 32-byte sector, 16-byte slots
+//   {kmer_lo, kmer_hi, begin, end}, capacity a power of two >= 2 x #k-mers; a probe examines both slots of a sector.  Replaces the sparsepp
 //   RegHashT<uint64_t, SAInterval> (reference include/RapMapUtils.hpp:65-67): same key -> [begin,end) map.
 #pragma once
 #include <cstdint>
@@ -153,7 +153,7 @@ __device__ __noinline__ int2 phfFind(const DeviceIndex& ix, uint64_t key) { retu
 // k-mer -> SA interval; {-1,-1} when absent.  (RegHashT::find, reference include/SACollector.hpp:196,541)
 __device__ __forceinline__ int2 hashFind(const DeviceIndex& ix, uint64_t key) {
   if (ix.hashKind) return phfFind(ix, key);
-  uint64_t s = mix64(key) & ix.tableMask;
+  uint64_t s = mix64(key) & ix.tableMask & ~1ULL;  // keys start at the even slot of their 32-byte sector
   while (true) {
     uint4 e = __ldg(ix.table + s);
     uint64_t kk = (static_cast<uint64_t>(e.y) << 32) | e.x;

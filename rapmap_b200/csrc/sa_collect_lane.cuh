@@ -191,20 +191,15 @@ __device__ __forceinline__ uint64_t query8(const LaneParams& P, const uint4* sm,
     const uint8_t* src = P.reads.off[mate] ? P.reads.seq[mate] + P.reads.off[mate][ri] : P.reads.seq[mate] + ri * P.reads.fixedLen;
     return query8Bytes(src, L, rc, p);
   }
-  uint32_t lo, hi;
-  if (!rc) {
-    const uint32_t a = v >> 8, b = v & 0xffu;
-    const uint32_t sa = ((a >> 6) & 3u) | (((a >> 4) & 3u) << 4) | (((a >> 2) & 3u) << 8) | ((a & 3u) << 12);
-    const uint32_t sb = ((b >> 6) & 3u) | (((b >> 4) & 3u) << 4) | (((b >> 2) & 3u) << 8) | ((b & 3u) << 12);
-    lo = __byte_perm(0x54474341u, 0u, sa);  // "ACGT"
-    hi = __byte_perm(0x54474341u, 0u, sb);
-  } else {
-    const uint32_t a = v & 0xffu, b = v >> 8;
-    const uint32_t sa = (a & 3u) | ((a & 0xCu) << 2) | ((a & 0x30u) << 4) | ((a & 0xC0u) << 6);
-    const uint32_t sb = (b & 3u) | ((b & 0xCu) << 2) | ((b & 0x30u) << 4) | ((b & 0xC0u) << 6);
-    lo = __byte_perm(0x41434754u, 0u, sa);  // complement: "TGCA"
-    hi = __byte_perm(0x41434754u, 0u, sb);
+  if (rc) {  // reverse the eight 2-bit codes and complement them: the strand's own 8 bases, first base in bits 15:14
+    v = __brev(v) >> 16;
+    v = (((v & 0x5555u) << 1) | ((v >> 1) & 0x5555u)) ^ 0xffffu;
   }
+  const uint32_t a = v >> 8, b = v & 0xffu;
+  const uint32_t sa = ((a >> 6) & 3u) | (((a >> 4) & 3u) << 4) | (((a >> 2) & 3u) << 8) | ((a & 3u) << 12);
+  const uint32_t sb = ((b >> 6) & 3u) | (((b >> 4) & 3u) << 4) | (((b >> 2) & 3u) << 8) | ((b & 3u) << 12);
+  const uint32_t lo = __byte_perm(0x54474341u, 0u, sa);  // "ACGT"
+  const uint32_t hi = __byte_perm(0x54474341u, 0u, sb);
   return (static_cast<uint64_t>(hi) << 32) | lo;
 }
 
@@ -254,26 +249,32 @@ __device__ __forceinline__ void hashFind2(const DeviceIndex& ix, uint64_t ka, ui
     }
     return;
   }
-  uint64_t sa = mix64(ka) & ix.tableMask, sb = mix64(kb) & ix.tableMask;
-  uint4 ea = __ldg(ix.table + sa), eb = __ldg(ix.table + sb);
+  // two 16-byte slots share a 32-byte sector: both are examined per probe (the scan order is still slot by slot, so the
+  // first empty slot ends the search exactly as in hashFind)
+  uint64_t sa = mix64(ka) & ix.tableMask & ~1ULL, sb = mix64(kb) & ix.tableMask & ~1ULL;
   bool da = false, db = false;
   ra = make_int2(-1, -1); rb = make_int2(-1, -1);
   for (;;) {
+    uint4 a0, a1, b0, b1;
+    if (!da) { a0 = __ldg(ix.table + sa); a1 = __ldg(ix.table + sa + 1); }
+    if (!db) { b0 = __ldg(ix.table + sb); b1 = __ldg(ix.table + sb + 1); }
     if (!da) {
-      const uint64_t kk = (static_cast<uint64_t>(ea.y) << 32) | ea.x;
-      if (kk == ka) { ra = make_int2(static_cast<int>(ea.z), static_cast<int>(ea.w)); da = true; }
-      else if (kk == kEmptyKey) da = true;
-      else sa = (sa + 1) & ix.tableMask;
+      const uint64_t k0 = (static_cast<uint64_t>(a0.y) << 32) | a0.x, k1 = (static_cast<uint64_t>(a1.y) << 32) | a1.x;
+      if (k0 == ka) { ra = make_int2(static_cast<int>(a0.z), static_cast<int>(a0.w)); da = true; }
+      else if (k0 == kEmptyKey) da = true;
+      else if (k1 == ka) { ra = make_int2(static_cast<int>(a1.z), static_cast<int>(a1.w)); da = true; }
+      else if (k1 == kEmptyKey) da = true;
+      else sa = (sa + 2) & ix.tableMask;
     }
     if (!db) {
-      const uint64_t kk = (static_cast<uint64_t>(eb.y) << 32) | eb.x;
-      if (kk == kb) { rb = make_int2(static_cast<int>(eb.z), static_cast<int>(eb.w)); db = true; }
-      else if (kk == kEmptyKey) db = true;
-      else sb = (sb + 1) & ix.tableMask;
+      const uint64_t k0 = (static_cast<uint64_t>(b0.y) << 32) | b0.x, k1 = (static_cast<uint64_t>(b1.y) << 32) | b1.x;
+      if (k0 == kb) { rb = make_int2(static_cast<int>(b0.z), static_cast<int>(b0.w)); db = true; }
+      else if (k0 == kEmptyKey) db = true;
+      else if (k1 == kb) { rb = make_int2(static_cast<int>(b1.z), static_cast<int>(b1.w)); db = true; }
+      else if (k1 == kEmptyKey) db = true;
+      else sb = (sb + 2) & ix.tableMask;
     }
     if (da && db) return;
-    if (!da) ea = __ldg(ix.table + sa);
-    if (!db) eb = __ldg(ix.table + sb);
   }
 }
 
@@ -384,34 +385,31 @@ __global__ void __launch_bounds__(NT, MINB) sa_collect_lane_kernel(LaneParams P)
     if (st == LST_SCAN || st == LST_WSTART || st == LST_MM) {
       const bool rc = (flags & LF_RC) != 0u;
       for (;;) {
-        if (st == LST_MM) {  // mismatching k-mer after an interval, :599-616
-          lookPos = rb + mlen - (k - 1);
-          if (kmerAt<NT>(sm, nw, L, k, rc, lookPos, w)) ready = true; else st = LST_POSTMM;
-          break;
-        }
-        if (rb + k > L) { st = (st == LST_SCAN) ? LST_FINAL : LST_WALKEND; break; }
-        lookPos = rb;
-        if (st == LST_SCAN) {  // first-hit scan, include/SACollector.hpp:167-237
-          if (!(flags & LF_NOMOREN)) {
+        if (st == LST_MM) lookPos = rb + mlen - (k - 1);  // mismatching k-mer after an interval, :599-616
+        else {
+          if (rb + k > L) { st = (st == LST_SCAN) ? LST_FINAL : LST_WALKEND; break; }
+          lookPos = rb;
+          if (st == LST_SCAN && !(flags & LF_NOMOREN)) {  // first-hit scan, include/SACollector.hpp:167-237
             const int ip = findNLane<NT>(sm, L, false, rb);
             if (ip == INT_MAX) flags |= LF_NOMOREN;
             else if (ip <= rb + k) { rb = ip + 1; continue; }  // note <= (SACollector.hpp:178)
           }
-          kmerAt<NT>(sm, nw, L, k, false, rb, w);
-          if (isHomopolymer(w, k)) { ++rb; continue; }
-          ready = true;
+        }
+        const bool valid = kmerAt<NT>(sm, nw, L, k, rc, lookPos, w);
+        if (st == LST_MM) {
+          if (valid) ready = true; else st = LST_POSTMM;
           break;
         }
-        const bool valid = kmerAt<NT>(sm, nw, L, k, rc, rb, w);  // getSAHits_ loop head, :505-536
-        if (!valid) {
+        if (st == LST_WSTART && !valid) {  // getSAHits_ loop head, :505-516
           const int ip = findNLane<NT>(sm, L, rc, rb);
           if (ip < rb + k) { rb = ip + 1; continue; }
         }
-        if (isHomopolymer(w, k)) { ++rb; continue; }
+        if (isHomopolymer(w, k)) { ++rb; continue; }  // :520-536
         ready = true;
         break;
       }
     }
+    __syncwarp();  // all lanes meet before the lookup phase
 
     // ---------------- B: one pair of lookups (k-mer, reverse complement)
     if (ready) {
@@ -451,6 +449,7 @@ __global__ void __launch_bounds__(NT, MINB) sa_collect_lane_kernel(LaneParams P)
     }
 
     // ---------------- D: one probe of the three binary searches (include/SASearcher.hpp:87-309)
+    __syncwarp();
     if (st == LST_EXT) {
       int cc, i0, m, sentIdx = -1;
       uint32_t sent = 0;
@@ -489,6 +488,7 @@ __global__ void __launch_bounds__(NT, MINB) sa_collect_lane_kernel(LaneParams P)
     }
 
     // ---------------- E: bookkeeping
+    __syncwarp();
     if (st == LST_EXTDONE) {
       if (o.doChaining && (flags & LF_FIRST) && !(flags & LF_SECOND) && !(mlen >= L) && mlen >= k + o.maxMMPExtension) {  // :568-575
         mQ = min(rb + k + o.maxMMPExtension, L) - rb;

@@ -1,8 +1,8 @@
 #!/bin/bash
+# A/B: bench every library under rapmap_b200/_build/ab/ (and the default build) on the same box; EXTRA="--selaln" etc.
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q --tb=line -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1; tail -4 gpurun_out/pytest_gpu.log | cut -c1-300
-run() { # name, lib, extra flags
-  RAPMAP_B200_LIB=$2 timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --oracle-sample 2000 $3 > gpurun_out/ab_$1.json 2> gpurun_out/ab_$1.log
+run() { # name, lib
+  RAPMAP_B200_LIB=$2 timeout 600 python bench.py --steps ${STEPS:-5} --warmup 3 --no-cpu-baseline --oracle-sample 2000 $EXTRA > gpurun_out/ab_$1.json 2> gpurun_out/ab_$1.log
   python - <<PY
 import json
 try:
@@ -10,7 +10,9 @@ try:
 except Exception as e: print("$1", "ERR", e, open("gpurun_out/ab_$1.log").read()[-400:])
 PY
 }
-run tab "" ""
-run notab $PWD/rapmap_b200/_build/ab/lib_notab.so ""
-run tab_sel "" "--selaln"
-run notab_sel $PWD/rapmap_b200/_build/ab/lib_notab.so "--selaln"
+run default ""
+for lib in rapmap_b200/_build/ab/lib_*.so; do
+  [ -f "$lib" ] || continue
+  n=$(basename $lib .so); n=${n#lib_}
+  run $n $PWD/$lib
+done
