@@ -62,10 +62,52 @@ __global__ void build_table_kernel(const KmerRecord* recs, uint64_t n, uint4* ta
   }
 }
 
+__global__ void build_filter_kernel(const KmerRecord* recs, uint64_t n, uint32_t* filter, uint32_t shift) {
+  for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    uint64_t word;
+    uint32_t mask;
+    filterSlot(mix64(recs[i].kmer), shift, word, mask);
+    atomicOr(filter + word, mask);
+  }
+}
+
+// Packed-text records from the ASCII text (device_index.cuh: TextRec).  *bad is raised when a character lies outside
+// '$'..'z': the packed compare orders the search sentinels '#' and '{' against every text character without looking.
+__global__ void build_text2_kernel(const uint8_t* text, uint64_t n, TextRec* recs, uint64_t numRecs, uint32_t* bad) {
+  for (uint64_t j = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; j < numRecs; j += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    uint64_t c[2] = {0, 0};
+    uint32_t inv[2] = {0, 0};
+    for (int h = 0; h < 2; ++h) {
+      for (int b = 0; b < 32; ++b) {
+        const uint64_t p = j * 32 + static_cast<uint64_t>(h) * 32 + b;
+        uint32_t code = 0;
+        bool ok = false;
+        if (p < n) {
+          const uint8_t ch = text[p];
+          if (ch == 'A') { code = 0; ok = true; } else if (ch == 'C') { code = 1; ok = true; }
+          else if (ch == 'G') { code = 2; ok = true; } else if (ch == 'T') { code = 3; ok = true; }
+          else if (ch < '$' || ch > 'z') *bad = 1u;
+        }
+        c[h] |= static_cast<uint64_t>(code) << (62 - 2 * b);
+        if (!ok) inv[h] |= 1u << b;
+      }
+    }
+    TextRec r;
+    r.c0lo = static_cast<uint32_t>(c[0]); r.c0hi = static_cast<uint32_t>(c[0] >> 32);
+    r.c1lo = static_cast<uint32_t>(c[1]); r.c1hi = static_cast<uint32_t>(c[1] >> 32);
+    r.inv0 = inv[0]; r.inv1 = inv[1]; r.pad0 = 0; r.pad1 = 0;
+    recs[j] = r;
+  }
+}
+
 DeviceIndex viewOf(const uint8_t* blob, const ImageHeader& h) {
   DeviceIndex d;
   d.SA = reinterpret_cast<const int32_t*>(blob + h.offSA);
   d.text = blob + h.offText;
+  d.text2 = h.offText2 ? reinterpret_cast<const TextRec*>(blob + h.offText2) : nullptr;
+  d.filter = h.offFilter ? reinterpret_cast<const uint32_t*>(blob + h.offFilter) : nullptr;
+  d.filterShift = 64;
+  for (uint64_t w = h.filterWords; w > 1; w >>= 1) --d.filterShift;
   d.rank = reinterpret_cast<const uint4*>(blob + h.offRank);
   d.txpOffsets = reinterpret_cast<const int32_t*>(blob + h.offTxpOffsets);
   d.txpLens = reinterpret_cast<const int32_t*>(blob + h.offTxpLens);
@@ -158,10 +200,10 @@ static constexpr int kWarps = 8;
 #define RAPMAP_LANE_THREADS 256
 #endif
 #ifndef RAPMAP_LANE_MINB
-#define RAPMAP_LANE_MINB 4
+#define RAPMAP_LANE_MINB 3
 #endif
 static constexpr int kLaneThreads = RAPMAP_LANE_THREADS;  // lane-per-read SA-lookup kernel: threads per block
-static constexpr int kLaneMinBlocks = RAPMAP_LANE_MINB;   // 4 x 256 threads: 64 registers per thread
+static constexpr int kLaneMinBlocks = RAPMAP_LANE_MINB;   // 3 x 256 threads, 80 registers: the 64-register build spills and is 13 % slower
 
 extern "C" {
 
@@ -219,6 +261,14 @@ int rapmap_cuda_index_load(const char* index_dir, int device, rapmap_cuda_index_
   hdr.offTxpOffsets = off; off = align256(off + T * 4);
   hdr.offTxpLens = off; off = align256(off + T * 4);
   hdr.offTable = off; off = align256(off + slots * 16);
+  if (!h.perfectHash && !h.kmers.empty()) {  // ~6 bits per k-mer, capped at 64 MB (L2-resident)
+    uint64_t words = 1024;
+    while (words * 32 < 6 * h.kmers.size() && words < (1ull << 24)) words <<= 1;
+    hdr.filterWords = words;
+    hdr.offFilter = off; off = align256(off + words * 4);
+  }
+  const uint64_t text2Recs = n / 32 + 2;
+  hdr.offText2 = off; off = align256(off + text2Recs * sizeof(TextRec));
   // -p index: level table, concatenated bitsets and rank samples, _final_hash, data_, lens_, overflow_
   uint64_t phfWords = 0, phfRanks = 0;
   std::vector<PhfLevelDev> lvDev;
@@ -280,12 +330,33 @@ int rapmap_cuda_index_load(const char* index_dir, int device, rapmap_cuda_index_
     if (!h.phf.lens.empty()) IDX_TRY(cudaMemcpy(idx->blob + hdr.offPhfLens, h.phf.lens.data(), h.phf.lens.size(), cudaMemcpyHostToDevice));
     if (!h.phf.overflow.empty()) IDX_TRY(cudaMemcpy(idx->blob + hdr.offPhfOverflow, h.phf.overflow.data(), h.phf.overflow.size() * 8, cudaMemcpyHostToDevice));
   }
+  {  // packed text
+    uint32_t* dBad = nullptr;
+    IDX_TRY(cudaMalloc(&dBad, 4));
+    IDX_TRY(cudaMemset(dBad, 0, 4));
+    build_text2_kernel<<<2048, 256>>>(idx->blob + hdr.offText, n, reinterpret_cast<TextRec*>(idx->blob + hdr.offText2), text2Recs, dBad);
+    uint32_t bad = 0;
+    cudaError_t e4 = cudaMemcpy(&bad, dBad, 4, cudaMemcpyDeviceToHost);
+    cudaFree(dBad);
+    if (e4 != cudaSuccess) return bail(std::string("packed text build: ") + cudaGetErrorString(e4));
+    if (bad) {
+      hdr.offText2 = 0;
+      idx->hdr = hdr;
+      IDX_TRY(cudaMemcpy(idx->blob, &hdr, sizeof(hdr), cudaMemcpyHostToDevice));
+    }
+  }
   if (!h.kmers.empty()) {
     KmerRecord* dRecs = nullptr;
     IDX_TRY(cudaMalloc(&dRecs, h.kmers.size() * sizeof(KmerRecord)));
     cudaError_t e3 = cudaMemcpy(dRecs, h.kmers.data(), h.kmers.size() * sizeof(KmerRecord), cudaMemcpyHostToDevice);
     if (e3 == cudaSuccess) {
       build_table_kernel<<<2048, 256>>>(dRecs, h.kmers.size(), reinterpret_cast<uint4*>(idx->blob + hdr.offTable), slots - 1);
+      if (hdr.offFilter) {
+        uint32_t shift = 64;
+        for (uint64_t w = hdr.filterWords; w > 1; w >>= 1) --shift;
+        e3 = cudaMemset(idx->blob + hdr.offFilter, 0, hdr.filterWords * 4);
+        if (e3 == cudaSuccess) build_filter_kernel<<<2048, 256>>>(dRecs, h.kmers.size(), reinterpret_cast<uint32_t*>(idx->blob + hdr.offFilter), shift);
+      }
       e3 = cudaDeviceSynchronize();
     }
     cudaFree(dRecs);

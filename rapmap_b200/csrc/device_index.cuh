@@ -3,7 +3,16 @@
 // HBM layout (one contiguous blob, sections 256-byte aligned, so the whole index is a single
 // ncclBroadcast / cudaMemcpy):
 //   ImageHeader | SA int32[n] | text u8[n + pad] | rank uint4[ceil(n/64)+1] | txpOffsets int32[T] |
-//   txpLens int32[T] | hash table uint4[slots]
+//   txpLens int32[T] | hash table uint4[slots] | packed text TextRec[ceil(n/32)+1] | k-mer filter u32[F]
+// * k-mer filter: a word-blocked Bloom filter over the indexed k-mers (3 bits inside one 32-bit word, ~6 bits per key,
+//   at most 64 MB so that it stays resident in the 126 MB L2, loads carry an L2 evict_last policy).  ~90 % of the
+//   lookups of a read with sequencing errors are for k-mers that are not in the index (the 31 windows covering a
+//   mismatch, both orientations); the filter answers ~92 % of those from L2 without touching the table in HBM.
+//   No false negatives, so every lookup result is unchanged.
+// * packed text: one 32-byte record per 32 text positions holding the 2-bit codes of the NEXT 64 positions and
+//   their non-ACGT mask, so the 32-base window at ANY position p lies inside record p/32: one aligned 256-bit load
+//   (one DRAM sector) feeds 32 character comparisons of extendSearchNaive.  The ASCII text stays for exact
+//   fall-backs ('$', IUPAC) and for the selective-alignment windows.
 // * rank: one 16-byte record per 64 text positions {bits_lo, bits_hi, #'$' before this word, 0}: a
 //   transcript id is ONE 16-byte load + popcount (replaces rank9b::rank, reference src/rank9b.cpp:55-60,
 //   which needs three loads; same value: number of set bits strictly before p).
@@ -26,6 +35,9 @@ struct ImageHeader {
   uint32_t k;
   uint32_t hashKind;       // 0: dense open-addressing table, 1: BooPHF + FrugalBooMap arrays (-p index)
   uint64_t offSA, offText, offRank, offTxpOffsets, offTxpLens, offTable;
+  uint64_t offFilter;      // 0: no filter
+  uint64_t filterWords;    // power of two
+  uint64_t offText2;       // 0: the text holds characters the packed compare cannot order (outside '$'..'z'); ASCII path only
   // -p index only
   uint32_t phfLevels, phfPad;
   uint64_t phfLastRank, phfNumData, phfNumFinal, phfNumOverflow;
@@ -42,9 +54,17 @@ struct PhfLevelDev {
 };
 static constexpr uint64_t kImageMagic = 0x31474D4932424D52ULL;
 
+// 64 bases starting at text position 32 j: codes (first base in bits 63:62 of c0), non-ACGT mask (first base in bit 0 of inv0).
+struct __align__(32) TextRec {
+  uint32_t c0lo, c0hi, c1lo, c1hi, inv0, inv1, pad0, pad1;
+};
+
 struct DeviceIndex {
   const int32_t* SA;
   const uint8_t* text;
+  const TextRec* text2;    // nullptr: no packed text (see ImageHeader::offText2)
+  const uint32_t* filter;  // nullptr: no k-mer filter
+  uint32_t filterShift;    // 64 - log2(filter words)
   const uint4* rank;
   const int32_t* txpOffsets;
   const int32_t* txpLens;
@@ -76,7 +96,39 @@ __host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
   return x;
 }
 
+// Filter word / bit mask of a k-mer from its table hash h = mix64(key).
+__host__ __device__ __forceinline__ void filterSlot(uint64_t h, uint32_t shift, uint64_t& word, uint32_t& mask) {
+  const uint64_t g = (h ^ (h >> 29)) * 0x9E3779B97F4A7C15ULL;
+  word = g >> shift;
+  mask = (1u << (g & 31)) | (1u << ((g >> 5) & 31)) | (1u << ((g >> 10) & 31));
+}
+
 #ifdef __CUDACC__
+// 32-bit load that asks L2 to keep the line (createpolicy evict_last): the k-mer filter is re-read ~50x per batch.
+__device__ __forceinline__ uint32_t ldgKeep(const uint32_t* p) {
+  uint32_t v;
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+
+// One aligned 256-bit load (LDG.E.256, sm_100): eight 32-bit words of one 32-byte DRAM sector.
+struct __align__(32) Words8 { uint32_t v[8]; };
+__device__ __forceinline__ Words8 ldg256(const void* p) {
+  Words8 r;
+#ifdef RAPMAP_LDCG
+  asm volatile("ld.global.cg.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#elif defined(RAPMAP_LDNA)
+  asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#else
+  asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#endif
+               : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+               : "l"(p));
+  return r;
+}
+
 // boomphf hash of a key (HashFunctors::hash64, reference include/BooPHF.hpp:394-407)
 __device__ __forceinline__ uint64_t phfHash64(uint64_t key, uint64_t seed) {
   uint64_t hash = seed;

@@ -61,12 +61,11 @@ __device__ __noinline__ bool encodeKmer(const uint8_t* s, int k, uint64_t& w) {
 }
 
 __device__ __forceinline__ uint64_t kmerRC(uint64_t w, int k) {  // include/Kmer.hpp:92-100
-  w = ((w >> 2) & 0x3333333333333333ULL) | ((w & 0x3333333333333333ULL) << 2);
-  w = ((w >> 4) & 0x0F0F0F0F0F0F0F0FULL) | ((w & 0x0F0F0F0F0F0F0F0FULL) << 4);
-  w = ((w >> 8) & 0x00FF00FF00FF00FFULL) | ((w & 0x00FF00FF00FF00FFULL) << 8);
-  w = ((w >> 16) & 0x0000FFFF0000FFFFULL) | ((w & 0x0000FFFF0000FFFFULL) << 16);
-  w = (w >> 32) | (w << 32);
-  return (~w) >> (2 * (32 - k));
+  // reverse the 2-bit groups: full bit reversal (two BREVs), then swap the two bits of every group back
+  const uint32_t lo = __brev(static_cast<uint32_t>(w >> 32)), hi = __brev(static_cast<uint32_t>(w));
+  const uint32_t lo2 = ((lo & 0x55555555u) << 1) | ((lo >> 1) & 0x55555555u), hi2 = ((hi & 0x55555555u) << 1) | ((hi >> 1) & 0x55555555u);
+  const uint64_t r = (static_cast<uint64_t>(hi2) << 32) | lo2;
+  return (~r) >> (2 * (32 - k));
 }
 
 __device__ __forceinline__ bool isHomopolymer(uint64_t w, int k) {  // include/Kmer.hpp:484-487

@@ -176,21 +176,16 @@ __device__ __noinline__ uint64_t query8Bytes(const uint8_t* src, int L, bool rc,
 
 // 8 upper-cased characters of a strand at p .. p+7 (byte j = position p + j; positions >= L unspecified).
 template <int NT>
-__device__ __forceinline__ uint64_t query8(const LaneParams& P, const uint4* sm, uint32_t r, int L, bool rc, int p) {
+__device__ __forceinline__ uint64_t query8(const uint4* sm, int nw, const uint8_t* src, int L, bool rc, int p) {
   const int q = rc ? L - 8 - p : p;
   const int qs = q < 0 ? 0 : q;
   uint64_t val;
   uint32_t invw;
-  loadWin<NT>(sm, static_cast<int>(P.nw), qs, val, invw);
+  loadWin<NT>(sm, nw, qs, val, invw);
   uint32_t v = static_cast<uint32_t>(val >> 48);  // 8 bases, base qs in bits 15:14
   invw &= 0xffu;
   if (q < 0) { v >>= 2 * (-q); invw &= (1u << (8 + q)) - 1u; }
-  if (invw != 0u) {  // a non-ACGT base in the window: exact characters from the original read
-    const int mate = r >= P.reads.n ? 1 : 0;
-    const uint64_t ri = r - static_cast<uint64_t>(mate) * P.reads.n;
-    const uint8_t* src = P.reads.off[mate] ? P.reads.seq[mate] + P.reads.off[mate][ri] : P.reads.seq[mate] + ri * P.reads.fixedLen;
-    return query8Bytes(src, L, rc, p);
-  }
+  if (invw != 0u) return query8Bytes(src, L, rc, p);  // a non-ACGT base in the window: exact characters from the original read
   if (rc) {  // reverse the eight 2-bit codes and complement them: the strand's own 8 bases, first base in bits 15:14
     v = __brev(v) >> 16;
     v = (((v & 0x5555u) << 1) | ((v >> 1) & 0x5555u)) ^ 0xffffu;
@@ -206,22 +201,23 @@ __device__ __forceinline__ uint64_t query8(const LaneParams& P, const uint4* sm,
 // One suffix comparison of extendSearchNaive (include/SASearcher.hpp:160-176 and the two sentinel searches): query
 // q[i] vs text[t + i] for i >= i0 while i < m and t + i < n; q[sentIdx] reads `sent` when sentIdx >= 0.  Returns the
 // index at which the reference's inner loop stops; rel = -1 (query < text), +1 (query > text), 0 (ran off).
+// Byte-exact form on the ASCII text, 8 characters per step: the fall-back of cmpSuffixPacked.
 template <int NT>
-__device__ __forceinline__ int cmpSuffix(const LaneParams& P, const uint4* sm, uint32_t r, int L, bool rc, int rb, int m, int32_t t, int i0,
-                                         int sentIdx, uint32_t sent, int& rel) {
-  const int64_t limL = P.ix.n - static_cast<int64_t>(t);
+__device__ __noinline__ int cmpSuffixAscii(const uint8_t* text, int64_t n, const uint4* sm, int nw, const uint8_t* src, int L, bool rc, int rb, int m,
+                                           int32_t t, int i0, int sentIdx, uint32_t sent, int& rel) {
+  const int64_t limL = n - static_cast<int64_t>(t);
   const int lim = limL < static_cast<int64_t>(m) ? static_cast<int>(limL) : m;
   rel = 0;
   if (i0 >= lim) return i0;
   int i = i0;
-  const uint8_t* tp = P.ix.text + t + i;
+  const uint8_t* tp = text + t + i;
   const uint64_t* a = reinterpret_cast<const uint64_t*>(reinterpret_cast<uintptr_t>(tp) & ~static_cast<uintptr_t>(7));
   const unsigned sh = static_cast<unsigned>(reinterpret_cast<uintptr_t>(tp) & 7) * 8;
   uint64_t lo = __ldg(a);
   for (;;) {
     const uint64_t hi = __ldg(a + 1);  // the text section is padded: reads past n are in bounds
     const uint64_t tw = sh ? ((lo >> sh) | (hi << (64 - sh))) : lo;
-    uint64_t qw = query8<NT>(P, sm, r, L, rc, rb + i);
+    uint64_t qw = query8<NT>(sm, nw, src, L, rc, rb + i);
     const unsigned sd = static_cast<unsigned>(sentIdx - i);
     if (sd < 8u) qw = (qw & ~(0xffULL << (8 * sd))) | (static_cast<uint64_t>(sent) << (8 * sd));
     uint64_t x = tw ^ qw;
@@ -239,8 +235,70 @@ __device__ __forceinline__ int cmpSuffix(const LaneParams& P, const uint4* sm, u
   }
 }
 
+// The same comparison on the packed text, 32 characters per step: one 256-bit load of the text record, the query window
+// from shared memory (reverse-complemented in registers for the rc strand), XOR + count-leading-zeros.  A, C, G, T order
+// like their codes; a window with any other character before the first difference ('$' at a transcript end, N or IUPAC
+// in the read) is handed to cmpSuffixAscii from the current index on.  The sentinels '#' / '{' order below / above
+// every text character (checked when the index image is built).
+template <int NT>
+__device__ __forceinline__ int cmpSuffix(const LaneParams& P, const uint4* sm, uint32_t r, int L, bool rc, int rb, int m, int32_t t, int i0,
+                                         int sentIdx, uint32_t sent, int& rel) {
+  const int nw = static_cast<int>(P.nw);
+  const int64_t limL = P.ix.n - static_cast<int64_t>(t);
+  const int lim = limL < static_cast<int64_t>(m) ? static_cast<int>(limL) : m;
+  rel = 0;
+  if (i0 >= lim) return i0;
+  int i = i0;
+  bool exact = P.ix.text2 == nullptr;
+  if (!exact) {
+    const int cmpLim = (sentIdx >= 0 && sentIdx < lim) ? sentIdx : lim;  // ordinary characters live below cmpLim
+    while (i < cmpLim) {
+      const int64_t pos = static_cast<int64_t>(t) + i;
+      const Words8 rec = ldg256(P.ix.text2 + (pos >> 5));
+      const int s = static_cast<int>(pos & 31);
+      const uint64_t c0 = (static_cast<uint64_t>(rec.v[1]) << 32) | rec.v[0], c1 = (static_cast<uint64_t>(rec.v[3]) << 32) | rec.v[2];
+      const uint64_t tc = s ? ((c0 << (2 * s)) | (c1 >> (64 - 2 * s))) : c0;
+      const uint32_t tinv = __funnelshift_r(rec.v[4], rec.v[5], s);
+      const int qp = rb + i;
+      uint64_t qc;
+      uint32_t qinv;
+      if (!rc) loadWin<NT>(sm, nw, qp, qc, qinv);
+      else {  // strand positions qp .. qp+31 = forward positions q+31 .. q, complemented
+        const int q = L - 32 - qp;
+        uint64_t val;
+        uint32_t inv;
+        loadWin<NT>(sm, nw, q < 0 ? 0 : q, val, inv);
+        if (q < 0) { val >>= 2 * (-q); inv <<= -q; }
+        qc = kmerRC(val, 32);
+        qinv = __brev(inv);
+      }
+      const int left = cmpLim - i;
+      const int nv = left < 32 ? left : 32;
+      uint64_t x = tc ^ qc;
+      uint32_t bad = tinv | qinv;
+      if (nv < 32) { x &= ~0ULL << (64 - 2 * nv); bad &= (1u << nv) - 1u; }
+      const int d = x ? (__clzll(static_cast<long long>(x)) >> 1) : nv;
+      if (bad != 0u && (__ffs(bad) - 1) <= d) { exact = true; break; }
+      if (d < nv) {
+        rel = ((qc >> (62 - 2 * d)) & 3ULL) < ((tc >> (62 - 2 * d)) & 3ULL) ? -1 : 1;
+        return i + d;
+      }
+      i += nv;
+    }
+    if (!exact) {
+      if (cmpLim < lim) { rel = sent == '#' ? -1 : 1; return cmpLim; }  // the sentinel meets a text character
+      return lim;
+    }
+  }
+  const int mate = r >= P.reads.n ? 1 : 0;
+  const uint64_t ri = r - static_cast<uint64_t>(mate) * P.reads.n;
+  const uint8_t* src = P.reads.off[mate] ? P.reads.seq[mate] + P.reads.off[mate][ri] : P.reads.seq[mate] + ri * P.reads.fixedLen;
+  return cmpSuffixAscii<NT>(P.ix.text, P.ix.n, sm, nw, src, L, rc, rb, m, t, i, sentIdx, sent, rel);
+}
+
 // k-mer and its reverse complement -> SA intervals; both table probes are in flight together.
-__device__ __forceinline__ void hashFind2(const DeviceIndex& ix, uint64_t ka, uint64_t kb, int2& ra, int2& rb) {
+// knownA / knownB: the filter already proved that key absent.
+__device__ __forceinline__ void hashFind2(const DeviceIndex& ix, uint64_t ka, uint64_t kb, bool knownA, bool knownB, int2& ra, int2& rb) {
   if (ix.hashKind) {  // -p index: the two BooPHF walks run one after the other (one inlined copy of the walk)
 #pragma unroll 1
     for (int which = 0; which < 2; ++which) {
@@ -252,25 +310,26 @@ __device__ __forceinline__ void hashFind2(const DeviceIndex& ix, uint64_t ka, ui
   // two 16-byte slots share a 32-byte sector: both are examined per probe (the scan order is still slot by slot, so the
   // first empty slot ends the search exactly as in hashFind)
   uint64_t sa = mix64(ka) & ix.tableMask & ~1ULL, sb = mix64(kb) & ix.tableMask & ~1ULL;
-  bool da = false, db = false;
+  bool da = knownA, db = knownB;
   ra = make_int2(-1, -1); rb = make_int2(-1, -1);
+  if (da && db) return;
   for (;;) {
-    uint4 a0, a1, b0, b1;
-    if (!da) { a0 = __ldg(ix.table + sa); a1 = __ldg(ix.table + sa + 1); }
-    if (!db) { b0 = __ldg(ix.table + sb); b1 = __ldg(ix.table + sb + 1); }
+    Words8 a, b;
+    if (!da) a = ldg256(ix.table + sa);
+    if (!db) b = ldg256(ix.table + sb);
     if (!da) {
-      const uint64_t k0 = (static_cast<uint64_t>(a0.y) << 32) | a0.x, k1 = (static_cast<uint64_t>(a1.y) << 32) | a1.x;
-      if (k0 == ka) { ra = make_int2(static_cast<int>(a0.z), static_cast<int>(a0.w)); da = true; }
+      const uint64_t k0 = (static_cast<uint64_t>(a.v[1]) << 32) | a.v[0], k1 = (static_cast<uint64_t>(a.v[5]) << 32) | a.v[4];
+      if (k0 == ka) { ra = make_int2(static_cast<int>(a.v[2]), static_cast<int>(a.v[3])); da = true; }
       else if (k0 == kEmptyKey) da = true;
-      else if (k1 == ka) { ra = make_int2(static_cast<int>(a1.z), static_cast<int>(a1.w)); da = true; }
+      else if (k1 == ka) { ra = make_int2(static_cast<int>(a.v[6]), static_cast<int>(a.v[7])); da = true; }
       else if (k1 == kEmptyKey) da = true;
       else sa = (sa + 2) & ix.tableMask;
     }
     if (!db) {
-      const uint64_t k0 = (static_cast<uint64_t>(b0.y) << 32) | b0.x, k1 = (static_cast<uint64_t>(b1.y) << 32) | b1.x;
-      if (k0 == kb) { rb = make_int2(static_cast<int>(b0.z), static_cast<int>(b0.w)); db = true; }
+      const uint64_t k0 = (static_cast<uint64_t>(b.v[1]) << 32) | b.v[0], k1 = (static_cast<uint64_t>(b.v[5]) << 32) | b.v[4];
+      if (k0 == kb) { rb = make_int2(static_cast<int>(b.v[2]), static_cast<int>(b.v[3])); db = true; }
       else if (k0 == kEmptyKey) db = true;
-      else if (k1 == kb) { rb = make_int2(static_cast<int>(b1.z), static_cast<int>(b1.w)); db = true; }
+      else if (k1 == kb) { rb = make_int2(static_cast<int>(b.v[6]), static_cast<int>(b.v[7])); db = true; }
       else if (k1 == kEmptyKey) db = true;
       else sb = (sb + 2) & ix.tableMask;
     }
@@ -311,6 +370,9 @@ enum : uint32_t {
 #ifndef RAPMAP_LANE_REFILL
 #define RAPMAP_LANE_REFILL 8   // fetch new reads once this many lanes of a warp are idle
 #endif
+#ifndef RAPMAP_LANE_SPIN
+#define RAPMAP_LANE_SPIN 4    // double misses (by the filter) a lane may consume per trip
+#endif
 #ifndef RAPMAP_LANE_CHUNK
 #define RAPMAP_LANE_CHUNK 256  // interval-arena records a warp reserves per atomic
 #endif
@@ -337,6 +399,9 @@ __global__ void __launch_bounds__(NT, MINB) sa_collect_lane_kernel(LaneParams P)
   int L = 0, rb = 0, lbIn = 0, ubIn = 0, l = 0, rr = 0, lcpLP = 0, lcpRP = 0, prevILow = 0, prevIHigh = 0;
   int mlen = 0, b0 = 0, b1 = 0, mQ = 0, pass = 0, guard = 0, prevMMPEnd = 0, nF = 0, nR = 0;
   uint32_t fwdHit = 0, rcHit = 0, fwdCov = 0, rcCov = 0;
+  bool ready = false;   // a k-mer (w, at lookPos) is waiting for its lookups
+  uint64_t w = 0;
+  int lookPos = 0;
 
   for (;;) {
     // ---------------- refill: idle lanes take the next reads of the batch
@@ -368,7 +433,7 @@ __global__ void __launch_bounds__(NT, MINB) sa_collect_lane_kernel(LaneParams P)
                 for (int j = 0; j < nw; ++j) smw[j * NT] = __ldg(src + j);
                 if (voteMode) for (uint32_t j = 0; j < 3 * P.voteWords; ++j) votes[j] = 0u;
                 L = static_cast<int>(len);
-                rb = 0; flags = 0; nF = 0; nR = 0; fwdHit = 0; rcHit = 0; fwdCov = 0; rcCov = 0;
+                rb = 0; flags = 0; nF = 0; nR = 0; fwdHit = 0; rcHit = 0; fwdCov = 0; rcCov = 0; ready = false;
                 st = LST_SCAN;
               }
             }
@@ -378,11 +443,12 @@ __global__ void __launch_bounds__(NT, MINB) sa_collect_lane_kernel(LaneParams P)
       if (__ballot_sync(0xffffffffu, st != LST_EXIT) == 0u) break;
     }
 
-    // ---------------- A: advance to the next k-mer that needs a lookup
-    bool ready = false;
-    uint64_t w = 0;
-    int lookPos = 0;
-    if (st == LST_SCAN || st == LST_WSTART || st == LST_MM) {
+    // ---------------- A: advance to the next k-mer that needs a lookup; k-mers the L2-resident filter proves absent in
+    // both orientations are double misses and are consumed on the spot (up to RAPMAP_LANE_SPIN per trip): the ~31
+    // windows that cover a sequencing error cost L2 round trips instead of trips through the whole state machine.
+    bool knownM = false, knownC = false;  // filter verdict "absent" for the waiting k-mer / its reverse complement
+    for (int spin = 0; spin < RAPMAP_LANE_SPIN; ++spin) {
+      if (ready || !(st == LST_SCAN || st == LST_WSTART || st == LST_MM)) break;
       const bool rc = (flags & LF_RC) != 0u;
       for (;;) {
         if (st == LST_MM) lookPos = rb + mlen - (k - 1);  // mismatching k-mer after an interval, :599-616
@@ -408,13 +474,29 @@ __global__ void __launch_bounds__(NT, MINB) sa_collect_lane_kernel(LaneParams P)
         ready = true;
         break;
       }
+      if (!ready || P.ix.filter == nullptr) break;
+      {
+        uint64_t wa, wb;
+        uint32_t ma, mb;
+        filterSlot(mix64(w), P.ix.filterShift, wa, ma);
+        filterSlot(mix64(kmerRC(w, k)), P.ix.filterShift, wb, mb);
+        const uint32_t fa = ldgKeep(P.ix.filter + wa), fb = ldgKeep(P.ix.filter + wb);
+        knownM = (fa & ma) != ma;
+        knownC = (fb & mb) != mb;
+      }
+      if (!(knownM && knownC)) break;
+      // double miss: no counter moves (strandHits / otherStrandHits, :541-546,:671); the walk steps one base (:673)
+      ready = false; knownM = false; knownC = false;
+      if (voteMode && st != LST_SCAN) voteLane(votes, P.voteWords, rc, lookPos, L, k, false, false);
+      if (st == LST_MM) st = LST_POSTMM; else ++rb;
     }
-    __syncwarp();  // all lanes meet before the lookup phase
+    __syncwarp();  // all lanes meet before the table phase
 
-    // ---------------- B: one pair of lookups (k-mer, reverse complement)
+    // ---------------- B: one pair of table lookups (k-mer, reverse complement)
     if (ready) {
+      ready = false;
       int2 fm, fc;
-      hashFind2(P.ix, w, kmerRC(w, k), fm, fc);
+      hashFind2(P.ix, w, kmerRC(w, k), knownM, knownC, fm, fc);
       const bool hm = fm.x >= 0, hc = fc.x >= 0;
       const bool rc = (flags & LF_RC) != 0u;
       if (st == LST_SCAN) {
@@ -457,7 +539,11 @@ __global__ void __launch_bounds__(NT, MINB) sa_collect_lane_kernel(LaneParams P)
       else { cc = static_cast<int>((static_cast<int64_t>(l) + rr) >> 1); i0 = lcpLP < lcpRP ? lcpLP : lcpRP; }
       if (pass == 1 || pass == 2) { m = mlen + 1; sentIdx = m - 1; sent = pass == 1 ? '#' : '{'; }
       else m = mQ;
+#ifdef RAPMAP_LDCG
+      const int32_t t = __ldcg(P.ix.SA + cc);
+#else
       const int32_t t = __ldg(P.ix.SA + cc);
+#endif
       int rel;
       const int i = cmpSuffix<NT>(P, sm, r, L, (flags & LF_RC) != 0u, rb, m, t, i0, sentIdx, sent, rel);
       if (pass == 3) {  // :109-126
