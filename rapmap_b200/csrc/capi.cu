@@ -171,6 +171,8 @@ struct rapmap_cuda_mapper {
   uint32_t lpad{0}, pmax{0}, warpSmem{0}, packOff{0}, ctxOff{0}, voteOff{0};
   // stage 1, lane-per-read form
   bool laneKernel{true};
+  bool laneMap{false};
+  int gridLaneMap{0};
   uint4* dPacked{nullptr};
   IntervalRec* dIvScratch{nullptr};
   uint32_t ivStride{0};
@@ -202,6 +204,12 @@ static constexpr int kWarps = 8;
 #ifndef RAPMAP_LANE_MINB
 #define RAPMAP_LANE_MINB 3
 #endif
+#ifndef RAPMAP_MAPLANE_CAP
+#define RAPMAP_MAPLANE_CAP 16
+#endif
+static constexpr int kMapLaneThreads = 128;                // lane-per-read hit resolution
+static constexpr int kMapLaneCap = RAPMAP_MAPLANE_CAP;     // SA entries per read it takes
+static constexpr uint32_t kMapLaneSmem = 2u * kMapLaneCap * kMapLaneThreads * 8u;
 static constexpr int kLaneThreads = RAPMAP_LANE_THREADS;  // lane-per-read SA-lookup kernel: threads per block
 static constexpr int kLaneMinBlocks = RAPMAP_LANE_MINB;   // 3 x 256 threads, 80 registers: the 64-register build spills and is 13 % slower
 
@@ -555,6 +563,16 @@ int rapmap_cuda_mapper_create(const rapmap_cuda_index_t* idx, const rapmap_cuda_
       M_TRY(cudaMalloc(&m->dVoteScratch, static_cast<uint64_t>(m->gridLane) * kLaneThreads * 3 * m->voteWords * 4));
     }
   }
+  {  // lane-per-read form of kernel 2 for plain quasimap (no chaining, no position lists); RAPMAP_B200_K2=warp turns it off
+    const char* sel = std::getenv("RAPMAP_B200_K2");
+    m->laneMap = !d.selAln && !d.fuzzy && !d.doChaining && !(sel && std::string(sel) == "warp");
+    if (m->laneMap) {
+      M_TRY(cudaFuncSetAttribute(hits_to_mappings_lane_kernel<kMapLaneThreads, kMapLaneCap>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMapLaneSmem)));
+      M_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hits_to_mappings_lane_kernel<kMapLaneThreads, kMapLaneCap>, kMapLaneThreads, kMapLaneSmem));
+      if (occ < 1) return bail("hits_to_mappings_lane_kernel does not fit on an SM");
+      m->gridLaneMap = m->numSMs * occ;
+    }
+  }
   m->mapSmem = static_cast<uint32_t>(workAreaBytes(m->smemEntries)) * kWarps;
   M_TRY(cudaFuncSetAttribute(hits_to_mappings_kernel<kWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(m->mapSmem)));
   M_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hits_to_mappings_kernel<kWarps>, kWarps * 32, m->mapSmem));
@@ -664,6 +682,12 @@ int rapmap_cuda_map_batch(rapmap_cuda_mapper_t* m, const rapmap_read_batch_t* re
     mp.posPool = m->dPosPool; mp.posCap = m->posCap; mp.posCursor = m->dCtl + 2;
     mp.scratch = m->dScratch; mp.scratchEntries = m->scratchEntries; mp.scratchStride = m->scratchStride; mp.smemEntries = m->smemEntries;
     mp.status = m->dCtl + 3;
+    if (m->laneMap) {  // small reads thread-per-read; the rest (marked) by the warp-per-read kernel below
+      const int gl = static_cast<int>(std::min<uint64_t>(m->gridLaneMap, (bv.numReads + kMapLaneThreads - 1) / kMapLaneThreads));
+      hits_to_mappings_lane_kernel<kMapLaneThreads, kMapLaneCap><<<gl, kMapLaneThreads, kMapLaneSmem, st>>>(mp);
+      ++launches;
+      mp.skipDone = 1;
+    }
     int g2 = static_cast<int>(std::min<uint64_t>(m->gridMap, (bv.numReads + kWarps - 1) / kWarps));
     hits_to_mappings_kernel<kWarps><<<g2, kWarps * 32, m->mapSmem, st>>>(mp);
     ++launches;

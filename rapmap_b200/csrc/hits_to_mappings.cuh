@@ -36,7 +36,10 @@ struct MapParams {
   uint64_t scratchStride;
   uint32_t smemEntries;
   uint32_t* status;
+  uint8_t skipDone;          // 1: reads already resolved by hits_to_mappings_lane_kernel are skipped (nQA != kTodoMark)
 };
+
+static constexpr uint32_t kTodoMark = 0xFFFFFFFFu;
 
 // Work-area view (either shared memory or the warp's global strip); every array has `cap` entries.
 struct WorkArea {
@@ -400,6 +403,7 @@ __global__ void __launch_bounds__(WARPS * 32) hits_to_mappings_kernel(MapParams 
   const bool needPos = P.opts.selAln || P.opts.fuzzy;
 
   for (uint64_t r = gw; r < P.numReads; r += static_cast<uint64_t>(gridDim.x) * WARPS) {
+    if (P.skipDone && P.qsumm[r].nQA != kTodoMark) continue;
     ReadSummary s = P.summ[r];
     QASummary out;
     out.qaOff = 0; out.nQA = 0;
@@ -504,6 +508,212 @@ __global__ void __launch_bounds__(WARPS * 32) hits_to_mappings_kernel(MapParams 
     }
     if (lane == 0) { out.qaOff = off; out.nQA = nFinal; P.qsumm[r] = out; }
     __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Lane-per-read form for the common small case: no chaining / position lists (plain quasimap), at most LANE_MAXIV
+// intervals and CAP expanded SA entries per read.  One thread resolves one read: the three dependent loads per SA entry
+// (SA -> rank record -> txpOffsets) are issued for ALL entries of the read stage by stage, so a lane has up to CAP
+// loads in flight and a warp 32 reads; the (tid, interval order, entry) keys are insertion-sorted in the lane's
+// shared-memory strip (interleaved across the block), segments are resolved with the same rules as resolveStrand
+// (strict / consensus intersection, leftmost anchor, PERFECT flag of a single read-spanning interval), the two strands
+// are merged by tid.  Anything bigger is marked kTodoMark and left to the warp-per-read kernel.
+static constexpr int kLaneMaxIv = 8;
+
+template <int NT, int CAP>
+__global__ void __launch_bounds__(NT) hits_to_mappings_lane_kernel(MapParams P) {
+  extern __shared__ __align__(16) uint8_t smemLaneRaw[];
+  uint64_t* keys = reinterpret_cast<uint64_t*>(smemLaneRaw) + threadIdx.x;  // entry i at keys[i * NT]
+  uint64_t* vals = keys + CAP * NT;
+  const int lane = threadIdx.x & 31;
+  const DeviceIndex& ix = P.ix;
+  const DevOpts& o = P.opts;
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * NT;
+  for (uint64_t base = static_cast<uint64_t>(blockIdx.x) * NT + (threadIdx.x & ~31); base < P.numReads; base += stride) {
+    const uint64_t r = base + lane;
+    const bool valid = r < P.numReads;
+    int nF = 0, nR = 0;
+    uint32_t ivOff = 0, readLen = 0;
+    if (valid) {
+      const ReadSummary s = P.summ[r];
+      nF = s.nFwd; nR = s.nRc; ivOff = s.ivOff; readLen = s.readLen;
+    }
+    const int nIv = nF + nR;
+    bool todo = false;
+    uint32_t totF = 0, totR = 0;
+    const IntervalRec* ivs = P.arena + ivOff;
+    if (nIv > kLaneMaxIv) todo = true;
+    else {
+      for (int j = 0; j < nIv; ++j) {
+        const uint32_t span = static_cast<uint32_t>(ivs[j].end - ivs[j].begin);
+        if (j < nF) totF += span; else totR += span;
+      }
+      if (totF + totR > static_cast<uint32_t>(CAP)) todo = true;
+    }
+    const uint32_t total = todo ? 0u : totF + totR;
+    // ---- stage 1: one key/value per SA entry (forward strand first); value carries the SA index for now
+    if (total > 0) {
+      uint32_t at = 0;
+      for (int strand = 0; strand < 2; ++strand) {
+        const int j0 = strand ? nF : 0, j1 = strand ? nIv : nF, n = j1 - j0;
+        int minIdx = 0, bestSpan = 0x7fffffff;  // smallest-span interval is processed first (first wins on ties, :636-641)
+        for (int j = 0; j < n; ++j) {
+          const int span = ivs[j0 + j].end - ivs[j0 + j].begin;
+          if (n > 1 && span < bestSpan) { bestSpan = span; minIdx = j; }
+        }
+        for (int j = 0; j < n; ++j) {
+          const IntervalRec iv = ivs[j0 + j];
+          const uint32_t ord = (n == 1) ? 0u : (j == minIdx ? 0u : static_cast<uint32_t>(j < minIdx ? j + 1 : j));
+          const int span = iv.end - iv.begin;
+          for (int e = 0; e < span; ++e) {
+            keys[at * NT] = (static_cast<uint64_t>(ord) << 16) | static_cast<uint64_t>(e);
+            vals[at * NT] = (static_cast<uint64_t>(static_cast<uint32_t>(iv.begin + e)) << 32) | (static_cast<uint64_t>(iv.qpos) << 16) | iv.len;
+            ++at;
+          }
+        }
+      }
+    }
+    // ---- stages 2-4: SA entry -> text position -> transcript -> position in the transcript (loads of a stage are independent)
+#pragma unroll 4
+    for (uint32_t i = 0; i < total; ++i) {
+      const uint64_t v = vals[i * NT];
+      const int32_t g = __ldg(ix.SA + (v >> 32));
+      vals[i * NT] = (static_cast<uint64_t>(static_cast<uint32_t>(g)) << 32) | (v & 0xffffffffULL);
+    }
+#pragma unroll 4
+    for (uint32_t i = 0; i < total; ++i) {
+      const uint32_t tid = transcriptAt(ix, static_cast<int32_t>(vals[i * NT] >> 32));
+      keys[i * NT] |= static_cast<uint64_t>(tid) << 32;
+    }
+#pragma unroll 4
+    for (uint32_t i = 0; i < total; ++i) {
+      const uint64_t v = vals[i * NT];
+      const int32_t pos = static_cast<int32_t>(v >> 32) - __ldg(ix.txpOffsets + (keys[i * NT] >> 32));
+      vals[i * NT] = (static_cast<uint64_t>(static_cast<uint32_t>(pos)) << 32) | (v & 0xffffffffULL);
+    }
+    // ---- per strand: sort by (tid, ord, entry), resolve the transcript segments, compact {tid, pos, chain} in place
+    uint32_t nOutF = 0, nOutR = 0;
+    for (int strand = 0; strand < 2 && total > 0; ++strand) {
+      const uint32_t b0 = strand ? totF : 0u, cnt = strand ? totR : totF;
+      const int n = strand ? nR : nF;
+      if (cnt == 0) continue;
+      for (uint32_t i = 1; i < cnt; ++i) {  // insertion sort (keys are unique)
+        const uint64_t kx = keys[(b0 + i) * NT], vx = vals[(b0 + i) * NT];
+        int32_t j = static_cast<int32_t>(i) - 1;
+        while (j >= 0 && keys[(b0 + j) * NT] > kx) {
+          keys[(b0 + j + 1) * NT] = keys[(b0 + j) * NT];
+          vals[(b0 + j + 1) * NT] = vals[(b0 + j) * NT];
+          --j;
+        }
+        keys[(b0 + j + 1) * NT] = kx; vals[(b0 + j + 1) * NT] = vx;
+      }
+      int32_t required = n, maxSlack = 0;  // :613-628
+      if (n > 1 && o.consensusFraction < 1.0f) {
+        const float requiredFrac = __fmul_rn(static_cast<float>(n), o.consensusFraction);
+        const int32_t fl = static_cast<int32_t>(floorf(requiredFrac));
+        required = fl > 1 ? fl : 1;
+        maxSlack = n - required;
+      }
+      const uint32_t ivLen0 = ivs[strand ? nF : 0].len, ivQpos0 = ivs[strand ? nF : 0].qpos;
+      uint32_t nOut = 0;
+      for (int pass = 0; pass < 2; ++pass) {  // pass 1 only when the consensus rule leaves no transcript: then all are kept (:667-686)
+        const bool keepAll = pass == 1;
+        uint32_t i = 0;
+        nOut = 0;
+        while (i < cnt) {
+          const uint32_t tid = static_cast<uint32_t>(keys[(b0 + i) * NT] >> 32);
+          uint32_t e = i;
+          int32_t distinct = 0;
+          uint32_t lastOrd = 0xffffffffu, bestPos = 0xffffffffu;
+          int32_t leftmost = 0, minHit = 0x7fffffff;
+          while (e < cnt && static_cast<uint32_t>(keys[(b0 + e) * NT] >> 32) == tid) {
+            const uint32_t ord = static_cast<uint32_t>(keys[(b0 + e) * NT] >> 16) & 0xffffu;
+            if (ord != lastOrd) { ++distinct; lastOrd = ord; }
+            const uint64_t v = vals[(b0 + e) * NT];
+            if (vPos(v) < bestPos) { bestPos = vPos(v); leftmost = static_cast<int32_t>(vPos(v) - vQpos(v)); }  // leftmost anchor (:308-322)
+            const int32_t hp = static_cast<int32_t>(vPos(v)) - static_cast<int32_t>(ivQpos0);
+            minHit = hp < minHit ? hp : minHit;
+            ++e;
+          }
+          const bool active = (n == 1) || keepAll || distinct >= required;
+          if (active && pass == (keepAll ? 1 : 0)) {
+            // single interval (:716-807): smallest position, PERFECT iff the MMP spans the read (:741-746)
+            const uint32_t chain = (n == 1 && ivLen0 == readLen) ? 0u : 4u;
+            const int32_t pos = (n == 1) ? minHit : leftmost;
+            // in-place: nOut <= i, so the write never overtakes the scan; the scan of this segment is already done
+            keys[(b0 + nOut) * NT] = (static_cast<uint64_t>(tid) << 32) | chain;
+            vals[(b0 + nOut) * NT] = static_cast<uint64_t>(static_cast<uint32_t>(pos));
+            ++nOut;
+          }
+          i = e;
+        }
+        if (nOut > 0 || !(n > 1 && maxSlack > 0)) break;
+        // consensus mode and nothing active: every transcript is kept.  The in-place compaction wrote nothing (nOut == 0),
+        // so the sorted entries are intact for the second pass.
+      }
+      if (strand) nOutR = nOut; else nOutF = nOut;
+    }
+    // ---- merge by tid (:834-881; without chain scores the forward hit wins a shared transcript) and publish
+    uint32_t nFinal = 0;
+    if (total > 0) {
+      uint32_t a = 0, b = 0;
+      while (a < nOutF || b < nOutR) {
+        if (b >= nOutR) { ++a; }
+        else if (a >= nOutF) { ++b; }
+        else {
+          const uint32_t ta = static_cast<uint32_t>(keys[a * NT] >> 32), tb = static_cast<uint32_t>(keys[(totF + b) * NT] >> 32);
+          if (ta == tb) { ++a; ++b; } else if (ta < tb) ++a; else ++b;
+        }
+        ++nFinal;
+      }
+    }
+    const unsigned pm = __ballot_sync(0xffffffffu, nFinal > 0);
+    uint32_t off = 0;
+    if (pm) {
+      int incl = static_cast<int>(nFinal);
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+      }
+      const uint32_t tot = static_cast<uint32_t>(__shfl_sync(0xffffffffu, incl, 31));
+      uint32_t wbase = 0;
+      if (lane == 0) wbase = atomicAdd(P.qaCursor, tot);
+      wbase = __shfl_sync(0xffffffffu, wbase, 0);
+      off = wbase + static_cast<uint32_t>(incl) - nFinal;
+      if (static_cast<uint64_t>(wbase) + tot > P.qaCap) {
+        if (lane == 0) atomicOr(P.status, kStatQAArenaFull);
+        nFinal = 0;
+      }
+    }
+    if (nFinal > 0) {
+      uint32_t a = 0, b = 0, w = 0;
+      while (a < nOutF || b < nOutR) {
+        bool takeA;
+        if (b >= nOutR) takeA = true;
+        else if (a >= nOutF) takeA = false;
+        else {
+          const uint32_t ta = static_cast<uint32_t>(keys[a * NT] >> 32), tb = static_cast<uint32_t>(keys[(totF + b) * NT] >> 32);
+          if (ta == tb) { takeA = true; ++b; } else takeA = ta < tb;
+        }
+        const uint32_t src = takeA ? a : totF + b;
+        const uint64_t kx = keys[src * NT];
+        QARec q;
+        q.tid = static_cast<uint32_t>(kx >> 32);
+        q.pos = static_cast<int32_t>(static_cast<uint32_t>(vals[src * NT]));
+        q.posOff = 0; q.nAll = 1; q.oppOff = 0; q.nOpp = 0;
+        q.fwd = takeA ? 1 : 0; q.chain = static_cast<uint8_t>(kx & 0xffu); q.pad = 0;
+        P.qaArena[off + w] = q;
+        ++w;
+        if (takeA) ++a; else ++b;
+      }
+    }
+    if (valid) {
+      QASummary out;
+      out.qaOff = off; out.nQA = todo ? kTodoMark : nFinal;
+      P.qsumm[r] = out;
+    }
   }
 }
 
