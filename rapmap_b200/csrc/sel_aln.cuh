@@ -49,7 +49,8 @@ struct SelAlnWork {
   int32_t* taskRef{nullptr};     // -1: own score, >= 0: copy of that slot (alignment cache hit)
   uint64_t* taskHash{nullptr};   // window hash, 0 = task never reaches the cache stage
   DPJob* jobs{nullptr};
-  uint32_t* jobCursor{nullptr};
+  uint32_t* slowList{nullptr};   // DP jobs the thread-per-job kernel leaves to the general warp kernel
+  uint32_t* jobCursor{nullptr};  // [0] job count, [1] slow-list count
   int32_t* hitScore{nullptr};    // [hitsCap] final per-hit score (INT_MIN = dropped)
   int32_t* pairBest{nullptr};    // [maxBatch]
   uint32_t* outCount{nullptr};   // [maxBatch + 1]
@@ -62,7 +63,7 @@ struct SelAlnWork {
 };
 
 inline void selAlnFree(SelAlnWork& w) {
-  cudaFree(w.taskScore); cudaFree(w.taskRef); cudaFree(w.taskHash); cudaFree(w.jobs); cudaFree(w.jobCursor); cudaFree(w.hitScore);
+  cudaFree(w.taskScore); cudaFree(w.taskRef); cudaFree(w.taskHash); cudaFree(w.jobs); cudaFree(w.slowList); cudaFree(w.jobCursor); cudaFree(w.hitScore);
   cudaFree(w.pairBest); cudaFree(w.outCount); cudaFree(w.outOff); cudaFree(w.outHits);
   if (w.hTotal) cudaFreeHost(w.hTotal);
   w = SelAlnWork();
@@ -70,14 +71,15 @@ inline void selAlnFree(SelAlnWork& w) {
 
 inline cudaError_t selAlnReserve(SelAlnWork& w, uint64_t hits) {
   if (hits <= w.hitsCap) return cudaSuccess;
-  cudaFree(w.taskScore); cudaFree(w.taskRef); cudaFree(w.taskHash); cudaFree(w.jobs); cudaFree(w.hitScore); cudaFree(w.outHits);
-  w.taskScore = nullptr; w.taskRef = nullptr; w.taskHash = nullptr; w.jobs = nullptr; w.hitScore = nullptr; w.outHits = nullptr;
+  cudaFree(w.taskScore); cudaFree(w.taskRef); cudaFree(w.taskHash); cudaFree(w.jobs); cudaFree(w.slowList); cudaFree(w.hitScore); cudaFree(w.outHits);
+  w.slowList = nullptr; w.taskScore = nullptr; w.taskRef = nullptr; w.taskHash = nullptr; w.jobs = nullptr; w.hitScore = nullptr; w.outHits = nullptr;
   uint64_t cap = hits + hits / 4 + 1024;
   cudaError_t e;
   if ((e = cudaMalloc(&w.taskScore, cap * 2 * 4)) != cudaSuccess) return e;
   if ((e = cudaMalloc(&w.taskRef, cap * 2 * 4)) != cudaSuccess) return e;
   if ((e = cudaMalloc(&w.taskHash, cap * 2 * 8)) != cudaSuccess) return e;
   if ((e = cudaMalloc(&w.jobs, cap * 2 * sizeof(DPJob))) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&w.slowList, cap * 2 * 4)) != cudaSuccess) return e;
   if ((e = cudaMalloc(&w.hitScore, cap * 4)) != cudaSuccess) return e;
   if ((e = cudaMalloc(&w.outHits, cap * sizeof(rapmap_hit_t))) != cudaSuccess) return e;
   w.hitsCap = cap;
@@ -88,7 +90,7 @@ inline cudaError_t selAlnAlloc(SelAlnWork& w, uint64_t maxBatch, uint32_t maxRea
   w.maxBatch = maxBatch;
   w.maxReadLen = maxReadLen;
   cudaError_t e;
-  if ((e = cudaMalloc(&w.jobCursor, 4)) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&w.jobCursor, 8)) != cudaSuccess) return e;
   if ((e = cudaMalloc(&w.pairBest, maxBatch * 4)) != cudaSuccess) return e;
   if ((e = cudaMalloc(&w.outCount, (maxBatch + 1) * 4)) != cudaSuccess) return e;
   if ((e = cudaMalloc(&w.outOff, (maxBatch + 1) * 8)) != cudaSuccess) return e;
@@ -282,6 +284,9 @@ struct KswParams {
   int8_t mat0, mat1, matN;  // match, mismatch, wildcard scores of the 5x5 matrix (KSW2Aligner.cpp:74-96)
   int8_t q, e;
   int32_t w;
+  const uint32_t* jobIdx;   // nullptr: jobs[0 .. *jobCount); else the jobs listed here (the ones the lane kernel left)
+  uint32_t* slowList;       // lane kernel: jobs it does not take
+  uint32_t* slowCount;
 };
 
 // General path: every geometry (any bandwidth, short windows).  State in shared memory, laid out as the reference's
@@ -523,7 +528,7 @@ __global__ void __launch_bounds__(WARPS * 32) ksw_extz_kernel(KswParams P) {
   uint8_t* mem = smem + static_cast<size_t>(warp) * P.warpSmemBytes;
   const uint32_t nJobs = *P.jobCount;
   for (uint32_t j = blockIdx.x * WARPS + warp; j < nJobs; j += gridDim.x * WARPS) {
-    const DPJob jb = P.jobs[j];
+    const DPJob jb = P.jobs[P.jobIdx ? P.jobIdx[j] : j];
     int minSc = P.mat1 < P.matN ? P.mat1 : P.matN;
     minSc = minSc < P.mat0 ? minSc : P.mat0;
     int32_t sc;
@@ -532,6 +537,128 @@ __global__ void __launch_bounds__(WARPS * 32) ksw_extz_kernel(KswParams P) {
     else sc = kswGeneral(P, jb, mem, lane);
     if (lane == 0) P.taskScore[jb.slot] = sc;
     __syncwarp();
+  }
+}
+
+// Thread-per-job form of the fast path (same preconditions as kswBand32: 0 <= w <= 15, window >= 64, and the code
+// strips fit the thread's shared-memory strip).  ksw_extz_kernel spends ~180 warp instructions per anti-diagonal of
+// ONE job (profiles/r01g: 47 G instructions, issue-bound at 70 %); here a thread owns a job, so a warp instruction
+// advances 32 jobs.  The 32 live columns of the band sit in registers in band order (slot c = column st + c): one packed
+// word {u, v, x, y} and one int32 H per column, the scores as 2-bit codes; when the 16-aligned window start moves, the
+// state shifts down 16 slots and the upper 16 restart from the kcalloc state.  The sweep over the slots is fully unrolled
+// (static register indices) and runs in ascending column order carrying the previous column's OLD x / v, which is what
+// the SSE code reads.  Cell arithmetic, stale lanes, block rounding and the H[] track are those of kswBand32.
+template <int NT, int SEQ>
+__global__ void __launch_bounds__(NT, 4) ksw_extz_lane_kernel(KswParams P) {
+  extern __shared__ __align__(16) uint8_t laneSeq[];
+  uint8_t* my = laneSeq + threadIdx.x;  // byte b of this thread's strip at my[b * NT]
+  const uint32_t nJobs = *P.jobCount;
+  const int8_t q = P.q, e = P.e;
+  const int qe = q + e;
+  const int8_t qe2 = static_cast<int8_t>((q + e) * 2);
+  const uint8_t maxSc = static_cast<uint8_t>(static_cast<int8_t>(P.mat0 + (q + e) * 2));
+  int minSc = P.mat1 < P.matN ? P.mat1 : P.matN;
+  minSc = minSc < P.mat0 ? minSc : P.mat0;
+  const int w = P.w;
+  for (uint32_t j = blockIdx.x * NT + threadIdx.x; j < nJobs; j += gridDim.x * NT) {
+    const DPJob jb = P.jobs[j];
+    const int qlen = jb.rlen, tlen = jb.tlen1;
+    const int tl16 = (tlen + 15) / 16 * 16, ql16 = (qlen + 15) / 16 * 16 + 16;
+    const bool degenerate = qlen <= 0 || tlen <= 0 || -minSc > 2 * (q + e);
+    if (degenerate || w < 0 || w > 15 || tlen < 64 || tl16 + ql16 > SEQ) {
+      P.slowList[atomicAdd(P.slowCount, 1u)] = j;
+      continue;
+    }
+    uint8_t* sf = my;
+    uint8_t* qr = my + static_cast<size_t>(tl16) * NT;
+    for (int i = 0; i < tl16 + ql16; ++i) my[static_cast<size_t>(i) * NT] = 0;
+    const uint8_t* read;
+    uint32_t rl;
+    readSpan(P.reads, jb.read, read, rl);
+    for (int t = 0; t < qlen; ++t) qr[static_cast<size_t>(t) * NT] = nt4(queryChar(read, rl, jb.rc != 0, jb.rskip + (qlen - 1 - t)));
+    for (int t = 0; t < tlen; ++t) sf[static_cast<size_t>(t) * NT] = nt4(__ldg(P.ix.text + jb.tpos + t));
+
+    uint32_t cell[32];
+    int32_t H[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) { cell[c] = 0u; H[c] = kKswNegInf; }
+    uint32_t sbLo = 0u, sbHi = 0u;  // 2-bit score codes of slots 0..15 / 16..31: 0 = kcalloc zero, 1 = match, 2 = mismatch, 3 = wildcard
+    int32_t Hleft = kKswNegInf, mqe = kKswNegInf, mte = kKswNegInf;
+    int curSt = 0;
+    for (int r = 0; r < qlen + tlen - 1; ++r) {
+      int st = 0, en = tlen - 1;
+      if (st < r - qlen + 1) st = r - qlen + 1;
+      if (en > r) en = r;
+      if (st < ((r - w + 1) >> 1)) st = (r - w + 1) >> 1;
+      if (en > ((r + w) >> 1)) en = (r + w) >> 1;
+      if (st > en) break;
+      const int st0 = st, en0 = en;
+      st = st / 16 * 16; en = (en + 16) / 16 * 16 - 1;
+      int xPrev, vPrev;  // old x / v of the column left of the current one
+      if (st != curSt) {  // the window moved one 16-lane block to the right: column st - 1 was slot 15
+        xPrev = static_cast<int8_t>(cell[15] >> 16); vPrev = static_cast<int8_t>(cell[15] >> 8);
+        Hleft = H[15];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) { cell[c] = cell[c + 16]; H[c] = H[c + 16]; cell[c + 16] = 0u; H[c + 16] = kKswNegInf; }
+        sbLo = sbHi; sbHi = 0u;
+        curSt = st;
+      } else if (st > 0) { xPrev = 0; vPrev = 0; }
+      else { xPrev = 0; vPrev = r ? q : 0; }
+      const int sEnd = st0 + ((en0 - st0) / 16 + 1) * 16;
+      const int cR = (en >= r) ? r - st : -1, cSt0 = st0 - st, cSEnd = sEnd - st, cEn = en - st, cEn0 = en0 - st;
+      const uint8_t* sfRow = sf + static_cast<size_t>(st) * NT;
+      const uint8_t* qrRow = qr + static_cast<size_t>(qlen - 1 - r + st) * NT;
+      int32_t hpCap = Hleft, hEn = 0, hSt = 0;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        const uint32_t cw = cell[c];
+        int8_t u = static_cast<int8_t>(cw), v = static_cast<int8_t>(cw >> 8), x = static_cast<int8_t>(cw >> 16), y = static_cast<int8_t>(cw >> 24);
+        const int8_t xo = x, vo = v;
+        if (c == cR) { y = 0; u = r ? q : 0; }
+        uint32_t code = ((c < 16 ? sbLo : sbHi) >> (2 * (c & 15))) & 3u;
+        if (c >= cSt0 && c < cSEnd) {
+          const uint8_t a1 = sfRow[static_cast<size_t>(c) * NT], a2 = qrRow[static_cast<size_t>(c) * NT];
+          code = (a1 == 4 || a2 == 4) ? 3u : (a1 == a2 ? 1u : 2u);
+          if (c < 16) sbLo = (sbLo & ~(3u << (2 * (c & 15)))) | (code << (2 * (c & 15)));
+          else sbHi = (sbHi & ~(3u << (2 * (c & 15)))) | (code << (2 * (c & 15)));
+        }
+        if (c <= cEn) {
+          const int8_t s = code == 0u ? static_cast<int8_t>(0) : (code == 1u ? P.mat0 : (code == 2u ? P.mat1 : P.matN));
+          const int8_t xt1 = static_cast<int8_t>(xPrev), vt1 = static_cast<int8_t>(vPrev);
+          const int8_t ut = u;
+          int8_t z = static_cast<int8_t>(s + qe2);
+          int8_t aa = static_cast<int8_t>(xt1 + vt1);
+          int8_t bb = static_cast<int8_t>(y + ut);
+          z = z > aa ? z : aa;
+          uint8_t zu = static_cast<uint8_t>(z), bu = static_cast<uint8_t>(bb);
+          zu = zu > bu ? zu : bu;
+          zu = zu < maxSc ? zu : maxSc;
+          z = static_cast<int8_t>(zu);
+          u = static_cast<int8_t>(z - vt1);
+          v = static_cast<int8_t>(z - ut);
+          z = static_cast<int8_t>(z - q);
+          aa = static_cast<int8_t>(aa - z);
+          bb = static_cast<int8_t>(bb - z);
+          x = aa > 0 ? aa : 0;
+          y = bb > 0 ? bb : 0;
+        }
+        cell[c] = static_cast<uint32_t>(static_cast<uint8_t>(u)) | (static_cast<uint32_t>(static_cast<uint8_t>(v)) << 8) |
+                  (static_cast<uint32_t>(static_cast<uint8_t>(x)) << 16) | (static_cast<uint32_t>(static_cast<uint8_t>(y)) << 24);
+        if (r > 0) {
+          if (c == cEn0 - 1) hpCap = H[c];  // H[en0 - 1] before this diagonal touches it
+          if (c >= cSt0 && c < cEn0) H[c] += static_cast<int32_t>(static_cast<uint8_t>(v)) - qe;
+          if (c == cEn0) H[c] = en0 > 0 ? hpCap + static_cast<int32_t>(static_cast<uint8_t>(u)) - qe : H[c] + static_cast<int32_t>(static_cast<uint8_t>(v)) - qe;
+        } else if (c == 0) {
+          H[c] = static_cast<int32_t>(static_cast<uint8_t>(v)) - qe - qe;
+        }
+        if (c == cEn0) hEn = H[c];
+        if (c == cSt0) hSt = H[c];
+        xPrev = xo; vPrev = vo;
+      }
+      if (en0 == tlen - 1 && hEn > mte) mte = hEn;
+      if (r - st0 == qlen - 1 && hSt > mqe) mqe = hSt;
+    }
+    P.taskScore[jb.slot] = mqe > mte ? mqe : mte;
   }
 }
 
@@ -621,7 +748,7 @@ inline int selAlnRun(SelAlnWork& w, const DeviceIndex& ix, const DevOpts& opts, 
   sp.ix = ix; sp.opts = opts; sp.reads = bv; sp.numPairs = n; sp.pairedInput = paired ? 1 : 0; sp.hits = dHits; sp.pairOff = dPairOff;
   sp.taskScore = w.taskScore; sp.taskRef = w.taskRef; sp.taskHash = w.taskHash; sp.jobs = w.jobs; sp.jobCursor = w.jobCursor; sp.hitScore = w.hitScore;
   sp.pairBest = w.pairBest; sp.outCount = w.outCount; sp.outOff = w.outOff; sp.outHits = w.outHits; sp.maxReadLen = w.maxReadLen;
-  if ((e = cudaMemsetAsync(w.jobCursor, 0, 4, st)) != cudaSuccess) return cuFail("memset", e);
+  if ((e = cudaMemsetAsync(w.jobCursor, 0, 8, st)) != cudaSuccess) return cuFail("memset", e);
   constexpr int W = 8;
   int g = static_cast<int>(std::min<uint64_t>(static_cast<uint64_t>(numSMs) * 8, (n + W - 1) / W));
   selaln_prepare_kernel<W><<<g, W * 32, 0, st>>>(sp);
@@ -649,6 +776,20 @@ inline int selAlnRun(SelAlnWork& w, const DeviceIndex& ix, const DevOpts& opts, 
   int occ = 1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ksw_extz_kernel<KW>, KW * 32, smemK);
   if (occ < 1) occ = 1;
+  static const bool laneKsw = !(std::getenv("RAPMAP_B200_KSW") && std::string(std::getenv("RAPMAP_B200_KSW")) == "warp");
+  if (laneKsw) {  // thread-per-job kernel first; what it leaves (short windows, wide bands, long reads) goes to the warp kernel
+    constexpr int LT = 128, LSEQ = 320;
+    kp.slowList = w.slowList; kp.slowCount = w.jobCursor + 1;
+    const uint32_t smemL = LT * LSEQ;
+    if ((e = cudaFuncSetAttribute(ksw_extz_lane_kernel<LT, LSEQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smemL))) != cudaSuccess)
+      return cuFail("cudaFuncSetAttribute(ksw lane)", e);
+    int occL = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occL, ksw_extz_lane_kernel<LT, LSEQ>, LT, smemL);
+    if (occL < 1) occL = 1;
+    ksw_extz_lane_kernel<LT, LSEQ><<<numSMs * occL, LT, smemL, st>>>(kp);
+    ++*launches;
+    kp.jobIdx = w.slowList; kp.jobCount = w.jobCursor + 1;
+  }
   ksw_extz_kernel<KW><<<numSMs * occ, KW * 32, smemK, st>>>(kp);
   ++*launches;
   int g3 = static_cast<int>(std::min<uint64_t>(static_cast<uint64_t>(numSMs) * 8, (n + 255) / 256));
