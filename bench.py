@@ -266,11 +266,11 @@ def main():
             sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        stages = {"sa": 0.0, "map": 0.0, "merge": 0.0, "selaln": 0.0, "h2d": 0.0, "d2h": 0.0, "launch": 0, "hits": 0, "retries": 0}
+        stages = {"pack": 0.0, "sa": 0.0, "map": 0.0, "merge": 0.0, "selaln": 0.0, "h2d": 0.0, "d2h": 0.0, "launch": 0, "hits": 0, "retries": 0}
         for i in range(steps):
             r = fn(warmup + i)
             t = mapper.timing()
-            stages["sa"] += t.ms_sa_collect; stages["map"] += t.ms_hits_to_mappings; stages["merge"] += t.ms_merge; stages["selaln"] += t.ms_sel_aln
+            stages["pack"] += t.ms_pack_reads; stages["sa"] += t.ms_sa_collect; stages["map"] += t.ms_hits_to_mappings; stages["merge"] += t.ms_merge; stages["selaln"] += t.ms_sel_aln
             stages["h2d"] += t.ms_h2d; stages["d2h"] += t.ms_d2h; stages["launch"] += t.launches; stages["hits"] += r.num_hits; stages["retries"] += t.retries
         e1.record(stream)
         torch.cuda.synchronize()
@@ -359,7 +359,7 @@ def main():
         sa_ms = st_res["sa"] / args.steps
         achieved = alg * B / (sa_ms / 1e3) / 1e9
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "sa_collect_traffic.json")
+        tp = os.path.join(ROOT, "profiles", "sa_collect_traffic_selaln.json" if args.selaln else "sa_collect_traffic.json")
         if os.path.exists(tp):
             with open(tp) as f:
                 traffic = json.load(f).get("dram_bytes_per_launch")
@@ -395,9 +395,10 @@ def main():
                     "note": "one mapper (CUDA stream) per host thread, chunks round-robin; each call synchronous for its caller"},
             "gpu_launches": int(st_res["launch"]),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "sa_collect_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "roofline": {"bound": "hbm", "kernel": "sa_collect_lane_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "alg_bytes_per_pair": alg, "kernel_ms_per_launch": sa_ms,
-                         "stage_ms_per_step": {k: st_res[k] / args.steps for k in ("sa", "map", "merge", "selaln", "h2d", "d2h")}},
+                         "stage_ms_per_step": {k: st_res[k] / args.steps for k in ("pack", "sa", "map", "merge", "selaln", "h2d", "d2h")},
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel at this batch size (profiles/)" if traffic else None},
             "cpu_baseline": cpu,
             "hits_per_pair": st_res["hits"] / (B * args.steps),
             "ops_per_pair": ops_per_pair,

@@ -107,7 +107,7 @@ typedef struct {
 /* Per-stage device time of the last rapmap_cuda_map_batch call, measured with CUDA events on the
  * mapper's stream (milliseconds), and launch counts. */
 typedef struct {
-  float ms_h2d, ms_sa_collect, ms_hits_to_mappings, ms_merge, ms_sel_aln, ms_compact, ms_d2h, ms_total;
+  float ms_h2d, ms_sa_collect, ms_hits_to_mappings, ms_merge, ms_sel_aln, ms_pack_reads, ms_d2h, ms_total;  /* ms_sa_collect: the SA-lookup kernel alone; ms_pack_reads: the 2-bit read packer before it */
   uint32_t launches;        /* kernels launched by the call */
   uint32_t retries;         /* arena-overflow relaunches    */
   uint64_t sa_intervals;    /* SAIntervalHit records produced by the SA-lookup kernel */

@@ -103,7 +103,7 @@ class HitBatch(C.Structure):
 class Timing(C.Structure):
     _fields_ = [
         ("ms_h2d", C.c_float), ("ms_sa_collect", C.c_float), ("ms_hits_to_mappings", C.c_float), ("ms_merge", C.c_float),
-        ("ms_sel_aln", C.c_float), ("ms_compact", C.c_float), ("ms_d2h", C.c_float), ("ms_total", C.c_float),
+        ("ms_sel_aln", C.c_float), ("ms_pack_reads", C.c_float), ("ms_d2h", C.c_float), ("ms_total", C.c_float),
         ("launches", C.c_uint32), ("retries", C.c_uint32), ("sa_intervals", C.c_uint64),
     ]
 

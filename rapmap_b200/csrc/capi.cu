@@ -666,6 +666,7 @@ int rapmap_cuda_map_batch(rapmap_cuda_mapper_t* m, const rapmap_read_batch_t* re
       lp.ivScratch = m->dIvScratch; lp.ivStride = m->ivStride; lp.voteScratch = m->dVoteScratch; lp.voteWords = m->voteWords; lp.readCursor = m->dCtl + 4;
       const int g0 = static_cast<int>(std::min<uint64_t>(static_cast<uint64_t>(m->numSMs) * 8, (bv.numReads + 7) / 8));
       pack_reads_kernel<<<g0, 256, 0, st>>>(lp);
+      CU_TRY(cudaEventRecord(m->ev[8], st));
       const int g1 = static_cast<int>(std::min<uint64_t>(m->gridLane, (bv.numReads + kLaneThreads - 1) / kLaneThreads));
       sa_collect_lane_kernel<kLaneThreads, kLaneMinBlocks><<<g1, kLaneThreads, m->laneSmem, st>>>(lp);
       launches += 2;
@@ -783,7 +784,8 @@ int rapmap_cuda_map_batch(rapmap_cuda_mapper_t* m, const rapmap_read_batch_t* re
   if (m->dopts.selAln) out->counters[3] = total;  // totHits is taken after the score filter (reference src/RapMapSAMapper.cpp:702)
   auto ms = [&](int a, int b) { float t = 0; cudaEventElapsedTime(&t, m->ev[a], m->ev[b]); return t; };
   m->timing.ms_h2d = ms(0, 1);
-  m->timing.ms_sa_collect = ms(1, 2);
+  m->timing.ms_sa_collect = m->laneKernel ? ms(8, 2) : ms(1, 2);
+  m->timing.ms_pack_reads = m->laneKernel ? ms(1, 8) : 0.0f;
   m->timing.ms_hits_to_mappings = ms(2, 3);
   m->timing.ms_merge = ms(3, 4) + ms(4, 5);
   m->timing.ms_sel_aln = ms(5, 6);

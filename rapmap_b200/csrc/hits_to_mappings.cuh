@@ -227,7 +227,10 @@ __device__ __forceinline__ uint32_t chainSegment(WorkArea& w, uint32_t b, uint32
 }
 
 // Resolves one strand: appends QARecs (ascending tid) to w.qa[nOut...], their positions to w.posTmp.
-__device__ __forceinline__ void resolveStrand(const MapParams& P, WorkArea& w, const IntervalRec* ivs, int nIv, bool isFw, uint32_t readLen,
+#ifndef RAPMAP_K2_STRAND_ATTR
+#define RAPMAP_K2_STRAND_ATTR __noinline__  // one copy of the strand code: the inlined pair thrashed the instruction cache (no_instruction stalls, profiles/r01g)
+#endif
+__device__ RAPMAP_K2_STRAND_ATTR void resolveStrand(const MapParams& P, WorkArea& w, const IntervalRec* ivs, int nIv, bool isFw, uint32_t readLen,
                                               int lane, uint32_t& nOut, uint32_t& posBase) {
   const DeviceIndex& ix = P.ix;
   const DevOpts& o = P.opts;

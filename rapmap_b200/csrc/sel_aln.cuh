@@ -543,20 +543,31 @@ __global__ void __launch_bounds__(WARPS * 32) ksw_extz_kernel(KswParams P) {
 // Thread-per-job form of the fast path (same preconditions as kswBand32: 0 <= w <= 15, window >= 64, and the code
 // strips fit the thread's shared-memory strip).  ksw_extz_kernel spends ~180 warp instructions per anti-diagonal of
 // ONE job (profiles/r01g: 47 G instructions, issue-bound at 70 %); here a thread owns a job, so a warp instruction
-// advances 32 jobs.  The 32 live columns of the band sit in registers in band order (slot c = column st + c): one packed
-// word {u, v, x, y} and one int32 H per column, the scores as 2-bit codes; when the 16-aligned window start moves, the
-// state shifts down 16 slots and the upper 16 restart from the kcalloc state.  The sweep over the slots is fully unrolled
-// (static register indices) and runs in ascending column order carrying the previous column's OLD x / v, which is what
-// the SSE code reads.  Cell arithmetic, stale lanes, block rounding and the H[] track are those of kswBand32.
+// advances 32 jobs, and the int8 lanes of the SSE code become byte lanes of 32-bit registers: the 32 live columns of
+// the band (slot c = column st + c) are 8 words each of u, v, x, y, s, updated with the wrapping byte-SIMD intrinsics
+// (__vadd4 / __vsub4 / __vmaxs4 / __vmaxu4 / __vminu4 = _mm_add_epi8 / _mm_sub_epi8 / _mm_max_epi8 / _mm_max_epu8 /
+// _mm_min_epu8), the left neighbours x[t-1], v[t-1] come from a byte permute of the OLD words, the int32 H[] track is one
+// register per column.  When the 16-aligned window start moves, the state shifts down 16 slots and the upper 16 restart
+// from the kcalloc state.  Everything is statically indexed (fully unrolled).  Stale lanes, block rounding and the H[]
+// track are those of kswBand32.
+__device__ __forceinline__ uint32_t rep4(int8_t v) { return static_cast<uint32_t>(static_cast<uint8_t>(v)) * 0x01010101u; }
+
+#ifndef RAPMAP_KSW_MINB
+#define RAPMAP_KSW_MINB 3  // 168 registers: the 128-register build spills ~600 bytes per thread and is 1.5x slower
+#endif
 template <int NT, int SEQ>
-__global__ void __launch_bounds__(NT, 4) ksw_extz_lane_kernel(KswParams P) {
+__global__ void __launch_bounds__(NT, RAPMAP_KSW_MINB) ksw_extz_lane_kernel(KswParams P) {
   extern __shared__ __align__(16) uint8_t laneSeq[];
-  uint8_t* my = laneSeq + threadIdx.x;  // byte b of this thread's strip at my[b * NT]
+  // strip of SEQ bytes per thread, interleaved word by word: byte b at ((b >> 2) * NT + tid) * 4 + (b & 3)
+  uint8_t* myB = laneSeq + static_cast<size_t>(threadIdx.x) * 4;
+  const uint32_t* myW = reinterpret_cast<const uint32_t*>(laneSeq) + threadIdx.x;
+  auto byteAt = [&](int b) -> uint8_t& { return myB[(static_cast<size_t>(b >> 2) * NT) * 4 + (b & 3)]; };
   const uint32_t nJobs = *P.jobCount;
   const int8_t q = P.q, e = P.e;
   const int qe = q + e;
-  const int8_t qe2 = static_cast<int8_t>((q + e) * 2);
-  const uint8_t maxSc = static_cast<uint8_t>(static_cast<int8_t>(P.mat0 + (q + e) * 2));
+  const uint32_t qe2x4 = rep4(static_cast<int8_t>((q + e) * 2)), qx4 = rep4(q);
+  const uint32_t maxScx4 = rep4(static_cast<int8_t>(P.mat0 + (q + e) * 2));
+  const uint32_t mat0x4 = rep4(P.mat0), mat1x4 = rep4(P.mat1), matNx4 = rep4(P.matN);
   int minSc = P.mat1 < P.matN ? P.mat1 : P.matN;
   minSc = minSc < P.mat0 ? minSc : P.mat0;
   const int w = P.w;
@@ -565,24 +576,24 @@ __global__ void __launch_bounds__(NT, 4) ksw_extz_lane_kernel(KswParams P) {
     const int qlen = jb.rlen, tlen = jb.tlen1;
     const int tl16 = (tlen + 15) / 16 * 16, ql16 = (qlen + 15) / 16 * 16 + 16;
     const bool degenerate = qlen <= 0 || tlen <= 0 || -minSc > 2 * (q + e);
-    if (degenerate || w < 0 || w > 15 || tlen < 64 || tl16 + ql16 > SEQ) {
+    if (degenerate || w < 0 || w > 15 || tlen < 64 || tl16 + ql16 + 36 > SEQ) {
       P.slowList[atomicAdd(P.slowCount, 1u)] = j;
       continue;
     }
-    uint8_t* sf = my;
-    uint8_t* qr = my + static_cast<size_t>(tl16) * NT;
-    for (int i = 0; i < tl16 + ql16; ++i) my[static_cast<size_t>(i) * NT] = 0;
+    // sf (target codes) at [0, tl16), qr (reversed query codes) at [tl16, tl16 + ql16): adjacent, as in the reference block
+    for (int i = 0; i < (tl16 + ql16 + 36) / 4; ++i) const_cast<uint32_t*>(myW)[static_cast<size_t>(i) * NT] = 0u;
     const uint8_t* read;
     uint32_t rl;
     readSpan(P.reads, jb.read, read, rl);
-    for (int t = 0; t < qlen; ++t) qr[static_cast<size_t>(t) * NT] = nt4(queryChar(read, rl, jb.rc != 0, jb.rskip + (qlen - 1 - t)));
-    for (int t = 0; t < tlen; ++t) sf[static_cast<size_t>(t) * NT] = nt4(__ldg(P.ix.text + jb.tpos + t));
+    for (int t = 0; t < qlen; ++t) byteAt(tl16 + t) = nt4(queryChar(read, rl, jb.rc != 0, jb.rskip + (qlen - 1 - t)));
+    for (int t = 0; t < tlen; ++t) byteAt(t) = nt4(__ldg(P.ix.text + jb.tpos + t));
 
-    uint32_t cell[32];
+    uint32_t U[8], V[8], X[8], Y[8], S[8];
     int32_t H[32];
 #pragma unroll
-    for (int c = 0; c < 32; ++c) { cell[c] = 0u; H[c] = kKswNegInf; }
-    uint32_t sbLo = 0u, sbHi = 0u;  // 2-bit score codes of slots 0..15 / 16..31: 0 = kcalloc zero, 1 = match, 2 = mismatch, 3 = wildcard
+    for (int g = 0; g < 8; ++g) { U[g] = 0u; V[g] = 0u; X[g] = 0u; Y[g] = 0u; S[g] = 0u; }
+#pragma unroll
+    for (int c = 0; c < 32; ++c) H[c] = kKswNegInf;
     int32_t Hleft = kKswNegInf, mqe = kKswNegInf, mte = kKswNegInf;
     int curSt = 0;
     for (int r = 0; r < qlen + tlen - 1; ++r) {
@@ -594,66 +605,89 @@ __global__ void __launch_bounds__(NT, 4) ksw_extz_lane_kernel(KswParams P) {
       if (st > en) break;
       const int st0 = st, en0 = en;
       st = st / 16 * 16; en = (en + 16) / 16 * 16 - 1;
-      int xPrev, vPrev;  // old x / v of the column left of the current one
+      uint32_t xPrevW, vPrevW;  // OLD x / v words of the group to the left (byte 3 = the column just left of this group)
       if (st != curSt) {  // the window moved one 16-lane block to the right: column st - 1 was slot 15
-        xPrev = static_cast<int8_t>(cell[15] >> 16); vPrev = static_cast<int8_t>(cell[15] >> 8);
+        xPrevW = X[3]; vPrevW = V[3];
         Hleft = H[15];
 #pragma unroll
-        for (int c = 0; c < 16; ++c) { cell[c] = cell[c + 16]; H[c] = H[c + 16]; cell[c + 16] = 0u; H[c + 16] = kKswNegInf; }
-        sbLo = sbHi; sbHi = 0u;
+        for (int g = 0; g < 4; ++g) {
+          U[g] = U[g + 4]; V[g] = V[g + 4]; X[g] = X[g + 4]; Y[g] = Y[g + 4]; S[g] = S[g + 4];
+          U[g + 4] = 0u; V[g + 4] = 0u; X[g + 4] = 0u; Y[g + 4] = 0u; S[g + 4] = 0u;
+        }
+#pragma unroll
+        for (int c = 0; c < 16; ++c) { H[c] = H[c + 16]; H[c + 16] = kKswNegInf; }
         curSt = st;
-      } else if (st > 0) { xPrev = 0; vPrev = 0; }
-      else { xPrev = 0; vPrev = r ? q : 0; }
+      } else if (st > 0) { xPrevW = 0u; vPrevW = 0u; }
+      else { xPrevW = 0u; vPrevW = static_cast<uint32_t>(static_cast<uint8_t>(r ? q : static_cast<int8_t>(0))) << 24; }
       const int sEnd = st0 + ((en0 - st0) / 16 + 1) * 16;
       const int cR = (en >= r) ? r - st : -1, cSt0 = st0 - st, cSEnd = sEnd - st, cEn = en - st, cEn0 = en0 - st;
-      const uint8_t* sfRow = sf + static_cast<size_t>(st) * NT;
-      const uint8_t* qrRow = qr + static_cast<size_t>(qlen - 1 - r + st) * NT;
+      // diagonal's new cell (y = 0, u = q), :343 of the general path
+      const int gR = cR >> 2;
+      const uint32_t mR = 0xffu << (8 * (cR & 3)), uR = static_cast<uint32_t>(static_cast<uint8_t>(r ? q : static_cast<int8_t>(0))) << (8 * (cR & 3));
+      // score window [cSt0, cSEnd): whole words between a partial first and a partial last word
+      const int gA = cSt0 >> 2, gB = cSEnd >> 2;
+      const uint32_t loMask = 0xffffffffu << (8 * (cSt0 & 3)), hiMask = (cSEnd & 3) ? ~(0xffffffffu << (8 * (cSEnd & 3))) : 0u;
+      // reversed-query bytes for slots 4g .. 4g+3 start at strip byte qB + 4g (any alignment)
+      const int qB = tl16 + (qlen - 1 - r + st);
+      const uint32_t qSel = 0x3210u + 0x1111u * static_cast<uint32_t>(qB & 3);
+      const uint32_t* qW = myW + static_cast<size_t>(qB >> 2) * NT;
+      const uint32_t* tW = myW + static_cast<size_t>(st >> 2) * NT;
+      uint32_t qLo = qW[0];
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const uint32_t qHi = qW[static_cast<size_t>(g + 1) * NT];
+        uint32_t u4 = U[g], y4 = Y[g];
+        const uint32_t xOld = X[g], vOld = V[g];
+        if (g == gR) { y4 &= ~mR; u4 = (u4 & ~mR) | uR; }
+        uint32_t m = 0u;
+        if (g >= gA && g <= gB) {
+          m = 0xffffffffu;
+          if (g == gA) m &= loMask;
+          if (g == gB) m &= hiMask;
+        }
+        if (m != 0u) {
+          const uint32_t a1 = tW[static_cast<size_t>(g) * NT], a2 = __byte_perm(qLo, qHi, qSel);
+          const uint32_t eq = __vcmpeq4(a1, a2);                                        // 0xff where the codes agree
+          const uint32_t nn = __vcmpeq4(a1 & 0x04040404u, 0x04040404u) | __vcmpeq4(a2 & 0x04040404u, 0x04040404u);  // code 4: wildcard
+          uint32_t s4 = (mat0x4 & eq) | (mat1x4 & ~eq);
+          s4 = (s4 & ~nn) | (matNx4 & nn);
+          S[g] = (S[g] & ~m) | (s4 & m);
+        }
+        qLo = qHi;
+        if (4 * g <= cEn) {
+          const uint32_t xt1 = __byte_perm(xPrevW, xOld, 0x6543u), vt1 = __byte_perm(vPrevW, vOld, 0x6543u);
+          uint32_t z = __vadd4(S[g], qe2x4);
+          uint32_t aa = __vadd4(xt1, vt1);
+          uint32_t bb = __vadd4(y4, u4);
+          z = __vmaxs4(z, aa);      // _mm_max_epi8
+          z = __vmaxu4(z, bb);      // _mm_max_epu8
+          z = __vminu4(z, maxScx4); // _mm_min_epu8
+          const uint32_t un = __vsub4(z, vt1), vn = __vsub4(z, u4);
+          z = __vsub4(z, qx4);
+          aa = __vsub4(aa, z);
+          bb = __vsub4(bb, z);
+          X[g] = __vmaxs4(aa, 0u);
+          y4 = __vmaxs4(bb, 0u);
+          u4 = un;
+          V[g] = vn;
+        }
+        U[g] = u4; Y[g] = y4;
+        xPrevW = xOld; vPrevW = vOld;
+      }
+      // exact max track (general path :397-412)
       int32_t hpCap = Hleft, hEn = 0, hSt = 0;
 #pragma unroll
       for (int c = 0; c < 32; ++c) {
-        const uint32_t cw = cell[c];
-        int8_t u = static_cast<int8_t>(cw), v = static_cast<int8_t>(cw >> 8), x = static_cast<int8_t>(cw >> 16), y = static_cast<int8_t>(cw >> 24);
-        const int8_t xo = x, vo = v;
-        if (c == cR) { y = 0; u = r ? q : 0; }
-        uint32_t code = ((c < 16 ? sbLo : sbHi) >> (2 * (c & 15))) & 3u;
-        if (c >= cSt0 && c < cSEnd) {
-          const uint8_t a1 = sfRow[static_cast<size_t>(c) * NT], a2 = qrRow[static_cast<size_t>(c) * NT];
-          code = (a1 == 4 || a2 == 4) ? 3u : (a1 == a2 ? 1u : 2u);
-          if (c < 16) sbLo = (sbLo & ~(3u << (2 * (c & 15)))) | (code << (2 * (c & 15)));
-          else sbHi = (sbHi & ~(3u << (2 * (c & 15)))) | (code << (2 * (c & 15)));
-        }
-        if (c <= cEn) {
-          const int8_t s = code == 0u ? static_cast<int8_t>(0) : (code == 1u ? P.mat0 : (code == 2u ? P.mat1 : P.matN));
-          const int8_t xt1 = static_cast<int8_t>(xPrev), vt1 = static_cast<int8_t>(vPrev);
-          const int8_t ut = u;
-          int8_t z = static_cast<int8_t>(s + qe2);
-          int8_t aa = static_cast<int8_t>(xt1 + vt1);
-          int8_t bb = static_cast<int8_t>(y + ut);
-          z = z > aa ? z : aa;
-          uint8_t zu = static_cast<uint8_t>(z), bu = static_cast<uint8_t>(bb);
-          zu = zu > bu ? zu : bu;
-          zu = zu < maxSc ? zu : maxSc;
-          z = static_cast<int8_t>(zu);
-          u = static_cast<int8_t>(z - vt1);
-          v = static_cast<int8_t>(z - ut);
-          z = static_cast<int8_t>(z - q);
-          aa = static_cast<int8_t>(aa - z);
-          bb = static_cast<int8_t>(bb - z);
-          x = aa > 0 ? aa : 0;
-          y = bb > 0 ? bb : 0;
-        }
-        cell[c] = static_cast<uint32_t>(static_cast<uint8_t>(u)) | (static_cast<uint32_t>(static_cast<uint8_t>(v)) << 8) |
-                  (static_cast<uint32_t>(static_cast<uint8_t>(x)) << 16) | (static_cast<uint32_t>(static_cast<uint8_t>(y)) << 24);
+        const int32_t vb = static_cast<int32_t>((V[c >> 2] >> (8 * (c & 3))) & 0xffu), ub = static_cast<int32_t>((U[c >> 2] >> (8 * (c & 3))) & 0xffu);
         if (r > 0) {
           if (c == cEn0 - 1) hpCap = H[c];  // H[en0 - 1] before this diagonal touches it
-          if (c >= cSt0 && c < cEn0) H[c] += static_cast<int32_t>(static_cast<uint8_t>(v)) - qe;
-          if (c == cEn0) H[c] = en0 > 0 ? hpCap + static_cast<int32_t>(static_cast<uint8_t>(u)) - qe : H[c] + static_cast<int32_t>(static_cast<uint8_t>(v)) - qe;
+          if (c >= cSt0 && c < cEn0) H[c] += vb - qe;
+          if (c == cEn0) H[c] = en0 > 0 ? hpCap + ub - qe : H[c] + vb - qe;
         } else if (c == 0) {
-          H[c] = static_cast<int32_t>(static_cast<uint8_t>(v)) - qe - qe;
+          H[c] = vb - qe - qe;
         }
         if (c == cEn0) hEn = H[c];
         if (c == cSt0) hSt = H[c];
-        xPrev = xo; vPrev = vo;
       }
       if (en0 == tlen - 1 && hEn > mte) mte = hEn;
       if (r - st0 == qlen - 1 && hSt > mqe) mqe = hSt;
@@ -778,7 +812,7 @@ inline int selAlnRun(SelAlnWork& w, const DeviceIndex& ix, const DevOpts& opts, 
   if (occ < 1) occ = 1;
   static const bool laneKsw = !(std::getenv("RAPMAP_B200_KSW") && std::string(std::getenv("RAPMAP_B200_KSW")) == "warp");
   if (laneKsw) {  // thread-per-job kernel first; what it leaves (short windows, wide bands, long reads) goes to the warp kernel
-    constexpr int LT = 128, LSEQ = 320;
+    constexpr int LT = 128, LSEQ = 352;
     kp.slowList = w.slowList; kp.slowCount = w.jobCursor + 1;
     const uint32_t smemL = LT * LSEQ;
     if ((e = cudaFuncSetAttribute(ksw_extz_lane_kernel<LT, LSEQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smemL))) != cudaSuccess)
