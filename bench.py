@@ -191,7 +191,7 @@ def main():
     ap.add_argument("--oracle-sample", type=int, default=20000, help="pairs checked against / counted by the CPU oracle at N=1")
     ap.add_argument("--cpu-baseline-pairs", type=int, default=1000000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-mappers", type=int, default=2, help="host threads (one mapper / CUDA stream each) of the end-to-end measurement")
+    ap.add_argument("--e2e-mappers", type=int, default=4, help="host threads (one mapper / CUDA stream each) of the end-to-end measurement")
     args = ap.parse_args()
 
     if args.impl == "reference":

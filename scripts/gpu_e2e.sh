@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-run() { # name, env, flags
-  env $2 timeout 600 python bench.py --steps 8 --warmup 3 --no-cpu-baseline --oracle-sample 2000 $3 > gpurun_out/e_$1.json 2> gpurun_out/e_$1.log
+run() { # name, flags
+  timeout 600 python bench.py --steps 12 --warmup 3 --no-cpu-baseline --oracle-sample 2000 $2 > gpurun_out/e_$1.json 2> gpurun_out/e_$1.log
   python - <<PY
 import json
 try:
@@ -9,10 +9,7 @@ try:
 except Exception as e: print("$1", "ERR", e, open("gpurun_out/e_$1.log").read()[-600:])
 PY
 }
-run m1 "A=1" "--e2e-mappers 1"
-run m2 "A=1" "--e2e-mappers 2"
-run m3 "A=1" "--e2e-mappers 3"
-run l2f32 "RAPMAP_B200_L2_FETCH=32" "--e2e-mappers 2"
-run l2f128 "RAPMAP_B200_L2_FETCH=128" "--e2e-mappers 2"
-run sel_m2 "A=1" "--e2e-mappers 2 --selaln"
-run sel_l2f32 "RAPMAP_B200_L2_FETCH=32" "--e2e-mappers 2 --selaln"
+run m2 "--e2e-mappers 2"
+run m3 "--e2e-mappers 3"
+run m4 "--e2e-mappers 4"
+run m3b "--e2e-mappers 3 --batch 524288"
