@@ -17,6 +17,7 @@
 #include "merge_pairs.cuh"
 #include "sa_collect.cuh"
 #include "sa_collect_lane.cuh"
+#include "sa_collect_regroup.cuh"
 #include "sam_writer.hpp"
 #include "sel_aln.cuh"
 
@@ -171,6 +172,10 @@ struct rapmap_cuda_mapper {
   uint32_t lpad{0}, pmax{0}, warpSmem{0}, packOff{0}, ctxOff{0}, voteOff{0};
   // stage 1, lane-per-read form
   bool laneKernel{true};
+  int regroup{0};            // 0: lane kernel; else threads per block of the regrouped SA-lookup kernel (128 / 256)
+  uint32_t regroupSmem{0};
+  int gridRegroup{0};
+  uint64_t scratchSlotsK1{0};
   bool laneMap{false};
   int gridLaneMap{0};
   uint4* dPacked{nullptr};
@@ -210,6 +215,7 @@ static constexpr int kWarps = 8;
 static constexpr int kMapLaneThreads = 128;                // lane-per-read hit resolution
 static constexpr int kMapLaneCap = RAPMAP_MAPLANE_CAP;     // SA entries per read it takes
 static constexpr uint32_t kMapLaneSmem = 2u * kMapLaneCap * kMapLaneThreads * 8u;
+static constexpr int kRegroupSlots = 512;                   // reads a block of the regrouped SA-lookup kernel keeps in flight
 static constexpr int kLaneThreads = RAPMAP_LANE_THREADS;  // lane-per-read SA-lookup kernel: threads per block
 static constexpr int kLaneMinBlocks = RAPMAP_LANE_MINB;   // 3 x 256 threads, 80 registers: the 64-register build spills and is 13 % slower
 
@@ -548,6 +554,26 @@ int rapmap_cuda_mapper_create(const rapmap_cuda_index_t* idx, const rapmap_cuda_
     M_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sa_collect_lane_kernel<kLaneThreads, kLaneMinBlocks>, kLaneThreads, m->laneSmem));
     if (occ < 1) return bail("sa_collect_lane_kernel does not fit on an SM");
     m->gridLane = m->numSMs * occ;
+    uint64_t scratchSlots = static_cast<uint64_t>(m->gridLane) * kLaneThreads;
+    {  // regrouped form (reads of a block sorted by their next step): RAPMAP_B200_K1=regroup128 / regroup256
+      const char* sel = std::getenv("RAPMAP_B200_K1");
+      const std::string mode = sel ? sel : "";
+      if ((mode == "regroup128" || mode == "regroup256") && m->laneWords <= 8) {
+        m->regroup = mode == "regroup128" ? 128 : 256;
+        m->regroupSmem = regroupSmemBytes(m->laneWords, kRegroupSlots);
+        if (m->regroup == 128) {
+          M_TRY(cudaFuncSetAttribute(sa_collect_regroup_kernel<128, kRegroupSlots>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(m->regroupSmem)));
+          M_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sa_collect_regroup_kernel<128, kRegroupSlots>, 128, m->regroupSmem));
+        } else {
+          M_TRY(cudaFuncSetAttribute(sa_collect_regroup_kernel<256, kRegroupSlots>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(m->regroupSmem)));
+          M_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sa_collect_regroup_kernel<256, kRegroupSlots>, 256, m->regroupSmem));
+        }
+        if (occ < 1) return bail("sa_collect_regroup_kernel does not fit on an SM");
+        m->gridRegroup = m->numSMs * occ;
+        scratchSlots = std::max<uint64_t>(scratchSlots, static_cast<uint64_t>(m->gridRegroup) * kRegroupSlots);
+      }
+    }
+    m->scratchSlotsK1 = scratchSlots;
     M_TRY(cudaMalloc(&m->dPacked, R * m->laneWords * sizeof(uint4)));
     {  // every resident warp reserves arena records RAPMAP_LANE_CHUNK at a time: allow for the unused tails
       const uint64_t want = static_cast<uint64_t>(m->ivCap) + static_cast<uint64_t>(m->gridLane) * (kLaneThreads / 32) * RAPMAP_LANE_CHUNK;
@@ -556,11 +582,11 @@ int rapmap_cuda_mapper_create(const rapmap_cuda_index_t* idx, const rapmap_cuda_
       M_TRY(cudaMalloc(&m->dIvArena, static_cast<uint64_t>(m->ivCap) * sizeof(IntervalRec)));
     }
     m->ivStride = std::min<uint32_t>(m->pmax, 24);
-    M_TRY(cudaMalloc(&m->dIvScratch, static_cast<uint64_t>(m->gridLane) * kLaneThreads * 2 * m->ivStride * sizeof(IntervalRec)));
+    M_TRY(cudaMalloc(&m->dIvScratch, scratchSlots * 2 * m->ivStride * sizeof(IntervalRec)));
     const bool voteMode = d.strictCheck && !(d.disableNIP && d.strictCheck);
     if (voteMode) {
       m->voteWords = (m->pmax + 31) / 32;
-      M_TRY(cudaMalloc(&m->dVoteScratch, static_cast<uint64_t>(m->gridLane) * kLaneThreads * 3 * m->voteWords * 4));
+      M_TRY(cudaMalloc(&m->dVoteScratch, scratchSlots * 3 * m->voteWords * 4));
     }
   }
   {  // lane-per-read form of kernel 2 for plain quasimap (no chaining, no position lists); RAPMAP_B200_K2=warp turns it off
@@ -664,11 +690,17 @@ int rapmap_cuda_map_batch(rapmap_cuda_mapper_t* m, const rapmap_read_batch_t* re
       lp.ix = m->idx->view; lp.reads = bv; lp.opts = m->dopts; lp.maxReadLen = m->maxReadLen; lp.nw = m->laneWords; lp.packed = m->dPacked;
       lp.summ = m->dSumm; lp.arena = m->dIvArena; lp.arenaCap = m->ivCap; lp.arenaCursor = m->dCtl + 0; lp.status = m->dCtl + 3;
       lp.ivScratch = m->dIvScratch; lp.ivStride = m->ivStride; lp.voteScratch = m->dVoteScratch; lp.voteWords = m->voteWords; lp.readCursor = m->dCtl + 4;
-      const int g0 = static_cast<int>(std::min<uint64_t>(static_cast<uint64_t>(m->numSMs) * 8, (bv.numReads + 7) / 8));
+      const int g0 = static_cast<int>(std::min<uint64_t>(static_cast<uint64_t>(m->numSMs) * 8, (bv.numReads * m->laneWords + 255) / 256));
       pack_reads_kernel<<<g0, 256, 0, st>>>(lp);
       CU_TRY(cudaEventRecord(m->ev[8], st));
-      const int g1 = static_cast<int>(std::min<uint64_t>(m->gridLane, (bv.numReads + kLaneThreads - 1) / kLaneThreads));
-      sa_collect_lane_kernel<kLaneThreads, kLaneMinBlocks><<<g1, kLaneThreads, m->laneSmem, st>>>(lp);
+      if (m->regroup) {
+        const int g1 = static_cast<int>(std::min<uint64_t>(m->gridRegroup, (bv.numReads + kRegroupSlots - 1) / kRegroupSlots));
+        if (m->regroup == 128) sa_collect_regroup_kernel<128, kRegroupSlots><<<g1, 128, m->regroupSmem, st>>>(lp);
+        else sa_collect_regroup_kernel<256, kRegroupSlots><<<g1, 256, m->regroupSmem, st>>>(lp);
+      } else {
+        const int g1 = static_cast<int>(std::min<uint64_t>(m->gridLane, (bv.numReads + kLaneThreads - 1) / kLaneThreads));
+        sa_collect_lane_kernel<kLaneThreads, kLaneMinBlocks><<<g1, kLaneThreads, m->laneSmem, st>>>(lp);
+      }
       launches += 2;
     } else {
       int g1 = static_cast<int>(std::min<uint64_t>(m->gridCollect, (bv.numReads + kWarps - 1) / kWarps));
@@ -720,7 +752,7 @@ int rapmap_cuda_map_batch(rapmap_cuda_mapper_t* m, const rapmap_read_batch_t* re
       if (m->ivStride >= m->pmax) return fail(RAPMAP_ERR_CAPACITY, "interval scratch overflow at worst-case size");
       cudaFree(m->dIvScratch); m->dIvScratch = nullptr;
       m->ivStride = m->pmax;
-      CU_TRY(cudaMalloc(&m->dIvScratch, static_cast<uint64_t>(m->gridLane) * kLaneThreads * 2 * m->ivStride * sizeof(IntervalRec)));
+      CU_TRY(cudaMalloc(&m->dIvScratch, m->scratchSlotsK1 * 2 * m->ivStride * sizeof(IntervalRec)));
       again = true;
     }
     if (status & kStatQAArenaFull) { int rc = growU32(reinterpret_cast<void**>(&m->dQaArena), m->qaCap, m->hStage->ctl[1], sizeof(QARec)); if (rc) return rc; again = true; }

@@ -48,14 +48,14 @@ struct LaneParams {
   uint32_t* readCursor;
 };
 
-// ---- K0: pack reads.  One warp per read; 32 bases per step (two OR-reductions, two ballots).
+// ---- K0: pack reads.  One thread per 32-base word of a read (a warp covers 8 reads x 4 words = 800 contiguous bytes).
 // Codes: A C G T = 0..3 (either case); 'U' = 3 with the invalid bit set (reverseRead turns U into A, so on the
 // reverse-complement strand it is a valid base, src/RapMapUtils.cpp:63-72); N = 1 + invalid; anything else 0 + invalid.
 __global__ void __launch_bounds__(256) pack_reads_kernel(LaneParams P) {
-  const int lane = threadIdx.x & 31;
-  const uint64_t gw = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const uint64_t nwarps = (static_cast<uint64_t>(gridDim.x) * blockDim.x) >> 5;
-  for (uint64_t r = gw; r < P.reads.numReads; r += nwarps) {
+  const uint64_t nWords = P.reads.numReads * P.nw;
+  for (uint64_t g = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; g < nWords; g += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    const uint64_t r = g / P.nw;
+    const uint32_t j = static_cast<uint32_t>(g - r * P.nw);
     const int mate = r >= P.reads.n ? 1 : 0;
     const uint64_t ri = r - static_cast<uint64_t>(mate) * P.reads.n;
     const uint8_t* src;
@@ -68,22 +68,22 @@ __global__ void __launch_bounds__(256) pack_reads_kernel(LaneParams P) {
       src = P.reads.seq[mate] + ri * P.reads.fixedLen;
       len = P.reads.fixedLen;
     }
-    uint4* dst = P.packed + r * P.nw;
-    if (len > P.maxReadLen) len = 0;  // reported by the lane kernel
+    if (len > P.maxReadLen) len = 0;  // reported by the SA-lookup kernel
     const int L = static_cast<int>(len);
-    for (uint32_t j = 0; j < P.nw; ++j) {
-      const int i = static_cast<int>(j) * 32 + lane;
-      const bool inb = i < L;
-      const uint8_t ch = inb ? __ldg(src + i) : 0;
-      const int cd = baseCode(ch);
-      const bool isN = (ch | 0x20) == 'n', isU = (ch | 0x20) == 'u';
-      const uint32_t code = !inb ? 0u : (cd >= 0 ? static_cast<uint32_t>(cd) : (isU ? 3u : (isN ? 1u : 0u)));
-      const uint32_t hi = __reduce_or_sync(0xffffffffu, lane < 16 ? (code << (30 - 2 * lane)) : 0u);
-      const uint32_t lo = __reduce_or_sync(0xffffffffu, lane >= 16 ? (code << (30 - 2 * (lane - 16))) : 0u);
-      const uint32_t inv = __ballot_sync(0xffffffffu, inb && cd < 0);
-      const uint32_t nn = __ballot_sync(0xffffffffu, inb && isN);
-      if (lane == 0) dst[j] = make_uint4(lo, hi, inv, nn);
+    const int i0 = static_cast<int>(j) * 32;
+    uint64_t codes = 0;
+    uint32_t inv = 0, nn = 0;
+    const int n = L - i0 < 32 ? L - i0 : 32;
+    for (int b = 0; b < n; ++b) {
+      const uint32_t ch = __ldg(src + i0 + b);
+      const uint32_t uc = ch & 0xDFu;
+      const bool ok = uc == 'A' || uc == 'C' || uc == 'G' || uc == 'T';
+      const uint32_t code = ok ? (((ch >> 1) ^ (ch >> 2)) & 3u) : (uc == 'U' ? 3u : (uc == 'N' ? 1u : 0u));
+      codes |= static_cast<uint64_t>(code) << (62 - 2 * b);
+      if (!ok) inv |= 1u << b;
+      if (uc == 'N') nn |= 1u << b;
     }
+    P.packed[g] = make_uint4(static_cast<uint32_t>(codes), static_cast<uint32_t>(codes >> 32), inv, nn);
   }
 }
 

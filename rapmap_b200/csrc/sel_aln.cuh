@@ -164,19 +164,45 @@ __device__ __forceinline__ int classifyTask(const DeviceIndex& ix, const DevOpts
   return 0;
 }
 
-__device__ __forceinline__ uint64_t windowHash(const uint8_t* t, int32_t n) {
-  uint64_t h = 0x9E3779B97F4A7C15ULL ^ static_cast<uint64_t>(static_cast<uint32_t>(n));
-  for (int32_t i = 0; i < n; ++i) h = mix64(h ^ (static_cast<uint64_t>(__ldg(t + i)) + 0x100ULL * static_cast<uint64_t>(i & 7)));
-  return h | 1ULL;  // never 0
+// 8 text bytes at any alignment (the text section is padded, reads past its end are in bounds).
+__device__ __forceinline__ uint64_t textLoad8(const uint8_t* p) {
+  const uint64_t* a = reinterpret_cast<const uint64_t*>(reinterpret_cast<uintptr_t>(p) & ~static_cast<uintptr_t>(7));
+  const unsigned sh = static_cast<unsigned>(reinterpret_cast<uintptr_t>(p) & 7) * 8;
+  const uint64_t lo = __ldg(a), hi = __ldg(a + 1);
+  return sh ? ((lo >> sh) | (hi << (64 - sh))) : lo;
 }
 
+// Hash of a reference window, 8 bytes per step.  It only has to be a function of (bytes, length): equal hashes are
+// confirmed byte by byte before a cached score is reused.
+__device__ __forceinline__ uint64_t windowHash(const uint8_t* t, int32_t n) {
+  uint64_t h = 0x9E3779B97F4A7C15ULL ^ static_cast<uint64_t>(static_cast<uint32_t>(n));
+  for (int32_t i = 0; i < n; i += 8) {
+    uint64_t w = textLoad8(t + i);
+    if (n - i < 8) w &= (1ULL << (8 * (n - i))) - 1ULL;
+    h = (h ^ w) * 0xff51afd7ed558ccdULL;
+    h ^= h >> 29;
+  }
+  return mix64(h) | 1ULL;  // never 0
+}
+
+__device__ __forceinline__ bool windowsEqual(const uint8_t* x, const uint8_t* y, int32_t n) {
+  for (int32_t i = 0; i < n; i += 8) {
+    uint64_t d = textLoad8(x + i) ^ textLoad8(y + i);
+    if (n - i < 8) d &= (1ULL << (8 * (n - i))) - 1ULL;
+    if (d) return false;
+  }
+  return true;
+}
+
+// One THREAD per pair (a pair has ~3.4 hits: with a warp per pair and a lane per hit 4 of 32 threads were active,
+// profiles/r01g).  Pass 1 classifies every (hit, read end) task and hashes its reference window, pass 2 resolves the
+// alignment cache against the earlier tasks of the same read end, scores UNGAPPED tasks and queues the DP jobs.
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) selaln_prepare_kernel(SelAlnParams P) {
-  const int lane = threadIdx.x & 31;
-  const uint64_t gw = static_cast<uint64_t>(blockIdx.x) * WARPS + (threadIdx.x >> 5);
+  const uint64_t gt = static_cast<uint64_t>(blockIdx.x) * (WARPS * 32) + threadIdx.x;
   const DevOpts& o = P.opts;
   const int32_t a = static_cast<int8_t>(o.ma), b = static_cast<int8_t>(o.mm);
-  for (uint64_t pi = gw; pi < P.numPairs; pi += static_cast<uint64_t>(gridDim.x) * WARPS) {
+  for (uint64_t pi = gt; pi < P.numPairs; pi += static_cast<uint64_t>(gridDim.x) * (WARPS * 32)) {
     const uint64_t h0 = P.pairOff[pi], h1 = P.pairOff[pi + 1];
     const uint32_t cnt = static_cast<uint32_t>(h1 - h0);
     if (cnt == 0) continue;
@@ -189,7 +215,7 @@ __global__ void __launch_bounds__(WARPS * 32) selaln_prepare_kernel(SelAlnParams
       readSpan(P.reads, r, read, rl);
       const int32_t maxScore = a * static_cast<int32_t>(rl);
       // ---- pass 1: classify + hash the window
-      for (uint32_t i = lane; i < cnt; i += 32) {
+      for (uint32_t i = 0; i < cnt; ++i) {
         const rapmap_hit_t h = P.hits[h0 + i];
         const uint64_t slot = 2 * (h0 + i) + end;
         const bool paired = h.mate_status == 3;
@@ -206,10 +232,9 @@ __global__ void __launch_bounds__(WARPS * 32) selaln_prepare_kernel(SelAlnParams
         P.taskHash[slot] = hash;
         P.taskRef[slot] = -1;
       }
-      __syncwarp();
       // ---- pass 2: alignment cache = first earlier task of this read end with an identical window (:320-333,:362-368);
       //      the cache only fills for multi-mapping reads.  Then score or queue the tasks that own their result.
-      for (uint32_t i = lane; i < cnt; i += 32) {
+      for (uint32_t i = 0; i < cnt; ++i) {
         const uint64_t slot = 2 * (h0 + i) + end;
         const uint64_t hash = P.taskHash[slot];
         if (hash == 0) continue;
@@ -233,9 +258,7 @@ __global__ void __launch_bounds__(WARPS * 32) selaln_prepare_kernel(SelAlnParams
             TaskGeom gj;
             classifyTask(P.ix, o, hj.tid, posj, static_cast<int32_t>(rl), csj, maxScore, gj, dummy);
             if (gj.keyLen != g.keyLen) continue;
-            bool same = true;
-            for (int32_t c = 0; c < g.keyLen && same; ++c) same = __ldg(P.ix.text + g.tpos + c) == __ldg(P.ix.text + gj.tpos + c);
-            if (same) ref = static_cast<int32_t>(sj);
+            if (windowsEqual(P.ix.text + g.tpos, P.ix.text + gj.tpos, g.keyLen)) ref = static_cast<int32_t>(sj);
           }
         }
         if (ref >= 0) { P.taskRef[slot] = ref; continue; }
@@ -257,7 +280,6 @@ __global__ void __launch_bounds__(WARPS * 32) selaln_prepare_kernel(SelAlnParams
           P.jobs[jx] = jb;
         }
       }
-      __syncwarp();
     }
   }
 }
@@ -784,7 +806,7 @@ inline int selAlnRun(SelAlnWork& w, const DeviceIndex& ix, const DevOpts& opts, 
   sp.pairBest = w.pairBest; sp.outCount = w.outCount; sp.outOff = w.outOff; sp.outHits = w.outHits; sp.maxReadLen = w.maxReadLen;
   if ((e = cudaMemsetAsync(w.jobCursor, 0, 8, st)) != cudaSuccess) return cuFail("memset", e);
   constexpr int W = 8;
-  int g = static_cast<int>(std::min<uint64_t>(static_cast<uint64_t>(numSMs) * 8, (n + W - 1) / W));
+  int g = static_cast<int>(std::min<uint64_t>(static_cast<uint64_t>(numSMs) * 8, (n + W * 32 - 1) / (W * 32)));
   selaln_prepare_kernel<W><<<g, W * 32, 0, st>>>(sp);
   ++*launches;
   // DP kernel: shared memory per warp = the reference's kcalloc block for the largest window + the int32 H track

@@ -311,3 +311,18 @@ def test_repeat_families_exercise_big_intervals_and_spill():
     mapper = make_mapper(index, opts, n, 100)
     res = mapper.map_batch(s1, s2, n=n, fixed_len=100)
     assert_same(res, OracleMapper(idx_dir, opts).map(s1, s2, 100), "repeats")
+
+
+@pytest.mark.parametrize("mode,sel", [("regroup256", False), ("regroup128", True), ("warp", False)])
+def test_alternative_sa_lookup_schedulers_match_oracle(monkeypatch, mode, sel):
+    """The SA-lookup kernel exists in three schedulings (lane per read = default, reads regrouped by their next step,
+    warp per read): same walk, so the same records.  The library reads RAPMAP_B200_K1 when a mapper is created."""
+    monkeypatch.setenv("RAPMAP_B200_K1", mode)
+    idx_dir, tx = synth_index(2500)
+    n = 20000
+    s1, s2 = tx.reads(n, rseed=99)
+    opts = rb.default_opts(sel_aln=sel)
+    index = rb.Index(idx_dir, 0)
+    mapper = make_mapper(index, opts, n, 100)
+    res = mapper.map_batch(s1, s2, n=n, fixed_len=100)
+    assert_same(res, OracleMapper(idx_dir, opts).map(s1, s2, 100), f"{mode} sel={sel}")
