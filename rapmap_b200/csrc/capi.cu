@@ -177,6 +177,7 @@ struct rapmap_cuda_mapper {
   int gridRegroup{0};
   uint64_t scratchSlotsK1{0};
   bool laneMap{false};
+  bool chainLaneMap{false};
   int gridLaneMap{0};
   uint4* dPacked{nullptr};
   IntervalRec* dIvScratch{nullptr};
@@ -212,6 +213,14 @@ static constexpr int kWarps = 8;
 #ifndef RAPMAP_MAPLANE_CAP
 #define RAPMAP_MAPLANE_CAP 16
 #endif
+#ifndef RAPMAP_CHAINLANE_CAP
+#define RAPMAP_CHAINLANE_CAP 16   // bigger strips lose more to tail divergence and occupancy than they save the warp kernel (sweep in DESIGN.md §5)
+#endif
+#ifndef RAPMAP_CHAINLANE_THREADS
+#define RAPMAP_CHAINLANE_THREADS 128
+#endif
+static constexpr int kChainLaneThreads = RAPMAP_CHAINLANE_THREADS;  // lane-per-read hit resolution with chaining (-s / -f)
+static constexpr int kChainLaneCap = RAPMAP_CHAINLANE_CAP;
 static constexpr int kMapLaneThreads = 128;                // lane-per-read hit resolution
 static constexpr int kMapLaneCap = RAPMAP_MAPLANE_CAP;     // SA entries per read it takes
 static constexpr uint32_t kMapLaneSmem = 2u * kMapLaneCap * kMapLaneThreads * 8u;
@@ -592,6 +601,14 @@ int rapmap_cuda_mapper_create(const rapmap_cuda_index_t* idx, const rapmap_cuda_
   {  // lane-per-read form of kernel 2 for plain quasimap (no chaining, no position lists); RAPMAP_B200_K2=warp turns it off
     const char* sel = std::getenv("RAPMAP_B200_K2");
     m->laneMap = !d.selAln && !d.fuzzy && !d.doChaining && !(sel && std::string(sel) == "warp");
+    m->chainLaneMap = !m->laneMap && !(sel && std::string(sel) == "warp");
+    if (m->chainLaneMap) {
+      const uint32_t smemC = chainLaneStride(kChainLaneCap) * kChainLaneThreads;
+      M_TRY(cudaFuncSetAttribute(hits_to_mappings_chain_lane_kernel<kChainLaneThreads, kChainLaneCap>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smemC)));
+      M_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hits_to_mappings_chain_lane_kernel<kChainLaneThreads, kChainLaneCap>, kChainLaneThreads, smemC));
+      if (occ < 1) return bail("hits_to_mappings_chain_lane_kernel does not fit on an SM");
+      m->gridLaneMap = m->numSMs * occ;
+    }
     if (m->laneMap) {
       M_TRY(cudaFuncSetAttribute(hits_to_mappings_lane_kernel<kMapLaneThreads, kMapLaneCap>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMapLaneSmem)));
       M_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hits_to_mappings_lane_kernel<kMapLaneThreads, kMapLaneCap>, kMapLaneThreads, kMapLaneSmem));
@@ -715,6 +732,12 @@ int rapmap_cuda_map_batch(rapmap_cuda_mapper_t* m, const rapmap_read_batch_t* re
     mp.posPool = m->dPosPool; mp.posCap = m->posCap; mp.posCursor = m->dCtl + 2;
     mp.scratch = m->dScratch; mp.scratchEntries = m->scratchEntries; mp.scratchStride = m->scratchStride; mp.smemEntries = m->smemEntries;
     mp.status = m->dCtl + 3;
+    if (m->chainLaneMap) {  // -s / -f: thread-per-read with chaining and position lists; the marked rest below
+      const int gl = static_cast<int>(std::min<uint64_t>(m->gridLaneMap, (bv.numReads + kChainLaneThreads - 1) / kChainLaneThreads));
+      hits_to_mappings_chain_lane_kernel<kChainLaneThreads, kChainLaneCap><<<gl, kChainLaneThreads, chainLaneStride(kChainLaneCap) * kChainLaneThreads, st>>>(mp);
+      ++launches;
+      mp.skipDone = 1;
+    }
     if (m->laneMap) {  // small reads thread-per-read; the rest (marked) by the warp-per-read kernel below
       const int gl = static_cast<int>(std::min<uint64_t>(m->gridLaneMap, (bv.numReads + kMapLaneThreads - 1) / kMapLaneThreads));
       hits_to_mappings_lane_kernel<kMapLaneThreads, kMapLaneCap><<<gl, kMapLaneThreads, kMapLaneSmem, st>>>(mp);

@@ -720,4 +720,280 @@ __global__ void __launch_bounds__(NT) hits_to_mappings_lane_kernel(MapParams P) 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Lane-per-read form WITH chaining / position lists (quasimap -s, -f): the warp-per-read kernel gives one lane to each
+// transcript segment of ONE read, so the chain DP of a read with 4 transcripts runs on 4 of 32 threads (17 active
+// threads per instruction, 34 % issue, profiles/r01h).  Here a thread owns a read with at most kChainLaneMaxIv intervals
+// and CAP expanded SA entries; its work arrays (keys / values / DP links / positions) are a private strip of shared
+// memory, so chainSegment() is used unchanged.  Loads are staged for all entries of the read as in the plain lane
+// kernel.  Everything bigger is marked kTodoMark for the warp-per-read kernel.
+static constexpr int kChainLaneMaxIv = 16;
+
+__host__ __device__ inline uint32_t chainLaneStride(uint32_t cap) { return (cap * 33u + 8u + 7u) / 8u * 8u; }
+
+template <int NT, int CAP>
+__global__ void __launch_bounds__(NT) hits_to_mappings_chain_lane_kernel(MapParams P) {
+  extern __shared__ __align__(16) uint8_t smemChain[];
+  uint8_t* base = smemChain + static_cast<size_t>(threadIdx.x) * chainLaneStride(CAP);
+  WorkArea w;
+  w.keys = reinterpret_cast<uint64_t*>(base);
+  w.vals = w.keys + CAP;
+  w.posTmp = reinterpret_cast<int32_t*>(w.vals + CAP);
+  w.p = w.posTmp + CAP;
+  w.aux = w.p + CAP;
+  uint32_t* outMeta = reinterpret_cast<uint32_t*>(w.aux + CAP);  // per resolved hit: posOff << 16 | nAll << 8 | chain
+  w.seen = reinterpret_cast<uint8_t*>(outMeta + CAP);
+  w.qaScore = nullptr; w.qa = nullptr; w.segs = nullptr; w.cap = CAP;
+  uint64_t* keys = w.keys;
+  uint64_t* vals = w.vals;
+  const int lane = threadIdx.x & 31;
+  const DeviceIndex& ix = P.ix;
+  const DevOpts& o = P.opts;
+  const bool needPos = o.selAln || o.fuzzy;
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * NT;
+  for (uint64_t rbase = static_cast<uint64_t>(blockIdx.x) * NT + (threadIdx.x & ~31); rbase < P.numReads; rbase += stride) {
+    const uint64_t r = rbase + lane;
+    const bool valid = r < P.numReads;
+    int nF = 0, nR = 0;
+    uint32_t ivOff = 0, readLen = 0;
+    if (valid) {
+      const ReadSummary s = P.summ[r];
+      nF = s.nFwd; nR = s.nRc; ivOff = s.ivOff; readLen = s.readLen;
+    }
+    const int nIv = nF + nR;
+    bool todo = false;
+    uint32_t totF = 0, totR = 0;
+    const IntervalRec* ivs = P.arena + ivOff;
+    if (nIv > kChainLaneMaxIv) todo = true;
+    else {
+      for (int j = 0; j < nIv; ++j) {
+        const uint32_t span = static_cast<uint32_t>(ivs[j].end - ivs[j].begin);
+        if (j < nF) totF += span; else totR += span;
+      }
+      if (totF + totR > static_cast<uint32_t>(CAP)) todo = true;
+    }
+    const uint32_t total = todo ? 0u : totF + totR;
+    // ---- stage 1: one key/value per SA entry (forward strand first); the value carries the SA index for now
+    if (total > 0) {
+      uint32_t at = 0;
+      for (int strand = 0; strand < 2; ++strand) {
+        const int j0 = strand ? nF : 0, j1 = strand ? nIv : nF, n = j1 - j0;
+        int minIdx = 0, bestSpan = 0x7fffffff;
+        for (int j = 0; j < n; ++j) {
+          const int span = ivs[j0 + j].end - ivs[j0 + j].begin;
+          if (n > 1 && span < bestSpan) { bestSpan = span; minIdx = j; }
+        }
+        for (int j = 0; j < n; ++j) {
+          const IntervalRec iv = ivs[j0 + j];
+          const uint32_t ord = (n == 1) ? 0u : (j == minIdx ? 0u : static_cast<uint32_t>(j < minIdx ? j + 1 : j));
+          const int span = iv.end - iv.begin;
+          for (int e = 0; e < span; ++e) {
+            keys[at] = (static_cast<uint64_t>(ord) << 16) | static_cast<uint64_t>(e);
+            vals[at] = (static_cast<uint64_t>(static_cast<uint32_t>(iv.begin + e)) << 32) | (static_cast<uint64_t>(iv.qpos) << 16) | iv.len;
+            ++at;
+          }
+        }
+      }
+    }
+    // ---- stages 2-4: SA entry -> text position -> transcript -> position in the transcript
+#pragma unroll 4
+    for (uint32_t i = 0; i < total; ++i) {
+      const uint64_t v = vals[i];
+      const int32_t g = __ldg(ix.SA + (v >> 32));
+      vals[i] = (static_cast<uint64_t>(static_cast<uint32_t>(g)) << 32) | (v & 0xffffffffULL);
+    }
+#pragma unroll 4
+    for (uint32_t i = 0; i < total; ++i) {
+      const uint32_t tid = transcriptAt(ix, static_cast<int32_t>(vals[i] >> 32));
+      keys[i] |= static_cast<uint64_t>(tid) << 32;
+    }
+#pragma unroll 4
+    for (uint32_t i = 0; i < total; ++i) {
+      const uint64_t v = vals[i];
+      const int32_t pos = static_cast<int32_t>(v >> 32) - __ldg(ix.txpOffsets + (keys[i] >> 32));
+      vals[i] = (static_cast<uint64_t>(static_cast<uint32_t>(pos)) << 32) | (v & 0xffffffffULL);
+    }
+    // ---- per strand: sort, resolve the transcript segments; hit o of a strand is compacted in place at [b0 + o]:
+    //      keys = tid << 32 | pos, vals = chain score (double bits), outMeta = posOff << 16 | nAll << 8 | chain
+    uint32_t nOutF = 0, nOutR = 0;
+    for (int strand = 0; strand < 2 && total > 0; ++strand) {
+      const uint32_t b0 = strand ? totF : 0u, cnt = strand ? totR : totF;
+      const int n = strand ? nR : nF;
+      if (cnt == 0) continue;
+      for (uint32_t i = 1; i < cnt; ++i) {  // insertion sort by (tid, ord, entry); keys are unique
+        const uint64_t kx = keys[b0 + i], vx = vals[b0 + i];
+        int32_t j = static_cast<int32_t>(i) - 1;
+        while (j >= 0 && keys[b0 + j] > kx) { keys[b0 + j + 1] = keys[b0 + j]; vals[b0 + j + 1] = vals[b0 + j]; --j; }
+        keys[b0 + j + 1] = kx; vals[b0 + j + 1] = vx;
+      }
+      int32_t required = n, maxSlack = 0;  // :613-628
+      if (n > 1 && o.consensusFraction < 1.0f) {
+        const float requiredFrac = __fmul_rn(static_cast<float>(n), o.consensusFraction);
+        const int32_t fl = static_cast<int32_t>(floorf(requiredFrac));
+        required = fl > 1 ? fl : 1;
+        maxSlack = n - required;
+      }
+      // does any transcript reach the required number of intervals?  (else, with slack, all are kept: :667-686)
+      bool keepAll = n == 1;
+      if (!keepAll && maxSlack > 0) {
+        bool any = false;
+        uint32_t i = 0;
+        while (i < cnt && !any) {
+          const uint32_t tid = static_cast<uint32_t>(keys[b0 + i] >> 32);
+          int32_t distinct = 0;
+          uint32_t lastOrd = 0xffffffffu;
+          while (i < cnt && static_cast<uint32_t>(keys[b0 + i] >> 32) == tid) {
+            const uint32_t ord = static_cast<uint32_t>(keys[b0 + i] >> 16) & 0xffffu;
+            if (ord != lastOrd) { ++distinct; lastOrd = ord; }
+            ++i;
+          }
+          any = distinct >= required;
+        }
+        keepAll = !any;
+      }
+      const bool chain = o.doChaining && n > 1;
+      const IntervalRec iv0 = ivs[strand ? nF : 0];
+      uint32_t nOut = 0, i = 0;
+      while (i < cnt) {
+        const uint32_t tid = static_cast<uint32_t>(keys[b0 + i] >> 32);
+        uint32_t e = i;
+        int32_t distinct = 0;
+        uint32_t lastOrd = 0xffffffffu;
+        while (e < cnt && static_cast<uint32_t>(keys[b0 + e] >> 32) == tid) {
+          const uint32_t ord = static_cast<uint32_t>(keys[b0 + e] >> 16) & 0xffffu;
+          if (ord != lastOrd) { ++distinct; lastOrd = ord; }
+          ++e;
+        }
+        if (keepAll || distinct >= required) {
+          QARec q;
+          q.tid = tid; q.pos = 0; q.nAll = 1; q.chain = 4;
+          double score = -1.7976931348623157e308;
+          const uint32_t b = b0 + i, en = b0 + e;
+          if (chain) {
+            q.nAll = chainSegment(w, b, en, readLen, static_cast<int32_t>(readLen), o.considerMultiPos, q, score);
+          } else if (n == 1) {  // collectFromSingleInterval (:716-807)
+            q.chain = (iv0.len == readLen) ? 0 : 4;
+            const int32_t qp = static_cast<int32_t>(iv0.qpos);
+            if (o.considerMultiPos) {
+              int32_t* out = w.posTmp + b;
+              uint32_t c2 = 0;
+              for (uint32_t t = b; t < en; ++t) {
+                const int32_t hp = static_cast<int32_t>(vPos(vals[t])) - qp;
+                int32_t j = static_cast<int32_t>(c2) - 1;
+                while (j >= 0 && out[j] > hp) { out[j + 1] = out[j]; --j; }
+                out[j + 1] = hp;
+                ++c2;
+              }
+              q.pos = out[0]; q.nAll = c2;
+            } else {
+              int32_t best = 0x7fffffff;
+              for (uint32_t t = b; t < en; ++t) { const int32_t hp = static_cast<int32_t>(vPos(vals[t])) - qp; best = hp < best ? hp : best; }
+              q.pos = best;
+              if (needPos) w.posTmp[b] = best;
+            }
+          } else {  // leftmost anchor (:308-322)
+            uint32_t bestPos = 0xffffffffu;
+            int32_t bestHit = 0;
+            for (uint32_t t = b; t < en; ++t) {
+              const uint64_t v = vals[t];
+              if (vPos(v) < bestPos) { bestPos = vPos(v); bestHit = static_cast<int32_t>(vPos(v) - vQpos(v)); }
+            }
+            q.pos = bestHit;
+            if (needPos) w.posTmp[b] = bestHit;
+          }
+          keys[b0 + nOut] = (static_cast<uint64_t>(tid) << 32) | static_cast<uint32_t>(q.pos);
+          vals[b0 + nOut] = static_cast<uint64_t>(__double_as_longlong(score));
+          outMeta[b0 + nOut] = (b << 16) | (q.nAll << 8) | q.chain;
+          ++nOut;
+        }
+        i = e;
+      }
+      if (strand) nOutR = nOut; else nOutF = nOut;
+    }
+    // ---- merge by tid (:834-881): equal tid => higher chain score first (forward on a tie); the winner takes the
+    //      loser's positions as oppositeStrandPositions.  First pass counts hits and positions.
+    uint32_t nFinal = 0, nPosTot = 0;
+    if (total > 0) {
+      uint32_t a = 0, b = 0;
+      while (a < nOutF || b < nOutR) {
+        bool takeA, both = false;
+        if (b >= nOutR) takeA = true;
+        else if (a >= nOutF) takeA = false;
+        else {
+          const uint32_t ta = static_cast<uint32_t>(keys[a] >> 32), tb = static_cast<uint32_t>(keys[totF + b] >> 32);
+          if (ta == tb) { both = true; takeA = true; } else takeA = ta < tb;
+        }
+        if (both) { nPosTot += ((outMeta[a] >> 8) & 0xffu) + ((outMeta[totF + b] >> 8) & 0xffu); ++a; ++b; }
+        else if (takeA) { nPosTot += (outMeta[a] >> 8) & 0xffu; ++a; }
+        else { nPosTot += (outMeta[totF + b] >> 8) & 0xffu; ++b; }
+        ++nFinal;
+      }
+    }
+    if (!needPos) nPosTot = 0;
+    const unsigned pm = __ballot_sync(0xffffffffu, nFinal > 0);
+    uint32_t off = 0, poolOff = 0;
+    if (pm) {
+      int incl = static_cast<int>(nFinal), inclP = static_cast<int>(nPosTot);
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, d), vp = __shfl_up_sync(0xffffffffu, inclP, d);
+        if (lane >= d) { incl += v; inclP += vp; }
+      }
+      const uint32_t tot = static_cast<uint32_t>(__shfl_sync(0xffffffffu, incl, 31)), totP = static_cast<uint32_t>(__shfl_sync(0xffffffffu, inclP, 31));
+      uint32_t wbase = 0, pbase = 0;
+      if (lane == 0) { wbase = atomicAdd(P.qaCursor, tot); if (totP) pbase = atomicAdd(P.posCursor, totP); }
+      wbase = __shfl_sync(0xffffffffu, wbase, 0); pbase = __shfl_sync(0xffffffffu, pbase, 0);
+      off = wbase + static_cast<uint32_t>(incl) - nFinal;
+      poolOff = pbase + static_cast<uint32_t>(inclP) - nPosTot;
+      bool ok = true;
+      if (static_cast<uint64_t>(wbase) + tot > P.qaCap) { if (lane == 0) atomicOr(P.status, kStatQAArenaFull); ok = false; }
+      if (static_cast<uint64_t>(pbase) + totP > P.posCap) { if (lane == 0) atomicOr(P.status, kStatPosPoolFull); ok = false; }
+      if (!ok) nFinal = 0;
+    }
+    if (nFinal > 0) {
+      uint32_t a = 0, b = 0, wr = 0, run = poolOff;
+      while (a < nOutF || b < nOutR) {
+        bool takeA, both = false;
+        if (b >= nOutR) takeA = true;
+        else if (a >= nOutF) takeA = false;
+        else {
+          const uint32_t ta = static_cast<uint32_t>(keys[a] >> 32), tb = static_cast<uint32_t>(keys[totF + b] >> 32);
+          if (ta == tb) { both = true; takeA = !(__longlong_as_double(static_cast<long long>(vals[totF + b])) > __longlong_as_double(static_cast<long long>(vals[a]))); }
+          else takeA = ta < tb;
+        }
+        const uint32_t win = takeA ? a : totF + b, lose = takeA ? totF + b : a;
+        const uint64_t kx = keys[win];
+        const uint32_t mw = outMeta[win];
+        QARec q;
+        q.tid = static_cast<uint32_t>(kx >> 32);
+        q.pos = static_cast<int32_t>(static_cast<uint32_t>(kx));
+        q.nAll = (mw >> 8) & 0xffu; q.chain = static_cast<uint8_t>(mw & 0xffu);
+        q.fwd = takeA ? 1 : 0; q.pad = 0;
+        q.posOff = 0; q.oppOff = 0; q.nOpp = 0;
+        if (both) q.nOpp = (outMeta[lose] >> 8) & 0xffu;
+        if (needPos) {
+          const int32_t* src = w.posTmp + (mw >> 16);
+          for (uint32_t t = 0; t < q.nAll; ++t) P.posPool[run + t] = src[t];
+          q.posOff = run;
+          run += q.nAll;
+          if (both) {
+            const int32_t* src2 = w.posTmp + (outMeta[lose] >> 16);
+            for (uint32_t t = 0; t < q.nOpp; ++t) P.posPool[run + t] = src2[t];
+          }
+          q.oppOff = run;
+          run += q.nOpp;
+        }
+        P.qaArena[off + wr] = q;
+        ++wr;
+        if (both) { ++a; ++b; } else if (takeA) ++a; else ++b;
+      }
+    }
+    if (valid) {
+      QASummary out;
+      out.qaOff = off; out.nQA = todo ? kTodoMark : nFinal;
+      P.qsumm[r] = out;
+    }
+  }
+}
+
 } // namespace rapmap_b200
