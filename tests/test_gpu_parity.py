@@ -326,3 +326,17 @@ def test_alternative_sa_lookup_schedulers_match_oracle(monkeypatch, mode, sel):
     mapper = make_mapper(index, opts, n, 100)
     res = mapper.map_batch(s1, s2, n=n, fixed_len=100)
     assert_same(res, OracleMapper(idx_dir, opts).map(s1, s2, 100), f"{mode} sel={sel}")
+
+
+@pytest.mark.parametrize("read_len,sel", [(150, False), (150, True), (250, True), (300, False)])
+def test_longer_reads_match_oracle(read_len, sel):
+    """Reads longer than the benchmark's 100 bases: 5..10 packed words per read in the SA-lookup kernel, ksw2 windows
+    beyond the thread-per-job kernel's strip (general warp kernel), more intervals / SA entries per read in hit resolution."""
+    idx_dir, tx = synth_index(2500)
+    n = 6000
+    s1, s2 = tx.reads(n, rseed=4242, read_len=read_len)
+    opts = rb.default_opts(sel_aln=sel)
+    index = rb.Index(idx_dir, 0)
+    mapper = make_mapper(index, opts, n, read_len)
+    res = mapper.map_batch(s1, s2, n=n, fixed_len=read_len)
+    assert_same(res, OracleMapper(idx_dir, opts).map(s1, s2, read_len), f"L={read_len} sel={sel}")
