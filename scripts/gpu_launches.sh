@@ -1,8 +1,9 @@
 #!/bin/bash
+# per-kernel time of a bench step from an ncu launch list; EXTRA="--selaln" (default) or EXTRA=""
 mkdir -p gpurun_out
 python bench.py --steps 1 --warmup 0 --no-cpu-baseline --oracle-sample 0 > /dev/null 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"sa_collect|pack_reads|hits_to_mappings|merge_|selaln|ksw" -c 200 --csv --log-file gpurun_out/launches_sel.csv \
-   python bench.py --steps 2 --warmup 1 --no-cpu-baseline --oracle-sample 0 --selaln > gpurun_out/ncu_launch_sel.json 2> gpurun_out/ncu_launch_sel.log
+   python bench.py --steps 2 --warmup 1 --no-cpu-baseline --oracle-sample 0 ${EXTRA---selaln} > gpurun_out/ncu_launch_sel.json 2> gpurun_out/ncu_launch_sel.log
 python - <<'PY'
 import csv, collections
 rows=list(csv.reader(l for l in open("gpurun_out/launches_sel.csv") if not l.startswith("==")))

@@ -13,8 +13,7 @@ for r in csv.reader(sys.stdin):
 "
 }
 run default A=1 ""
-run nofilter A=1 $PWD/rapmap_b200/_build/ab/lib_nofilter.so
-run ldcg A=1 $PWD/rapmap_b200/_build/ab/lib_ldcg.so
-run minb3 A=1 $PWD/rapmap_b200/_build/ab/lib_minb3.so
-timeout 900 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider -x > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
-STEPS=5 bash scripts/gpu_ab.sh
+for lib in rapmap_b200/_build/ab/lib_*.so; do   # e.g. build_variant.sh nofilter -DRAPMAP_NO_FILTER; build_variant.sh ldcg -DRAPMAP_LDCG
+  [ -f "$lib" ] || continue
+  n=$(basename $lib .so); run ${n#lib_} A=1 $PWD/$lib
+done
