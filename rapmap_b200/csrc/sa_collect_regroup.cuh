@@ -18,7 +18,7 @@ namespace rapmap_b200 {
 static constexpr int kRgStateWords = 17;
 
 __host__ __device__ inline uint32_t regroupSmemBytes(uint32_t nw, uint32_t slots) {
-  return slots * (16u * nw + 4u * kRgStateWords + 2u * 2u * 2u) + 64u;
+  return slots * (16u * nw + 4u * kRgStateWords + 3u * 2u * 2u) + 64u;
 }
 
 struct RgState {
@@ -70,8 +70,8 @@ __global__ void __launch_bounds__(NT, RAPMAP_RG_MINB) sa_collect_regroup_kernel(
   const int nw = static_cast<int>(P.nw);
   uint4* packW = reinterpret_cast<uint4*>(smemRg);                                   // [nw][SLOTS]
   uint32_t* stW = reinterpret_cast<uint32_t*>(packW + static_cast<size_t>(nw) * SLOTS);  // [17][SLOTS]
-  uint16_t* qBuf = reinterpret_cast<uint16_t*>(stW + kRgStateWords * SLOTS);        // [2 rounds][2 kinds][SLOTS]
-  uint32_t* ctl = reinterpret_cast<uint32_t*>(qBuf + 4 * SLOTS);                    // [0..3] queue counts, [4] chunk counter
+  uint16_t* qBuf = reinterpret_cast<uint16_t*>(stW + kRgStateWords * SLOTS);        // [3 queue sets][2 kinds][SLOTS]
+  uint32_t* ctl = reinterpret_cast<uint32_t*>(qBuf + 6 * SLOTS);                    // [0..5] queue counts, [6..8] chunk counters
   const int lane = threadIdx.x & 31;
   const int k = static_cast<int>(P.ix.k);
   const DevOpts& o = P.opts;
@@ -396,45 +396,38 @@ __global__ void __launch_bounds__(NT, RAPMAP_RG_MINB) sa_collect_regroup_kernel(
     }
   };
 
-  // ---- initial fill: every slot takes a read
-  if (threadIdx.x < 8) ctl[threadIdx.x] = 0u;
-  __syncthreads();
-  for (int s0 = (threadIdx.x & ~31); s0 < SLOTS; s0 += NT) {
-    const int s = s0 + lane;
-    RgState S;
-    S.r = 0; S.flags = 0; S.fwdHit = 0; S.rcHit = 0; S.fwdCov = 0; S.rcCov = 0; S.st = LST_IDLE; S.L = 0; S.rb = 0; S.lbIn = 0; S.ubIn = 0; S.l = 0; S.rr = 0;
-    S.lcpLP = 0; S.lcpRP = 0; S.prevILow = 0; S.prevIHigh = 0; S.mlen = 0; S.b0 = 0; S.b1 = 0; S.mQ = 0; S.pass = 0; S.guard = 0; S.prevMMPEnd = 0; S.nF = 0; S.nR = 0;
-    finishStep(S, s, s < SLOTS, 0);
+  // ---- every slot starts idle, queued as a LOOKUP item: its first step does nothing but take a read from the batch.
+  // Three queue sets rotate (input of this round, output of this round, the one being cleared for the next round), so a
+  // round needs a single block barrier.
+  if (threadIdx.x < 9) ctl[threadIdx.x] = threadIdx.x == 0 ? static_cast<uint32_t>(SLOTS) : 0u;
+  for (int s = threadIdx.x; s < SLOTS; s += NT) {
+    stW[2 * SLOTS + s] = static_cast<uint32_t>(LST_IDLE) << 16;
+    qBuf[s] = static_cast<uint16_t>(s);
   }
-
-  // ---- rounds
-  int cur = 0;
-  for (;;) {
-    __syncthreads();  // every push into queue set `cur` is done
-    const uint32_t nB = ctl[cur * 2 + 0], nD = ctl[cur * 2 + 1];
+  for (int in = 0;; in = in == 2 ? 0 : in + 1) {
+    __syncthreads();  // every push into queue set `in` is done, every read of the set before it too
+    const int out = in == 2 ? 0 : in + 1, clr = out == 2 ? 0 : out + 1;
+    const uint32_t nB = ctl[in * 2 + 0], nD = ctl[in * 2 + 1];
     if (nB + nD == 0u) break;
-    __syncthreads();  // everybody has the counts
-    if (threadIdx.x == 0) { ctl[(cur ^ 1) * 2 + 0] = 0u; ctl[(cur ^ 1) * 2 + 1] = 0u; ctl[4] = 0u; }
-    __syncthreads();
+    if (threadIdx.x == 0) { ctl[clr * 2 + 0] = 0u; ctl[clr * 2 + 1] = 0u; ctl[6 + clr] = 0u; }
     const uint32_t chunksB = (nB + 31u) >> 5, chunksD = (nD + 31u) >> 5;
     for (;;) {
       uint32_t c = 0;
-      if (lane == 0) c = atomicAdd(&ctl[4], 1u);
+      if (lane == 0) c = atomicAdd(&ctl[6 + in], 1u);
       c = __shfl_sync(0xffffffffu, c, 0);
       if (c >= chunksB + chunksD) break;
       const bool isB = c < chunksB;
       const uint32_t idx = (isB ? c : c - chunksB) * 32u + static_cast<uint32_t>(lane);
       const bool have = idx < (isB ? nB : nD);
-      const int s = have ? static_cast<int>(qBuf[(cur * 2 + (isB ? 0 : 1)) * SLOTS + idx]) : 0;
+      const int s = have ? static_cast<int>(qBuf[(in * 2 + (isB ? 0 : 1)) * SLOTS + idx]) : 0;
       RgState S;
       rgLoad<SLOTS>(stW, s, S);
       if (isB) lookupStep(S, s, have);  // every lane goes in: the step re-converges the warp before the table phase
       else if (have) probeStep(S, s);
       if (have) closure(S, s);
       __syncwarp();
-      finishStep(S, s, have, cur ^ 1);
+      finishStep(S, s, have, out);
     }
-    cur ^= 1;
   }
 }
 
