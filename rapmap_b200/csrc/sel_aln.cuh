@@ -696,23 +696,39 @@ __global__ void __launch_bounds__(NT, RAPMAP_KSW_MINB) ksw_extz_lane_kernel(KswP
         U[g] = u4; Y[g] = y4;
         xPrevW = xOld; vPrevW = vOld;
       }
-      // exact max track (general path :397-412)
-      int32_t hpCap = Hleft, hEn = 0, hSt = 0;
+      // exact max track (general path :397-412).  The sweep carries the previous column's OLD H, so H[en0] = H[en0 - 1]
+      // (before this diagonal) + u - qe needs no dynamically indexed register read.
+      if (r > 0) {
+        int32_t hPrevOld = Hleft;  // column st - 1
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        const int32_t vb = static_cast<int32_t>((V[c >> 2] >> (8 * (c & 3))) & 0xffu), ub = static_cast<int32_t>((U[c >> 2] >> (8 * (c & 3))) & 0xffu);
-        if (r > 0) {
-          if (c == cEn0 - 1) hpCap = H[c];  // H[en0 - 1] before this diagonal touches it
-          if (c >= cSt0 && c < cEn0) H[c] += vb - qe;
-          if (c == cEn0) H[c] = en0 > 0 ? hpCap + ub - qe : H[c] + vb - qe;
-        } else if (c == 0) {
-          H[c] = vb - qe - qe;
+        for (int c = 0; c < 32; ++c) {
+          const int32_t hOld = H[c];
+          const int32_t vb = static_cast<int32_t>((V[c >> 2] >> (8 * (c & 3))) & 0xffu);
+          int32_t hNew = hOld;
+          if (c >= cSt0 && c < cEn0) hNew = hOld + vb - qe;
+          if (c == cEn0) {
+            const int32_t ub = static_cast<int32_t>((U[c >> 2] >> (8 * (c & 3))) & 0xffu);
+            hNew = en0 > 0 ? hPrevOld + ub - qe : hOld + vb - qe;
+          }
+          H[c] = hNew;
+          hPrevOld = hOld;
         }
-        if (c == cEn0) hEn = H[c];
-        if (c == cSt0) hSt = H[c];
+      } else {
+        H[0] = static_cast<int32_t>(V[0] & 0xffu) - qe - qe;
       }
-      if (en0 == tlen - 1 && hEn > mte) mte = hEn;
-      if (r - st0 == qlen - 1 && hSt > mqe) mqe = hSt;
+      // the two read-outs happen on the last ~w + (tlen - qlen) diagonals only
+      if (en0 == tlen - 1) {
+        int32_t hEn = 0;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) if (c == cEn0) hEn = H[c];
+        if (hEn > mte) mte = hEn;
+      }
+      if (r - st0 == qlen - 1) {
+        int32_t hSt = 0;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) if (c == cSt0) hSt = H[c];  // st0 - st < 16
+        if (hSt > mqe) mqe = hSt;
+      }
     }
     P.taskScore[jb.slot] = mqe > mte ? mqe : mte;
   }
