@@ -7,8 +7,8 @@ HBM GB/s vs peak).
 
 Workload (configs[1]): GENCODE-like ~200k-transcript synthetic index (tools/synth.cpp, seed 12345, 37,000 genes),
 synthetic 2x100 bp pairs (seed 54321: 1% substitutions, 0.03% ins/del, 0.1% N), default `quasimap` flags (no -s).
-A step = one chunk ("batch") of --batch pairs per GPU through rapmap_cuda_map_batch; 10 default steps of 2^20
-pairs = the 10M-pair configuration.  Index replicated per GPU (one NCCL broadcast of the packed image), read
+A step = one chunk ("batch") of --batch pairs per GPU through rapmap_cuda_map_batch; 40 default steps of 2^20
+pairs (4 distinct batches cycled) = 4x the 10M-pair configuration, so that the timed region is long enough to sample clocks.  Index replicated per GPU (one NCCL broadcast of the packed image), read
 ranges sharded by rank, no data-path collective: weak scaling.
 """
 from __future__ import annotations
@@ -84,7 +84,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.gpu)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -141,13 +141,15 @@ def run_reference(args) -> None:
     os.makedirs(d, exist_ok=True)
     f1, f2 = os.path.join(d, f"r1_{total}.fastq"), os.path.join(d, f"r2_{total}.fastq")
     if not os.path.exists(f2):
-        s1, s2 = tx.reads(total, rseed=READ_SEED, first=0, read_len=READ_LEN)
         qual = b"I" * READ_LEN
-        for path, arr, m in ((f1, s1, 1), (f2, s2, 2)):
-            with open(path + ".tmp", "wb") as f:
-                rows = [b"@r%d/%d\n%s\n+\n%s\n" % (i, m, arr[i].tobytes(), qual) for i in range(total)]
-                f.write(b"".join(rows))
-            os.rename(path + ".tmp", path)
+        with open(f1 + ".tmp", "wb") as g1, open(f2 + ".tmp", "wb") as g2:
+            for first in range(0, total, 500000):  # chunked: bounded host memory whatever --steps says
+                cnt = min(500000, total - first)
+                s1, s2 = tx.reads(cnt, rseed=READ_SEED, first=first, read_len=READ_LEN)
+                for g, arr, m in ((g1, s1, 1), (g2, s2, 2)):
+                    g.write(b"".join(b"@r%d/%d\n%s\n+\n%s\n" % (first + i, m, arr[i].tobytes(), qual) for i in range(cnt)))
+        os.rename(f1 + ".tmp", f1)
+        os.rename(f2 + ".tmp", f2)
     flags = ["-s"] if args.selaln else []
 
     def once(n_pairs_files):
@@ -180,7 +182,7 @@ def run_reference(args) -> None:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=1 << 20, help="pairs per step per GPU")

@@ -6,10 +6,11 @@ nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv >> gpurun_ou
 timeout 1500 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 tail -4 gpurun_out/pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke exit $?"; tail -2 gpurun_out/smoke.log
 timeout 900 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.log
-timeout 1200 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_nosel.json 2> gpurun_out/bench_nosel.log
+timeout 1200 python bench.py > gpurun_out/bench_nosel.json 2> gpurun_out/bench_nosel.log
 echo "bench exit $?"
-timeout 900 python bench.py --steps 6 --warmup 3 --selaln > gpurun_out/bench_sel.json 2> gpurun_out/bench_sel.log
+timeout 900 python bench.py --steps 12 --warmup 3 --selaln > gpurun_out/bench_sel.json 2> gpurun_out/bench_sel.log
 python - <<'PY'
 import json
 for f in ("bench_ref","bench_nosel","bench_sel"):
