@@ -40,6 +40,16 @@ def log(*a):
     print("[bench]", *a, file=sys.stderr, flush=True)
 
 
+# The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on the first
+# collective), so file descriptor 1 is pointed at stderr for the whole run and the line goes to the saved descriptor.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -129,7 +139,7 @@ def run_reference(args) -> None:
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic"}
     if not os.path.exists(REF_BIN):
         line["unavailable"] = "oracle/_ref/rapmap_ref not built (needs /root/reference at build time)"
-        print(json.dumps(line))
+        emit(line)
         return
     import torch
 
@@ -176,7 +186,7 @@ def run_reference(args) -> None:
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     })
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
@@ -286,6 +296,7 @@ def main():
         return ms, stages, clocks
 
     ms_res, st_res, clocks = timed(step_resident, args.steps, args.warmup, sample_clocks=True)
+    log(f"rank {rank}: resident leg {ms_res / args.steps:.2f} ms per step")
 
     # ---- end to end: HOST buffers in, HOST buffers out, through rapmap_cuda_map_batch.  Like the reference's worker threads
     # (one SACollector per thread), --e2e-mappers host threads each own a mapper (= one CUDA stream) and take chunks
@@ -331,6 +342,7 @@ def main():
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         ms_e2e = float(tm.item())
     st_e2e = {"hits": e2e_hits}
+    log(f"rank {rank}: end-to-end leg {ms_e2e / args.steps:.2f} ms per step ({nm} host threads)")
     total_pairs = B * args.steps * world
     value = total_pairs / (ms_res / 1e3)
     e2e_value = total_pairs / (ms_e2e / 1e3)
@@ -406,7 +418,8 @@ def main():
             "ops_per_pair": ops_per_pair,
             "parity_checked_vs_oracle": parity,
         }
-        print(json.dumps(line))
+        emit(line)
+        log(f"rank 0: {value / 1e6:.1f} M pairs/s resident, {e2e_value / 1e6:.1f} M pairs/s end to end on {world} GPU(s)")
     barrier()
     if world > 1:
         dist.destroy_process_group()
