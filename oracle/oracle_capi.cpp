@@ -21,7 +21,7 @@ static Opts fromC(const rapmap_cuda_opts_t* c) {
   o.matchScore = c->match_score; o.mismatchPenalty = c->mismatch_penalty; o.gapOpenPenalty = c->gap_open_penalty;
   o.gapExtendPenalty = c->gap_extend_penalty; o.dpBandwidth = c->dp_bandwidth; o.hardFilter = c->hard_filter;
   o.alignmentPolicy = c->alignment_policy; o.noOrphans = c->no_orphans; o.noDovetail = c->no_dovetail;
-  o.maxMMPExtension = c->max_mmp_extension;
+  o.maxMMPExtension = c->max_mmp_extension; o.recoverOrphans = c->recover_orphans;
   return o;
 }
 
@@ -168,6 +168,7 @@ int main(int argc, char** argv) {
     else if (a == "--mimicBT2") mimicBT2 = true;
     else if (a == "--mimicStrictBT2") mimicStrict = true;
     else if (a == "--maxMMPExtension") c.max_mmp_extension = std::stoi(val());
+    else if (a == "--recoverOrphans") c.recover_orphans = 1;
     else if (a == "--ops") printOps = true;
     else if (a == "-n" || a == "--noOutput" || a == "-q" || a == "--quiet") {}
     else { std::fprintf(stderr, "unknown flag %s\n", a.c_str()); return 1; }

@@ -1132,6 +1132,96 @@ int32_t getAlnScore(Mapper& M, int32_t pos, const char* rptr, int32_t rlen, cons
 }
 } // namespace
 
+// edlibAlign(query, target, {k, EDLIB_MODE_HW, EDLIB_TASK_DISTANCE}) as recoverOrphans uses it
+// (include/SelectiveAlignmentUtils.hpp:147-148; third-party edlib vendored at src/edlib.cpp:290): the smallest edit
+// distance of the WHOLE query against any substring of the target (free end gaps in the target), -1 when it exceeds k,
+// and the first (leftmost) 0-based end position in the target that reaches it.  Edlib gets there with Myers'
+// bit-vector algorithm and an Ukkonen band; the value it returns is this DP's.
+static int semiGlobalDistance(const char* q, int m, const char* t, int n, int k, int& firstEnd) {
+  firstEnd = -1;
+  if (m <= 0 || n <= 0) return -1;
+  std::vector<int> prev(m + 1), cur(m + 1);
+  for (int i = 0; i <= m; ++i) prev[i] = i;   // column 0: the query against the empty prefix
+  int best = std::numeric_limits<int>::max();
+  for (int j = 1; j <= n; ++j) {
+    cur[0] = 0;                                // an alignment may start anywhere in the target
+    const char tc = t[j - 1];
+    for (int i = 1; i <= m; ++i) {
+      int d = prev[i - 1] + (q[i - 1] != tc ? 1 : 0);
+      if (prev[i] + 1 < d) d = prev[i] + 1;
+      if (cur[i - 1] + 1 < d) d = cur[i - 1] + 1;
+      cur[i] = d;
+    }
+    if (cur[m] < best) { best = cur[m]; firstEnd = j - 1; }
+    prev.swap(cur);
+  }
+  if (best > k) { firstEnd = -1; return -1; }
+  return best;
+}
+
+// selective_alignment::utils::recoverOrphans (include/SelectiveAlignmentUtils.hpp:35-257)
+static void recoverOrphans(const Index& idx, const std::string& leftRead, const std::string& rightRead, const std::vector<QuasiAlignment>& leftHits,
+                           const std::vector<QuasiAlignment>& rightHits, std::vector<QuasiAlignment>& jointHits) {
+  const int32_t l1 = static_cast<int32_t>(leftRead.size()), l2 = static_cast<int32_t>(rightRead.size());
+  const int32_t maxDistRight = l2 / 4, maxDistLeft = l1 / 4;
+  std::string rc1, rc2;
+  bool haveRc1 = false, haveRc2 = false;
+  auto recoverSingle = [&](const QuasiAlignment& anchor, bool anchorIsLeft) {
+    const uint32_t txp = anchor.tid;
+    const char* tseq = idx.seq.data() + idx.txpOffsets[txp];
+    const int32_t anchorPos = anchor.allPositions.front();
+    const bool anchorFwd = anchor.fwd;
+    const int32_t anchorLen = anchorIsLeft ? l1 : l2, otherLen = anchorIsLeft ? l2 : l1;
+    const int32_t maxDist = anchorIsLeft ? maxDistRight : maxDistLeft;
+    int32_t lpos = anchorIsLeft ? anchorPos : -1, rpos = anchorIsLeft ? -1 : anchorPos;
+    const bool lfwd = anchorIsLeft ? anchorFwd : !anchorFwd, rfwd = anchorIsLeft ? !anchorFwd : anchorFwd;
+    const std::string& other = anchorIsLeft ? rightRead : leftRead;
+    const uint8_t leftChain = anchorIsLeft ? anchor.chainLeft : static_cast<uint8_t>(REGULAR);
+    const uint8_t rightChain = anchorIsLeft ? static_cast<uint8_t>(REGULAR) : anchor.chainRight;
+    const int32_t refLength = static_cast<int32_t>(idx.txpLens[txp]);
+    const char* rptr;
+    int32_t startPos, windowLength;
+    if (anchorFwd) {  // look downstream for the reverse complement of the other end
+      std::string& rc = anchorIsLeft ? rc2 : rc1;
+      bool& have = anchorIsLeft ? haveRc2 : haveRc1;
+      if (!have) { reverseRead(other, rc); have = true; }
+      rptr = rc.data();
+      startPos = std::max(0, anchorPos);
+      windowLength = std::min(1000, refLength - startPos);
+    } else {          // look upstream for the other end as it is
+      rptr = other.data();
+      const int32_t endPos = std::min(refLength, anchorPos + anchorLen);
+      startPos = std::max(0, endPos - 1000);
+      windowLength = std::min(1000, endPos);
+    }
+    int firstEnd;
+    const int dist = semiGlobalDistance(rptr, otherLen, tseq + startPos, windowLength, maxDist, firstEnd);
+    if (dist > -1) {
+      if (anchorIsLeft) rpos = startPos + firstEnd - otherLen; else lpos = startPos + firstEnd - otherLen;
+      const int32_t startRead1 = std::max(lpos, 0), startRead2 = std::max(rpos, 0);
+      const bool read1First = startRead1 < startRead2;
+      const int32_t fragStartPos = read1First ? startRead1 : startRead2;
+      const int32_t fragEndPos = read1First ? (startRead2 + l2) : (startRead1 + l1);
+      QuasiAlignment qa;
+      qa.tid = txp; qa.pos = lpos; qa.fwd = lfwd; qa.readLen = static_cast<uint32_t>(l1);
+      qa.fragLen = static_cast<uint32_t>(fragEndPos - fragStartPos); qa.isPaired = true;
+      qa.mateLen = static_cast<uint32_t>(otherLen); qa.matePos = rpos; qa.mateIsFwd = rfwd;
+      qa.mateStatus = PAIRED_END_PAIRED;
+      qa.chainLeft = leftChain; qa.chainRight = rightChain;
+      jointHits.push_back(qa);
+    }
+  };
+  size_t li = 0, ri = 0;
+  while (li < leftHits.size() && ri < rightHits.size()) {
+    const uint32_t lt = leftHits[li].tid, rt = rightHits[ri].tid;
+    if (lt < rt) recoverSingle(leftHits[li++], true);
+    else if (rt < lt) recoverSingle(rightHits[ri++], false);
+    else { std::fprintf(stderr, "recoverOrphans: transcript in common between left and right hits (the reference exits here)\n"); std::exit(1); }
+  }
+  while (li < leftHits.size()) recoverSingle(leftHits[li++], true);
+  while (ri < rightHits.size()) recoverSingle(rightHits[ri++], false);
+}
+
 // src/RapMapSAMapper.cpp:461-711
 void Mapper::mapPair(const std::string& r1, const std::string& r2, std::vector<QuasiAlignment>& jointHits) {
   jointHits.clear();
@@ -1145,8 +1235,15 @@ void Mapper::mapPair(const std::string& r1, const std::string& r2, std::vector<Q
   hitsToMappingsSimple(PAIRED_END_LEFT, leftHC, leftHits);
   hitsToMappingsSimple(PAIRED_END_RIGHT, rightHC, rightHits);
   bool useSmartIntersect = o.fuzzy || o.selAln;
-  if (useSmartIntersect) mergeLeftRightHitsFuzzy(lh, rh, leftHits, rightHits, jointHits, o.maxNumHits, tooManyHits, ctr);
-  else mergeLeftRightHits(leftHits, rightHits, jointHits, o.maxNumHits, tooManyHits, ctr);
+  if (useSmartIntersect) {
+    const MergeResult mergeRes = mergeLeftRightHitsFuzzy(lh, rh, leftHits, rightHits, jointHits, o.maxNumHits, tooManyHits, ctr);
+    const bool mergeStatusOK = mergeRes == MergeResult::HAD_EMPTY_INTERSECTION || mergeRes == MergeResult::HAD_ONLY_LEFT || mergeRes == MergeResult::HAD_ONLY_RIGHT;
+    if (mergeStatusOK && o.recoverOrphans && !tooManyHits && leftHits.size() + rightHits.size() > 0) {  // :498-530
+      // the merge "moved" the orphans into jointHits: the reference swaps them back and starts from an empty joint list
+      if (mergeRes == MergeResult::HAD_ONLY_LEFT || mergeRes == MergeResult::HAD_ONLY_RIGHT) jointHits.clear();
+      recoverOrphans(idx, r1, r2, leftHits, rightHits, jointHits);
+    }
+  } else mergeLeftRightHits(leftHits, rightHits, jointHits, o.maxNumHits, tooManyHits, ctr);
   if (jointHits.size() > o.maxNumHits) jointHits.clear();
   if (!jointHits.empty() && o.noOrphans) {
     if (jointHits.front().mateStatus != PAIRED_END_PAIRED) jointHits.clear();

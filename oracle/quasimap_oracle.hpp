@@ -58,6 +58,7 @@ struct Opts {
   int alignmentPolicy{0};      // 0 DEFAULT, 1 BT2, 2 BT2_STRICT
   bool noOrphans{false}, noDovetail{false};
   int maxMMPExtension{7};
+  bool recoverOrphans{false};  // --recoverOrphans (needs -s or -f)
 };
 
 enum MateStatus : uint8_t { SINGLE_END = 0, PAIRED_END_LEFT = 1, PAIRED_END_RIGHT = 2, PAIRED_END_PAIRED = 3 };

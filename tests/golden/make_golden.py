@@ -40,6 +40,8 @@ FLAGSETS = {
     "cov07": ["-z", "0.7"],
     "nosensitive": ["--noSensitive"],
     "nostrict": ["--noStrictCheck"],
+    "selaln_recover": ["-s", "--recoverOrphans"],
+    "fuzzy_recover": ["-f", "--recoverOrphans"],
 }
 SYNTH_PAIRS = 1500
 KEEP_SAM = {"default", "selaln"}

@@ -80,6 +80,7 @@ def flag_opts(fname):
         elif a == "-z": o.quasi_coverage = float(next(it))
         elif a == "--noSensitive": o.sensitive = 0
         elif a == "--noStrictCheck": o.strict_check = 0
+        elif a == "--recoverOrphans": o.recover_orphans = 1
         else: raise ValueError(a)
     if bt2 or strict:  # reference src/RapMapSAMapper.cpp:1150-1174
         o.sel_aln = 1; o.alignment_policy = 1 if bt2 else 2; o.no_orphans = 1; o.no_dovetail = 1; o.consensus_slack = 0.35; o.max_num_hits = 1000

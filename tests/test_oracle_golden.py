@@ -66,7 +66,8 @@ def test_oracle_matches_live_reference_noisy_reads(fastqs, tmp_path):
     subprocess.run([SYNTH_BIN, "reads", "--genes", "8", "--seed", "777", "--pairs", "2500", "--rseed", "99", "--sub", "40000", "--ins", "5000", "--del", "5000",
                     "--n", "8000", "--out1", str(d / "a1.fastq"), "--out2", str(d / "a2.fastq")], check=True)
     for flags in ([], ["-s"], ["-s", "--dpBandwidth", "3"], ["--noSensitive"], ["--noStrictCheck"], ["--noSensitive", "--noStrictCheck"],
-                  ["-s", "--noSensitive"], ["-f", "--noStrictCheck"]):
+                  ["-s", "--noSensitive"], ["-f", "--noStrictCheck"], ["-s", "--recoverOrphans"], ["-f", "--recoverOrphans"],
+                  ["-s", "--recoverOrphans", "--hardFilter"]):
         subprocess.run([REF_BIN, "quasimap", "-i", os.path.join(GOLD, "synth_idx"), "-1", str(d / "a1.fastq"), "-2", str(d / "a2.fastq"), "-t", "1", "-o", str(d / "ref.sam")] + flags,
                        check=True, capture_output=True)
         subprocess.run([ORACLE_CLI, "-i", os.path.join(GOLD, "synth_idx"), "-1", str(d / "a1.fastq"), "-2", str(d / "a2.fastq"), "-o", str(d / "ora.sam")] + flags,
