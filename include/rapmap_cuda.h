@@ -55,7 +55,7 @@ typedef struct {
   uint8_t no_orphans;           /* --noOrphans  */
   uint8_t no_dovetail;          /* --noDovetail */
   int32_t max_mmp_extension;    /* --maxMMPExtension (7) */
-  uint8_t recover_orphans;      /* --recoverOrphans: RAPMAP_ERR_UNSUPPORTED on the device path */
+  uint8_t recover_orphans;      /* --recoverOrphans: orphan rescue next to the anchor hit (include/SelectiveAlignmentUtils.hpp:35-257); acts with sel_aln / fuzzy */
 } rapmap_cuda_opts_t;
 
 /* One QuasiAlignment (include/RapMapUtils.hpp:399-502), the fields that reach SAM / Salmon. 28 bytes. */

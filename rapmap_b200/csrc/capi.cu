@@ -438,7 +438,6 @@ int rapmap_cuda_index_from_image(const rapmap_cuda_index_t* meta, int device, vo
 
 // -------------------------------------------------------------------------------------------------
 static int deriveOpts(const rapmap_cuda_opts_t& o, DevOpts& d) {
-  if (o.recover_orphans) return fail(RAPMAP_ERR_UNSUPPORTED, "--recoverOrphans is not implemented on the device path");
   if (o.sel_aln) {
     // validateOpts, reference src/RapMapSAMapper.cpp:911-954
     if (o.consensus_slack < 0 || o.consensus_slack > 1) return fail(RAPMAP_ERR_ARG, "--consensusSlack must be between 0.0 and 1.0");
@@ -468,6 +467,7 @@ static int deriveOpts(const rapmap_cuda_opts_t& o, DevOpts& d) {
     d.maxMMPExtension = o.max_mmp_extension;
   }
   d.noOrphans = o.no_orphans;
+  d.recoverOrphans = o.recover_orphans;  // acts only with the fuzzy merge (-s / -f), src/RapMapSAMapper.cpp:498
   d.noDovetail = o.no_dovetail;
   d.hardFilter = o.hard_filter;
   d.alignmentPolicy = o.alignment_policy;
@@ -753,6 +753,7 @@ int rapmap_cuda_map_batch(rapmap_cuda_mapper_t* m, const rapmap_read_batch_t* re
     gp.opts = m->dopts; gp.numPairs = n; gp.pairedInput = paired ? 1 : 0; gp.qsumm = m->dQSumm; gp.qaArena = m->dQaArena; gp.summ = m->dSumm;
     gp.pairCount = m->dPairCount; gp.pairOffset = m->dPairOff; gp.hits = m->dHits; gp.hitsCap = m->hitsCap; gp.counters = m->dCounters;
     gp.posPool = m->dPosPool;
+    gp.reads = bv; gp.text = m->idx->view.text; gp.txpOffsets = m->idx->view.txpOffsets; gp.txpLens = m->idx->view.txpLens;
     int g3 = static_cast<int>(std::min<uint64_t>(static_cast<uint64_t>(m->numSMs) * 8, (n + 255) / 256));
     CU_TRY(cudaMemsetAsync(m->dPairCount + n, 0, 4, st));
     if (m->dopts.selAln || m->dopts.fuzzy) merge_count_kernel<true><<<g3, 256, 0, st>>>(gp);

@@ -59,6 +59,7 @@ struct DevOpts {
   uint8_t doChaining, considerMultiPos, fuzzy, selAln;
   uint8_t disableNIP, strictCheck;   // SACollector::disableNIP_ / strictCheck_ (coverage mode when both are set)
   uint8_t noOrphans, noDovetail, hardFilter, alignmentPolicy;
+  uint8_t recoverOrphans;            // --recoverOrphans (acts only with the fuzzy merge: -s / -f)
   int16_t ma, mm, go, ge;
   int32_t dpBandwidth;
   double minScoreFraction;

@@ -8,6 +8,7 @@
 // right grain; both passes stream coalesced QASummary records.
 #pragma once
 #include "kernels.cuh"
+#include "orphan_recovery.cuh"
 
 namespace rapmap_b200 {
 
@@ -24,6 +25,11 @@ struct MergeParams {
   uint64_t hitsCap;
   Counters5* counters;      // pass 0 only
   const int32_t* posPool;   // allPositions / oppositeStrandPositions (fuzzy merge)
+  // orphan recovery (--recoverOrphans)
+  BatchView reads;
+  const uint8_t* text;
+  const int32_t* txpOffsets;
+  const int32_t* txpLens;
 };
 
 __device__ __forceinline__ bool dovetailDrop(const rapmap_hit_t& h) {  // src/RapMapSAMapper.cpp:687-696
@@ -169,6 +175,29 @@ __device__ __forceinline__ bool bestFwRc(const int32_t* fw, uint32_t nFw, const 
   return true;
 }
 
+// recoverSingleOrphan of selective_alignment::utils::recoverOrphans (include/SelectiveAlignmentUtils.hpp:69-176): looks for
+// the other read end in the <= 1000 bases downstream (anchor forward: the reverse complement of the other end) or
+// upstream (anchor reverse: the other end as it is) of the anchor hit.  Plain arguments only: the function is out of line.
+__device__ __noinline__ bool recoverOne(const uint8_t* text, const int32_t* txpOffsets, const int32_t* txpLens, const uint8_t* otherRead, int32_t otherLen,
+                                        int32_t anchorLen, int32_t anchorPos, bool anchorFwd, uint32_t tid, int32_t& otherPos) {
+  const int64_t toff = txpOffsets[tid];
+  const int32_t refLength = txpLens[tid];
+  int32_t startPos, windowLength;
+  if (anchorFwd) {
+    startPos = anchorPos > 0 ? anchorPos : 0;
+    windowLength = min(1000, refLength - startPos);
+  } else {
+    const int32_t endPos = min(refLength, anchorPos + anchorLen);
+    startPos = endPos - 1000 > 0 ? endPos - 1000 : 0;
+    windowLength = min(1000, endPos);
+  }
+  int firstEnd;
+  const int d = semiGlobalMyers(otherRead, otherLen, anchorFwd, text + toff + startPos, windowLength, otherLen / 4, firstEnd);
+  if (d < 0) return false;
+  otherPos = startPos + firstEnd - otherLen;
+  return true;
+}
+
 // mergeLeftRightHitsFuzzy (include/RapMapUtils.hpp:864-1183) + the post-merge steps of src/RapMapSAMapper.cpp:533-551.
 // With selAln the hits are scored and filtered afterwards (sel_aln.cuh); --noDovetail is applied there.
 template <bool WRITE>
@@ -200,9 +229,51 @@ __device__ __forceinline__ uint32_t mergeFuzzy(const MergeParams& P, uint64_t pi
     h.chain_status = side ? static_cast<uint8_t>(4 | (q.chain << 4)) : static_cast<uint8_t>(q.chain | (4 << 4));
     return h;
   };
+  // --recoverOrphans (src/RapMapSAMapper.cpp:498-530): the orphans of the listed sides are not reported; every one of them
+  // is an anchor next to which the other read end is searched, and the pairs found this way are the pair's hits.
+  auto runRecovery = [&](uint32_t nlR, uint32_t nrR) -> uint32_t {
+    if (WRITE && room == 0) return 0;
+    const uint8_t* reads[2];
+    for (int e = 0; e < 2; ++e) {
+      const uint64_t ri = pi;
+      reads[e] = P.reads.off[e] ? P.reads.seq[e] + P.reads.off[e][ri] : P.reads.seq[e] + ri * P.reads.fixedLen;
+    }
+    uint32_t nRec = 0;
+    auto rec = [&](const QARec& a, bool anchorIsLeft) {
+      const int32_t anchorPos = P.posPool[a.posOff];  // allPositions.front()
+      const int32_t otherLen = anchorIsLeft ? rLen : lLen, anchorLen = anchorIsLeft ? lLen : rLen;
+      int32_t otherPos = -1;
+      if (!recoverOne(P.text, P.txpOffsets, P.txpLens, reads[anchorIsLeft ? 1 : 0], otherLen, anchorLen, anchorPos, a.fwd != 0, a.tid, otherPos)) return;
+      ++nRec;
+      const int32_t lpos = anchorIsLeft ? anchorPos : otherPos, rpos = anchorIsLeft ? otherPos : anchorPos;
+      const int32_t s1 = lpos > 0 ? lpos : 0, s2 = rpos > 0 ? rpos : 0;
+      const bool read1First = s1 < s2;
+      const int32_t fragStart = read1First ? s1 : s2;
+      const int32_t fragEnd = read1First ? (s2 + static_cast<int32_t>(rLen)) : (s1 + static_cast<int32_t>(lLen));
+      rapmap_hit_t h;
+      h.tid = a.tid; h.pos = lpos; h.mate_pos = rpos; h.frag_len = static_cast<uint32_t>(fragEnd - fragStart);
+      h.read_len = lLen; h.mate_len = static_cast<uint16_t>(otherLen);  // the reference stores the OTHER end's length as mateLen
+      h.aln_score = 0;
+      h.fwd = anchorIsLeft ? a.fwd : !a.fwd; h.mate_fwd = anchorIsLeft ? !a.fwd : a.fwd; h.mate_status = 3;
+      h.chain_status = anchorIsLeft ? static_cast<uint8_t>(a.chain | (4 << 4)) : static_cast<uint8_t>(4 | (a.chain << 4));
+      if (!(!o.selAln && o.noDovetail && dovetailDrop(h))) emit(h);
+    };
+    uint32_t li = 0, ri = 0;
+    while (li < nlR && ri < nrR) {
+      const uint32_t lt = L[li].tid, rt = R[ri].tid;
+      if (lt < rt) rec(L[li++], true);
+      else if (rt < lt) rec(R[ri++], false);
+      else { ++li; ++ri; }  // a shared transcript cannot occur here (the reference exits on it)
+    }
+    while (li < nlR) rec(L[li++], true);
+    while (ri < nrR) rec(R[ri++], false);
+    if (nRec > o.maxNumHits) return 0;  // src/RapMapSAMapper.cpp:533-536
+    if (!WRITE && !o.selAln) ctr[3] += nOut;
+    return nOut;
+  };
   bool tooManyHits = false;
   int mode = 0;  // 0 nothing, 1 only right, 2 only left, 3 paired
-  uint32_t numHits = 0;
+  uint32_t numHits = 0, sameTxp = 0;
   if (nl == 0) {
     if (!lsum.found && nr > 0) mode = 1;   // orphans only if the other end had no k-mer hit at all (:880-899)
   } else if (nr == 0) {
@@ -214,6 +285,7 @@ __device__ __forceinline__ uint32_t mergeFuzzy(const MergeParams& P, uint64_t pi
   if (mode == 1 || mode == 2) {
     const uint32_t n = mode == 1 ? nr : nl;
     if (!WRITE) { ctr[2] += n; ctr[1] += n; }  // seHits, and peHits counts every non-empty jointHits (:1176-1179)
+    if (o.recoverOrphans) return runRecovery(mode == 2 ? nl : 0u, mode == 1 ? nr : 0u);
     uint32_t size = n;
     if (size > o.maxNumHits) size = 0;
     if (o.noOrphans) size = 0;
@@ -238,6 +310,7 @@ __device__ __forceinline__ uint32_t mergeFuzzy(const MergeParams& P, uint64_t pi
       if (lt < rt) { ++li; }
       else {
         if (!(rt < lt)) {
+          ++sameTxp;
           const QARec& l = L[li];
           const QARec& r = R[ri];
           const int32_t* lAll = P.posPool + l.posOff; const int32_t* lOpp = P.posPool + l.oppOff;
@@ -279,6 +352,7 @@ __device__ __forceinline__ uint32_t mergeFuzzy(const MergeParams& P, uint64_t pi
     if (pass == 0) {
       uint32_t nJoint = tooManyHits ? 0 : numHits;
       if (!WRITE) { if (tooManyHits) ctr[4] += 1; ctr[1] += nJoint; }
+      if (o.recoverOrphans && !tooManyHits && numHits == 0 && sameTxp == 0) return runRecovery(nl, nr);  // HAD_EMPTY_INTERSECTION
       if (nJoint == 0 || nJoint > o.maxNumHits) return 0;
     }
   }

@@ -56,7 +56,10 @@ def synth_small():
 
 
 def flag_opts(fname):
-    flags = GOLDEN[f"synth/{fname}"]["flags"]
+    return opts_from_flags(GOLDEN[f"synth/{fname}"]["flags"])
+
+
+def opts_from_flags(flags):
     o = rb.default_opts()
     it = iter(flags)
     bt2 = strict = False
@@ -341,3 +344,16 @@ def test_longer_reads_match_oracle(read_len, sel):
     mapper = make_mapper(index, opts, n, read_len)
     res = mapper.map_batch(s1, s2, n=n, fixed_len=read_len)
     assert_same(res, OracleMapper(idx_dir, opts).map(s1, s2, read_len), f"L={read_len} sel={sel}")
+
+
+@pytest.mark.parametrize("flags", [["-s", "--recoverOrphans"], ["-f", "--recoverOrphans", "--noDovetail"], ["-s", "--recoverOrphans", "--hardFilter", "--noOrphans"]])
+def test_orphan_recovery_matches_oracle(flags):
+    """--recoverOrphans on 20k noisy pairs of the 13.9k-transcript index (about one pair in eight goes through recovery)."""
+    idx_dir, tx = synth_index(2500)
+    n = 20000
+    s1, s2 = tx.reads(n, rseed=2718, sub=30000, ins=3000, dele=3000, nn=3000)
+    opts = opts_from_flags(flags)
+    index = rb.Index(idx_dir, 0)
+    mapper = make_mapper(index, opts, n, 100)
+    res = mapper.map_batch(s1, s2, n=n, fixed_len=100)
+    assert_same(res, OracleMapper(idx_dir, opts).map(s1, s2, 100), " ".join(flags))
