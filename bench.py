@@ -199,7 +199,7 @@ def main():
     ap.add_argument("--genes", type=int, default=37000, help="synthetic genes (37000 -> ~203k transcripts)")
     ap.add_argument("--selaln", action="store_true", help="quasimap -s (configs[2])")
     ap.add_argument("--distinct", type=int, default=4, help="distinct read batches cycled through the steps")
-    ap.add_argument("--ref-pairs-per-step", type=int, default=200000)
+    ap.add_argument("--ref-pairs-per-step", type=int, default=100000, help="pairs per step of the reference arm (bounded sample: 40 steps = 4M pairs, ~5 s of 16-thread CPU mapping)")
     ap.add_argument("--oracle-sample", type=int, default=20000, help="pairs checked against / counted by the CPU oracle at N=1")
     ap.add_argument("--cpu-baseline-pairs", type=int, default=1000000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
