@@ -72,6 +72,24 @@ __global__ void build_filter_kernel(const KmerRecord* recs, uint64_t n, uint32_t
   }
 }
 
+__global__ void build_filter_from_text_kernel(const uint8_t* text, uint64_t n, uint32_t k, uint32_t* filter, uint32_t shift) {
+  for (uint64_t p = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; p + k <= n; p += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    uint64_t w = 0;
+    bool ok = true;
+    for (uint32_t j = 0; j < k; ++j) {  // same encoding as the verification step of phfFindImpl
+      const uint8_t ch = text[p + j];
+      uint32_t cd;
+      if (ch == 'A') cd = 0; else if (ch == 'C') cd = 1; else if (ch == 'G') cd = 2; else if (ch == 'T') cd = 3; else { ok = false; break; }
+      w |= static_cast<uint64_t>(cd) << (2 * (k - 1 - j));
+    }
+    if (!ok) continue;
+    uint64_t word;
+    uint32_t mask;
+    filterSlot(mix64(w), shift, word, mask);
+    atomicOr(filter + word, mask);
+  }
+}
+
 // Packed-text records from the ASCII text (device_index.cuh: TextRec).  *bad is raised when a character lies outside
 // '$'..'z': the packed compare orders the search sentinels '#' and '{' against every text character without looking.
 __global__ void build_text2_kernel(const uint8_t* text, uint64_t n, TextRec* recs, uint64_t numRecs, uint32_t* bad) {
@@ -284,9 +302,10 @@ int rapmap_cuda_index_load(const char* index_dir, int device, rapmap_cuda_index_
   hdr.offTxpOffsets = off; off = align256(off + T * 4);
   hdr.offTxpLens = off; off = align256(off + T * 4);
   hdr.offTable = off; off = align256(off + slots * 16);
-  if (!h.perfectHash && !h.kmers.empty()) {  // ~6 bits per k-mer, capped at 64 MB (L2-resident)
+  const uint64_t numKeys = h.perfectHash ? h.phf.data.size() : h.kmers.size();
+  if (numKeys > 0) {  // ~6 bits per k-mer, capped at 64 MB (L2-resident)
     uint64_t words = 1024;
-    while (words * 32 < 6 * h.kmers.size() && words < (1ull << 24)) words <<= 1;
+    while (words * 32 < 6 * numKeys && words < (1ull << 24)) words <<= 1;
     hdr.filterWords = words;
     hdr.offFilter = off; off = align256(off + words * 4);
   }
@@ -352,6 +371,15 @@ int rapmap_cuda_index_load(const char* index_dir, int device, rapmap_cuda_index_
     if (!h.phf.data.empty()) IDX_TRY(cudaMemcpy(idx->blob + hdr.offPhfData, h.phf.data.data(), h.phf.data.size() * 4, cudaMemcpyHostToDevice));
     if (!h.phf.lens.empty()) IDX_TRY(cudaMemcpy(idx->blob + hdr.offPhfLens, h.phf.lens.data(), h.phf.lens.size(), cudaMemcpyHostToDevice));
     if (!h.phf.overflow.empty()) IDX_TRY(cudaMemcpy(idx->blob + hdr.offPhfOverflow, h.phf.overflow.data(), h.phf.overflow.size() * 8, cudaMemcpyHostToDevice));
+  }
+  if (h.perfectHash && hdr.offFilter) {
+    // -p index: the k-mer records are not stored, so the filter is filled from the text.  Every key FrugalBooMap::find can
+    // return is verified against 31 text bases (include/FrugalBooMap.hpp:149-167), i.e. it is a k-mer of the text.
+    uint32_t shift = 64;
+    for (uint64_t w = hdr.filterWords; w > 1; w >>= 1) --shift;
+    IDX_TRY(cudaMemset(idx->blob + hdr.offFilter, 0, hdr.filterWords * 4));
+    build_filter_from_text_kernel<<<4096, 256>>>(idx->blob + hdr.offText, n, hdr.k, reinterpret_cast<uint32_t*>(idx->blob + hdr.offFilter), shift);
+    IDX_TRY(cudaDeviceSynchronize());
   }
   {  // packed text
     uint32_t* dBad = nullptr;

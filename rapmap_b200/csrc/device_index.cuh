@@ -8,7 +8,8 @@
 //   at most 64 MB so that it stays resident in the 126 MB L2, loads carry an L2 evict_last policy).  ~90 % of the
 //   lookups of a read with sequencing errors are for k-mers that are not in the index (the 31 windows covering a
 //   mismatch, both orientations); the filter answers ~92 % of those from L2 without touching the table in HBM.
-//   No false negatives, so every lookup result is unchanged.
+//   No false negatives, so every lookup result is unchanged.  For -p indexes (no k-mer records on disk) the filter is
+//   filled from the text: every key FrugalBooMap::find can return is verified against 31 text bases.
 // * packed text: one 32-byte record per 32 text positions holding the 2-bit codes of the NEXT 64 positions and
 //   their non-ACGT mask, so the 32-base window at ANY position p lies inside record p/32: one aligned 256-bit load
 //   (one DRAM sector) feeds 32 character comparisons of extendSearchNaive.  The ASCII text stays for exact

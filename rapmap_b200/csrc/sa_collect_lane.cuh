@@ -302,7 +302,7 @@ __device__ __forceinline__ void hashFind2(const DeviceIndex& ix, uint64_t ka, ui
   if (ix.hashKind) {  // -p index: the two BooPHF walks run one after the other (one inlined copy of the walk)
 #pragma unroll 1
     for (int which = 0; which < 2; ++which) {
-      const int2 res = phfFindImpl(ix, which ? kb : ka);
+      const int2 res = (which ? knownB : knownA) ? make_int2(-1, -1) : phfFindImpl(ix, which ? kb : ka);
       if (which) rb = res; else ra = res;
     }
     return;
