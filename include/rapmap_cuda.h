@@ -111,6 +111,9 @@ typedef struct {
   uint32_t launches;        /* kernels launched by the call */
   uint32_t retries;         /* arena-overflow relaunches    */
   uint64_t sa_intervals;    /* SAIntervalHit records produced by the SA-lookup kernel */
+  float ms_ksw;             /* the ksw2 DP kernels alone (part of ms_sel_aln) */
+  uint32_t dp_jobs;         /* ksw_extz2 DP problems of the batch (getAlnScore calls that reach the aligner) */
+  uint32_t dp_jobs_general; /* of those, the ones the thread-per-job kernel left to the general warp-per-job kernel */
 } rapmap_cuda_timing_t;
 
 /* Thread-local message for the last non-zero status. */
@@ -133,7 +136,8 @@ uint32_t rapmap_cuda_index_k(const rapmap_cuda_index_t* idx);
 uint64_t rapmap_cuda_index_device_bytes(const rapmap_cuda_index_t* idx);
 /* Packed device image, for replicating the index to other GPUs (one ncclBroadcast of this blob):
  * export copies the image to a caller buffer of `bytes` (device memory on idx's device);
- * import builds an index object on `device` around a received blob. */
+ * import builds an index object on `device` around a received blob (256-byte aligned device memory that the caller
+ * keeps alive); the image carries the transcript names and lengths, so meta_src may be NULL. */
 int rapmap_cuda_index_image_bytes(const rapmap_cuda_index_t* idx, uint64_t* bytes);
 int rapmap_cuda_index_image_ptr(const rapmap_cuda_index_t* idx, void** device_ptr);
 int rapmap_cuda_index_from_image(const rapmap_cuda_index_t* meta_src, int device, void* device_blob, uint64_t bytes,
@@ -148,6 +152,14 @@ void rapmap_cuda_mapper_free(rapmap_cuda_mapper_t* m);
 /* The hot path: body of the `for (auto& rpair : rg)` loop of processReadsPairSA for a whole chunk
  * (src/RapMapSAMapper.cpp:461-711), up to and excluding SAM formatting. */
 int rapmap_cuda_map_batch(rapmap_cuda_mapper_t* m, const rapmap_read_batch_t* reads, rapmap_hit_batch_t* out);
+/* The same call split in two, so that ONE host thread can keep several mappers (CUDA streams) busy — the reference gets
+ * its overlap from N worker threads around a shared parser queue (src/RapMapSAMapper.cpp:853-909); here chunk i+1 is
+ * enqueued on another mapper while chunk i runs.  _async validates, enqueues the copies and every kernel of the batch on
+ * the mapper's stream and returns without waiting; `reads`, its buffers, `out` and its buffers must stay valid and
+ * untouched until rapmap_cuda_mapper_wait(m) returns, which fills out->num_hits / counters and the caller's buffers.
+ * One batch in flight per mapper.  rapmap_cuda_map_batch == _async followed by _wait. */
+int rapmap_cuda_map_batch_async(rapmap_cuda_mapper_t* m, const rapmap_read_batch_t* reads, rapmap_hit_batch_t* out);
+int rapmap_cuda_mapper_wait(rapmap_cuda_mapper_t* m);
 int rapmap_cuda_last_timing(const rapmap_cuda_mapper_t* m, rapmap_cuda_timing_t* t);
 /* The mapper's CUDA stream (cudaStream_t as void*): every kernel and copy of map_batch is issued on it, so a caller
  * can bracket calls with its own CUDA events. */
@@ -165,10 +177,15 @@ typedef struct {
 int rapmap_cuda_debug_intervals(rapmap_cuda_mapper_t* m, uint64_t read_index, rapmap_sa_interval_t* out, uint32_t cap,
                                 uint32_t* n_fwd, uint32_t* n_rc, uint8_t* found_hit);
 
-/* Host-side SAM text for a chunk (src/RapMapUtils.cpp:313-588,137-196; include/RapMapUtils.hpp:687-810):
- * names are '\0'-separated per read.  Returns a malloc'ed buffer the caller frees with rapmap_cuda_free. */
+/* Host-side SAM text for a chunk: paired reads (writeAlignmentsToStream / writeUnalignedPairToStream,
+ * src/RapMapUtils.cpp:313-588,137-196) or, when reads->seq2 == NULL, unmated reads (:198-311; names2 may be NULL);
+ * include/RapMapUtils.hpp:687-810 for flags and soft clipping.  names are '\0'-separated per read.  Returns a malloc'ed
+ * buffer the caller frees with rapmap_cuda_free.  _mt splits the chunk over `threads` host threads (the reference formats
+ * inside its N worker threads); the text is identical. */
 int rapmap_cuda_format_sam(const rapmap_cuda_index_t* idx, const rapmap_cuda_opts_t* opts, const rapmap_read_batch_t* reads,
                            const char* names1, const char* names2, rapmap_hit_batch_t* hits, char** sam, uint64_t* sam_len);
+int rapmap_cuda_format_sam_mt(const rapmap_cuda_index_t* idx, const rapmap_cuda_opts_t* opts, const rapmap_read_batch_t* reads,
+                              const char* names1, const char* names2, rapmap_hit_batch_t* hits, uint32_t threads, char** sam, uint64_t* sam_len);
 int rapmap_cuda_sam_header(const rapmap_cuda_index_t* idx, char** sam, uint64_t* sam_len);
 void rapmap_cuda_free(void* p);
 

@@ -201,8 +201,17 @@ int main(int argc, char** argv) {
       M.samPair(n1, s1, n2, s2, joint, sam);
       std::fwrite(sam.data(), 1, sam.size(), out);
     }
+  } else if (!ru.empty()) {
+    std::ifstream f(ru);
+    std::string n, sq;
+    while (nextFastq(f, n, sq)) {
+      M.mapSingle(sq, joint);
+      sam.clear();
+      M.samSingle(n, sq, joint, sam);
+      std::fwrite(sam.data(), 1, sam.size(), out);
+    }
   } else {
-    std::fprintf(stderr, "unmated SAM output not implemented in the oracle CLI\n");
+    std::fprintf(stderr, "no reads given (-1/-2 or -r)\n");
     return 1;
   }
   if (out != stdout) std::fclose(out);

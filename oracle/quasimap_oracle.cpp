@@ -1473,4 +1473,31 @@ void Mapper::samPair(const std::string& n1, const std::string& s1, const std::st
   }
 }
 
+// src/RapMapUtils.cpp:198-311 (unmated reads): writeUnalignedSingleToStream / the single-read writeAlignmentsToStream with
+// getSamFlags(qa, flags) of include/RapMapUtils.hpp:737-768.  The name is cut at the first space only.
+void Mapper::samSingle(const std::string& name, const std::string& seq, std::vector<QuasiAlignment>& hits, std::string& out) {
+  std::string rn = name.substr(0, std::min(name.find(' '), name.size()));
+  auto T = [](long v) { return std::to_string(v); };
+  if (hits.empty()) {
+    out += rn + "\t4\t*\t0\t255\t*\t*\t0\t0\t" + seq + "\t*\tNH:i:0\tHI:i:0\tAS:i:0\n";
+    return;
+  }
+  std::string nh = "NH:i:" + T(static_cast<long>(hits.size()));
+  std::string rev, cigar;
+  bool haveRev = false;
+  uint32_t alnCtr = 0;
+  size_t i = 0;
+  for (auto& qa : hits) {
+    ++i;
+    uint16_t flags = qa.fwd ? 0 : 0x10;
+    if (alnCtr != 0) flags |= 0x900;
+    const std::string* rs = &seq;
+    if (!qa.fwd) { if (!haveRev) { reverseRead(seq, rev); haveRev = true; } rs = &rev; }
+    adjustOverhang(qa.pos, qa.readLen, static_cast<uint32_t>(idx.txpLens[qa.tid]), cigar);
+    out += rn + "\t" + T(flags) + "\t" + idx.txpNames[qa.tid] + "\t" + T(qa.pos + 1) + "\t255\t" + cigar + "\t*\t0\t" + T(qa.fragLen) + "\t" + *rs +
+           "\t*\t" + nh + "\tHI:i:" + T(static_cast<long>(i)) + "\tAS:i:" + T(qa.alnScore) + "\n";
+    ++alnCtr;
+  }
+}
+
 } // namespace oracle

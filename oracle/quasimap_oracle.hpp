@@ -114,6 +114,7 @@ public:
   // src/RapMapUtils.cpp:313-588 / :137-196 (SAM text for one pair)
   void samPair(const std::string& n1, const std::string& s1, const std::string& n2, const std::string& s2,
                std::vector<QuasiAlignment>& jointHits, std::string& out);
+  void samSingle(const std::string& name, const std::string& seq, std::vector<QuasiAlignment>& hits, std::string& out);
   std::string samHeader() const;
   // src/ksw2pp/KSW2Aligner.cpp:205-234 -> src/ksw2pp/ksw2_extz2_sse.c:18-304 (score only); returns max(mqe,mte)
   int32_t kswExtzScore(const char* q, int qlen, const char* t, int tlen);

@@ -105,6 +105,7 @@ class Timing(C.Structure):
         ("ms_h2d", C.c_float), ("ms_sa_collect", C.c_float), ("ms_hits_to_mappings", C.c_float), ("ms_merge", C.c_float),
         ("ms_sel_aln", C.c_float), ("ms_pack_reads", C.c_float), ("ms_d2h", C.c_float), ("ms_total", C.c_float),
         ("launches", C.c_uint32), ("retries", C.c_uint32), ("sa_intervals", C.c_uint64),
+        ("ms_ksw", C.c_float), ("dp_jobs", C.c_uint32), ("dp_jobs_general", C.c_uint32),
     ]
 
 
@@ -117,8 +118,9 @@ SYMBOLS = [
     "rapmap_cuda_last_error", "rapmap_cuda_opts_default", "rapmap_cuda_opts_selaln", "rapmap_cuda_index_load", "rapmap_cuda_index_free",
     "rapmap_cuda_index_num_transcripts", "rapmap_cuda_index_transcript_name", "rapmap_cuda_index_transcript_len", "rapmap_cuda_index_k",
     "rapmap_cuda_index_device_bytes", "rapmap_cuda_index_image_bytes", "rapmap_cuda_index_image_ptr", "rapmap_cuda_index_from_image",
-    "rapmap_cuda_mapper_create", "rapmap_cuda_mapper_free", "rapmap_cuda_map_batch", "rapmap_cuda_last_timing", "rapmap_cuda_mapper_stream", "rapmap_cuda_debug_intervals",
-    "rapmap_cuda_format_sam", "rapmap_cuda_sam_header", "rapmap_cuda_free",
+    "rapmap_cuda_mapper_create", "rapmap_cuda_mapper_free", "rapmap_cuda_map_batch", "rapmap_cuda_map_batch_async", "rapmap_cuda_mapper_wait",
+    "rapmap_cuda_last_timing", "rapmap_cuda_mapper_stream", "rapmap_cuda_debug_intervals",
+    "rapmap_cuda_format_sam", "rapmap_cuda_format_sam_mt", "rapmap_cuda_sam_header", "rapmap_cuda_free",
 ]
 
 _lib = None
@@ -153,11 +155,15 @@ def lib() -> C.CDLL:
     L.rapmap_cuda_mapper_create.argtypes = [C.c_void_p, C.POINTER(Opts), C.c_uint64, C.c_uint32, C.POINTER(C.c_void_p)]
     L.rapmap_cuda_mapper_free.argtypes = [C.c_void_p]
     L.rapmap_cuda_map_batch.argtypes = [C.c_void_p, C.POINTER(ReadBatch), C.POINTER(HitBatch)]
+    L.rapmap_cuda_map_batch_async.argtypes = [C.c_void_p, C.POINTER(ReadBatch), C.POINTER(HitBatch)]
+    L.rapmap_cuda_mapper_wait.argtypes = [C.c_void_p]
     L.rapmap_cuda_last_timing.argtypes = [C.c_void_p, C.POINTER(Timing)]
     L.rapmap_cuda_mapper_stream.argtypes = [C.c_void_p]
     L.rapmap_cuda_mapper_stream.restype = C.c_void_p
     L.rapmap_cuda_debug_intervals.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(SAInterval), C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint8)]
     L.rapmap_cuda_format_sam.argtypes = [C.c_void_p, C.POINTER(Opts), C.POINTER(ReadBatch), C.c_char_p, C.c_char_p, C.POINTER(HitBatch), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    L.rapmap_cuda_format_sam_mt.argtypes = [C.c_void_p, C.POINTER(Opts), C.POINTER(ReadBatch), C.c_char_p, C.c_char_p, C.POINTER(HitBatch), C.c_uint32,
+                                            C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
     L.rapmap_cuda_sam_header.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
     L.rapmap_cuda_free.argtypes = [C.c_void_p]
     _lib = L
@@ -270,6 +276,7 @@ class Mapper:
         _check(lib().rapmap_cuda_mapper_create(index._h, C.byref(self.opts), max_batch, max_read_len, C.byref(self._h)))
         self._hits_buf = None
         self._off_buf = None
+        self._pending = None
 
     def _read_batch(self, seq1, seq2, n, fixed_len, off1, off2, location) -> ReadBatch:
         rb = ReadBatch()
@@ -285,7 +292,22 @@ class Mapper:
     def map_batch(self, seq1, seq2=None, n: Optional[int] = None, fixed_len: int = 0, off1=None, off2=None,
                   location: int = LOC_HOST, hits_out=None, offsets_out=None, out_location: int = LOC_HOST, capacity: Optional[int] = None) -> BatchResult:
         """Maps one chunk. ``seq*``: uint8 numpy arrays (host) or torch CUDA tensors (location=LOC_DEVICE).
-        Fixed-length reads: row-major ``n x fixed_len``; otherwise pass uint64 offset arrays of n+1 entries."""
+        Fixed-length reads: row-major ``n x fixed_len``; otherwise pass uint64 offset arrays of n+1 entries.
+        Without ``hits_out`` the result arrays are views of buffers the mapper reuses: copy them before the next call."""
+        self.map_batch_async(seq1, seq2, n, fixed_len, off1, off2, location, hits_out, offsets_out, out_location, capacity)
+        try:
+            return self.wait()
+        except RapMapCudaError as e:
+            if e.code == ERR_CAPACITY and hits_out is None:
+                self._hits_buf = np.empty(int(self._pending[1].num_hits) + 1024, dtype=HIT_DTYPE)
+                self._pending = None
+                return self.map_batch(seq1, seq2, n, fixed_len, off1, off2, location, None, None, out_location, None)
+            raise
+
+    def map_batch_async(self, seq1, seq2=None, n: Optional[int] = None, fixed_len: int = 0, off1=None, off2=None,
+                        location: int = LOC_HOST, hits_out=None, offsets_out=None, out_location: int = LOC_HOST, capacity: Optional[int] = None) -> None:
+        """rapmap_cuda_map_batch_async: enqueues the chunk on the mapper's stream and returns; :meth:`wait` collects it.
+        The input and output buffers must stay alive and untouched until then (the mapper keeps references)."""
         if n is None:
             n = (len(off1) - 1) if off1 is not None else int(np.prod(seq1.shape)) // fixed_len
         rb = self._read_batch(seq1, seq2, n, fixed_len, off1, off2, location)
@@ -301,11 +323,19 @@ class Mapper:
         hb.hits = _as_ptr(hits_out)
         hb.hits_capacity = capacity if capacity is not None else (len(hits_out) if isinstance(hits_out, np.ndarray) else hits_out.numel() // 28)
         hb.pair_offsets = _as_ptr(offsets_out)
-        rc = lib().rapmap_cuda_map_batch(self._h, C.byref(rb), C.byref(hb))
-        if rc == ERR_CAPACITY and isinstance(hits_out, np.ndarray) and hits_out is self._hits_buf:
-            self._hits_buf = np.empty(int(hb.num_hits) + 1024, dtype=HIT_DTYPE)
-            return self.map_batch(seq1, seq2, n, fixed_len, off1, off2, location, None, None, out_location, None)
+        self._pending = (rb, hb, hits_out, offsets_out, n, (seq1, seq2, off1, off2))
+        rc = lib().rapmap_cuda_map_batch_async(self._h, C.byref(rb), C.byref(hb))
+        if rc != OK:
+            self._pending = None
         _check(rc)
+
+    def wait(self) -> BatchResult:
+        """rapmap_cuda_mapper_wait: blocks until the chunk in flight is mapped and its result is in the output buffers."""
+        if self._pending is None:
+            raise RapMapCudaError(ERR_ARG, "no batch in flight")
+        rb, hb, hits_out, offsets_out, n, _keep = self._pending
+        _check(lib().rapmap_cuda_mapper_wait(self._h))
+        self._pending = None
         nh = int(hb.num_hits)
         if isinstance(hits_out, np.ndarray):
             return BatchResult(hits_out[:nh], offsets_out[: n + 1], np.array(list(hb.counters), dtype=np.uint64), nh)
@@ -329,8 +359,9 @@ class Mapper:
         ivs = [(int(b.begin), int(b.end), int(b.len), int(b.query_pos), int(b.query_rc)) for b in buf[: nf.value + nr.value]]
         return bool(found.value), nf.value, nr.value, ivs
 
-    def format_sam(self, seq1, seq2, names1, names2, result: BatchResult, n: int, fixed_len: int = 0, off1=None, off2=None) -> bytes:
-        """SAM text of a chunk (host side; reference src/RapMapUtils.cpp:313-588). names*: lists of str."""
+    def format_sam(self, seq1, seq2, names1, names2, result: BatchResult, n: int, fixed_len: int = 0, off1=None, off2=None, threads: int = 1) -> bytes:
+        """SAM text of a chunk (host side; reference src/RapMapUtils.cpp:230-588). names*: lists of str; seq2 / names2 None for
+        unmated reads."""
         rb = self._read_batch(seq1, seq2, n, fixed_len, off1, off2, LOC_HOST)
         hb = HitBatch()
         hits = np.ascontiguousarray(result.hits)
@@ -342,7 +373,7 @@ class Mapper:
         n1 = b"\0".join(s.encode() for s in names1) + b"\0"
         n2 = (b"\0".join(s.encode() for s in names2) + b"\0") if names2 is not None else None
         p, ln = C.c_void_p(), C.c_uint64()
-        _check(lib().rapmap_cuda_format_sam(self.index._h, C.byref(self.opts), C.byref(rb), n1, n2, C.byref(hb), C.byref(p), C.byref(ln)))
+        _check(lib().rapmap_cuda_format_sam_mt(self.index._h, C.byref(self.opts), C.byref(rb), n1, n2, C.byref(hb), threads, C.byref(p), C.byref(ln)))
         try:
             return C.string_at(p, ln.value)
         finally:

@@ -7,7 +7,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
+#include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/rapmap_cuda.h"
@@ -15,9 +18,7 @@
 #include "index_loader.hpp"
 #include "kernels.cuh"
 #include "merge_pairs.cuh"
-#include "sa_collect.cuh"
 #include "sa_collect_lane.cuh"
-#include "sa_collect_regroup.cuh"
 #include "sam_writer.hpp"
 #include "sel_aln.cuh"
 
@@ -38,6 +39,20 @@ int fail(int code, const std::string& msg) {
     if (e__ != cudaSuccess)                                                                              \
       return fail(RAPMAP_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));                \
   } while (0)
+
+// No exception crosses the C-ABI: allocation failures and the like become error codes.
+template <class F>
+int guarded(F&& f) {
+  try {
+    return f();
+  } catch (const std::bad_alloc&) {
+    return fail(RAPMAP_ERR_IO, "out of host memory (or a corrupt size field in the index)");
+  } catch (const std::exception& e) {
+    return fail(RAPMAP_ERR_IO, std::string("exception: ") + e.what());
+  } catch (...) {
+    return fail(RAPMAP_ERR_IO, "unknown exception");
+  }
+}
 
 inline uint64_t align256(uint64_t x) { return (x + 255) / 256 * 256; }
 
@@ -171,11 +186,18 @@ struct rapmap_cuda_mapper {
   uint8_t* dSeq[2]{nullptr, nullptr};
   uint64_t* dOff[2]{nullptr, nullptr};
   uint64_t seqCap{0};
-  // stage 1
+  // stage 1: SA lookup (lane per read)
   ReadSummary* dSumm{nullptr};
   IntervalRec* dIvArena{nullptr};
   uint32_t ivCap{0};
-  // stage 2
+  uint64_t scratchSlotsK1{0};
+  uint4* dPacked{nullptr};
+  IntervalRec* dIvScratch{nullptr};
+  uint32_t ivStride{0};
+  uint32_t* dVoteScratch{nullptr};
+  uint32_t voteWords{0}, laneWords{0}, laneSmem{0}, pmax{0};
+  int gridLane{0};
+  // stage 2: hit resolution
   QASummary* dQSumm{nullptr};
   QARec* dQaArena{nullptr};
   uint32_t qaCap{0};
@@ -185,40 +207,36 @@ struct rapmap_cuda_mapper {
   uint32_t scratchEntries{0};
   uint64_t scratchStride{0};
   uint32_t smemEntries{64};
-  int gridCollect{0}, gridMap{0};
-  uint32_t collectSmem{0}, mapSmem{0};
-  uint32_t lpad{0}, pmax{0}, warpSmem{0}, packOff{0}, ctxOff{0}, voteOff{0};
-  // stage 1, lane-per-read form
-  bool laneKernel{true};
-  int regroup{0};            // 0: lane kernel; else threads per block of the regrouped SA-lookup kernel (128 / 256)
-  uint32_t regroupSmem{0};
-  int gridRegroup{0};
-  uint64_t scratchSlotsK1{0};
+  int gridMap{0};
+  uint32_t mapSmem{0};
   bool laneMap{false};
   bool chainLaneMap{false};
   int gridLaneMap{0};
-  uint4* dPacked{nullptr};
-  IntervalRec* dIvScratch{nullptr};
-  uint32_t ivStride{0};
-  uint32_t* dVoteScratch{nullptr};
-  uint32_t voteWords{0}, laneWords{0}, laneSmem{0};
-  int gridLane{0};
-  // stage 3
+  // stage 3: mate merge
   uint32_t* dPairCount{nullptr};
   uint64_t* dPairOff{nullptr};
   rapmap_hit_t* dHits{nullptr};
   uint64_t hitsCap{0};
+  // stage 4: selective alignment
   SelAlnWork selaln{};
+  SelAlnLaunch selLaunch{};
   void* dCubTemp{nullptr};
   size_t cubTempBytes{0};
   // control words: [0] interval cursor, [1] qa cursor, [2] pos cursor, [3] status, [4] read cursor of the lane kernel
   uint32_t* dCtl{nullptr};
   Counters5* dCounters{nullptr};
-  struct Stage { uint32_t ctl[4]; Counters5 counters; uint64_t total; }* hStage{nullptr};
-  cudaEvent_t ev[9]{};
+  // pinned block the stream writes at the end of an attempt; the host reads it after ONE synchronisation
+  struct Stage { uint32_t ctl[4]; uint64_t mergeTotal; uint64_t selTotal; uint32_t dpJobs[2]; Counters5 counters; }* hStage{nullptr};
+  cudaEvent_t ev[11]{};
+  cudaEvent_t evDone{nullptr};   // cudaEventBlockingSync: a waiting host thread sleeps instead of spinning
   rapmap_cuda_timing_t timing{};
   BatchView lastView{};
   uint64_t lastReads{0};
+  // the batch in flight between map_batch_async and mapper_wait
+  bool inFlight{false};
+  bool paired{false};
+  rapmap_hit_batch_t* pendingOut{nullptr};
+  uint32_t launches{0};
 };
 
 static constexpr int kWarps = 8;
@@ -242,7 +260,6 @@ static constexpr int kChainLaneCap = RAPMAP_CHAINLANE_CAP;
 static constexpr int kMapLaneThreads = 128;                // lane-per-read hit resolution
 static constexpr int kMapLaneCap = RAPMAP_MAPLANE_CAP;     // SA entries per read it takes
 static constexpr uint32_t kMapLaneSmem = 2u * kMapLaneCap * kMapLaneThreads * 8u;
-static constexpr int kRegroupSlots = 512;                   // reads a block of the regrouped SA-lookup kernel keeps in flight
 static constexpr int kLaneThreads = RAPMAP_LANE_THREADS;  // lane-per-read SA-lookup kernel: threads per block
 static constexpr int kLaneMinBlocks = RAPMAP_LANE_MINB;   // 3 x 256 threads, 80 registers: the 64-register build spills and is 13 % slower
 
@@ -271,19 +288,18 @@ void rapmap_cuda_opts_selaln(rapmap_cuda_opts_t* o) {
   o->sel_aln = 1;
 }
 
-int rapmap_cuda_index_load(const char* index_dir, int device, rapmap_cuda_index_t** out) {
+static int indexLoadImpl(const char* index_dir, int device, rapmap_cuda_index_t** out) {
   if (!index_dir || !out) return fail(RAPMAP_ERR_ARG, "null argument");
   *out = nullptr;
+  HostIndex h;
+  std::string err;
+  if (!h.load(index_dir, err)) return fail(h.unsupported ? RAPMAP_ERR_UNSUPPORTED : RAPMAP_ERR_IO, err);
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
     return fail(RAPMAP_ERR_CUDA, std::string("no CUDA device available (") + cudaGetErrorString(e) + "); this engine has no CPU path");
   if (device < 0 || device >= ndev) return fail(RAPMAP_ERR_ARG, "bad device ordinal");
   CU_TRY(cudaSetDevice(device));
-
-  HostIndex h;
-  std::string err;
-  if (!h.load(index_dir, err)) return fail(RAPMAP_ERR_IO, err);
 
   const uint64_t n = h.SA.size();
   const uint64_t T = h.txpOffsets.size();
@@ -333,6 +349,9 @@ int rapmap_cuda_index_load(const char* index_dir, int device, rapmap_cuda_index_
     hdr.offPhfLens = off; off = align256(off + h.phf.lens.size() + 1);
     hdr.offPhfOverflow = off; off = align256(off + (h.phf.overflow.size() + 1) * 8);
   }
+  uint64_t namesBytes = 0;
+  for (const auto& nm : h.txpNames) namesBytes += nm.size() + 1;
+  hdr.offNames = off; hdr.namesBytes = namesBytes; off = align256(off + namesBytes + 1);
   hdr.totalBytes = off;
 
   auto* idx = new rapmap_cuda_index();
@@ -358,6 +377,12 @@ int rapmap_cuda_index_load(const char* index_dir, int device, rapmap_cuda_index_
   }
   IDX_TRY(cudaMemcpy(idx->blob + hdr.offTxpOffsets, h.txpOffsets.data(), T * 4, cudaMemcpyHostToDevice));
   IDX_TRY(cudaMemcpy(idx->blob + hdr.offTxpLens, h.txpLens.data(), T * 4, cudaMemcpyHostToDevice));
+  {
+    std::string names;
+    names.reserve(namesBytes);
+    for (const auto& nm : h.txpNames) { names += nm; names.push_back('\0'); }
+    IDX_TRY(cudaMemcpy(idx->blob + hdr.offNames, names.data(), names.size(), cudaMemcpyHostToDevice));
+  }
   IDX_TRY(cudaMemset(idx->blob + hdr.offTable, 0xFF, slots * 16));
   if (h.perfectHash) {
     IDX_TRY(cudaMemset(idx->blob + hdr.offPhfLevels, 0, hdr.totalBytes - hdr.offPhfLevels));
@@ -421,6 +446,10 @@ int rapmap_cuda_index_load(const char* index_dir, int device, rapmap_cuda_index_
   return RAPMAP_OK;
 }
 
+int rapmap_cuda_index_load(const char* index_dir, int device, rapmap_cuda_index_t** out) {
+  return guarded([&] { return indexLoadImpl(index_dir, device, out); });
+}
+
 void rapmap_cuda_index_free(rapmap_cuda_index_t* idx) {
   if (!idx) return;
   if (idx->ownsBlob && idx->blob) { cudaSetDevice(idx->device); cudaFree(idx->blob); }
@@ -447,21 +476,53 @@ int rapmap_cuda_index_image_ptr(const rapmap_cuda_index_t* idx, void** p) {
   *p = idx->blob;
   return RAPMAP_OK;
 }
-int rapmap_cuda_index_from_image(const rapmap_cuda_index_t* meta, int device, void* blob, uint64_t bytes, rapmap_cuda_index_t** out) {
+static int indexFromImageImpl(int device, void* blob, uint64_t bytes, rapmap_cuda_index_t** out) {
   if (!blob || !out) return fail(RAPMAP_ERR_ARG, "null argument");
+  *out = nullptr;
+  if (reinterpret_cast<uintptr_t>(blob) % 256 != 0) return fail(RAPMAP_ERR_ARG, "index image must be 256-byte aligned (the kernels use 256-bit loads)");
+  if (bytes < sizeof(ImageHeader)) return fail(RAPMAP_ERR_ARG, "not an index image (too small)");
   CU_TRY(cudaSetDevice(device));
   ImageHeader hdr;
   CU_TRY(cudaMemcpy(&hdr, blob, sizeof(hdr), cudaMemcpyDeviceToHost));
   if (hdr.magic != kImageMagic || hdr.totalBytes != bytes) return fail(RAPMAP_ERR_ARG, "not an index image (bad magic or size)");
+  {  // every section must lie inside the blob
+    const uint64_t n = hdr.n, T = hdr.numTxp;
+    struct { uint64_t off, len; } sec[] = {
+      {hdr.offSA, n * 4}, {hdr.offText, n + 256}, {hdr.offRank, (n / 64 + 1) * 16}, {hdr.offTxpOffsets, T * 4}, {hdr.offTxpLens, T * 4},
+      {hdr.offTable, hdr.tableSlots * 16}, {hdr.offFilter, hdr.offFilter ? hdr.filterWords * 4 : 0}, {hdr.offText2, hdr.offText2 ? (n / 32 + 2) * sizeof(TextRec) : 0},
+      {hdr.offNames, hdr.namesBytes}};
+    for (const auto& sc : sec)
+      if (sc.off > bytes || sc.len > bytes - sc.off) return fail(RAPMAP_ERR_ARG, "index image: a section lies outside the blob");
+    if (hdr.tableSlots == 0 || (hdr.tableSlots & (hdr.tableSlots - 1)) != 0) return fail(RAPMAP_ERR_ARG, "index image: table size is not a power of two");
+    if (hdr.hashKind && (hdr.offPhfLevels > bytes || hdr.offPhfOverflow > bytes)) return fail(RAPMAP_ERR_ARG, "index image: a section lies outside the blob");
+  }
   auto* idx = new rapmap_cuda_index();
   idx->device = device;
   idx->blob = static_cast<uint8_t*>(blob);
   idx->ownsBlob = false;
   idx->hdr = hdr;
   idx->view = viewOf(idx->blob, hdr);
-  if (meta) { idx->names = meta->names; idx->lens = meta->lens; }
+  // transcript names and lengths travel inside the image
+  std::string names(hdr.namesBytes, '\0');
+  idx->lens.resize(hdr.numTxp);
+  cudaError_t e1 = hdr.namesBytes ? cudaMemcpy(&names[0], idx->blob + hdr.offNames, hdr.namesBytes, cudaMemcpyDeviceToHost) : cudaSuccess;
+  cudaError_t e2 = hdr.numTxp ? cudaMemcpy(idx->lens.data(), idx->blob + hdr.offTxpLens, hdr.numTxp * 4, cudaMemcpyDeviceToHost) : cudaSuccess;
+  if (e1 != cudaSuccess || e2 != cudaSuccess) { delete idx; return fail(RAPMAP_ERR_CUDA, "index image: reading the transcript table failed"); }
+  idx->names.reserve(hdr.numTxp);
+  for (size_t p = 0; p < names.size() && idx->names.size() < hdr.numTxp;) {
+    const size_t e = names.find('\0', p);
+    if (e == std::string::npos) break;
+    idx->names.emplace_back(names, p, e - p);
+    p = e + 1;
+  }
+  if (idx->names.size() != hdr.numTxp) { delete idx; return fail(RAPMAP_ERR_ARG, "index image: transcript name table is inconsistent"); }
   *out = idx;
   return RAPMAP_OK;
+}
+
+int rapmap_cuda_index_from_image(const rapmap_cuda_index_t* /*meta_src: unused since the image carries the names*/, int device, void* blob, uint64_t bytes,
+                                 rapmap_cuda_index_t** out) {
+  return guarded([&] { return indexFromImageImpl(device, blob, bytes, out); });
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -514,11 +575,19 @@ static void freeMapperBuffers(rapmap_cuda_mapper* m) {
   selAlnFree(m->selaln);
   if (m->hStage) cudaFreeHost(m->hStage);
   for (auto& e : m->ev) if (e) cudaEventDestroy(e);
+  if (m->evDone) cudaEventDestroy(m->evDone);
   if (m->stream) cudaStreamDestroy(m->stream);
 }
 
-int rapmap_cuda_mapper_create(const rapmap_cuda_index_t* idx, const rapmap_cuda_opts_t* opts, uint64_t max_batch, uint32_t max_read_len,
-                              rapmap_cuda_mapper_t** out) {
+// RAPMAP_B200_TINY_ARENAS=1 (tests only): every growable device work area starts far too small, so that the first batch
+// of a mapper walks through each overflow -> grow -> re-run path of finishBatch().
+static bool tinyArenas() {
+  const char* t = std::getenv("RAPMAP_B200_TINY_ARENAS");
+  return t && t[0] == '1';
+}
+
+static int mapperCreateImpl(const rapmap_cuda_index_t* idx, const rapmap_cuda_opts_t* opts, uint64_t max_batch, uint32_t max_read_len,
+                            rapmap_cuda_mapper_t** out) {
   if (!idx || !opts || !out || max_batch == 0) return fail(RAPMAP_ERR_ARG, "null / zero argument");
   *out = nullptr;
   if (max_read_len < idx->hdr.k || max_read_len > 1000) return fail(RAPMAP_ERR_ARG, "max_read_len must be in [k, 1000]");
@@ -531,11 +600,14 @@ int rapmap_cuda_mapper_create(const rapmap_cuda_index_t* idx, const rapmap_cuda_
   m->idx = idx; m->opts = *opts; m->dopts = d; m->maxBatch = max_batch; m->maxReadLen = max_read_len;
   auto bail = [&](const std::string& msg) { freeMapperBuffers(m); delete m; return fail(RAPMAP_ERR_CUDA, msg); };
 #define M_TRY(call) do { cudaError_t e2 = (call); if (e2 != cudaSuccess) return bail(std::string(#call) + ": " + cudaGetErrorString(e2)); } while (0)
+  const bool tiny = tinyArenas();
+  const bool needPos = opts->sel_aln || opts->fuzzy;
   cudaDeviceProp prop;
   M_TRY(cudaGetDeviceProperties(&prop, idx->device));
   m->numSMs = prop.multiProcessorCount;
   M_TRY(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
   for (auto& e : m->ev) M_TRY(cudaEventCreate(&e));
+  M_TRY(cudaEventCreateWithFlags(&m->evDone, cudaEventBlockingSync | cudaEventDisableTiming));
   const uint64_t R = 2 * max_batch;
   m->seqCap = max_batch * max_read_len;
   for (int i = 0; i < 2; ++i) {
@@ -543,16 +615,15 @@ int rapmap_cuda_mapper_create(const rapmap_cuda_index_t* idx, const rapmap_cuda_
     M_TRY(cudaMalloc(&m->dOff[i], (max_batch + 1) * 8));
   }
   M_TRY(cudaMalloc(&m->dSumm, R * sizeof(ReadSummary)));
-  m->ivCap = static_cast<uint32_t>(std::min<uint64_t>(R * (opts->sel_aln ? 10 : 4) + 1024, 0xFFFFFFF0ull));
-  M_TRY(cudaMalloc(&m->dIvArena, static_cast<uint64_t>(m->ivCap) * sizeof(IntervalRec)));
   M_TRY(cudaMalloc(&m->dQSumm, R * sizeof(QASummary)));
-  m->qaCap = static_cast<uint32_t>(std::min<uint64_t>(R * 8 + 1024, 0xFFFFFFF0ull));
+  m->qaCap = tiny ? 8u : static_cast<uint32_t>(std::min<uint64_t>(R * 8 + 1024, 0xFFFFFFF0ull));
   M_TRY(cudaMalloc(&m->dQaArena, static_cast<uint64_t>(m->qaCap) * sizeof(QARec)));
-  m->posCap = opts->sel_aln ? static_cast<uint32_t>(std::min<uint64_t>(R * 12 + 1024, 0xFFFFFFF0ull)) : 16;
+  // position lists exist whenever the fuzzy merge runs (-s or -f)
+  m->posCap = (needPos && !tiny) ? static_cast<uint32_t>(std::min<uint64_t>(R * 12 + 1024, 0xFFFFFFF0ull)) : 16;
   M_TRY(cudaMalloc(&m->dPosPool, static_cast<uint64_t>(m->posCap) * 4));
   M_TRY(cudaMalloc(&m->dPairCount, (max_batch + 1) * 4));
   M_TRY(cudaMalloc(&m->dPairOff, (max_batch + 1) * 8));
-  m->hitsCap = max_batch * 6 + 1024;
+  m->hitsCap = tiny ? 8 : max_batch * 6 + 1024;
   M_TRY(cudaMalloc(&m->dHits, m->hitsCap * sizeof(rapmap_hit_t)));
   M_TRY(cudaMalloc(&m->dCtl, 8 * 4));
   M_TRY(cudaMalloc(&m->dCounters, sizeof(Counters5)));
@@ -563,27 +634,11 @@ int rapmap_cuda_mapper_create(const rapmap_cuda_index_t* idx, const rapmap_cuda_
     M_TRY(cudaMalloc(&m->dCubTemp, m->cubTempBytes + 16));
   }
   // ---- launch geometry: persistent grids, whole multiples of the SM count
-  m->lpad = (max_read_len + 15) / 16 * 16;
   m->pmax = max_read_len - idx->hdr.k + 1;
-  m->packOff = (2 * m->lpad + 2 * m->pmax * 8 + 2 * m->pmax * static_cast<uint32_t>(sizeof(IntervalRec)) + 15) / 16 * 16;
-  m->ctxOff = (m->packOff + (m->lpad / 32 + 2) * (2 * 8 + 4 * 4) + 15) / 16 * 16;
-  m->voteOff = (m->ctxOff + static_cast<uint32_t>(sizeof(WarpCtx)) + 15) / 16 * 16;
-  m->warpSmem = (m->voteOff + 2 * m->pmax + 15) / 16 * 16;
-  m->collectSmem = m->warpSmem * kWarps;
-  if (m->collectSmem > 227 * 1024) return bail("max_read_len too large for the shared-memory read cache");
-  M_TRY(cudaFuncSetAttribute(sa_collect_kernel<kWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(m->collectSmem)));
-  // NB: no cudaSharedmemCarveoutMaxShared here - these kernels live off L1 hits on the text / SA / table sectors; forcing the
-  // maximum shared-memory carve-out shrank L1 and cost 20 % (profiles/r01_notes.md).
   int occ = 0;
-  M_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sa_collect_kernel<kWarps>, kWarps * 32, m->collectSmem));
-  if (occ < 1) return bail("sa_collect_kernel does not fit on an SM");
-  m->gridCollect = m->numSMs * occ;
-  // lane-per-read form of kernel 1 (default); RAPMAP_B200_K1=warp selects the warp-per-read form for A/B runs
-  {
-    const char* sel = std::getenv("RAPMAP_B200_K1");
-    m->laneKernel = !(sel && std::string(sel) == "warp");
-  }
-  if (m->laneKernel) {
+  // NB: no cudaSharedmemCarveoutMaxShared here - these kernels live off L1 hits on the text / SA / table sectors; forcing the
+  // maximum shared-memory carve-out shrank L1 and cost 20 %.
+  {  // SA-lookup kernel: one thread per read
     m->laneWords = (max_read_len + 31) / 32;
     m->laneSmem = m->laneWords * 16u * kLaneThreads;
     if (m->laneSmem > 227 * 1024) return bail("max_read_len too large for the shared-memory read words");
@@ -591,45 +646,26 @@ int rapmap_cuda_mapper_create(const rapmap_cuda_index_t* idx, const rapmap_cuda_
     M_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sa_collect_lane_kernel<kLaneThreads, kLaneMinBlocks>, kLaneThreads, m->laneSmem));
     if (occ < 1) return bail("sa_collect_lane_kernel does not fit on an SM");
     m->gridLane = m->numSMs * occ;
-    uint64_t scratchSlots = static_cast<uint64_t>(m->gridLane) * kLaneThreads;
-    {  // regrouped form (reads of a block sorted by their next step): RAPMAP_B200_K1=regroup128 / regroup256
-      const char* sel = std::getenv("RAPMAP_B200_K1");
-      const std::string mode = sel ? sel : "";
-      if ((mode == "regroup128" || mode == "regroup256") && m->laneWords <= 8) {
-        m->regroup = mode == "regroup128" ? 128 : 256;
-        m->regroupSmem = regroupSmemBytes(m->laneWords, kRegroupSlots);
-        if (m->regroup == 128) {
-          M_TRY(cudaFuncSetAttribute(sa_collect_regroup_kernel<128, kRegroupSlots>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(m->regroupSmem)));
-          M_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sa_collect_regroup_kernel<128, kRegroupSlots>, 128, m->regroupSmem));
-        } else {
-          M_TRY(cudaFuncSetAttribute(sa_collect_regroup_kernel<256, kRegroupSlots>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(m->regroupSmem)));
-          M_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sa_collect_regroup_kernel<256, kRegroupSlots>, 256, m->regroupSmem));
-        }
-        if (occ < 1) return bail("sa_collect_regroup_kernel does not fit on an SM");
-        m->gridRegroup = m->numSMs * occ;
-        scratchSlots = std::max<uint64_t>(scratchSlots, static_cast<uint64_t>(m->gridRegroup) * kRegroupSlots);
-      }
-    }
-    m->scratchSlotsK1 = scratchSlots;
+    m->scratchSlotsK1 = static_cast<uint64_t>(m->gridLane) * kLaneThreads;
     M_TRY(cudaMalloc(&m->dPacked, R * m->laneWords * sizeof(uint4)));
-    {  // every resident warp reserves arena records RAPMAP_LANE_CHUNK at a time: allow for the unused tails
-      const uint64_t want = static_cast<uint64_t>(m->ivCap) + static_cast<uint64_t>(m->gridLane) * (kLaneThreads / 32) * RAPMAP_LANE_CHUNK;
-      cudaFree(m->dIvArena); m->dIvArena = nullptr;
-      m->ivCap = static_cast<uint32_t>(std::min<uint64_t>(want, 0xFFFFFFF0ull));
-      M_TRY(cudaMalloc(&m->dIvArena, static_cast<uint64_t>(m->ivCap) * sizeof(IntervalRec)));
-    }
-    m->ivStride = std::min<uint32_t>(m->pmax, 24);
-    M_TRY(cudaMalloc(&m->dIvScratch, scratchSlots * 2 * m->ivStride * sizeof(IntervalRec)));
+    // interval arena: 4 (10 with chaining) records per read, plus the unused tails of the RAPMAP_LANE_CHUNK-record slices
+    // every resident warp reserves
+    const uint64_t want = R * (needPos ? 10 : 4) + 1024 + static_cast<uint64_t>(m->gridLane) * (kLaneThreads / 32) * RAPMAP_LANE_CHUNK;
+    m->ivCap = tiny ? 64u : static_cast<uint32_t>(std::min<uint64_t>(want, 0xFFFFFFF0ull));
+    M_TRY(cudaMalloc(&m->dIvArena, static_cast<uint64_t>(m->ivCap) * sizeof(IntervalRec)));
+    m->ivStride = tiny ? 1u : std::min<uint32_t>(m->pmax, 24);
+    M_TRY(cudaMalloc(&m->dIvScratch, m->scratchSlotsK1 * 2 * m->ivStride * sizeof(IntervalRec)));
     const bool voteMode = d.strictCheck && !(d.disableNIP && d.strictCheck);
     if (voteMode) {
       m->voteWords = (m->pmax + 31) / 32;
-      M_TRY(cudaMalloc(&m->dVoteScratch, scratchSlots * 3 * m->voteWords * 4));
+      M_TRY(cudaMalloc(&m->dVoteScratch, m->scratchSlotsK1 * 3 * m->voteWords * 4));
     }
   }
-  {  // lane-per-read form of kernel 2 for plain quasimap (no chaining, no position lists); RAPMAP_B200_K2=warp turns it off
+  {  // lane-per-read hit resolution: plain form for default quasimap, chaining form for -s / -f; RAPMAP_B200_K2=warp turns both off
     const char* sel = std::getenv("RAPMAP_B200_K2");
-    m->laneMap = !d.selAln && !d.fuzzy && !d.doChaining && !(sel && std::string(sel) == "warp");
-    m->chainLaneMap = !m->laneMap && !(sel && std::string(sel) == "warp");
+    const bool off = sel && std::string(sel) == "warp";
+    m->laneMap = !d.selAln && !d.fuzzy && !d.doChaining && !off;
+    m->chainLaneMap = !m->laneMap && !off;
     if (m->chainLaneMap) {
       const uint32_t smemC = chainLaneStride(kChainLaneCap) * kChainLaneThreads;
       M_TRY(cudaFuncSetAttribute(hits_to_mappings_chain_lane_kernel<kChainLaneThreads, kChainLaneCap>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smemC)));
@@ -652,23 +688,19 @@ int rapmap_cuda_mapper_create(const rapmap_cuda_index_t* idx, const rapmap_cuda_
   // global work strip per resident warp: the worst case of one strand is (pmax intervals) x (maxInterval-1 entries);
   // 8192 entries cover every read whose expanded intervals total <= 4096 SA entries (pow2 padding), larger reads are
   // reported through kStatScratchFull and re-run with a strip sized from the actual maximum.
-  m->scratchEntries = 8192;
+  m->scratchEntries = tiny ? 128 : 8192;
   m->scratchStride = workAreaBytes(m->scratchEntries);
   M_TRY(cudaMalloc(&m->dScratch, m->scratchStride * static_cast<uint64_t>(m->gridMap) * kWarps));
   if (opts->sel_aln) {
-    cudaError_t e2 = selAlnAlloc(m->selaln, max_batch, max_read_len);
+    cudaError_t e2 = selAlnAlloc(m->selaln, max_batch, max_read_len, m->hitsCap);
     if (e2 != cudaSuccess) return bail(std::string("selAlnAlloc: ") + cudaGetErrorString(e2));
+    std::string serr;
+    int rc2 = selAlnSetup(m->selaln, m->selLaunch, serr);
+    if (rc2) { freeMapperBuffers(m); delete m; return fail(rc2, serr); }
   }
 #undef M_TRY
   *out = m;
   return RAPMAP_OK;
-}
-
-void rapmap_cuda_mapper_free(rapmap_cuda_mapper_t* m) {
-  if (!m) return;
-  cudaSetDevice(m->idx->device);
-  freeMapperBuffers(m);
-  delete m;
 }
 
 static int growU32(void** p, uint32_t& cap, uint64_t need, size_t elem) {
@@ -681,9 +713,108 @@ static int growU32(void** p, uint32_t& cap, uint64_t need, size_t elem) {
   return RAPMAP_OK;
 }
 
-int rapmap_cuda_map_batch(rapmap_cuda_mapper_t* m, const rapmap_read_batch_t* reads, rapmap_hit_batch_t* out) {
+// Enqueues one attempt at the batch on the mapper's stream: K0 pack, K1 SA lookup, K2 hit resolution, K3 merge
+// (count -> scan -> write), K4 selective alignment, then the copy of the control block to pinned host memory.  Nothing
+// here waits for the device: every kernel launches against the CURRENT capacities and raises a status bit instead of
+// writing past them (finishBatch grows what overflowed and calls this again).
+static int enqueueAttempt(rapmap_cuda_mapper* m) {
+  cudaStream_t st = m->stream;
+  const BatchView& bv = m->lastView;
+  const uint64_t n = bv.n;
+  const bool paired = m->paired;
+  CU_TRY(cudaMemsetAsync(m->dCtl, 0, 32, st));
+  CU_TRY(cudaMemsetAsync(m->dCounters, 0, sizeof(Counters5), st));
+  // ---- kernel 1: SA lookup
+  LaneParams lp{};
+  lp.ix = m->idx->view; lp.reads = bv; lp.opts = m->dopts; lp.maxReadLen = m->maxReadLen; lp.nw = m->laneWords; lp.packed = m->dPacked;
+  lp.summ = m->dSumm; lp.arena = m->dIvArena; lp.arenaCap = m->ivCap; lp.arenaCursor = m->dCtl + 0; lp.status = m->dCtl + 3;
+  lp.ivScratch = m->dIvScratch; lp.ivStride = m->ivStride; lp.voteScratch = m->dVoteScratch; lp.voteWords = m->voteWords; lp.readCursor = m->dCtl + 4;
+  const int g0 = static_cast<int>(std::min<uint64_t>(static_cast<uint64_t>(m->numSMs) * 8, (bv.numReads * m->laneWords + 255) / 256));
+  pack_reads_kernel<<<g0, 256, 0, st>>>(lp);
+  CU_TRY(cudaEventRecord(m->ev[8], st));
+  const int g1 = static_cast<int>(std::min<uint64_t>(m->gridLane, (bv.numReads + kLaneThreads - 1) / kLaneThreads));
+  sa_collect_lane_kernel<kLaneThreads, kLaneMinBlocks><<<g1, kLaneThreads, m->laneSmem, st>>>(lp);
+  m->launches += 2;
+  CU_TRY(cudaEventRecord(m->ev[2], st));
+  // ---- kernel 2: hit resolution
+  MapParams mp{};
+  mp.ix = m->idx->view; mp.opts = m->dopts; mp.numReads = bv.numReads; mp.numPairs = n; mp.pairedInput = paired ? 1 : 0;
+  mp.summ = m->dSumm; mp.arena = m->dIvArena; mp.qsumm = m->dQSumm; mp.qaArena = m->dQaArena; mp.qaCap = m->qaCap; mp.qaCursor = m->dCtl + 1;
+  mp.posPool = m->dPosPool; mp.posCap = m->posCap; mp.posCursor = m->dCtl + 2;
+  mp.scratch = m->dScratch; mp.scratchEntries = m->scratchEntries; mp.scratchStride = m->scratchStride; mp.smemEntries = m->smemEntries;
+  mp.status = m->dCtl + 3;
+  if (m->chainLaneMap) {  // -s / -f: thread-per-read with chaining and position lists; the marked rest below
+    const int gl = static_cast<int>(std::min<uint64_t>(m->gridLaneMap, (bv.numReads + kChainLaneThreads - 1) / kChainLaneThreads));
+    hits_to_mappings_chain_lane_kernel<kChainLaneThreads, kChainLaneCap><<<gl, kChainLaneThreads, chainLaneStride(kChainLaneCap) * kChainLaneThreads, st>>>(mp);
+    ++m->launches;
+    mp.skipDone = 1;
+  }
+  if (m->laneMap) {  // small reads thread-per-read; the rest (marked) by the warp-per-read kernel below
+    const int gl = static_cast<int>(std::min<uint64_t>(m->gridLaneMap, (bv.numReads + kMapLaneThreads - 1) / kMapLaneThreads));
+    hits_to_mappings_lane_kernel<kMapLaneThreads, kMapLaneCap><<<gl, kMapLaneThreads, kMapLaneSmem, st>>>(mp);
+    ++m->launches;
+    mp.skipDone = 1;
+  }
+  const int g2 = static_cast<int>(std::min<uint64_t>(m->gridMap, (bv.numReads + kWarps - 1) / kWarps));
+  hits_to_mappings_kernel<kWarps><<<g2, kWarps * 32, m->mapSmem, st>>>(mp);
+  ++m->launches;
+  CU_TRY(cudaEventRecord(m->ev[3], st));
+  // ---- kernel 3: mate merge: count -> exclusive scan -> write at the final, input-ordered offsets
+  MergeParams gp{};
+  gp.opts = m->dopts; gp.numPairs = n; gp.pairedInput = paired ? 1 : 0; gp.qsumm = m->dQSumm; gp.qaArena = m->dQaArena; gp.summ = m->dSumm;
+  gp.pairCount = m->dPairCount; gp.pairOffset = m->dPairOff; gp.hits = m->dHits; gp.hitsCap = m->hitsCap; gp.counters = m->dCounters;
+  gp.posPool = m->dPosPool;
+  gp.reads = bv; gp.text = m->idx->view.text; gp.txpOffsets = m->idx->view.txpOffsets; gp.txpLens = m->idx->view.txpLens;
+  const int g3 = static_cast<int>(std::min<uint64_t>(static_cast<uint64_t>(m->numSMs) * 8, (n + 255) / 256));
+  const bool fuzzy = paired && (m->dopts.selAln || m->dopts.fuzzy);  // unmated reads have no mate merge (processReadsSingleSA)
+  CU_TRY(cudaMemsetAsync(m->dPairCount + n, 0, 4, st));
+  if (fuzzy) merge_count_kernel<true><<<g3, 256, 0, st>>>(gp);
+  else merge_count_kernel<false><<<g3, 256, 0, st>>>(gp);
+  ++m->launches;
+  {
+    cub::TransformInputIterator<uint64_t, CastU64, uint32_t*> it(m->dPairCount, CastU64());
+    size_t tb = m->cubTempBytes;
+    CU_TRY(cub::DeviceScan::ExclusiveSum(m->dCubTemp, tb, it, m->dPairOff, static_cast<int>(n + 1), st));
+  }
+  CU_TRY(cudaMemcpyAsync(&m->hStage->mergeTotal, m->dPairOff + n, 8, cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaEventRecord(m->ev[4], st));
+  // optimistic: written against hitsCap (a pair whose slice would pass it is skipped; the host sees mergeTotal > hitsCap)
+  if (fuzzy) merge_write_kernel<true><<<g3, 256, 0, st>>>(gp);
+  else merge_write_kernel<false><<<g3, 256, 0, st>>>(gp);
+  ++m->launches;
+  CU_TRY(cudaEventRecord(m->ev[5], st));
+  // ---- selective alignment (ksw2 scoring + score filter): survivors to selaln.outHits, dPairOff rewritten in place
+  m->hStage->selTotal = 0; m->hStage->dpJobs[0] = 0; m->hStage->dpJobs[1] = 0;
+  if (m->dopts.selAln) {
+    int rc = selAlnEnqueue(m->selaln, m->selLaunch, m->idx->view, m->dopts, bv, n, paired, m->dHits, m->dPairOff, m->hitsCap, m->dCubTemp, m->cubTempBytes,
+                           m->numSMs, st, &m->launches, &m->hStage->selTotal, m->hStage->dpJobs, m->ev[9], m->ev[10], g_err);
+    if (rc) return rc;
+  }
+  CU_TRY(cudaEventRecord(m->ev[6], st));
+  CU_TRY(cudaMemcpyAsync(m->hStage->ctl, m->dCtl, 16, cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaMemcpyAsync(&m->hStage->counters, m->dCounters, sizeof(Counters5), cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaEventRecord(m->evDone, st));
+  return RAPMAP_OK;
+}
+
+// Host threads sleep on the blocking event for big batches (several mappers per process: spinning threads fight the
+// launching ones for cores); small batches spin, the wake-up latency would show.
+static cudaError_t waitAttempt(rapmap_cuda_mapper* m) {
+  if (m->lastView.n >= 32768) return cudaEventSynchronize(m->evDone);
+  return cudaStreamSynchronize(m->stream);
+}
+
+static int mapBatchAsyncImpl(rapmap_cuda_mapper_t* m, const rapmap_read_batch_t* reads, rapmap_hit_batch_t* out) {
   if (!m || !reads || !out) return fail(RAPMAP_ERR_ARG, "null argument");
-  if (reads->n == 0) { out->num_hits = 0; std::memset(out->counters, 0, sizeof(out->counters)); if (out->pair_offsets && out->location == RAPMAP_LOC_HOST) out->pair_offsets[0] = 0; return RAPMAP_OK; }
+  if (m->inFlight) return fail(RAPMAP_ERR_ARG, "the mapper already has a batch in flight (call rapmap_cuda_mapper_wait first)");
+  m->pendingOut = out;
+  std::memset(&m->timing, 0, sizeof(m->timing));
+  if (reads->n == 0) {
+    m->lastView = BatchView{};
+    m->lastReads = 0;
+    m->inFlight = true;
+    return RAPMAP_OK;
+  }
   if (reads->n > m->maxBatch) return fail(RAPMAP_ERR_ARG, "batch larger than the mapper's max_batch");
   if (!reads->seq1) return fail(RAPMAP_ERR_ARG, "seq1 is null");
   if (!reads->off1 && (reads->fixed_len == 0 || reads->fixed_len > m->maxReadLen)) return fail(RAPMAP_ERR_ARG, "fixed_len must be in [1, max_read_len]");
@@ -692,15 +823,13 @@ int rapmap_cuda_map_batch(rapmap_cuda_mapper_t* m, const rapmap_read_batch_t* re
   CU_TRY(cudaSetDevice(m->idx->device));
   cudaStream_t st = m->stream;
   const uint64_t n = reads->n;
-  const bool paired = reads->seq2 != nullptr;
-  std::memset(&m->timing, 0, sizeof(m->timing));
+  m->paired = reads->seq2 != nullptr;
 
   // ---- reads to the device
   CU_TRY(cudaEventRecord(m->ev[0], st));
   BatchView bv{};
-  bv.n = n; bv.numReads = paired ? 2 * n : n; bv.fixedLen = reads->fixed_len;
-  uint64_t h2d = 0;
-  for (int mate = 0; mate < (paired ? 2 : 1); ++mate) {
+  bv.n = n; bv.numReads = m->paired ? 2 * n : n; bv.fixedLen = reads->fixed_len;
+  for (int mate = 0; mate < (m->paired ? 2 : 1); ++mate) {
     const uint8_t* seq = mate ? reads->seq2 : reads->seq1;
     const uint64_t* off = mate ? reads->off2 : reads->off1;
     if (reads->location == RAPMAP_LOC_DEVICE) {
@@ -710,93 +839,45 @@ int rapmap_cuda_map_batch(rapmap_cuda_mapper_t* m, const rapmap_read_batch_t* re
       if (off && off[0] != 0) return fail(RAPMAP_ERR_ARG, "offsets must start at 0");
       if (bytes > m->seqCap) return fail(RAPMAP_ERR_ARG, "read bases exceed max_batch * max_read_len");
       CU_TRY(cudaMemcpyAsync(m->dSeq[mate], seq, bytes, cudaMemcpyHostToDevice, st));
-      h2d += bytes;
       bv.seq[mate] = m->dSeq[mate];
-      if (off) { CU_TRY(cudaMemcpyAsync(m->dOff[mate], off, (n + 1) * 8, cudaMemcpyHostToDevice, st)); bv.off[mate] = m->dOff[mate]; h2d += (n + 1) * 8; }
+      if (off) { CU_TRY(cudaMemcpyAsync(m->dOff[mate], off, (n + 1) * 8, cudaMemcpyHostToDevice, st)); bv.off[mate] = m->dOff[mate]; }
       else bv.off[mate] = nullptr;
     }
   }
   m->lastView = bv;
   m->lastReads = bv.numReads;
   CU_TRY(cudaEventRecord(m->ev[1], st));
+  m->launches = 0;
+  int rc = enqueueAttempt(m);
+  if (rc) return rc;
+  m->inFlight = true;
+  return RAPMAP_OK;
+}
 
-  uint32_t launches = 0, retries = 0;
+// Waits for the attempt in flight; grows what overflowed and re-runs (deterministic: same batch, bigger arenas); then copies
+// the result to the caller's buffers.  Two host synchronisations in the common case: one for the control block, one for
+// the result copy whose size the control block gives.
+static int mapperWaitImpl(rapmap_cuda_mapper_t* m) {
+  if (!m) return fail(RAPMAP_ERR_ARG, "null argument");
+  if (!m->inFlight) return fail(RAPMAP_ERR_ARG, "no batch in flight");
+  m->inFlight = false;
+  rapmap_hit_batch_t* out = m->pendingOut;
+  const uint64_t n = m->lastView.n;
+  if (n == 0) {
+    out->num_hits = 0;
+    std::memset(out->counters, 0, sizeof(out->counters));
+    if (out->pair_offsets && out->location == RAPMAP_LOC_HOST) out->pair_offsets[0] = 0;
+    return RAPMAP_OK;
+  }
+  CU_TRY(cudaSetDevice(m->idx->device));
+  cudaStream_t st = m->stream;
+  uint32_t retries = 0;
   uint64_t total = 0;
   for (;; ++retries) {
-    if (retries > 6) return fail(RAPMAP_ERR_CAPACITY, "device work arenas kept overflowing");
-    CU_TRY(cudaMemsetAsync(m->dCtl, 0, 32, st));
-    CU_TRY(cudaMemsetAsync(m->dCounters, 0, sizeof(Counters5), st));
-    // ---- kernel 1: SA lookup
-    CollectParams cp{};
-    cp.ix = m->idx->view; cp.reads = bv; cp.opts = m->dopts; cp.maxReadLen = m->maxReadLen; cp.lpad = m->lpad; cp.pmax = m->pmax;
-    cp.warpSmemBytes = m->warpSmem; cp.packOff = m->packOff; cp.ctxOff = m->ctxOff; cp.voteOff = m->voteOff; cp.summ = m->dSumm; cp.arena = m->dIvArena; cp.arenaCap = m->ivCap; cp.arenaCursor = m->dCtl + 0; cp.status = m->dCtl + 3;
-    if (m->laneKernel) {
-      LaneParams lp{};
-      lp.ix = m->idx->view; lp.reads = bv; lp.opts = m->dopts; lp.maxReadLen = m->maxReadLen; lp.nw = m->laneWords; lp.packed = m->dPacked;
-      lp.summ = m->dSumm; lp.arena = m->dIvArena; lp.arenaCap = m->ivCap; lp.arenaCursor = m->dCtl + 0; lp.status = m->dCtl + 3;
-      lp.ivScratch = m->dIvScratch; lp.ivStride = m->ivStride; lp.voteScratch = m->dVoteScratch; lp.voteWords = m->voteWords; lp.readCursor = m->dCtl + 4;
-      const int g0 = static_cast<int>(std::min<uint64_t>(static_cast<uint64_t>(m->numSMs) * 8, (bv.numReads * m->laneWords + 255) / 256));
-      pack_reads_kernel<<<g0, 256, 0, st>>>(lp);
-      CU_TRY(cudaEventRecord(m->ev[8], st));
-      if (m->regroup) {
-        const int g1 = static_cast<int>(std::min<uint64_t>(m->gridRegroup, (bv.numReads + kRegroupSlots - 1) / kRegroupSlots));
-        if (m->regroup == 128) sa_collect_regroup_kernel<128, kRegroupSlots><<<g1, 128, m->regroupSmem, st>>>(lp);
-        else sa_collect_regroup_kernel<256, kRegroupSlots><<<g1, 256, m->regroupSmem, st>>>(lp);
-      } else {
-        const int g1 = static_cast<int>(std::min<uint64_t>(m->gridLane, (bv.numReads + kLaneThreads - 1) / kLaneThreads));
-        sa_collect_lane_kernel<kLaneThreads, kLaneMinBlocks><<<g1, kLaneThreads, m->laneSmem, st>>>(lp);
-      }
-      launches += 2;
-    } else {
-      int g1 = static_cast<int>(std::min<uint64_t>(m->gridCollect, (bv.numReads + kWarps - 1) / kWarps));
-      sa_collect_kernel<kWarps><<<g1, kWarps * 32, m->collectSmem, st>>>(cp);
-      ++launches;
-    }
-    CU_TRY(cudaEventRecord(m->ev[2], st));
-    // ---- kernel 2: hit resolution
-    MapParams mp{};
-    mp.ix = m->idx->view; mp.opts = m->dopts; mp.numReads = bv.numReads; mp.numPairs = n; mp.pairedInput = paired ? 1 : 0;
-    mp.summ = m->dSumm; mp.arena = m->dIvArena; mp.qsumm = m->dQSumm; mp.qaArena = m->dQaArena; mp.qaCap = m->qaCap; mp.qaCursor = m->dCtl + 1;
-    mp.posPool = m->dPosPool; mp.posCap = m->posCap; mp.posCursor = m->dCtl + 2;
-    mp.scratch = m->dScratch; mp.scratchEntries = m->scratchEntries; mp.scratchStride = m->scratchStride; mp.smemEntries = m->smemEntries;
-    mp.status = m->dCtl + 3;
-    if (m->chainLaneMap) {  // -s / -f: thread-per-read with chaining and position lists; the marked rest below
-      const int gl = static_cast<int>(std::min<uint64_t>(m->gridLaneMap, (bv.numReads + kChainLaneThreads - 1) / kChainLaneThreads));
-      hits_to_mappings_chain_lane_kernel<kChainLaneThreads, kChainLaneCap><<<gl, kChainLaneThreads, chainLaneStride(kChainLaneCap) * kChainLaneThreads, st>>>(mp);
-      ++launches;
-      mp.skipDone = 1;
-    }
-    if (m->laneMap) {  // small reads thread-per-read; the rest (marked) by the warp-per-read kernel below
-      const int gl = static_cast<int>(std::min<uint64_t>(m->gridLaneMap, (bv.numReads + kMapLaneThreads - 1) / kMapLaneThreads));
-      hits_to_mappings_lane_kernel<kMapLaneThreads, kMapLaneCap><<<gl, kMapLaneThreads, kMapLaneSmem, st>>>(mp);
-      ++launches;
-      mp.skipDone = 1;
-    }
-    int g2 = static_cast<int>(std::min<uint64_t>(m->gridMap, (bv.numReads + kWarps - 1) / kWarps));
-    hits_to_mappings_kernel<kWarps><<<g2, kWarps * 32, m->mapSmem, st>>>(mp);
-    ++launches;
-    CU_TRY(cudaEventRecord(m->ev[3], st));
-    // ---- kernel 3: mate merge (count)
-    MergeParams gp{};
-    gp.opts = m->dopts; gp.numPairs = n; gp.pairedInput = paired ? 1 : 0; gp.qsumm = m->dQSumm; gp.qaArena = m->dQaArena; gp.summ = m->dSumm;
-    gp.pairCount = m->dPairCount; gp.pairOffset = m->dPairOff; gp.hits = m->dHits; gp.hitsCap = m->hitsCap; gp.counters = m->dCounters;
-    gp.posPool = m->dPosPool;
-    gp.reads = bv; gp.text = m->idx->view.text; gp.txpOffsets = m->idx->view.txpOffsets; gp.txpLens = m->idx->view.txpLens;
-    int g3 = static_cast<int>(std::min<uint64_t>(static_cast<uint64_t>(m->numSMs) * 8, (n + 255) / 256));
-    CU_TRY(cudaMemsetAsync(m->dPairCount + n, 0, 4, st));
-    if (m->dopts.selAln || m->dopts.fuzzy) merge_count_kernel<true><<<g3, 256, 0, st>>>(gp);
-    else merge_count_kernel<false><<<g3, 256, 0, st>>>(gp);
-    ++launches;
-    {
-        cub::TransformInputIterator<uint64_t, CastU64, uint32_t*> it(m->dPairCount, CastU64());
-      size_t tb = m->cubTempBytes;
-      CU_TRY(cub::DeviceScan::ExclusiveSum(m->dCubTemp, tb, it, m->dPairOff, static_cast<int>(n + 1), st));
-    }
-    CU_TRY(cudaMemcpyAsync(m->hStage->ctl, m->dCtl, 16, cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaMemcpyAsync(&m->hStage->total, m->dPairOff + n, 8, cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaStreamSynchronize(st));
+    CU_TRY(waitAttempt(m));
     CU_TRY(cudaGetLastError());
-    uint32_t status = m->hStage->ctl[3];
+    if (retries > 8) return fail(RAPMAP_ERR_CAPACITY, "device work arenas kept overflowing");
+    const uint32_t status = m->hStage->ctl[3];
     if (status & kStatReadTooLong) return fail(RAPMAP_ERR_ARG, "a read is longer than the mapper's max_read_len");
     bool again = false;
     if (status & kStatIntervalArenaFull) { int rc = growU32(reinterpret_cast<void**>(&m->dIvArena), m->ivCap, m->hStage->ctl[0], sizeof(IntervalRec)); if (rc) return rc; again = true; }
@@ -823,34 +904,21 @@ int rapmap_cuda_map_batch(rapmap_cuda_mapper_t* m, const rapmap_read_batch_t* re
       CU_TRY(cudaMalloc(&m->dScratch, m->scratchStride * static_cast<uint64_t>(m->gridMap) * kWarps));
       again = true;
     }
-    total = m->hStage->total;
-    if (!again && total > m->hitsCap) {
+    if (!again && m->hStage->mergeTotal > m->hitsCap) {  // the merge produced more records than the hit array holds
       cudaFree(m->dHits); m->dHits = nullptr;
-      m->hitsCap = total + total / 4 + 1024;
+      m->hitsCap = m->hStage->mergeTotal + m->hStage->mergeTotal / 4 + 1024;
       CU_TRY(cudaMalloc(&m->dHits, m->hitsCap * sizeof(rapmap_hit_t)));
-      gp.hits = m->dHits; gp.hitsCap = m->hitsCap;
+      if (m->dopts.selAln) {
+        cudaError_t e2 = selAlnReserve(m->selaln, m->hitsCap);
+        if (e2 != cudaSuccess) return fail(RAPMAP_ERR_CUDA, std::string("selAlnReserve: ") + cudaGetErrorString(e2));
+      }
+      again = true;
     }
-    if (again) continue;
-    CU_TRY(cudaEventRecord(m->ev[4], st));
-    // ---- kernel 3: mate merge (write)
-    if (total > 0) {
-      if (m->dopts.selAln || m->dopts.fuzzy) merge_write_kernel<true><<<g3, 256, 0, st>>>(gp);
-      else merge_write_kernel<false><<<g3, 256, 0, st>>>(gp);
-      ++launches;
-    }
-    CU_TRY(cudaEventRecord(m->ev[5], st));
-    break;
-  }
-  // ---- selective alignment (ksw2 scoring + score filter), rewrites dHits / dPairOff in place
-  if (m->dopts.selAln && total > 0) {
-    uint32_t l2 = 0;
-    int rc = selAlnRun(m->selaln, m->idx->view, m->dopts, bv, n, paired, m->dHits, m->dPairOff, total, m->dCubTemp, m->cubTempBytes, m->numSMs, st,
-                       &l2, &total, g_err);
+    if (!again) break;
+    int rc = enqueueAttempt(m);
     if (rc) return rc;
-    launches += l2;
   }
-  CU_TRY(cudaEventRecord(m->ev[6], st));
-  CU_TRY(cudaMemcpyAsync(&m->hStage->counters, m->dCounters, sizeof(Counters5), cudaMemcpyDeviceToHost, st));
+  total = m->dopts.selAln ? m->hStage->selTotal : m->hStage->mergeTotal;
   // ---- results out
   out->num_hits = total;
   int rcOut = RAPMAP_OK;
@@ -858,28 +926,63 @@ int rapmap_cuda_map_batch(rapmap_cuda_mapper_t* m, const rapmap_read_batch_t* re
     rcOut = fail(RAPMAP_ERR_CAPACITY, "hits_capacity too small for this batch (see num_hits)");
   } else {
     cudaMemcpyKind kind = out->location == RAPMAP_LOC_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
-    rapmap_hit_t* src = (m->dopts.selAln && total > 0) ? m->selaln.outHits : m->dHits;
+    const rapmap_hit_t* src = m->dopts.selAln ? m->selaln.outHits : m->dHits;
     if (total > 0) CU_TRY(cudaMemcpyAsync(out->hits, src, total * sizeof(rapmap_hit_t), kind, st));
     CU_TRY(cudaMemcpyAsync(out->pair_offsets, m->dPairOff, (n + 1) * 8, kind, st));
   }
   CU_TRY(cudaEventRecord(m->ev[7], st));
-  CU_TRY(cudaStreamSynchronize(st));
+  CU_TRY(cudaEventRecord(m->evDone, st));
+  CU_TRY(waitAttempt(m));
   for (int c = 0; c < 5; ++c) out->counters[c] = m->hStage->counters.v[c];
-  if (m->dopts.selAln) out->counters[3] = total;  // totHits is taken after the score filter (reference src/RapMapSAMapper.cpp:702)
+  // paired reads: totHits is taken after the score filter (reference src/RapMapSAMapper.cpp:702); unmated: before (:241-246)
+  if (m->dopts.selAln && m->paired) out->counters[3] = total;
   auto ms = [&](int a, int b) { float t = 0; cudaEventElapsedTime(&t, m->ev[a], m->ev[b]); return t; };
   m->timing.ms_h2d = ms(0, 1);
-  m->timing.ms_sa_collect = m->laneKernel ? ms(8, 2) : ms(1, 2);
-  m->timing.ms_pack_reads = m->laneKernel ? ms(1, 8) : 0.0f;
-  m->timing.ms_hits_to_mappings = ms(2, 3);
-  m->timing.ms_merge = ms(3, 4) + ms(4, 5);
-  m->timing.ms_sel_aln = ms(5, 6);
-  m->timing.ms_d2h = ms(6, 7);
+  if (retries == 0) {  // the events of a re-run attempt do not line up with ev[0]/ev[1]: stage times are reported for clean batches only
+    m->timing.ms_pack_reads = ms(1, 8);
+    m->timing.ms_sa_collect = ms(8, 2);
+    m->timing.ms_hits_to_mappings = ms(2, 3);
+    m->timing.ms_merge = ms(3, 5);
+    m->timing.ms_sel_aln = ms(5, 6);
+    m->timing.ms_ksw = m->dopts.selAln ? ms(9, 10) : 0.0f;
+    m->timing.ms_d2h = ms(6, 7);
+  }
   m->timing.ms_total = ms(0, 7);
-  m->timing.launches = launches;
+  m->timing.launches = m->launches;
   m->timing.retries = retries;
   m->timing.sa_intervals = m->hStage->ctl[0];
-  (void)h2d;
+  m->timing.dp_jobs = m->hStage->dpJobs[0];
+  m->timing.dp_jobs_general = m->hStage->dpJobs[1];
   return rcOut;
+}
+
+int rapmap_cuda_mapper_create(const rapmap_cuda_index_t* idx, const rapmap_cuda_opts_t* opts, uint64_t max_batch, uint32_t max_read_len,
+                              rapmap_cuda_mapper_t** out) {
+  return guarded([&] { return mapperCreateImpl(idx, opts, max_batch, max_read_len, out); });
+}
+
+void rapmap_cuda_mapper_free(rapmap_cuda_mapper_t* m) {
+  if (!m) return;
+  cudaSetDevice(m->idx->device);
+  if (m->inFlight) cudaStreamSynchronize(m->stream);
+  freeMapperBuffers(m);
+  delete m;
+}
+
+int rapmap_cuda_map_batch_async(rapmap_cuda_mapper_t* m, const rapmap_read_batch_t* reads, rapmap_hit_batch_t* out) {
+  return guarded([&] { return mapBatchAsyncImpl(m, reads, out); });
+}
+
+int rapmap_cuda_mapper_wait(rapmap_cuda_mapper_t* m) {
+  return guarded([&] { return mapperWaitImpl(m); });
+}
+
+int rapmap_cuda_map_batch(rapmap_cuda_mapper_t* m, const rapmap_read_batch_t* reads, rapmap_hit_batch_t* out) {
+  return guarded([&] {
+    int rc = mapBatchAsyncImpl(m, reads, out);
+    if (rc) return rc;
+    return mapperWaitImpl(m);
+  });
 }
 
 int rapmap_cuda_last_timing(const rapmap_cuda_mapper_t* m, rapmap_cuda_timing_t* t) {
@@ -890,16 +993,17 @@ int rapmap_cuda_last_timing(const rapmap_cuda_mapper_t* m, rapmap_cuda_timing_t*
 
 void* rapmap_cuda_mapper_stream(const rapmap_cuda_mapper_t* m) { return m ? static_cast<void*>(m->stream) : nullptr; }
 
-int rapmap_cuda_debug_intervals(rapmap_cuda_mapper_t* m, uint64_t read_index, rapmap_sa_interval_t* out, uint32_t cap, uint32_t* n_fwd,
-                                uint32_t* n_rc, uint8_t* found_hit) {
+static int debugIntervalsImpl(rapmap_cuda_mapper_t* m, uint64_t read_index, rapmap_sa_interval_t* out, uint32_t cap, uint32_t* n_fwd,
+                              uint32_t* n_rc, uint8_t* found_hit) {
   if (!m || !n_fwd || !n_rc || !found_hit) return fail(RAPMAP_ERR_ARG, "null argument");
+  if (m->inFlight) return fail(RAPMAP_ERR_ARG, "a batch is in flight");
   if (read_index >= m->lastReads) return fail(RAPMAP_ERR_ARG, "read index out of range of the last batch");
   CU_TRY(cudaSetDevice(m->idx->device));
   ReadSummary s;
   CU_TRY(cudaMemcpy(&s, m->dSumm + read_index, sizeof(s), cudaMemcpyDeviceToHost));
   *n_fwd = s.nFwd; *n_rc = s.nRc; *found_hit = s.found;
   uint32_t tot = static_cast<uint32_t>(s.nFwd) + s.nRc;
-  if (tot > cap) return fail(RAPMAP_ERR_CAPACITY, "interval buffer too small");
+  if (tot > cap || (tot > 0 && !out)) return fail(RAPMAP_ERR_CAPACITY, "interval buffer too small");
   if (tot == 0) return RAPMAP_OK;
   std::vector<IntervalRec> tmp(tot);
   CU_TRY(cudaMemcpy(tmp.data(), m->dIvArena + s.ivOff, tot * sizeof(IntervalRec), cudaMemcpyDeviceToHost));
@@ -909,6 +1013,11 @@ int rapmap_cuda_debug_intervals(rapmap_cuda_mapper_t* m, uint64_t read_index, ra
     out[i].query_rc = i >= s.nFwd ? 1 : 0;
   }
   return RAPMAP_OK;
+}
+
+int rapmap_cuda_debug_intervals(rapmap_cuda_mapper_t* m, uint64_t read_index, rapmap_sa_interval_t* out, uint32_t cap, uint32_t* n_fwd,
+                                uint32_t* n_rc, uint8_t* found_hit) {
+  return guarded([&] { return debugIntervalsImpl(m, read_index, out, cap, n_fwd, n_rc, found_hit); });
 }
 
 static int dupOut(const std::string& s, char** sam, uint64_t* len) {
@@ -923,34 +1032,77 @@ static int dupOut(const std::string& s, char** sam, uint64_t* len) {
 
 int rapmap_cuda_sam_header(const rapmap_cuda_index_t* idx, char** sam, uint64_t* sam_len) {
   if (!idx || !sam || !sam_len) return fail(RAPMAP_ERR_ARG, "null argument");
-  return dupOut(samHeader(idx->names, idx->lens), sam, sam_len);
+  if (idx->names.size() != idx->hdr.numTxp || idx->lens.size() != idx->hdr.numTxp) return fail(RAPMAP_ERR_ARG, "index has no transcript name table");
+  return guarded([&] { return dupOut(samHeader(idx->names, idx->lens), sam, sam_len); });
+}
+
+// Formats pairs [first, last) of the chunk into `out` (one worker of rapmap_cuda_format_sam).
+static void formatRange(const rapmap_cuda_index_t* idx, const rapmap_cuda_opts_t* opts, const rapmap_read_batch_t* reads, const std::vector<const char*>& n1,
+                        const std::vector<const char*>& n2, rapmap_hit_batch_t* hits, uint64_t first, uint64_t last, std::string& out) {
+  const bool paired = reads->seq2 != nullptr;
+  out.reserve((last - first) * (paired ? 700 : 350));
+  for (uint64_t i = first; i < last; ++i) {
+    const char* s1; const char* s2 = nullptr; size_t l1, l2 = 0;
+    if (reads->off1) {
+      s1 = reinterpret_cast<const char*>(reads->seq1) + reads->off1[i]; l1 = reads->off1[i + 1] - reads->off1[i];
+      if (paired) { s2 = reinterpret_cast<const char*>(reads->seq2) + reads->off2[i]; l2 = reads->off2[i + 1] - reads->off2[i]; }
+    } else {
+      s1 = reinterpret_cast<const char*>(reads->seq1) + i * reads->fixed_len; l1 = reads->fixed_len;
+      if (paired) { s2 = reinterpret_cast<const char*>(reads->seq2) + i * reads->fixed_len; l2 = reads->fixed_len; }
+    }
+    const uint64_t b = hits->pair_offsets[i], e = hits->pair_offsets[i + 1];
+    if (paired) samPair(idx->names, idx->lens, opts->max_num_hits, n1[i], s1, l1, n2[i], s2, l2, hits->hits + b, e - b, out);
+    else samSingle(idx->names, idx->lens, n1[i], s1, l1, hits->hits + b, e - b, out);
+  }
+}
+
+static int formatSamImpl(const rapmap_cuda_index_t* idx, const rapmap_cuda_opts_t* opts, const rapmap_read_batch_t* reads, const char* names1,
+                         const char* names2, rapmap_hit_batch_t* hits, uint32_t threads, char** sam, uint64_t* sam_len) {
+  if (!idx || !opts || !reads || !names1 || !hits || !sam || !sam_len) return fail(RAPMAP_ERR_ARG, "null argument");
+  if (reads->location != RAPMAP_LOC_HOST || hits->location != RAPMAP_LOC_HOST) return fail(RAPMAP_ERR_ARG, "format_sam needs host buffers");
+  const bool paired = reads->seq2 != nullptr;
+  if (paired && !names2) return fail(RAPMAP_ERR_ARG, "names2 is null for paired reads");
+  if (idx->names.size() != idx->hdr.numTxp) return fail(RAPMAP_ERR_ARG, "index has no transcript name table");
+  const uint64_t n = reads->n;
+  std::vector<const char*> n1(n), n2(paired ? n : 0);
+  {
+    const char* p = names1;
+    for (uint64_t i = 0; i < n; ++i) { n1[i] = p; p += std::strlen(p) + 1; }
+    if (paired) { p = names2; for (uint64_t i = 0; i < n; ++i) { n2[i] = p; p += std::strlen(p) + 1; } }
+  }
+  const uint32_t T = static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>(threads ? threads : 1, (n + 4095) / 4096)));
+  std::vector<std::string> parts(T);
+  if (T == 1) formatRange(idx, opts, reads, n1, n2, hits, 0, n, parts[0]);
+  else {
+    std::vector<std::thread> th;
+    std::vector<int> failed(T, 0);
+    for (uint32_t t = 0; t < T; ++t)
+      th.emplace_back([&, t] {
+        try { formatRange(idx, opts, reads, n1, n2, hits, n * t / T, n * (t + 1) / T, parts[t]); } catch (...) { failed[t] = 1; }
+      });
+    for (auto& x : th) x.join();
+    for (int f : failed) if (f) return fail(RAPMAP_ERR_IO, "out of host memory while formatting SAM");
+  }
+  uint64_t total = 0;
+  for (const auto& p : parts) total += p.size();
+  char* buf = static_cast<char*>(std::malloc(total + 1));
+  if (!buf) return fail(RAPMAP_ERR_ARG, "out of host memory");
+  uint64_t at = 0;
+  for (const auto& p : parts) { std::memcpy(buf + at, p.data(), p.size()); at += p.size(); }
+  buf[total] = 0;
+  *sam = buf;
+  *sam_len = total;
+  return RAPMAP_OK;
 }
 
 int rapmap_cuda_format_sam(const rapmap_cuda_index_t* idx, const rapmap_cuda_opts_t* opts, const rapmap_read_batch_t* reads, const char* names1,
                            const char* names2, rapmap_hit_batch_t* hits, char** sam, uint64_t* sam_len) {
-  if (!idx || !opts || !reads || !names1 || !hits || !sam || !sam_len) return fail(RAPMAP_ERR_ARG, "null argument");
-  if (reads->location != RAPMAP_LOC_HOST || hits->location != RAPMAP_LOC_HOST) return fail(RAPMAP_ERR_ARG, "format_sam needs host buffers");
-  if (!reads->seq2 || !names2) return fail(RAPMAP_ERR_UNSUPPORTED, "SAM text for unmated reads is not implemented (SURVEY.md f1)");
-  if (idx->names.empty()) return fail(RAPMAP_ERR_ARG, "index was created from an image without transcript names");
-  std::string out;
-  out.reserve(reads->n * 700);
-  const char* n1 = names1;
-  const char* n2 = names2;
-  for (uint64_t i = 0; i < reads->n; ++i) {
-    const char* s1; const char* s2; size_t l1, l2;
-    if (reads->off1) {
-      s1 = reinterpret_cast<const char*>(reads->seq1) + reads->off1[i]; l1 = reads->off1[i + 1] - reads->off1[i];
-      s2 = reinterpret_cast<const char*>(reads->seq2) + reads->off2[i]; l2 = reads->off2[i + 1] - reads->off2[i];
-    } else {
-      s1 = reinterpret_cast<const char*>(reads->seq1) + i * reads->fixed_len; l1 = reads->fixed_len;
-      s2 = reinterpret_cast<const char*>(reads->seq2) + i * reads->fixed_len; l2 = reads->fixed_len;
-    }
-    uint64_t b = hits->pair_offsets[i], e = hits->pair_offsets[i + 1];
-    samPair(idx->names, idx->lens, opts->max_num_hits, n1, s1, l1, n2, s2, l2, hits->hits + b, e - b, out);
-    n1 += std::strlen(n1) + 1;
-    n2 += std::strlen(n2) + 1;
-  }
-  return dupOut(out, sam, sam_len);
+  return guarded([&] { return formatSamImpl(idx, opts, reads, names1, names2, hits, 1, sam, sam_len); });
+}
+
+int rapmap_cuda_format_sam_mt(const rapmap_cuda_index_t* idx, const rapmap_cuda_opts_t* opts, const rapmap_read_batch_t* reads, const char* names1,
+                              const char* names2, rapmap_hit_batch_t* hits, uint32_t threads, char** sam, uint64_t* sam_len) {
+  return guarded([&] { return formatSamImpl(idx, opts, reads, names1, names2, hits, threads, sam, sam_len); });
 }
 
 void rapmap_cuda_free(void* p) { std::free(p); }

@@ -27,7 +27,7 @@
 namespace rapmap_b200 {
 
 struct ImageHeader {
-  uint64_t magic;          // 'RMB2IMG1'
+  uint64_t magic;          // 'RMB2IMG2'
   uint64_t totalBytes;
   uint64_t n;              // text / SA length
   uint64_t numTxp;
@@ -43,6 +43,9 @@ struct ImageHeader {
   uint32_t phfLevels, phfPad;
   uint64_t phfLastRank, phfNumData, phfNumFinal, phfNumOverflow;
   uint64_t offPhfLevels, offPhfBits, offPhfRanks, offPhfFinal, offPhfData, offPhfLens, offPhfOverflow;
+  // host-readable trailer: transcript names, '\0'-terminated, in transcript order (a replica built from the image alone can
+  // print SAM headers and records; the lengths are the txpLens section)
+  uint64_t offNames, namesBytes;
 };
 
 // One level of the MPHF (boomphf::level, reference include/BooPHF.hpp:820-842): bitset of `domain` bits with a rank
@@ -53,7 +56,7 @@ struct PhfLevelDev {
   uint64_t ranksOff;   // first rank sample of this level
   uint64_t pad;
 };
-static constexpr uint64_t kImageMagic = 0x31474D4932424D52ULL;
+static constexpr uint64_t kImageMagic = 0x32474D4932424D52ULL;  // 'RMB2IMG2'
 
 // 64 bases starting at text position 32 j: codes (first base in bits 63:62 of c0), non-ACGT mask (first base in bit 0 of inv0).
 struct __align__(32) TextRec {

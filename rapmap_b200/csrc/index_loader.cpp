@@ -95,6 +95,7 @@ bool HostIndex::load(const std::string& dirIn, std::string& err) {
   if (bigSA) {
     // 64-bit suffix arrays (text > 2^31) are row f4 of SURVEY.md §8; refuse loudly rather than truncate.
     err = "BigSA (64-bit suffix array) indexes are not supported by the device path yet";
+    unsupported = true;
     return false;
   }
 
@@ -103,6 +104,8 @@ bool HostIndex::load(const std::string& dirIn, std::string& err) {
     if (!f.ok()) { err = "cannot open sa.bin"; return false; }
     uint64_t n = 0;
     if (!f.get(n)) { err = "sa.bin: truncated"; return false; }
+    if (n > (f.size() - 8) / sizeof(int32_t)) { err = "sa.bin: element count exceeds the file size"; return false; }
+    if (n >= (1ull << 31)) { err = "sa.bin: more than 2^31 suffixes in a 32-bit index"; return false; }
     SA.resize(n);
     if (!f.read(SA.data(), n * sizeof(int32_t))) { err = "sa.bin: truncated"; return false; }
   }
@@ -110,21 +113,27 @@ bool HostIndex::load(const std::string& dirIn, std::string& err) {
     File f(dir + "txpInfo.bin");
     if (!f.ok()) { err = "cannot open txpInfo.bin"; return false; }
     uint64_t n = 0;
+    const uint64_t fsz = f.size();
     if (!f.get(n)) { err = "txpInfo.bin: truncated"; return false; }
+    if (n > fsz / 8) { err = "txpInfo.bin: transcript count exceeds the file size"; return false; }
     txpNames.resize(n);
     for (auto& s : txpNames) {
       uint64_t l = 0;
       if (!f.get(l)) { err = "txpInfo.bin: truncated"; return false; }
+      if (l > fsz) { err = "txpInfo.bin: name length exceeds the file size"; return false; }
       s.resize(l);
       if (!f.read(&s[0], l)) { err = "txpInfo.bin: truncated"; return false; }
     }
     if (!f.get(n)) { err = "txpInfo.bin: truncated"; return false; }
+    if (n > fsz / 4) { err = "txpInfo.bin: offset count exceeds the file size"; return false; }
     txpOffsets.resize(n);
     if (!f.read(txpOffsets.data(), n * sizeof(int32_t))) { err = "txpInfo.bin: truncated"; return false; }
     if (!f.get(n)) { err = "txpInfo.bin: truncated"; return false; }
+    if (n > fsz) { err = "txpInfo.bin: text length exceeds the file size"; return false; }
     text.resize(n);
     if (!f.read(&text[0], n)) { err = "txpInfo.bin: truncated"; return false; }
     if (!f.get(n)) { err = "txpInfo.bin: truncated"; return false; }
+    if (n > fsz / 4) { err = "txpInfo.bin: length count exceeds the file size"; return false; }
     txpCompleteLens.resize(n);
     if (!f.read(txpCompleteLens.data(), n * sizeof(uint32_t))) { err = "txpInfo.bin: truncated"; return false; }
   }
@@ -134,9 +143,19 @@ bool HostIndex::load(const std::string& dirIn, std::string& err) {
     File f(dir + "rsd.bin");
     if (!f.ok()) { err = "cannot open rsd.bin"; return false; }
     if (!f.get(numBits)) { err = "rsd.bin: truncated"; return false; }
+    if (numBits != SA.size()) { err = "rsd.bin: bit count differs from the text length"; return false; }
     uint64_t nbytes = (numBits + 7) / 8;
     rsdBits.assign((numBits + 63) / 64 + 1, 0);
     if (!f.read(rsdBits.data(), nbytes)) { err = "rsd.bin: truncated"; return false; }
+  }
+  {  // cheap range checks: a malformed index must fail here, not as out-of-bounds reads on the device
+    const int64_t n = static_cast<int64_t>(SA.size());
+    for (size_t i = 0; i < txpOffsets.size(); ++i) {
+      if (txpOffsets[i] < 0 || txpOffsets[i] >= n || (i > 0 && txpOffsets[i] <= txpOffsets[i - 1])) { err = "txpInfo.bin: transcript offsets are not increasing inside the text"; return false; }
+    }
+    uint32_t bad = 0;
+    for (int32_t v : SA) bad |= static_cast<uint32_t>(v < 0 || v >= n);
+    if (bad) { err = "sa.bin: suffix array entry outside the text"; return false; }
   }
   txpLens.resize(txpOffsets.size());
   for (size_t i = 0; i + 1 < txpOffsets.size(); ++i) txpLens[i] = (txpOffsets[i + 1] - 1) - txpOffsets[i];
@@ -157,6 +176,12 @@ bool HostIndex::load(const std::string& dirIn, std::string& err) {
     std::fseek(f.f, static_cast<long>(hdr + meta), SEEK_SET);
     kmers.resize(numBuckets);
     if (!f.read(kmers.data(), numBuckets * rec)) { err = "hash.bin: truncated"; return false; }
+    {
+      const int64_t n = static_cast<int64_t>(SA.size());
+      uint32_t bad = 0;
+      for (const auto& r : kmers) bad |= static_cast<uint32_t>(r.begin < 0 || r.end < r.begin || r.end > n);
+      if (bad) { err = "hash.bin: k-mer interval outside the suffix array"; return false; }
+    }
   } else {
     // ---- hash_info.bph: boomphf::mphf::save (include/BooPHF.hpp:1172-1197)
     File f(dir + "hash_info.bph");
@@ -166,9 +191,12 @@ bool HostIndex::load(const std::string& dirIn, std::string& err) {
     phf.levels.resize(static_cast<size_t>(phf.nbLevels));
     for (auto& lv : phf.levels) {
       uint64_t nchar = 0, nranks = 0;
+      const uint64_t bsz = f.size();
       if (!f.get(lv.sizeBits) || !f.get(nchar)) { err = "hash_info.bph: truncated"; return false; }
+      if (nchar > bsz / 8) { err = "hash_info.bph: bitset size exceeds the file size"; return false; }
       lv.bits.resize(nchar);
       if (!f.read(lv.bits.data(), nchar * 8) || !f.get(nranks)) { err = "hash_info.bph: truncated"; return false; }
+      if (nranks > bsz / 8) { err = "hash_info.bph: rank table size exceeds the file size"; return false; }
       lv.ranks.resize(nranks);
       if (!f.read(lv.ranks.data(), nranks * 8)) { err = "hash_info.bph: truncated"; return false; }
     }
@@ -184,6 +212,7 @@ bool HostIndex::load(const std::string& dirIn, std::string& err) {
     }
     uint64_t nfinal = 0;
     if (!f.get(nfinal)) { err = "hash_info.bph: truncated"; return false; }
+    if (nfinal > f.size() / 16) { err = "hash_info.bph: final-hash size exceeds the file size"; return false; }
     phf.finalHash.resize(nfinal);
     for (auto& kv : phf.finalHash)
       if (!f.get(kv.first) || !f.get(kv.second)) { err = "hash_info.bph: truncated"; return false; }
@@ -193,8 +222,10 @@ bool HostIndex::load(const std::string& dirIn, std::string& err) {
     if (!v.ok()) { err = "cannot open hash_info.val"; return false; }
     uint64_t n = 0;
     if (!v.get(n)) { err = "hash_info.val: truncated"; return false; }
+    if (n > v.size() / 4) { err = "hash_info.val: element count exceeds the file size"; return false; }
     phf.data.resize(n);
     if (!v.read(phf.data.data(), n * 4) || !v.get(n)) { err = "hash_info.val: truncated"; return false; }
+    if (n > v.size()) { err = "hash_info.val: element count exceeds the file size"; return false; }
     phf.lens.resize(n);
     if (!v.read(phf.lens.data(), n)) { err = "hash_info.val: truncated"; return false; }
     if (phf.lens.size() != phf.data.size()) { err = "hash_info.val: data_/lens_ size mismatch"; return false; }
@@ -211,6 +242,12 @@ bool HostIndex::load(const std::string& dirIn, std::string& err) {
     for (auto& kv : phf.overflow)
       if (!v.get(kv.first) || !v.get(kv.second)) { err = "hash_info.val: truncated"; return false; }
     std::sort(phf.overflow.begin(), phf.overflow.end());
+    {
+      const int64_t n = static_cast<int64_t>(SA.size());
+      uint32_t bad = 0;
+      for (int32_t v2 : phf.data) bad |= static_cast<uint32_t>(v2 < 0 || v2 >= n);
+      if (bad) { err = "hash_info.val: interval start outside the suffix array"; return false; }
+    }
   }
   return true;
 }

@@ -39,6 +39,7 @@ struct HostIndex {
   uint32_t k{31};
   bool bigSA{false};
   bool perfectHash{false};
+  bool unsupported{false};            // load() failed because of a flavour the device path does not implement (not a malformed file)
   std::vector<int32_t> SA;            // suffix array (32-bit indexes only, see load())
   std::string text;                   // concatenated transcripts, '$' after each
   std::vector<std::string> txpNames;

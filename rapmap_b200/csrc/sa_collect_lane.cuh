@@ -25,7 +25,7 @@
 // contain a non-ACGT base take exact slow paths (partial k-mer words of Kmer::fromChars, original bytes re-read).
 #pragma once
 #include <climits>
-#include "sa_collect.cuh"
+#include "kmer_utils.cuh"
 
 namespace rapmap_b200 {
 
@@ -690,12 +690,17 @@ __global__ void __launch_bounds__(NT, MINB) sa_collect_lane_kernel(LaneParams P)
       }
       if (fin) {
         if (tot > 0) {
+          // A read whose records cannot be stored publishes an EMPTY summary (the later kernels of this attempt must not
+          // follow ivOff into unwritten or out-of-range arena memory); the status bit makes the host grow and re-run.
+          bool stored = false;
           if (flags & LF_OVF) atomicOr(P.status, kStatIvScratchFull);
           else if (static_cast<uint64_t>(off) + static_cast<uint64_t>(tot) > P.arenaCap) atomicOr(P.status, kStatIntervalArenaFull);
           else {
             for (int i = 0; i < nF; ++i) P.arena[off + i] = scr[i];
             for (int i = 0; i < nR; ++i) P.arena[off + nF + i] = scr[P.ivStride + i];
+            stored = true;
           }
+          if (!stored) { nF = 0; nR = 0; off = 0; }
         }
         ReadSummary s;
         s.ivOff = off; s.nFwd = static_cast<uint16_t>(nF); s.nRc = static_cast<uint16_t>(nR);

@@ -143,4 +143,33 @@ inline void samPair(const std::vector<std::string>& names, const std::vector<int
   }
 }
 
+// One unmated read (processReadsSingleSA, src/RapMapSAMapper.cpp:156-371): writeAlignmentsToStream for single reads
+// (src/RapMapUtils.cpp:230-311; flags of getSamFlags(qa, flags), include/RapMapUtils.hpp:737-768: only 0x10, and 0x900
+// on every record after the first) or writeUnalignedSingleToStream (src/RapMapUtils.cpp:198-227).  The read name is cut
+// at the first space only (no "/1" stripping here).
+inline void samSingle(const std::vector<std::string>& names, const std::vector<int32_t>& lens, const char* name, const char* s, size_t l,
+                      rapmap_hit_t* hits, size_t nh, std::string& out) {
+  size_t nameLen = std::char_traits<char>::length(name);
+  for (size_t i = 0; i < nameLen; ++i)
+    if (name[i] == ' ') { nameLen = i; break; }
+  if (nh == 0) {
+    out.append(name, nameLen); out += "\t4\t*\t0\t255\t*\t*\t0\t0\t"; out.append(s, l); out += "\t*\tNH:i:0\tHI:i:0\tAS:i:0\n";
+    return;
+  }
+  const std::string nhFlag = "NH:i:" + std::to_string(nh);
+  std::string rev, cigar;
+  bool haveRev = false;
+  for (size_t i = 0; i < nh; ++i) {
+    rapmap_hit_t& qa = hits[i];
+    uint16_t flags = qa.fwd ? 0 : 0x10;
+    if (i != 0) flags |= 0x900;
+    const char* q = s; size_t ql = l;
+    if (!qa.fwd) { if (!haveRev) { samReverseRead(s, l, rev); haveRev = true; } q = rev.data(); ql = rev.size(); }
+    samOverhang(qa.pos, qa.read_len, static_cast<uint32_t>(lens[qa.tid]), cigar);
+    out.append(name, nameLen); out += '\t'; samAppendInt(out, flags); out += '\t'; out += names[qa.tid]; out += '\t'; samAppendInt(out, qa.pos + 1);
+    out += "\t255\t"; out += cigar; out += "\t*\t0\t"; samAppendInt(out, qa.frag_len); out += '\t'; out.append(q, ql);
+    out += "\t*\t"; out += nhFlag; out += "\tHI:i:"; samAppendInt(out, static_cast<long>(i + 1)); out += "\tAS:i:"; samAppendInt(out, qa.aln_score); out += '\n';
+  }
+}
+
 } // namespace rapmap_b200

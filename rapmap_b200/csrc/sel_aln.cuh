@@ -26,7 +26,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include "kernels.cuh"
-#include "sa_collect.cuh"
+#include "kmer_utils.cuh"
 
 namespace rapmap_b200 {
 
@@ -59,13 +59,11 @@ struct SelAlnWork {
   uint64_t hitsCap{0};
   uint64_t maxBatch{0};
   uint32_t maxReadLen{0};
-  uint64_t* hTotal{nullptr};     // pinned
 };
 
 inline void selAlnFree(SelAlnWork& w) {
   cudaFree(w.taskScore); cudaFree(w.taskRef); cudaFree(w.taskHash); cudaFree(w.jobs); cudaFree(w.slowList); cudaFree(w.jobCursor); cudaFree(w.hitScore);
   cudaFree(w.pairBest); cudaFree(w.outCount); cudaFree(w.outOff); cudaFree(w.outHits);
-  if (w.hTotal) cudaFreeHost(w.hTotal);
   w = SelAlnWork();
 }
 
@@ -73,7 +71,7 @@ inline cudaError_t selAlnReserve(SelAlnWork& w, uint64_t hits) {
   if (hits <= w.hitsCap) return cudaSuccess;
   cudaFree(w.taskScore); cudaFree(w.taskRef); cudaFree(w.taskHash); cudaFree(w.jobs); cudaFree(w.slowList); cudaFree(w.hitScore); cudaFree(w.outHits);
   w.slowList = nullptr; w.taskScore = nullptr; w.taskRef = nullptr; w.taskHash = nullptr; w.jobs = nullptr; w.hitScore = nullptr; w.outHits = nullptr;
-  uint64_t cap = hits + hits / 4 + 1024;
+  uint64_t cap = hits;
   cudaError_t e;
   if ((e = cudaMalloc(&w.taskScore, cap * 2 * 4)) != cudaSuccess) return e;
   if ((e = cudaMalloc(&w.taskRef, cap * 2 * 4)) != cudaSuccess) return e;
@@ -86,7 +84,7 @@ inline cudaError_t selAlnReserve(SelAlnWork& w, uint64_t hits) {
   return cudaSuccess;
 }
 
-inline cudaError_t selAlnAlloc(SelAlnWork& w, uint64_t maxBatch, uint32_t maxReadLen) {
+inline cudaError_t selAlnAlloc(SelAlnWork& w, uint64_t maxBatch, uint32_t maxReadLen, uint64_t hitsCap) {
   w.maxBatch = maxBatch;
   w.maxReadLen = maxReadLen;
   cudaError_t e;
@@ -94,8 +92,7 @@ inline cudaError_t selAlnAlloc(SelAlnWork& w, uint64_t maxBatch, uint32_t maxRea
   if ((e = cudaMalloc(&w.pairBest, maxBatch * 4)) != cudaSuccess) return e;
   if ((e = cudaMalloc(&w.outCount, (maxBatch + 1) * 4)) != cudaSuccess) return e;
   if ((e = cudaMalloc(&w.outOff, (maxBatch + 1) * 8)) != cudaSuccess) return e;
-  if ((e = cudaMallocHost(&w.hTotal, 16)) != cudaSuccess) return e;
-  return selAlnReserve(w, maxBatch * 6 + 1024);
+  return selAlnReserve(w, hitsCap);
 }
 
 struct SelAlnParams {
@@ -117,6 +114,7 @@ struct SelAlnParams {
   const uint64_t* outOff;
   rapmap_hit_t* outHits;
   uint32_t maxReadLen;
+  uint64_t hitsCap;        // records the hit / task arrays hold: a batch whose merge produced more is skipped here (the host grows and re-runs)
 };
 
 __device__ __forceinline__ void readSpan(const BatchView& b, uint64_t r, const uint8_t*& p, uint32_t& len) {
@@ -202,6 +200,7 @@ __global__ void __launch_bounds__(WARPS * 32) selaln_prepare_kernel(SelAlnParams
   const uint64_t gt = static_cast<uint64_t>(blockIdx.x) * (WARPS * 32) + threadIdx.x;
   const DevOpts& o = P.opts;
   const int32_t a = static_cast<int8_t>(o.ma), b = static_cast<int8_t>(o.mm);
+  if (P.pairOff[P.numPairs] > P.hitsCap) return;  // merge output did not fit: nothing to score in this attempt
   for (uint64_t pi = gt; pi < P.numPairs; pi += static_cast<uint64_t>(gridDim.x) * (WARPS * 32)) {
     const uint64_t h0 = P.pairOff[pi], h1 = P.pairOff[pi + 1];
     const uint32_t cnt = static_cast<uint32_t>(h1 - h0);
@@ -743,7 +742,9 @@ __device__ __forceinline__ int32_t taskValue(const SelAlnParams& P, uint64_t slo
 __global__ void __launch_bounds__(256) selaln_score_kernel(SelAlnParams P) {
   const DevOpts& o = P.opts;
   const int32_t a = static_cast<int8_t>(o.ma);
+  const bool skip = P.pairOff[P.numPairs] > P.hitsCap;
   for (uint64_t pi = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; pi < P.numPairs; pi += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    if (skip) { P.outCount[pi] = 0; continue; }
     const uint64_t h0 = P.pairOff[pi], h1 = P.pairOff[pi + 1];
     if (h0 == h1) { P.outCount[pi] = 0; continue; }
     const uint8_t* rd;
@@ -789,6 +790,7 @@ __global__ void __launch_bounds__(256) selaln_score_kernel(SelAlnParams P) {
 
 __global__ void __launch_bounds__(256) selaln_write_kernel(SelAlnParams P) {
   const DevOpts& o = P.opts;
+  if (P.pairOff[P.numPairs] > P.hitsCap) return;
   for (uint64_t pi = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; pi < P.numPairs; pi += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
     const uint64_t h0 = P.pairOff[pi], h1 = P.pairOff[pi + 1];
     const int32_t best = P.pairBest[pi];
@@ -809,30 +811,66 @@ struct CastU64b {
   __host__ __device__ uint64_t operator()(uint32_t v) const { return v; }
 };
 
-// Runs the four stages; on return dPairOff holds the post-filter offsets, w.outHits the surviving hits.
-inline int selAlnRun(SelAlnWork& w, const DeviceIndex& ix, const DevOpts& opts, const BatchView& bv, uint64_t n, bool paired, rapmap_hit_t* dHits,
-                     uint64_t* dPairOff, uint64_t total, void* dCubTemp, size_t cubTempBytes, int numSMs, cudaStream_t st, uint32_t* launches,
-                     uint64_t* totalOut, std::string& err) {
+// Launch geometry of the DP kernels, fixed per mapper (computed once by selAlnSetup).
+struct SelAlnLaunch {
+  uint32_t warpSmemBytes{0};
+  int32_t tl16max{0};
+  uint32_t smemK{0}, smemL{0};
+  int occK{1}, occL{1};
+  bool laneKsw{true};
+};
+static constexpr int kKswWarps = 4, kKswLaneThreads = 128, kKswLaneSeq = 352;
+
+inline int selAlnSetup(const SelAlnWork& w, SelAlnLaunch& L, std::string& err) {
   auto cuFail = [&](const char* what, cudaError_t e) { err = std::string(what) + ": " + cudaGetErrorString(e); return RAPMAP_ERR_CUDA; };
-  cudaError_t e = selAlnReserve(w, total);
-  if (e != cudaSuccess) return cuFail("selAlnReserve", e);
+  // DP kernel: shared memory per warp = the reference's kcalloc block for the largest window + the int32 H track
+  const int tlenMax = static_cast<int>(w.maxReadLen) + 20;
+  const int tl16 = (tlenMax + 15) / 16 * 16;
+  const int qlen_ = (static_cast<int>(w.maxReadLen) + 15) / 16;
+  L.tl16max = tl16;
+  L.warpSmemBytes = static_cast<uint32_t>((tl16 / 16 * 6 + qlen_ + 1) * 16 + tl16 * 4);
+  L.smemK = L.warpSmemBytes * kKswWarps;
+  if (L.smemK > 200 * 1024) { err = "max_read_len too large for the ksw2 shared-memory layout"; return RAPMAP_ERR_ARG; }
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute(ksw_extz_kernel<kKswWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L.smemK))) != cudaSuccess)
+    return cuFail("cudaFuncSetAttribute(ksw)", e);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&L.occK, ksw_extz_kernel<kKswWarps>, kKswWarps * 32, L.smemK);
+  if (L.occK < 1) L.occK = 1;
+  const char* sel = std::getenv("RAPMAP_B200_KSW");
+  L.laneKsw = !(sel && std::string(sel) == "warp");
+  if (L.laneKsw) {
+    L.smemL = kKswLaneThreads * kKswLaneSeq;
+    if ((e = cudaFuncSetAttribute(ksw_extz_lane_kernel<kKswLaneThreads, kKswLaneSeq>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L.smemL))) != cudaSuccess)
+      return cuFail("cudaFuncSetAttribute(ksw lane)", e);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&L.occL, ksw_extz_lane_kernel<kKswLaneThreads, kKswLaneSeq>, kKswLaneThreads, L.smemL);
+    if (L.occL < 1) L.occL = 1;
+  }
+  return RAPMAP_OK;
+}
+
+// Enqueues the four stages on `st` (no host synchronisation): afterwards dPairOff holds the post-filter offsets,
+// w.outHits the surviving hits, *hTotal (pinned) their number and hJobs[0..1] the DP job counts (all / left to the
+// general kernel).  The work arrays must hold hitsCap records (selAlnReserve); a batch whose merge produced more is
+// skipped by the kernels and re-run by the caller after growing.
+inline int selAlnEnqueue(SelAlnWork& w, const SelAlnLaunch& L, const DeviceIndex& ix, const DevOpts& opts, const BatchView& bv, uint64_t n, bool paired,
+                         rapmap_hit_t* dHits, uint64_t* dPairOff, uint64_t hitsCap, void* dCubTemp, size_t cubTempBytes, int numSMs, cudaStream_t st,
+                         uint32_t* launches, uint64_t* hTotal, uint32_t* hJobs, cudaEvent_t evKsw0, cudaEvent_t evKsw1, std::string& err) {
+  auto cuFail = [&](const char* what, cudaError_t e) { err = std::string(what) + ": " + cudaGetErrorString(e); return RAPMAP_ERR_CUDA; };
+  cudaError_t e;
   SelAlnParams sp{};
   sp.ix = ix; sp.opts = opts; sp.reads = bv; sp.numPairs = n; sp.pairedInput = paired ? 1 : 0; sp.hits = dHits; sp.pairOff = dPairOff;
   sp.taskScore = w.taskScore; sp.taskRef = w.taskRef; sp.taskHash = w.taskHash; sp.jobs = w.jobs; sp.jobCursor = w.jobCursor; sp.hitScore = w.hitScore;
   sp.pairBest = w.pairBest; sp.outCount = w.outCount; sp.outOff = w.outOff; sp.outHits = w.outHits; sp.maxReadLen = w.maxReadLen;
+  sp.hitsCap = hitsCap < w.hitsCap ? hitsCap : w.hitsCap;
   if ((e = cudaMemsetAsync(w.jobCursor, 0, 8, st)) != cudaSuccess) return cuFail("memset", e);
   constexpr int W = 8;
   int g = static_cast<int>(std::min<uint64_t>(static_cast<uint64_t>(numSMs) * 8, (n + W * 32 - 1) / (W * 32)));
   selaln_prepare_kernel<W><<<g, W * 32, 0, st>>>(sp);
   ++*launches;
-  // DP kernel: shared memory per warp = the reference's kcalloc block for the largest window + the int32 H track
   KswParams kp{};
   kp.ix = ix; kp.reads = bv; kp.jobs = w.jobs; kp.jobCount = w.jobCursor; kp.taskScore = w.taskScore;
-  const int tlenMax = static_cast<int>(w.maxReadLen) + 20;
-  const int tl16 = (tlenMax + 15) / 16 * 16;
-  const int qlen_ = (static_cast<int>(w.maxReadLen) + 15) / 16;
-  kp.tl16max = tl16;
-  kp.warpSmemBytes = static_cast<uint32_t>((tl16 / 16 * 6 + qlen_ + 1) * 16 + tl16 * 4);
+  kp.tl16max = L.tl16max;
+  kp.warpSmemBytes = L.warpSmemBytes;
   {
     int a = opts.ma, b = opts.mm;  // KSW2Aligner ctor (:74-96)
     a = a < 0 ? -a : a;
@@ -840,30 +878,16 @@ inline int selAlnRun(SelAlnWork& w, const DeviceIndex& ix, const DevOpts& opts, 
     kp.mat0 = static_cast<int8_t>(a); kp.mat1 = static_cast<int8_t>(b); kp.matN = 0;
   }
   kp.q = static_cast<int8_t>(opts.go); kp.e = static_cast<int8_t>(opts.ge); kp.w = opts.dpBandwidth;
-  constexpr int KW = 4;
-  const uint32_t smemK = kp.warpSmemBytes * KW;
-  if (smemK > 200 * 1024) { err = "max_read_len too large for the ksw2 shared-memory layout"; return RAPMAP_ERR_ARG; }
-  if ((e = cudaFuncSetAttribute(ksw_extz_kernel<KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smemK))) != cudaSuccess)
-    return cuFail("cudaFuncSetAttribute(ksw)", e);
-  int occ = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ksw_extz_kernel<KW>, KW * 32, smemK);
-  if (occ < 1) occ = 1;
-  static const bool laneKsw = !(std::getenv("RAPMAP_B200_KSW") && std::string(std::getenv("RAPMAP_B200_KSW")) == "warp");
-  if (laneKsw) {  // thread-per-job kernel first; what it leaves (short windows, wide bands, long reads) goes to the warp kernel
-    constexpr int LT = 128, LSEQ = 352;
+  if (evKsw0 && (e = cudaEventRecord(evKsw0, st)) != cudaSuccess) return cuFail("event", e);
+  if (L.laneKsw) {  // thread-per-job kernel first; what it leaves (short windows, wide bands, long reads) goes to the warp kernel
     kp.slowList = w.slowList; kp.slowCount = w.jobCursor + 1;
-    const uint32_t smemL = LT * LSEQ;
-    if ((e = cudaFuncSetAttribute(ksw_extz_lane_kernel<LT, LSEQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smemL))) != cudaSuccess)
-      return cuFail("cudaFuncSetAttribute(ksw lane)", e);
-    int occL = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occL, ksw_extz_lane_kernel<LT, LSEQ>, LT, smemL);
-    if (occL < 1) occL = 1;
-    ksw_extz_lane_kernel<LT, LSEQ><<<numSMs * occL, LT, smemL, st>>>(kp);
+    ksw_extz_lane_kernel<kKswLaneThreads, kKswLaneSeq><<<numSMs * L.occL, kKswLaneThreads, L.smemL, st>>>(kp);
     ++*launches;
     kp.jobIdx = w.slowList; kp.jobCount = w.jobCursor + 1;
   }
-  ksw_extz_kernel<KW><<<numSMs * occ, KW * 32, smemK, st>>>(kp);
+  ksw_extz_kernel<kKswWarps><<<numSMs * L.occK, kKswWarps * 32, L.smemK, st>>>(kp);
   ++*launches;
+  if (evKsw1 && (e = cudaEventRecord(evKsw1, st)) != cudaSuccess) return cuFail("event", e);
   int g3 = static_cast<int>(std::min<uint64_t>(static_cast<uint64_t>(numSMs) * 8, (n + 255) / 256));
   if ((e = cudaMemsetAsync(w.outCount + n, 0, 4, st)) != cudaSuccess) return cuFail("memset", e);
   selaln_score_kernel<<<g3, 256, 0, st>>>(sp);
@@ -875,11 +899,9 @@ inline int selAlnRun(SelAlnWork& w, const DeviceIndex& ix, const DevOpts& opts, 
   }
   selaln_write_kernel<<<g3, 256, 0, st>>>(sp);
   ++*launches;
-  if ((e = cudaMemcpyAsync(w.hTotal, w.outOff + n, 8, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuFail("memcpy", e);
+  if ((e = cudaMemcpyAsync(hTotal, w.outOff + n, 8, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuFail("memcpy", e);
+  if ((e = cudaMemcpyAsync(hJobs, w.jobCursor, 8, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuFail("memcpy", e);
   if ((e = cudaMemcpyAsync(dPairOff, w.outOff, (n + 1) * 8, cudaMemcpyDeviceToDevice, st)) != cudaSuccess) return cuFail("memcpy", e);
-  if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return cuFail("selAln sync", e);
-  if ((e = cudaGetLastError()) != cudaSuccess) return cuFail("selAln kernels", e);
-  *totalOut = *w.hTotal;
   return RAPMAP_OK;
 }
 

@@ -3,7 +3,8 @@
 
 Run in the build container, where /root/reference exists:   python tests/golden/make_golden.py
   sample_idx/            quasiindex of the reference's sample_data/transcripts.fasta (15 transcripts)
-  sample_reads_{1,2}.fastq.gz   first 2000 pairs of sample_data/reads_{1,2}.fastq (2 x 50 bp, error free)
+  sample_reads_{1,2}.fastq.gz   all 10,000 pairs of sample_data/reads_{1,2}.fastq (2 x 50 bp, error free): the md5s of
+                         sample/default and sample/selaln are the known answers of SURVEY.md §4
   synth_idx/, synth_idx_p/      quasiindex (dense, -p) of `synth txome --genes 8 --seed 777`
   golden.json            md5 of `rapmap_ref quasimap -t 1 <flags>` SAM for every (dataset, flag set)
   *.sam.gz               full SAM for the default and -s flag sets (for readable diffs)
@@ -73,8 +74,13 @@ def head_fastq(src, dst, pairs):
 
 def quasimap(idx, r1, r2, flags):
     with tempfile.NamedTemporaryFile(suffix=".sam") as t:
-        run([REF, "quasimap", "-i", idx, "-1", r1, "-2", r2, "-t", "1", "-o", t.name] + flags)
+        reads = ["-1", r1, "-2", r2] if r2 else ["-r", r1]
+        run([REF, "quasimap", "-i", idx] + reads + ["-t", "1", "-o", t.name] + flags)
         return open(t.name, "rb").read()
+
+
+# unmated reads (quasimap -r: processReadsSingleSA): mate-1 reads of the synthetic set
+UNMATED_FLAGSETS = {"default": [], "selaln": ["-s"], "selaln_hard": ["-s", "--hardFilter"], "maxhits2": ["-m", "2"], "nosensitive": ["--noSensitive"]}
 
 
 def main():
@@ -83,8 +89,8 @@ def main():
     tmp = tempfile.mkdtemp()
     # ---- sample_data
     index(os.path.join(REFDATA, "transcripts.fasta"), os.path.join(HERE, "sample_idx"))
-    head_fastq(os.path.join(REFDATA, "reads_1.fastq"), os.path.join(HERE, "sample_reads_1.fastq.gz"), 2000)
-    head_fastq(os.path.join(REFDATA, "reads_2.fastq"), os.path.join(HERE, "sample_reads_2.fastq.gz"), 2000)
+    head_fastq(os.path.join(REFDATA, "reads_1.fastq"), os.path.join(HERE, "sample_reads_1.fastq.gz"), 10000)
+    head_fastq(os.path.join(REFDATA, "reads_2.fastq"), os.path.join(HERE, "sample_reads_2.fastq.gz"), 10000)
     for m in (1, 2):
         with gzip.open(os.path.join(HERE, f"sample_reads_{m}.fastq.gz"), "rt") as f, open(os.path.join(tmp, f"s{m}.fastq"), "w") as g:
             g.write(f.read())
@@ -99,14 +105,15 @@ def main():
         "sample": (os.path.join(HERE, "sample_idx"), os.path.join(tmp, "s1.fastq"), os.path.join(tmp, "s2.fastq")),
         "synth": (os.path.join(HERE, "synth_idx"), os.path.join(tmp, "y1.fastq"), os.path.join(tmp, "y2.fastq")),
         "synth_p": (os.path.join(HERE, "synth_idx_p"), os.path.join(tmp, "y1.fastq"), os.path.join(tmp, "y2.fastq")),
+        "synth_r": (os.path.join(HERE, "synth_idx"), os.path.join(tmp, "y1.fastq"), None),
     }
     for dname, (idx, r1, r2) in datasets.items():
-        for fname, flags in FLAGSETS.items():
-            if dname != "synth" and fname not in ("default", "selaln"):
+        for fname, flags in (UNMATED_FLAGSETS if dname == "synth_r" else FLAGSETS).items():
+            if dname not in ("synth", "synth_r") and fname not in ("default", "selaln"):
                 continue
             sam = quasimap(idx, r1, r2, flags)
             golden[f"{dname}/{fname}"] = {"flags": flags, "md5": hashlib.md5(sam).hexdigest(), "lines": sam.count(b"\n")}
-            if fname in KEEP_SAM and dname != "synth_p":
+            if fname in KEEP_SAM and dname == "synth":
                 with gzip.open(os.path.join(HERE, f"{dname}_{fname}.sam.gz"), "wb", compresslevel=9) as g:
                     g.write(sam)
             print(dname, fname, golden[f"{dname}/{fname}"]["md5"], golden[f"{dname}/{fname}"]["lines"])

@@ -211,6 +211,50 @@ def synth_index(genes: int, seed: int = 12345, repeats: int = 0, perfect: bool =
     return os.path.join(d, "idx") + "/", tx
 
 
+ANTISENSE = {"seed": 2024, "genes": 60}
+
+
+def antisense_index() -> tuple[str, SynthTxome, str]:
+    """Index of a small synthetic transcriptome to which diverged ANTISENSE copies are added: for every second
+    transcript, the reverse complement of bases [60, 460) with a substitution every 41-67 bases, between random flanks.
+    A read of such a transcript has k-mer hits on BOTH strands with different coverage, so the strand decision of
+    SACollector (coverage vs k-mer votes vs none: --noStrictCheck / --noSensitive) and the NIP skip change the result -
+    on the plain synthetic transcriptomes those flags provably change nothing (tests/golden/golden.json: synth/nosensitive
+    == synth/nostrict == synth/default).  Built with the reference's quasiindex, cached under CACHE.
+    Returns (index dir, transcriptome the reads are drawn from, fasta path)."""
+    import random
+
+    d = os.path.join(CACHE, f"antisense_g{ANTISENSE['genes']}_s{ANTISENSE['seed']}")
+    tx = SynthTxome(ANTISENSE["seed"], ANTISENSE["genes"])
+    fa2 = os.path.join(d, "t_antisense.fasta")
+    if not os.path.exists(os.path.join(d, "idx", "header.json")):
+        os.makedirs(d, exist_ok=True)
+        fa = os.path.join(d, "t.fasta")
+        tx.write_fasta(fa)
+        names, seqs = [], []
+        with open(fa) as f:
+            for line in f:
+                if line.startswith(">"):
+                    names.append(line[1:].strip())
+                    seqs.append("")
+                else:
+                    seqs[-1] += line.strip()
+        comp = {"A": "T", "C": "G", "G": "C", "T": "A"}
+        rng = random.Random(5)
+        with open(fa2, "w") as g:
+            for i, (nm, s) in enumerate(zip(names, seqs)):
+                g.write(f">{nm}\n{s}\n")
+                if i % 2 == 0 and len(s) > 500:
+                    seg = list(s[60:460])
+                    for p in range(37, len(seg), rng.choice([41, 53, 67])):
+                        seg[p] = rng.choice([c for c in "ACGT" if c != seg[p]])
+                    rcseg = "".join(comp[c] for c in reversed(seg))
+                    flank = "".join(rng.choice("ACGT") for _ in range(120))
+                    g.write(f">{nm}_as\n{flank}{rcseg}{flank[::-1]}\n")
+        build_index(fa2, os.path.join(d, "idx"))
+    return os.path.join(d, "idx") + "/", tx, fa2
+
+
 # ----------------------------------------------------------------------------------------------
 # golden fixtures
 # ----------------------------------------------------------------------------------------------

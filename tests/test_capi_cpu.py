@@ -53,3 +53,49 @@ def test_product_does_not_reference_oracle():
             if re.search(r"oracle/|liboracle|quasimap_oracle|oracle_", txt):
                 bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def _corrupt_copy(tmp_path, name, mutate):
+    import shutil
+
+    d = tmp_path / name
+    shutil.copytree(os.path.join(GOLD, "sample_idx"), d)
+    mutate(d)
+    return str(d)
+
+
+@pytest.mark.parametrize("what", ["truncated_sa", "huge_count", "sa_out_of_range", "bad_offsets", "truncated_hash", "missing_file"])
+def test_malformed_index_is_an_io_error_not_a_crash(tmp_path, what):
+    """rapmap_cuda_index_load on a damaged index directory returns RAPMAP_ERR_IO (no exception or abort crosses the C-ABI,
+    no unbounded allocation from a corrupt size field); the files are validated before any device work."""
+    import struct
+
+    def mutate(d):
+        if what == "truncated_sa":
+            b = (d / "sa.bin").read_bytes()
+            (d / "sa.bin").write_bytes(b[: len(b) // 2])
+        elif what == "huge_count":
+            b = bytearray((d / "txpInfo.bin").read_bytes())
+            b[0:8] = struct.pack("<Q", 1 << 60)
+            (d / "txpInfo.bin").write_bytes(bytes(b))
+        elif what == "sa_out_of_range":
+            b = bytearray((d / "sa.bin").read_bytes())
+            b[8 + 40 : 8 + 44] = struct.pack("<i", 0x7FFFFFF0)
+            (d / "sa.bin").write_bytes(bytes(b))
+        elif what == "bad_offsets":
+            b = bytearray((d / "txpInfo.bin").read_bytes())
+            n = struct.unpack_from("<Q", b, 0)[0]
+            p = 8
+            for _ in range(n):
+                p += 8 + struct.unpack_from("<Q", b, p)[0]
+            b[p + 8 + 4 : p + 8 + 8] = struct.pack("<i", -5)  # second transcript offset
+            (d / "txpInfo.bin").write_bytes(bytes(b))
+        elif what == "truncated_hash":
+            b = (d / "hash.bin").read_bytes()
+            (d / "hash.bin").write_bytes(b[: len(b) - 100])
+        elif what == "missing_file":
+            os.remove(d / "rsd.bin")
+
+    with pytest.raises(rb.RapMapCudaError) as e:
+        rb.Index(_corrupt_copy(tmp_path, what, mutate), 0)
+    assert e.value.code == rb.ERR_IO, str(e.value)

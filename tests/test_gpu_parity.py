@@ -17,11 +17,6 @@ with open(os.path.join(GOLD, "golden.json")) as f:
 META = GOLDEN["_meta"]["synth"]
 
 
-def _supported(opts):
-    """Mapper for opts, or skip if the device path refuses the option set (it must refuse, never approximate)."""
-    return opts
-
-
 def assert_same(res, ref, what=""):
     assert res.num_hits == ref.num_hits, f"{what}: hits {res.num_hits} != {ref.num_hits}\n" + explain_mismatch(res, ref)
     assert np.array_equal(res.pair_offsets, ref.pair_offsets), f"{what}: offsets differ\n" + explain_mismatch(res, ref)
@@ -217,13 +212,40 @@ def test_empty_and_single_read_batches(synth_small):
     assert hb.num_hits == 0
 
 
-def test_unmated_reads(synth_small):
+@pytest.mark.parametrize("fname", sorted(k.split("/")[1] for k in GOLDEN if k.startswith("synth_r/")))
+def test_unmated_reads_match_oracle_and_golden_sam(synth_small, fname):
+    """quasimap -r (processReadsSingleSA): records == oracle, SAM text == what the reference printed."""
     idx_dir, index, s1, s2, L, tx = synth_small
-    opts = rb.default_opts()
-    n = 500
+    opts = opts_from_flags(GOLDEN[f"synth_r/{fname}"]["flags"])
+    n = s1.shape[0]
     mapper = make_mapper(index, opts, n, L)
-    res = mapper.map_batch(s1[:n].copy(), None, n=n, fixed_len=L)
-    assert_same(res, OracleMapper(idx_dir, opts).map(s1[:n].copy(), None, L, n=n), "unmated")
+    res = mapper.map_batch(s1, None, n=n, fixed_len=L)
+    assert_same(res, OracleMapper(idx_dir, opts).map(s1, None, L, n=n), f"unmated {fname}")
+    sam = index.sam_header() + mapper.format_sam(s1, None, synth_names(tx, n)[0], None, res, n, fixed_len=L)
+    assert md5(sam) == GOLDEN[f"synth_r/{fname}"]["md5"], f"unmated {fname}: SAM differs from the reference's golden SAM"
+
+
+def synth_names(tx, n):
+    """Read names as the generator CLI writes them into FASTQ (r<i>:<txp>:<pos>:<fraglen>/<mate>)."""
+    from helpers import synth_lib
+
+    truth = np.zeros((n, 4), dtype=np.int64)
+    a, b = np.empty((n, 100), dtype=np.uint8), np.empty((n, 100), dtype=np.uint8)
+    synth_lib().synth_reads(tx.h, META["rseed"], 0, n, 100, META["sub"], META["ins"], META["del"], META["n"], a.ctypes.data, b.ctypes.data, truth.ctypes.data)
+    return ([f"r{i}:{truth[i,0]}:{truth[i,1]}:{truth[i,2]}/1" for i in range(n)], [f"r{i}:{truth[i,0]}:{truth[i,1]}:{truth[i,2]}/2" for i in range(n)])
+
+
+def test_sam_formatting_threads_give_identical_text(synth_small):
+    idx_dir, index, s1, s2, L, tx = synth_small
+    opts = rb.default_opts(sel_aln=True)
+    n = s1.shape[0]
+    mapper = make_mapper(index, opts, n, L)
+    res = mapper.map_batch(s1, s2, n=n, fixed_len=L)
+    res = rb.BatchResult(res.hits.copy(), res.pair_offsets.copy(), res.counters, res.num_hits)
+    n1, n2 = synth_names(tx, n)
+    one = mapper.format_sam(s1, s2, n1, n2, rb.BatchResult(res.hits.copy(), res.pair_offsets, res.counters, res.num_hits), n, fixed_len=L, threads=1)
+    many = mapper.format_sam(s1, s2, n1, n2, rb.BatchResult(res.hits.copy(), res.pair_offsets, res.counters, res.num_hits), n, fixed_len=L, threads=7)
+    assert one == many and md5(index.sam_header() + one) == GOLDEN["synth/selaln"]["md5"]
 
 
 def test_device_resident_inputs_match_host_inputs(synth_small):
@@ -317,21 +339,6 @@ def test_repeat_families_exercise_big_intervals_and_spill():
     assert_same(res, OracleMapper(idx_dir, opts).map(s1, s2, 100), "repeats")
 
 
-@pytest.mark.parametrize("mode,sel", [("regroup256", False), ("regroup128", True), ("warp", False)])
-def test_alternative_sa_lookup_schedulers_match_oracle(monkeypatch, mode, sel):
-    """The SA-lookup kernel exists in three schedulings (lane per read = default, reads regrouped by their next step,
-    warp per read): same walk, so the same records.  The library reads RAPMAP_B200_K1 when a mapper is created."""
-    monkeypatch.setenv("RAPMAP_B200_K1", mode)
-    idx_dir, tx = synth_index(2500)
-    n = 20000
-    s1, s2 = tx.reads(n, rseed=99)
-    opts = rb.default_opts(sel_aln=sel)
-    index = rb.Index(idx_dir, 0)
-    mapper = make_mapper(index, opts, n, 100)
-    res = mapper.map_batch(s1, s2, n=n, fixed_len=100)
-    assert_same(res, OracleMapper(idx_dir, opts).map(s1, s2, 100), f"{mode} sel={sel}")
-
-
 @pytest.mark.parametrize("read_len,sel", [(150, False), (150, True), (250, True), (300, False)])
 def test_longer_reads_match_oracle(read_len, sel):
     """Reads longer than the benchmark's 100 bases: 5..10 packed words per read in the SA-lookup kernel, ksw2 windows
@@ -357,3 +364,177 @@ def test_orphan_recovery_matches_oracle(flags):
     mapper = make_mapper(index, opts, n, 100)
     res = mapper.map_batch(s1, s2, n=n, fixed_len=100)
     assert_same(res, OracleMapper(idx_dir, opts).map(s1, s2, 100), " ".join(flags))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# flags that only matter when a read hits BOTH strands: transcriptome with diverged antisense copies
+# ---------------------------------------------------------------------------------------------------------------
+DISCRIMINATING = [["--noSensitive"], ["--noStrictCheck"], ["--noSensitive", "--noStrictCheck"], ["-s"], ["-s", "--noSensitive"], ["-s", "--noStrictCheck"],
+                  ["-s", "--noSensitive", "--noStrictCheck"], ["-z", "0.7"], ["-m", "2"], ["-f"], ["-f", "--noStrictCheck"]]
+
+
+@pytest.fixture(scope="module")
+def antisense():
+    if not have_ref():
+        pytest.skip("needs oracle/_ref to build the antisense index")
+    from helpers import antisense_index
+
+    idx_dir, tx, _ = antisense_index()
+    n = 12000
+    s1, s2 = tx.reads(n, rseed=77, sub=15000, ins=1000, dele=1000, nn=1000)
+    base = OracleMapper(idx_dir, rb.default_opts()).map(s1, s2, 100)
+    return idx_dir, rb.Index(idx_dir, 0), s1, s2, n, base
+
+
+@pytest.mark.parametrize("flags", [[]] + DISCRIMINATING, ids=lambda f: " ".join(f) or "default")
+def test_strand_and_skip_flags_on_antisense_transcriptome(antisense, flags):
+    """Each flag set gives records identical to the oracle AND different from the default flags' (the fixture discriminates:
+    a wrong NIP skip, lce, k-mer vote or strand filter cannot hide)."""
+    idx_dir, index, s1, s2, n, base = antisense
+    opts = opts_from_flags(flags)
+    ref = OracleMapper(idx_dir, opts).map(s1, s2, 100)
+    if flags:
+        assert not (ref.num_hits == base.num_hits and np.array_equal(ref.hits, base.hits)), f"{flags}: oracle output equals the default output"
+    mapper = make_mapper(index, opts, n, 100)
+    assert_same(mapper.map_batch(s1, s2, n=n, fixed_len=100), ref, " ".join(flags))
+
+
+@pytest.mark.parametrize("flags", [[], ["--noSensitive"], ["--noStrictCheck"], ["--noSensitive", "--noStrictCheck"], ["-s"], ["-s", "--noSensitive"]],
+                         ids=lambda f: " ".join(f) or "default")
+def test_sa_interval_stage_under_flags_on_antisense_transcriptome(antisense, flags):
+    """Kernel 1 alone under the flags that steer it: SAIntervalHit lists == SACollector::operator() of the oracle, read by read;
+    under every non-default flag set at least one read's lists differ from the default ones."""
+    idx_dir, index, s1, s2, _, _ = antisense
+    n = 1500
+    opts = opts_from_flags(flags)
+    mapper = make_mapper(index, opts, n, 100)
+    mapper.map_batch(s1[:n].copy(), s2[:n].copy(), n=n, fixed_len=100)
+    om, om0 = OracleMapper(idx_dir, opts), OracleMapper(idx_dir, rb.default_opts())
+    differs = 0
+    for r in range(2 * n):
+        read = (s1 if r < n else s2)[r % n].tobytes()
+        exp = om.collect(read)
+        assert mapper.debug_intervals(r) == exp, f"read {r}: {read!r}"
+        differs += exp != om0.collect(read)
+    if flags:
+        assert differs > 0, f"{flags}: no read's interval lists differ from the default walk"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the boundary: overflow -> grow -> re-run, asynchronous calls, concurrent mappers, index replicas
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.skipif(not have_ref(), reason="needs oracle/_ref to build the mid-size index")
+@pytest.mark.parametrize("flags", [[], ["-s"], ["-f"], ["-s", "--recoverOrphans"]], ids=lambda f: " ".join(f) or "default")
+def test_every_arena_overflow_retry_path(monkeypatch, flags):
+    """RAPMAP_B200_TINY_ARENAS=1 starts every growable device work area far too small (interval arena 64 records, 1 interval
+    per strand in the per-thread lists, 8 hit records, 8 QA records, 16 positions, 128-entry work strips): the first batch
+    must walk through each overflow -> grow -> re-run path and still equal the oracle; the second batch runs clean."""
+    monkeypatch.setenv("RAPMAP_B200_TINY_ARENAS", "1")
+    idx_dir, tx = synth_index(600, seed=4711, repeats=6)
+    n = 8000
+    s1, s2 = tx.reads(n, rseed=7)
+    opts = opts_from_flags(flags)
+    mapper = make_mapper(rb.Index(idx_dir, 0), opts, n, 100)
+    monkeypatch.delenv("RAPMAP_B200_TINY_ARENAS")
+    ref = OracleMapper(idx_dir, opts).map(s1, s2, 100)
+    res = mapper.map_batch(s1, s2, n=n, fixed_len=100)
+    assert mapper.timing().retries >= 2, "the tiny arenas did not force a re-run"
+    assert_same(res, ref, "after forced retries")
+    res2 = mapper.map_batch(s1, s2, n=n, fixed_len=100)
+    assert mapper.timing().retries == 0
+    assert_same(res2, ref, "second batch")
+
+
+@pytest.mark.skipif(not have_ref(), reason="needs oracle/_ref to build the mid-size index")
+@pytest.mark.parametrize("sel", [False, True])
+def test_async_calls_one_thread_four_mappers(sel):
+    """rapmap_cuda_map_batch_async / rapmap_cuda_mapper_wait: one host thread keeps four mappers (streams) busy on one shared
+    index; every chunk equals the oracle's result for that chunk."""
+    idx_dir, tx = synth_index(2500)
+    index = rb.Index(idx_dir, 0)
+    opts = rb.default_opts(sel_aln=sel)
+    n, chunks = 5000, 12
+    data = [tx.reads(n, rseed=1000 + c) for c in range(chunks)]
+    om = OracleMapper(idx_dir, opts)
+    refs = [om.map(a, b, 100) for a, b in data]
+    mappers = [make_mapper(index, opts, n, 100) for _ in range(4)]
+    outs = [(np.empty(16 * n, dtype=rb.HIT_DTYPE), np.empty(n + 1, dtype=np.uint64)) for _ in range(4)]
+    pending = [None] * 4
+    done = {}
+    for c in range(chunks + 4):
+        k = c % 4
+        if pending[k] is not None:
+            r = mappers[k].wait()
+            done[pending[k]] = rb.BatchResult(r.hits.copy(), r.pair_offsets.copy(), r.counters, r.num_hits)
+            pending[k] = None
+        if c < chunks:
+            mappers[k].map_batch_async(data[c][0], data[c][1], n=n, fixed_len=100, hits_out=outs[k][0], offsets_out=outs[k][1])
+            pending[k] = c
+    for c in range(chunks):
+        assert_same(done[c], refs[c], f"chunk {c}")
+    with pytest.raises(rb.RapMapCudaError):
+        mappers[0].wait()  # nothing in flight
+
+
+@pytest.mark.skipif(not have_ref(), reason="needs oracle/_ref to build the mid-size index")
+def test_concurrent_mappers_on_host_threads():
+    """Four host threads, each with its own mapper on ONE shared index (the reference's worker-thread model): every chunk of
+    every thread equals the oracle."""
+    import threading
+
+    idx_dir, tx = synth_index(2500)
+    index = rb.Index(idx_dir, 0)
+    opts = rb.default_opts(sel_aln=True)
+    n, per = 4000, 5
+    data = [[tx.reads(n, rseed=5000 + 10 * t + c) for c in range(per)] for t in range(4)]
+    om = OracleMapper(idx_dir, opts)
+    refs = [[om.map(a, b, 100) for a, b in row] for row in data]
+    got = [[None] * per for _ in range(4)]
+    errs = []
+
+    def work(t):
+        try:
+            mp = rb.Mapper(index, opts, max_batch=n, max_read_len=100)
+            for c in range(per):
+                r = mp.map_batch(data[t][c][0], data[t][c][1], n=n, fixed_len=100)
+                got[t][c] = rb.BatchResult(r.hits.copy(), r.pair_offsets.copy(), r.counters, r.num_hits)
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    ths = [threading.Thread(target=work, args=(t,)) for t in range(4)]
+    [th.start() for th in ths]
+    [th.join() for th in ths]
+    assert not errs, errs
+    for t in range(4):
+        for c in range(per):
+            assert_same(got[t][c], refs[t][c], f"thread {t} chunk {c}")
+
+
+def test_index_replica_from_image_carries_names(synth_small):
+    """An index built around a copy of the packed image (what another rank receives over NCCL) maps identically and can print
+    SAM: transcript names and lengths travel inside the image."""
+    import torch
+
+    idx_dir, index, s1, s2, L, tx = synth_small
+    ptr, nbytes = index.image()
+    blob = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    src = torch.empty(0, dtype=torch.uint8, device="cuda")
+    # device-to-device copy of the image through the CUDA runtime
+    import ctypes as C
+    try:
+        rt = C.CDLL("libcudart.so.12")
+    except OSError:
+        rt = C.CDLL("/usr/local/cuda/lib64/libcudart.so.12")
+    assert rt.cudaMemcpy(C.c_void_p(blob.data_ptr()), C.c_void_p(ptr), C.c_size_t(nbytes), 3) == 0
+    replica = rb.Index.from_image(0, blob.data_ptr(), nbytes)
+    assert replica.sam_header() == index.sam_header()
+    assert replica.transcript_name(3) == index.transcript_name(3) and replica.transcript_len(3) == index.transcript_len(3)
+    opts = rb.default_opts()
+    n = s1.shape[0]
+    a = make_mapper(index, opts, n, L).map_batch(s1, s2, n=n, fixed_len=L)
+    a_hits = a.hits.copy()
+    b = make_mapper(replica, opts, n, L).map_batch(s1, s2, n=n, fixed_len=L)
+    assert np.array_equal(a_hits, b.hits)
+    with pytest.raises(rb.RapMapCudaError):
+        rb.Index.from_image(0, blob.data_ptr() + 32, nbytes - 32)  # misaligned / not an image
+    del src

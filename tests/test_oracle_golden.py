@@ -32,10 +32,11 @@ def fastqs(tmp_path_factory):
                     "--sub", str(META["sub"]), "--ins", str(META["ins"]), "--del", str(META["del"]), "--n", str(META["n"]),
                     "--out1", str(d / "y1.fastq"), "--out2", str(d / "y2.fastq")], check=True)
     out["synth"] = out["synth_p"] = (str(d / "y1.fastq"), str(d / "y2.fastq"))
+    out["synth_r"] = (str(d / "y1.fastq"), None)  # unmated reads (-r): the mate-1 file alone
     return out
 
 
-IDX = {"sample": "sample_idx", "synth": "synth_idx", "synth_p": "synth_idx_p"}
+IDX = {"sample": "sample_idx", "synth": "synth_idx", "synth_p": "synth_idx_p", "synth_r": "synth_idx"}
 
 
 @pytest.mark.parametrize("case", CASES)
@@ -43,7 +44,8 @@ def test_oracle_matches_reference_golden(case, fastqs, tmp_path):
     dname, fname = case.split("/")
     r1, r2 = fastqs[dname]
     out = tmp_path / "o.sam"
-    subprocess.run([ORACLE_CLI, "-i", os.path.join(GOLD, IDX[dname]), "-1", r1, "-2", r2, "-o", str(out)] + GOLDEN[case]["flags"], check=True, capture_output=True)
+    reads = ["-1", r1, "-2", r2] if r2 else ["-r", r1]
+    subprocess.run([ORACLE_CLI, "-i", os.path.join(GOLD, IDX[dname])] + reads + ["-o", str(out)] + GOLDEN[case]["flags"], check=True, capture_output=True)
     sam = out.read_bytes()
     if md5(sam) != GOLDEN[case]["md5"]:
         gz = os.path.join(GOLD, f"{dname}_{fname}.sam.gz")
@@ -73,3 +75,40 @@ def test_oracle_matches_live_reference_noisy_reads(fastqs, tmp_path):
         subprocess.run([ORACLE_CLI, "-i", os.path.join(GOLD, "synth_idx"), "-1", str(d / "a1.fastq"), "-2", str(d / "a2.fastq"), "-o", str(d / "ora.sam")] + flags,
                        check=True, capture_output=True)
         assert (d / "ref.sam").read_bytes() == (d / "ora.sam").read_bytes(), flags
+
+
+def test_sample_goldens_are_the_surveys_known_answers():
+    """config 1 (all 10,000 sample pairs, -t 1): the md5s SURVEY.md section 4 records for the unmodified reference."""
+    assert GOLDEN["sample/default"]["md5"] == "5271acf4e1c0e5d22b43ab7859f825d3" and GOLDEN["sample/default"]["lines"] == 28523
+    assert GOLDEN["sample/selaln"]["md5"] == "ddd30824c80623c4e272324cd6e7784f" and GOLDEN["sample/selaln"]["lines"] == 28523
+
+
+ANTISENSE_FLAGS = [[], ["--noSensitive"], ["--noStrictCheck"], ["--noSensitive", "--noStrictCheck"], ["-s"], ["-s", "--noSensitive"], ["-s", "--noStrictCheck"],
+                   ["-s", "--noSensitive", "--noStrictCheck"], ["-z", "0.7"], ["-m", "2"], ["-f"], ["-f", "--noStrictCheck"]]
+
+
+@pytest.mark.skipif(not have_ref(), reason="compiled reference (oracle/_ref) not present")
+def test_oracle_matches_live_reference_on_antisense_transcriptome(tmp_path):
+    """Transcriptome with diverged antisense copies (helpers.antisense_index): reads hit both strands, so --noSensitive
+    (NIP skip + k-mer votes), --noStrictCheck (no strand filter) and their combinations really change the output.  The
+    oracle must equal the reference under each, and each must differ from the default output (the fixture discriminates)."""
+    from helpers import ANTISENSE, antisense_index
+
+    idx, _, _ = antisense_index()
+    d = tmp_path
+    subprocess.run([SYNTH_BIN, "reads", "--genes", str(ANTISENSE["genes"]), "--seed", str(ANTISENSE["seed"]), "--pairs", "4000", "--rseed", "77", "--sub", "15000",
+                    "--ins", "1000", "--del", "1000", "--n", "1000", "--out1", str(d / "a1.fastq"), "--out2", str(d / "a2.fastq")], check=True)
+    seen = {}
+    for flags in ANTISENSE_FLAGS:
+        subprocess.run([REF_BIN, "quasimap", "-i", idx, "-1", str(d / "a1.fastq"), "-2", str(d / "a2.fastq"), "-t", "1", "-o", str(d / "ref.sam")] + flags,
+                       check=True, capture_output=True)
+        subprocess.run([ORACLE_CLI, "-i", idx, "-1", str(d / "a1.fastq"), "-2", str(d / "a2.fastq"), "-o", str(d / "ora.sam")] + flags, check=True, capture_output=True)
+        ref = (d / "ref.sam").read_bytes()
+        assert ref == (d / "ora.sam").read_bytes(), flags
+        seen[" ".join(flags)] = md5(ref)
+    assert len(set(seen.values())) == len(seen), f"flag sets with identical output: {seen}"
+    # unmated reads (-r) on the same index
+    for flags in ([], ["-s"], ["--noSensitive"], ["-s", "--noStrictCheck"], ["-m", "1"]):
+        subprocess.run([REF_BIN, "quasimap", "-i", idx, "-r", str(d / "a1.fastq"), "-t", "1", "-o", str(d / "ref.sam")] + flags, check=True, capture_output=True)
+        subprocess.run([ORACLE_CLI, "-i", idx, "-r", str(d / "a1.fastq"), "-o", str(d / "ora.sam")] + flags, check=True, capture_output=True)
+        assert (d / "ref.sam").read_bytes() == (d / "ora.sam").read_bytes(), ["-r"] + flags
