@@ -5,11 +5,19 @@ HBM GB/s vs peak).
     python bench.py --gpus N --steps K --warmup W            # this engine
     python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU `quasimap` on the host cores
 
-Workload (configs[1]): GENCODE-like ~200k-transcript synthetic index (tools/synth.cpp, seed 12345, 37,000 genes),
-synthetic 2x100 bp pairs (seed 54321: 1% substitutions, 0.03% ins/del, 0.1% N), default `quasimap` flags (no -s).
-A step = one chunk ("batch") of --batch pairs per GPU through rapmap_cuda_map_batch; 40 default steps of 2^20
-pairs (4 distinct batches cycled) = 4x the 10M-pair configuration, so that the timed region is long enough to sample clocks.  Index replicated per GPU (one NCCL broadcast of the packed image), read
-ranges sharded by rank, no data-path collective: weak scaling.
+Workload: GENCODE-like ~203k-transcript synthetic index (tools/synth.cpp, seed 12345, 37,000 genes), synthetic 2x100 bp
+pairs (seed 54321: 1% substitutions, 0.03% ins/del, 0.1% N).  A STEP is one pass over the 10M-read configuration of
+BASELINE.json configs[1]: --chunks (10) chunks of --batch (2^20) pairs per GPU, each chunk one rapmap_cuda_map_batch call
+(4 distinct chunks cycled; every chunk's bases are larger than L2).  The ONE JSON line carries
+
+  * the headline: configs[1], default `quasimap` flags (no -s): `value` with reads resident in HBM, `e2e` through the C-ABI
+    with pinned HOST buffers (copies inside the timed region), the SA-lookup kernel's roofline, the reference CPU baseline;
+  * `legs.selaln`       configs[2] (and, under torchrun, configs[4]): the same index and reads with `quasimap -s`;
+  * `legs.perfect_hash` configs[3]: the same transcriptome indexed with -p (BooPHF + FrugalBooMap walked on the device).
+
+Every leg is parity-checked before its number is printed (CPU oracle on a bounded sample; -p against the dense results).
+Index replicated per GPU (one NCCL broadcast of the packed image), read ranges sharded by rank, no data-path collective:
+weak scaling.
 """
 from __future__ import annotations
 
@@ -36,6 +44,11 @@ TX_SEED, READ_SEED = 12345, 54321
 CACHE = os.environ.get("RAPMAP_B200_CACHE", "/tmp/rapmap_b200_cache")
 
 
+def workload_name(genes: int) -> str:
+    """The same string in both arms (this engine and --impl reference)."""
+    return f"configs[1]: GENCODE-like {genes}-gene (~203k-transcript at 37000 genes) synthetic index, synthetic 2x100bp read pairs, quasimap default flags (no -s)"
+
+
 def log(*a):
     print("[bench]", *a, file=sys.stderr, flush=True)
 
@@ -58,27 +71,33 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def index_dir(genes: int) -> str:
-    return os.path.join(CACHE, f"bench_g{genes}_s{TX_SEED}", "idx")
+def index_dir(genes: int, perfect: bool = False) -> str:
+    return os.path.join(CACHE, f"bench_g{genes}_s{TX_SEED}", "idx_p" if perfect else "idx")
 
 
-def ensure_index(genes: int, use_gpu: bool) -> str:
-    """Reference-format index of the synthetic transcriptome (tools/build_index.py), cached per box under CACHE."""
-    d = index_dir(genes)
-    if os.path.exists(os.path.join(d, "header.json")):
-        return d + "/"
+def ensure_index(genes: int, use_gpu: bool, perfect: bool = False) -> str:
+    """Reference-format index of the synthetic transcriptome (tools/build_index.py: dense flavour and the -p flavour of the same
+    suffix array, written in one go), cached per box under CACHE."""
+    d, dp = index_dir(genes), index_dir(genes, True)
+    want = dp if perfect else d
+    if os.path.exists(os.path.join(want, "header.json")):
+        return want + "/"
     from build_index import build_synth_index
 
-    tmp = d + ".tmp%d" % os.getpid()
+    tmp, tmpp = d + ".tmp%d" % os.getpid(), dp + ".tmp%d" % os.getpid()
     t0 = time.time()
-    build_synth_index(tmp, TX_SEED, genes, 0, device="cuda" if use_gpu else "cpu", verbose=False)
+    info = build_synth_index(tmp, TX_SEED, genes, 0, device="cuda" if use_gpu else "cpu", verbose=False, perfect_dir=tmpp)
     os.makedirs(os.path.dirname(d), exist_ok=True)
-    try:
-        os.rename(tmp, d)
-    except OSError:
-        pass
-    log(f"built index for {genes} genes in {time.time() - t0:.1f}s -> {d}")
-    return d + "/"
+    for name in ("sa.bin", "txpInfo.bin", "rsd.bin"):  # the links of the -p flavour point at the dense directory's final place
+        os.remove(os.path.join(tmpp, name))
+        os.symlink(os.path.join("..", "idx", name), os.path.join(tmpp, name))
+    for a, b in ((tmp, d), (tmpp, dp)):
+        try:
+            os.rename(a, b)
+        except OSError:
+            pass
+    log(f"built dense + perfect-hash index for {genes} genes in {time.time() - t0:.1f}s ({info['kmers']} k-mers) -> {d}")
+    return want + "/"
 
 
 class ClockSampler:
@@ -127,6 +146,32 @@ def alg_bytes_per_pair(ops: dict, pairs: int) -> float:
     return 2 * READ_LEN + (16.0 * ops["hashFind"] + 4.0 * ops["saProbes"] + 1.0 * ops["textCmp"]) / pairs
 
 
+def write_fastq_prefix(tx, total: int, d: str):
+    """First `total` pairs of the benchmark read stream as FASTQ (for the reference binary), cached."""
+    os.makedirs(d, exist_ok=True)
+    f1, f2 = os.path.join(d, f"r1_{total}.fastq"), os.path.join(d, f"r2_{total}.fastq")
+    if not os.path.exists(f2):
+        qual = b"I" * READ_LEN
+        with open(f1 + ".tmp", "wb") as g1, open(f2 + ".tmp", "wb") as g2:
+            for first in range(0, total, 500000):  # chunked: bounded host memory whatever --steps says
+                cnt = min(500000, total - first)
+                s1, s2 = tx.reads(cnt, rseed=READ_SEED, first=first, read_len=READ_LEN)
+                for g, arr, m in ((g1, s1, 1), (g2, s2, 2)):
+                    g.write(b"".join(b"@r%d/%d\n%s\n+\n%s\n" % (first + i, m, arr[i].tobytes(), qual) for i in range(cnt)))
+        os.rename(f1 + ".tmp", f1)
+        os.rename(f2 + ".tmp", f2)
+    return f1, f2
+
+
+def reference_quasimap(ref_bin, idx, f1, f2, cores, flags):
+    """`rapmap_ref quasimap -n`: (mapping seconds from the reference's own ScopedTimer, wall seconds incl. index load)."""
+    t0 = time.time()
+    p = subprocess.run([ref_bin, "quasimap", "-i", idx, "-1", f1, "-2", f2, "-t", str(cores), "-n"] + flags, capture_output=True, text=True)
+    wall = time.time() - t0
+    m = re.findall(r"Elapsed time: ([0-9.eE+-]+)s", p.stdout + p.stderr)
+    return (float(m[-1]) if m else wall), wall
+
+
 def run_reference(args) -> None:
     """The reference's own multithreaded CPU `quasimap` (oracle/_ref/rapmap_ref, unmodified sources) on the host cores."""
     rank = int(os.environ.get("RANK", "0"))
@@ -148,40 +193,23 @@ def run_reference(args) -> None:
     total = sample * args.steps
     tx = SynthTxome(TX_SEED, args.genes)
     d = os.path.join(CACHE, "ref_reads")
-    os.makedirs(d, exist_ok=True)
-    f1, f2 = os.path.join(d, f"r1_{total}.fastq"), os.path.join(d, f"r2_{total}.fastq")
-    if not os.path.exists(f2):
-        qual = b"I" * READ_LEN
-        with open(f1 + ".tmp", "wb") as g1, open(f2 + ".tmp", "wb") as g2:
-            for first in range(0, total, 500000):  # chunked: bounded host memory whatever --steps says
-                cnt = min(500000, total - first)
-                s1, s2 = tx.reads(cnt, rseed=READ_SEED, first=first, read_len=READ_LEN)
-                for g, arr, m in ((g1, s1, 1), (g2, s2, 2)):
-                    g.write(b"".join(b"@r%d/%d\n%s\n+\n%s\n" % (first + i, m, arr[i].tobytes(), qual) for i in range(cnt)))
-        os.rename(f1 + ".tmp", f1)
-        os.rename(f2 + ".tmp", f2)
+    f1, f2 = write_fastq_prefix(tx, total, d)
     flags = ["-s"] if args.selaln else []
-
-    def once(n_pairs_files):
-        t0 = time.time()
-        p = subprocess.run([REF_BIN, "quasimap", "-i", idx, "-1", n_pairs_files[0], "-2", n_pairs_files[1], "-t", str(cores), "-n"] + flags,
-                           capture_output=True, text=True)
-        wall = time.time() - t0
-        m = re.findall(r"Elapsed time: ([0-9.eE+-]+)s", p.stdout + p.stderr)
-        return (float(m[-1]) if m else wall), wall
-
     if args.warmup > 0:  # one untimed pass warms the page cache (the CLI is one-shot: warm-up steps cannot be separated)
         w1, w2 = os.path.join(d, "w1.fastq"), os.path.join(d, "w2.fastq")
         for src, dst in ((f1, w1), (f2, w2)):
             with open(src, "rb") as f, open(dst, "wb") as g:
                 g.write(b"".join(f.readline() for _ in range(4 * 2000)))
-        once((w1, w2))
-    mapping_s, wall = once((f1, f2))
+        reference_quasimap(REF_BIN, idx, w1, w2, cores, flags)
+    mapping_s, wall = reference_quasimap(REF_BIN, idx, f1, f2, cores, flags)
     value = total / mapping_s
     line.update({
         "value": value, "ms_per_step": 1e3 * mapping_s / args.steps,
-        "config": {"workload": f"GENCODE-like {args.genes}-gene synthetic index, 2x100bp synthetic pairs, quasimap{' -s' if args.selaln else ''} -n -t {cores}",
-                   "pairs_per_step": sample, "timed": "reference ScopedTimer 'Elapsed time' around mapReads (index load excluded)", "wall_s_incl_index_load": wall},
+        "config": {"workload": workload_name(args.genes) + (" + -s" if args.selaln else ""),
+                   "pairs_per_step": sample, "command": f"rapmap_ref quasimap{' -s' if args.selaln else ''} -n -t {cores}",
+                   "timed": "reference ScopedTimer 'Elapsed time' around mapReads: FASTQ parsing (page cache warm) + mapping, index load excluded",
+                   "wall_s_incl_index_load": wall,
+                   "note": "each step is a bounded sample of the workload (the CPU needs ~12 s for one 10M-pair pass)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": f"{total} pairs (first pairs of the benchmark read stream)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -192,18 +220,21 @@ def run_reference(args) -> None:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=1 << 20, help="pairs per step per GPU")
+    ap.add_argument("--batch", type=int, default=1 << 20, help="pairs per chunk (one rapmap_cuda_map_batch call) per GPU")
+    ap.add_argument("--chunks", type=int, default=10, help="chunks per step per GPU (10 x 2^20 = the 10M-read configuration)")
     ap.add_argument("--genes", type=int, default=37000, help="synthetic genes (37000 -> ~203k transcripts)")
-    ap.add_argument("--selaln", action="store_true", help="quasimap -s (configs[2])")
-    ap.add_argument("--distinct", type=int, default=4, help="distinct read batches cycled through the steps")
-    ap.add_argument("--ref-pairs-per-step", type=int, default=100000, help="pairs per step of the reference arm (bounded sample: 40 steps = 4M pairs, ~5 s of 16-thread CPU mapping)")
+    ap.add_argument("--selaln", action="store_true", help="headline leg with quasimap -s (configs[2]) instead of the default flags")
+    ap.add_argument("--legs", default="selaln,perfect_hash", help="extra legs in the JSON line (comma separated; 'none' to skip)")
+    ap.add_argument("--leg-steps", type=int, default=0, help="steps of the extra legs (0: min(--steps, 10))")
+    ap.add_argument("--distinct", type=int, default=4, help="distinct read chunks cycled through the steps")
+    ap.add_argument("--ref-pairs-per-step", type=int, default=100000, help="pairs per step of the reference arm (bounded sample)")
     ap.add_argument("--oracle-sample", type=int, default=20000, help="pairs checked against / counted by the CPU oracle at N=1")
     ap.add_argument("--cpu-baseline-pairs", type=int, default=1000000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-mappers", type=int, default=4, help="host threads (one mapper / CUDA stream each) of the end-to-end measurement")
+    ap.add_argument("--e2e-mappers", type=int, default=3, help="mappers (CUDA streams) the ONE host thread of the end-to-end leg keeps busy")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -229,24 +260,39 @@ def main():
         if world > 1:
             dist.barrier()
 
+    def max_over_ranks(ms: float) -> float:
+        if world > 1:
+            tm = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            return float(tm.item())
+        return ms
+
+    legs_wanted = [] if args.legs in ("", "none") else [x for x in args.legs.split(",") if x]
+    if world > 1:
+        legs_wanted = [x for x in legs_wanted if x == "selaln"]  # configs[4]: the -s scaling curve
+    if args.selaln:
+        legs_wanted = [x for x in legs_wanted if x != "selaln"]
+
     # ---- index: rank 0 builds (cached) + loads from the reference-format files; other ranks receive the packed image over NCCL
-    if rank == 0:
-        idx_dir = ensure_index(args.genes, True)
-    barrier()
-    idx_dir = index_dir(args.genes) + "/"
-    t0 = time.time()
     from rapmap_b200.sharding import replicate_index
 
-    index = rb.Index(idx_dir, local) if rank == 0 else None
-    index, _image_keepalive = replicate_index(index, rank, local)
-    log(f"rank {rank}: index ready in {time.time() - t0:.1f}s ({index.device_bytes / 2**30:.2f} GiB in HBM, {index.num_transcripts} transcripts)")
+    def load_index(perfect: bool):
+        if rank == 0:
+            ensure_index(args.genes, True, perfect)
+        barrier()
+        d = index_dir(args.genes, perfect) + "/"
+        t0 = time.time()
+        ix = rb.Index(d, local) if rank == 0 else None
+        ix, keep = replicate_index(ix, rank, local)
+        log(f"rank {rank}: {'-p ' if perfect else ''}index ready in {time.time() - t0:.1f}s ({ix.device_bytes / 2**30:.2f} GiB in HBM, {ix.num_transcripts} transcripts)")
+        return d, ix, keep
+
+    idx_dir, index, _keep0 = load_index(False)
 
     # ---- reads: rank-sharded contiguous ranges of the counter-based stream; pinned host copies + device copies
-    B = args.batch
-    opts = rb.default_opts(sel_aln=args.selaln)
-    mapper = rb.Mapper(index, opts, max_batch=B, max_read_len=READ_LEN)
+    B, CH = args.batch, max(1, args.chunks)
     tx = SynthTxome(TX_SEED, args.genes)
-    nd = max(1, min(args.distinct, args.steps + args.warmup))
+    nd = max(1, args.distinct)
     host, devb = [], []
     t0 = time.time()
     for b in range(nd):
@@ -260,166 +306,235 @@ def main():
     cap = B * 8
     d_hits = torch.empty(cap * 28, dtype=torch.uint8, device="cuda")
     d_off = torch.empty(B + 1, dtype=torch.int64, device="cuda")
-    h_hits = torch.empty(cap * 28, dtype=torch.uint8).pin_memory()
-    h_off = torch.empty(B + 1, dtype=torch.int64).pin_memory()
-    stream = torch.cuda.ExternalStream(mapper.stream_ptr, device=torch.device("cuda", local))
+    nm = max(1, args.e2e_mappers)
+    h_out = [(torch.empty(cap * 28, dtype=torch.uint8).pin_memory(), torch.empty(B + 1, dtype=torch.int64).pin_memory()) for _ in range(nm)]
+    dev = torch.device("cuda", local)
 
-    def step_resident(i):
-        a, b = devb[i % nd]
-        return mapper.map_batch(a, b, n=B, fixed_len=READ_LEN, location=rb.LOC_DEVICE, hits_out=d_hits, offsets_out=d_off, out_location=rb.LOC_DEVICE, capacity=cap)
+    STAGES = ("pack", "sa", "map", "merge", "selaln", "ksw", "h2d", "d2h")
 
-    def timed(fn, steps, warmup, sample_clocks=False):
-        for i in range(warmup):
-            fn(i)
+    def run_leg(ix, opts, steps, warmup, sample_clocks=False):
+        """Resident leg (device buffers in and out, one mapper, CUDA events on its stream) and end-to-end leg (pinned host buffers
+        in and out through rapmap_cuda_map_batch_async / _wait: ONE host thread keeps `nm` mappers busy, so one chunk's PCIe
+        copies overlap another chunk's kernels) over the same chunk sequence; the two legs must produce the same hits."""
+        mappers = [rb.Mapper(ix, opts, max_batch=B, max_read_len=READ_LEN) for _ in range(nm)]
+        mapper = mappers[0]
+        stream = torch.cuda.ExternalStream(mapper.stream_ptr, device=dev)
+
+        def resident(c):
+            a, b = devb[c % nd]
+            return mapper.map_batch(a, b, n=B, fixed_len=READ_LEN, location=rb.LOC_DEVICE, hits_out=d_hits, offsets_out=d_off, out_location=rb.LOC_DEVICE, capacity=cap)
+
+        for c in range(warmup * CH):
+            resident(c)
         torch.cuda.synchronize()
         barrier()
         sampler = ClockSampler(local) if sample_clocks else None
         if sampler:
             sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        st = {k: 0.0 for k in STAGES}
+        st.update({"launch": 0, "hits": 0, "retries": 0, "dp_jobs": 0, "dp_jobs_general": 0})
         e0.record(stream)
-        stages = {"pack": 0.0, "sa": 0.0, "map": 0.0, "merge": 0.0, "selaln": 0.0, "h2d": 0.0, "d2h": 0.0, "launch": 0, "hits": 0, "retries": 0}
-        for i in range(steps):
-            r = fn(warmup + i)
+        for c in range(steps * CH):
+            r = resident(warmup * CH + c)
             t = mapper.timing()
-            stages["pack"] += t.ms_pack_reads; stages["sa"] += t.ms_sa_collect; stages["map"] += t.ms_hits_to_mappings; stages["merge"] += t.ms_merge; stages["selaln"] += t.ms_sel_aln
-            stages["h2d"] += t.ms_h2d; stages["d2h"] += t.ms_d2h; stages["launch"] += t.launches; stages["hits"] += r.num_hits; stages["retries"] += t.retries
+            st["pack"] += t.ms_pack_reads; st["sa"] += t.ms_sa_collect; st["map"] += t.ms_hits_to_mappings; st["merge"] += t.ms_merge
+            st["selaln"] += t.ms_sel_aln; st["ksw"] += t.ms_ksw; st["h2d"] += t.ms_h2d; st["d2h"] += t.ms_d2h
+            st["launch"] += t.launches; st["hits"] += r.num_hits; st["retries"] += t.retries; st["dp_jobs"] += t.dp_jobs; st["dp_jobs_general"] += t.dp_jobs_general
         e1.record(stream)
         torch.cuda.synchronize()
         barrier()
         clocks = sampler.stop() if sampler else None
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            tm = torch.tensor([ms], dtype=torch.float64, device="cuda")
-            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-            ms = float(tm.item())
-        return ms, stages, clocks
+        ms_res = max_over_ranks(e0.elapsed_time(e1))
 
-    ms_res, st_res, clocks = timed(step_resident, args.steps, args.warmup, sample_clocks=True)
-    log(f"rank {rank}: resident leg {ms_res / args.steps:.2f} ms per step")
+        # ---- end to end
+        def e2e(first, count):
+            pending = [None] * nm
+            hits = 0
+            for c in range(first, first + count + nm):
+                k = c % nm
+                if pending[k]:
+                    hits += mappers[k].wait().num_hits
+                    pending[k] = False
+                if c < first + count:
+                    a, b = host[c % nd]
+                    mappers[k].map_batch_async(a, b, n=B, fixed_len=READ_LEN, location=rb.LOC_HOST, hits_out=h_out[k][0], offsets_out=h_out[k][1],
+                                               out_location=rb.LOC_HOST, capacity=cap)
+                    pending[k] = True
+            return hits
 
-    # ---- end to end: HOST buffers in, HOST buffers out, through rapmap_cuda_map_batch.  Like the reference's worker threads
-    # (one SACollector per thread), --e2e-mappers host threads each own a mapper (= one CUDA stream) and take chunks
-    # round-robin, so one chunk's PCIe copies overlap another chunk's kernels.  Every call is synchronous for its caller.
-    nm = max(1, args.e2e_mappers)
-    lanes = [(mapper, h_hits, h_off)]
-    for _ in range(nm - 1):
-        lanes.append((rb.Mapper(index, opts, max_batch=B, max_read_len=READ_LEN), torch.empty(cap * 28, dtype=torch.uint8).pin_memory(),
-                      torch.empty(B + 1, dtype=torch.int64).pin_memory()))
+        e2e(0, max(warmup * CH, 2 * nm))
+        torch.cuda.synchronize()
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(stream)
+        e2e_hits = e2e(warmup * CH, steps * CH)
+        f1.record(stream)  # every chunk has been waited for: the event marks the end of the host-visible work
+        torch.cuda.synchronize()
+        barrier()
+        ms_e2e = max_over_ranks(f0.elapsed_time(f1))
+        if e2e_hits != st["hits"]:
+            raise SystemExit(f"end-to-end leg produced {e2e_hits} hits, resident leg {st['hits']} over the same chunks; refusing to report a number")
+        return {"ms_res": ms_res, "ms_e2e": ms_e2e, "st": st, "clocks": clocks, "mapper": mapper, "mappers": mappers, "steps": steps}
 
-    def e2e_worker(t, first, count, acc):
-        torch.cuda.set_device(local)
-        mp, hh, ho = lanes[t]
-        hits = 0
-        for i in range(first + t, first + count, nm):
-            a, b = host[i % nd]
-            r = mp.map_batch(a.numpy(), b.numpy(), n=B, fixed_len=READ_LEN, location=rb.LOC_HOST, hits_out=hh, offsets_out=ho, out_location=rb.LOC_HOST, capacity=cap)
-            hits += r.num_hits
-        acc[t] = hits
+    def oracle_check(o_idx_dir, opts, mapper, ns):
+        """Parity + operation counts on the first `ns` pairs of chunk 0 (CPU oracle; N == 1 only)."""
+        a, b = host[0][0].numpy()[:ns].copy(), host[0][1].numpy()[:ns].copy()
+        om = OracleMapper(o_idx_dir, opts)
+        t0 = time.time()
+        ref = om.map(a, b, READ_LEN)
+        port_s = time.time() - t0
+        got = mapper.map_batch(a, b, n=ns, fixed_len=READ_LEN)
+        ok = bool(got.num_hits == ref.num_hits and np.array_equal(got.hits, ref.hits) and np.array_equal(got.pair_offsets, ref.pair_offsets)
+                  and np.array_equal(got.counters, ref.counters))
+        return ok, om.op_counts(), port_s
 
-    def run_e2e(first, count):
-        acc = [0] * nm
-        ths = [threading.Thread(target=e2e_worker, args=(t, first, count, acc)) for t in range(nm)]
-        for th in ths:
-            th.start()
-        for th in ths:
-            th.join()
-        return sum(acc)
+    def cpu_baseline(flags, ns):
+        if args.no_cpu_baseline or not os.path.exists(REF_BIN):
+            return None
+        cores = os.cpu_count() or 1
+        f1, f2 = write_fastq_prefix(tx, ns, os.path.join(CACHE, "cpu_reads"))
+        s, _ = reference_quasimap(REF_BIN, idx_dir, f1, f2, cores, flags)
+        return {"value": ns / s, "unit": UNIT, "cores": cores, "kind": "reference",
+                "sample": f"first {ns} pairs of the benchmark stream, rapmap_ref quasimap{' ' + ' '.join(flags) if flags else ''} -n -t {cores}, reference ScopedTimer (FASTQ parsing + mapping, index load excluded)"}
 
-    w_e2e = max(3, args.warmup)
-    run_e2e(0, w_e2e * nm)
-    torch.cuda.synchronize()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    e2e_hits = run_e2e(w_e2e * nm, args.steps)
-    e1.record()
-    torch.cuda.synchronize()
-    barrier()
-    ms_e2e = e0.elapsed_time(e1)
-    if world > 1:
-        tm = torch.tensor([ms_e2e], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        ms_e2e = float(tm.item())
-    st_e2e = {"hits": e2e_hits}
-    log(f"rank {rank}: end-to-end leg {ms_e2e / args.steps:.2f} ms per step ({nm} host threads)")
-    total_pairs = B * args.steps * world
-    value = total_pairs / (ms_res / 1e3)
-    e2e_value = total_pairs / (ms_e2e / 1e3)
+    def leg_numbers(L, total_pairs_per_step):
+        steps = L["steps"]
+        return total_pairs_per_step * steps / (L["ms_res"] / 1e3), total_pairs_per_step * steps / (L["ms_e2e"] / 1e3)
 
-    if rank == 0:
+    def roofline(L, ops, ns, selaln):
         peak, peak_src = measured_peaks()
-        # ---- oracle leg: parity check + operation counts on a bounded sample (N == 1 only)
-        ops_per_pair, parity = None, None
-        alg = None
-        if world == 1 and args.oracle_sample > 0:
-            ns = min(args.oracle_sample, B)
-            a, b = host[0][0].numpy()[:ns].copy(), host[0][1].numpy()[:ns].copy()
-            om = OracleMapper(idx_dir, opts)
-            t0 = time.time()
-            ref = om.map(a, b, READ_LEN)
-            port_s = time.time() - t0
-            got = mapper.map_batch(a, b, n=ns, fixed_len=READ_LEN)
-            parity = bool(got.num_hits == ref.num_hits and np.array_equal(got.hits, ref.hits) and np.array_equal(got.pair_offsets, ref.pair_offsets)
-                          and np.array_equal(got.counters, ref.counters))
-            ops = om.op_counts()
-            ops_per_pair = {k: v / ns for k, v in ops.items()}
+        nchunks = L["steps"] * CH
+        sa_ms = L["st"]["sa"] / nchunks
+        if ops is not None:
             alg = alg_bytes_per_pair(ops, ns)
-            log(f"oracle sample: {ns} pairs in {port_s:.1f}s, parity={parity}, ops/pair={ops_per_pair}")
-            if not parity:
-                raise SystemExit("PARITY FAILURE against the CPU oracle on the benchmark sample; refusing to report a number")
-        if alg is None:
-            alg = 2 * READ_LEN + 16.0 * 96.4 + 4.0 * 17.7 + 654.0  # counted on this workload (no -s)
-        sa_ms = st_res["sa"] / args.steps
+        else:  # DESIGN.md: counted on this workload by the instrumented oracle
+            alg = (2 * READ_LEN + 16.0 * 121.9 + 4.0 * 61.1 + 792.0) if selaln else (2 * READ_LEN + 16.0 * 96.98 + 4.0 * 17.55 + 648.8)
         achieved = alg * B / (sa_ms / 1e3) / 1e9
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "sa_collect_traffic_selaln.json" if args.selaln else "sa_collect_traffic.json")
+        tp = os.path.join(ROOT, "profiles", "sa_collect_traffic_selaln.json" if selaln else "sa_collect_traffic.json")
         if os.path.exists(tp):
             with open(tp) as f:
                 traffic = json.load(f).get("dram_bytes_per_launch")
-        # ---- cpu baseline: the reference binary on the host cores (bounded sample)
-        cpu = None
-        if world == 1 and not args.no_cpu_baseline and os.path.exists(REF_BIN):
-            ns = args.cpu_baseline_pairs
-            cores = os.cpu_count() or 1
-            d = os.path.join(CACHE, "cpu_reads")
-            os.makedirs(d, exist_ok=True)
-            f1, f2 = os.path.join(d, f"r1_{ns}.fastq"), os.path.join(d, f"r2_{ns}.fastq")
-            if not os.path.exists(f2):
-                s1, s2 = tx.reads(ns, rseed=READ_SEED, first=0, read_len=READ_LEN)
-                qual = b"I" * READ_LEN
-                for path, arr, m in ((f1, s1, 1), (f2, s2, 2)):
-                    with open(path, "wb") as f:
-                        f.write(b"".join(b"@r%d/%d\n%s\n+\n%s\n" % (i, m, arr[i].tobytes(), qual) for i in range(ns)))
-            p = subprocess.run([REF_BIN, "quasimap", "-i", idx_dir, "-1", f1, "-2", f2, "-t", str(cores), "-n"] + (["-s"] if args.selaln else []),
-                               capture_output=True, text=True)
-            m = re.findall(r"Elapsed time: ([0-9.eE+-]+)s", p.stdout + p.stderr)
-            if m:
-                cpu = {"value": ns / float(m[-1]), "unit": UNIT, "cores": cores, "kind": "reference",
-                       "sample": f"first {ns} pairs of the benchmark stream, rapmap_ref quasimap -n -t {cores}, reference ScopedTimer (index load excluded)"}
+        return {"bound": "hbm", "kernel": "sa_collect_lane_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "peak_source": peak_src, "alg_bytes_per_pair": alg, "pairs_per_launch": B, "kernel_ms_per_launch": sa_ms,
+                "stage_ms_per_chunk": {k: L["st"][k] / nchunks for k in STAGES},
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel at this batch size (profiles/)" if traffic else None}
+
+    pairs_per_step = B * CH * world
+    # ---- headline leg
+    opts = rb.default_opts(sel_aln=args.selaln)
+    H = run_leg(index, opts, args.steps, args.warmup, sample_clocks=True)
+    value, e2e_value = leg_numbers(H, pairs_per_step)
+    log(f"rank {rank}: headline: resident {H['ms_res'] / args.steps:.2f} ms/step, end to end {H['ms_e2e'] / args.steps:.2f} ms/step ({nm} mappers, one host thread)")
+    parity, ops, ops_per_pair, ns = None, None, None, 0
+    if rank == 0 and world == 1 and args.oracle_sample > 0:
+        ns = min(args.oracle_sample, B)
+        parity, ops, port_s = oracle_check(idx_dir, opts, H["mapper"], ns)
+        ops_per_pair = {k: v / ns for k, v in ops.items()}
+        log(f"oracle sample: {ns} pairs in {port_s:.1f}s, parity={parity}, ops/pair={ops_per_pair}")
+        if not parity:
+            raise SystemExit("PARITY FAILURE against the CPU oracle on the benchmark sample; refusing to report a number")
+    headline_hits_chunk0 = None
+    if "perfect_hash" in legs_wanted:  # kept for the -p leg: full-chunk results of the dense index
+        r0 = H["mapper"].map_batch(host[0][0], host[0][1], n=B, fixed_len=READ_LEN, hits_out=h_out[0][0], offsets_out=h_out[0][1], capacity=cap)
+        headline_hits_chunk0 = (r0.num_hits, h_out[0][0][: r0.num_hits * 28].clone(), h_out[0][1].clone())
+    line = None
+    if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": H["ms_res"] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32", "data": "synthetic",
-            "config": {"workload": f"configs[1]: GENCODE-like {args.genes}-gene (~{index.num_transcripts} txp) synthetic index, 2x100bp synthetic pairs, quasimap{' -s' if args.selaln else ''} default flags",
-                       "pairs_per_step_per_gpu": B, "distinct_batches": nd, "l2_policy": f"inputs larger than L2 ({2 * B * READ_LEN / 2**20:.0f} MiB of read bases per step, {index.device_bytes / 2**30:.1f} GiB index)",
+            "config": {"workload": workload_name(args.genes) + (" + -s" if args.selaln else ""), "transcripts": index.num_transcripts,
+                       "pairs_per_step_per_gpu": B * CH, "chunks_per_step": CH, "pairs_per_chunk": B, "distinct_chunks": nd,
+                       "l2_policy": f"inputs larger than L2 ({2 * B * READ_LEN / 2**20:.0f} MiB of read bases per chunk, {index.device_bytes / 2**30:.1f} GiB index)",
                        "index": "replicated per GPU (one NCCL broadcast of the packed image)", "sharding": "contiguous read ranges per rank, no data-path collective"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * B * READ_LEN, "d2h_bytes_per_step": int(st_e2e["hits"] / args.steps * 28 + (B + 1) * 8),
-                    "ms_per_step": ms_e2e / args.steps, "api": "rapmap_cuda_map_batch with pinned HOST buffers", "host_threads": nm,
-                    "note": "one mapper (CUDA stream) per host thread, chunks round-robin; each call synchronous for its caller"},
-            "gpu_launches": int(st_res["launch"]),
-            "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "sa_collect_lane_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "peak_source": peak_src, "alg_bytes_per_pair": alg, "kernel_ms_per_launch": sa_ms,
-                         "stage_ms_per_step": {k: st_res[k] / args.steps for k in ("pack", "sa", "map", "merge", "selaln", "h2d", "d2h")},
-                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel at this batch size (profiles/)" if traffic else None},
-            "cpu_baseline": cpu,
-            "hits_per_pair": st_res["hits"] / (B * args.steps),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * B * READ_LEN * CH, "d2h_bytes_per_step": int(H["st"]["hits"] / args.steps * 28 + (B + 1) * 8 * CH),
+                    "ms_per_step": H["ms_e2e"] / args.steps, "api": "rapmap_cuda_map_batch_async + rapmap_cuda_mapper_wait with pinned HOST buffers (ASCII bases in, rapmap_hit_t records + offsets out)",
+                    "host_threads": 1, "mappers": nm, "hits_equal_resident_leg": True},
+            "gpu_launches": int(H["st"]["launch"]),
+            "clocks": H["clocks"],
+            "roofline": roofline(H, ops, ns, args.selaln),
+            "cpu_baseline": cpu_baseline(["-s"] if args.selaln else [], args.cpu_baseline_pairs) if world == 1 else None,
+            "hits_per_pair": H["st"]["hits"] / (B * CH * args.steps),
             "ops_per_pair": ops_per_pair,
             "parity_checked_vs_oracle": parity,
+            "legs": {},
         }
+    for mp in H["mappers"]:
+        mp.close()
+    del H
+
+    # ---- extra legs
+    leg_steps = args.leg_steps or min(args.steps, 10)
+    for name in legs_wanted:
+        if name == "selaln":
+            lopts = rb.default_opts(sel_aln=True)
+            L = run_leg(index, lopts, leg_steps, args.warmup)
+            v, e = leg_numbers(L, pairs_per_step)
+            log(f"rank {rank}: leg selaln: resident {L['ms_res'] / leg_steps:.2f} ms/step, end to end {L['ms_e2e'] / leg_steps:.2f} ms/step")
+            if rank == 0:
+                lp, lops, lns = None, None, 0
+                if world == 1 and args.oracle_sample > 0:
+                    lns = min(args.oracle_sample, B)
+                    lp, lops, _ = oracle_check(idx_dir, lopts, L["mapper"], lns)
+                    if not lp:
+                        raise SystemExit("PARITY FAILURE (-s) against the CPU oracle on the benchmark sample; refusing to report a number")
+                nchunks = leg_steps * CH
+                ksw_s = L["st"]["ksw"] / 1e3
+                cells_per_job = (lops["kswCells"] / max(1, lops["kswCalls"])) if lops else None
+                line["legs"]["selaln"] = {
+                    "config": "configs[2]" + (" / configs[4] (scaling)" if world > 1 else "") + ": same index and reads, quasimap -s (ksw2 selective alignment on)",
+                    "value": v, "unit": UNIT, "ms_per_step": L["ms_res"] / leg_steps, "steps": leg_steps, "n_gpus": world,
+                    "e2e": {"value": e, "unit": UNIT, "ms_per_step": L["ms_e2e"] / leg_steps, "host_threads": 1, "mappers": nm, "hits_equal_resident_leg": True},
+                    "roofline": roofline(L, lops, lns, True),
+                    "ksw": {"dp_jobs_per_pair": L["st"]["dp_jobs"] / (B * nchunks), "dp_jobs_per_s": L["st"]["dp_jobs"] / ksw_s if ksw_s > 0 else None,
+                            "general_kernel_share": L["st"]["dp_jobs_general"] / max(1, L["st"]["dp_jobs"]),
+                            "band_cells_per_job": cells_per_job,
+                            "cell_updates_per_s": (L["st"]["dp_jobs"] * cells_per_job / ksw_s) if (cells_per_job and ksw_s > 0) else None,
+                            "note": "band cells = sum over anti-diagonals of (en - st + 1) of ksw_extz2_sse41's loop bounds (counted by the oracle on the sample); time = the two ksw kernels, CUDA events"},
+                    "hits_per_pair": L["st"]["hits"] / (B * nchunks),
+                    "gpu_launches": int(L["st"]["launch"]),
+                    "parity": lp, "parity_method": f"records, offsets and counters of the first {lns} pairs identical to the CPU oracle (-s)" if lp is not None else None,
+                    "cpu_baseline": cpu_baseline(["-s"], args.cpu_baseline_pairs // 2) if world == 1 else None,
+                }
+            for mp in L["mappers"]:
+                mp.close()
+            del L
+        elif name == "perfect_hash":
+            pdir, pindex, _keep1 = load_index(True)
+            lopts = rb.default_opts()
+            L = run_leg(pindex, lopts, leg_steps, args.warmup)
+            v, e = leg_numbers(L, pairs_per_step)
+            log(f"rank {rank}: leg perfect_hash: resident {L['ms_res'] / leg_steps:.2f} ms/step, end to end {L['ms_e2e'] / leg_steps:.2f} ms/step")
+            if rank == 0:
+                r1 = L["mapper"].map_batch(host[0][0], host[0][1], n=B, fixed_len=READ_LEN, hits_out=h_out[0][0], offsets_out=h_out[0][1], capacity=cap)
+                n0, hh, oo = headline_hits_chunk0
+                same = bool(r1.num_hits == n0 and torch.equal(h_out[0][0][: n0 * 28], hh) and torch.equal(h_out[0][1], oo))
+                if not same:
+                    raise SystemExit("PARITY FAILURE: the -p index does not give the dense index's hits; refusing to report a number")
+                nchunks = leg_steps * CH
+                line["legs"]["perfect_hash"] = {
+                    "config": f"configs[3]: the same {index.num_transcripts}-transcript transcriptome indexed with -p (BooPHF minimum perfect hash + FrugalBooMap), same reads, quasimap default flags",
+                    "value": v, "unit": UNIT, "ms_per_step": L["ms_res"] / leg_steps, "steps": leg_steps, "n_gpus": world,
+                    "e2e": {"value": e, "unit": UNIT, "ms_per_step": L["ms_e2e"] / leg_steps, "host_threads": 1, "mappers": nm, "hits_equal_resident_leg": True},
+                    "sa_lookup_ms_per_launch": L["st"]["sa"] / nchunks,
+                    "stage_ms_per_chunk": {k: L["st"][k] / nchunks for k in STAGES},
+                    "index_image_bytes": pindex.device_bytes, "dense_index_image_bytes": index.device_bytes,
+                    "index_files": "hash_info.bph / hash_info.val written by tools/build_index.py (byte-identical to `quasiindex -p` output on the test transcriptomes, tests/test_index_builder.py)",
+                    "gpu_launches": int(L["st"]["launch"]),
+                    "parity": same, "parity_method": f"all {B} pairs of chunk 0: hit records and offsets byte-identical to the dense index's (which is checked against the CPU oracle)",
+                }
+            for mp in L["mappers"]:
+                mp.close()
+            del L, pindex, _keep1
+        else:
+            raise SystemExit(f"unknown leg {name}")
+
+    if rank == 0:
         emit(line)
-        log(f"rank 0: {value / 1e6:.1f} M pairs/s resident, {e2e_value / 1e6:.1f} M pairs/s end to end on {world} GPU(s)")
+        log(f"rank 0: {value / 1e6:.1f} M pairs/s resident, {e2e_value / 1e6:.1f} M pairs/s end to end on {world} GPU(s); legs: "
+            + ", ".join(f"{k} {v['value'] / 1e6:.1f}/{v['e2e']['value'] / 1e6:.1f}" for k, v in line["legs"].items()))
     barrier()
     if world > 1:
         dist.destroy_process_group()

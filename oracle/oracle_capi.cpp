@@ -103,11 +103,11 @@ int oracle_collect(void* mp, const uint8_t* seq, uint32_t len, rapmap_sa_interva
 }
 
 // Operation counters accumulated since the mapper was created: hashFind, saProbes,
-// textCmp, rankCalls, intervals, kswCalls, alnCalls.
+// textCmp, rankCalls, intervals, kswCalls, alnCalls, kswCells (8 values).
 void oracle_op_counts(void* mp, uint64_t* out7) {
   Mapper& M = *static_cast<Mapper*>(mp);
   out7[0] = M.ops.hashFind; out7[1] = M.ops.saProbes; out7[2] = M.ops.textCmp; out7[3] = M.ops.rankCalls;
-  out7[4] = M.ops.intervals; out7[5] = M.ops.kswCalls; out7[6] = M.ops.alnCalls;
+  out7[4] = M.ops.intervals; out7[5] = M.ops.kswCalls; out7[6] = M.ops.alnCalls; out7[7] = M.ops.kswCells;
 }
 
 // Known-answer hook for the DP alone.

@@ -1020,6 +1020,7 @@ int32_t Mapper::kswExtzScore(const char* qs, int qlen, const char* ts, int tlen)
     if (en > ((r + wl) >> 1)) en = (r + wl) >> 1;
     if (st > en) break; // zdropped
     const int st0 = st, en0 = en;
+    ops.kswCells += static_cast<uint64_t>(en0 - st0 + 1);  // cells of the band on this anti-diagonal (before the 16-lane rounding)
     st = st / 16 * 16; en = (en + 16) / 16 * 16 - 1;
     int8_t x1, v1;
     if (st > 0) {

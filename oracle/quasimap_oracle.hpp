@@ -98,7 +98,7 @@ struct QuasiAlignment {
 struct Counters { uint64_t numReads{0}, peHits{0}, seHits{0}, totHits{0}, tooManyHits{0}; };
 
 // Operation counters for the roofline's "algorithmic bytes per pair" (SURVEY.md §8d).
-struct OpCounts { uint64_t hashFind{0}, saProbes{0}, textCmp{0}, rankCalls{0}, intervals{0}, kswCalls{0}, alnCalls{0}; };
+struct OpCounts { uint64_t hashFind{0}, saProbes{0}, textCmp{0}, rankCalls{0}, intervals{0}, kswCalls{0}, alnCalls{0}, kswCells{0}; };
 
 class Mapper {
 public:

@@ -108,9 +108,9 @@ class OracleMapper:
         return bool(found.value), nf.value, nr.value, ivs
 
     def op_counts(self):
-        out = (C.c_uint64 * 7)()
+        out = (C.c_uint64 * 8)()
         self.L.oracle_op_counts(self.h, out)
-        return dict(zip(["hashFind", "saProbes", "textCmp", "rankCalls", "intervals", "kswCalls", "alnCalls"], [int(x) for x in out]))
+        return dict(zip(["hashFind", "saProbes", "textCmp", "rankCalls", "intervals", "kswCalls", "alnCalls", "kswCells"], [int(x) for x in out]))
 
     def ksw(self, q: bytes, t: bytes) -> int:
         return self.L.oracle_ksw_extz_score(self.h, q, len(q), t, len(t))

@@ -101,29 +101,32 @@ def kmer_intervals(text: torch.Tensor, sa: torch.Tensor, k: int):
     return w[b], b, e
 
 
-def build_synth_index(out_dir: str, seed: int, genes: int, repeats: int = 0, k: int = 31, device: str | None = None, verbose: bool = True) -> dict:
-    from helpers import SynthTxome, synth_lib
+def _header(perfect: bool, k: int) -> dict:
+    return {"value0": {"IndexType": 1, "IndexVersion": "q5", "UsesKmers": True, "KmerLen": k, "BigSA": False, "PerfectHash": perfect,
+                       "SeqHash": "", "NameHash": "", "SeqHash512": "", "NameHash512": ""}}
 
-    t0 = time.time()
+
+def _synth_lib():
+    from helpers import synth_lib
+
     L = synth_lib()
     L.synth_txome_concat.restype = C.c_int64
     L.synth_txome_concat.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.synth_txome_name.argtypes = [C.c_uint64, C.c_int64, C.c_int, C.c_void_p, C.c_int64]
     L.synth_write_dense_hash.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_char_p]
-    tx = SynthTxome(seed, genes, repeats)
-    ntxp = tx.ntxp
-    tlen = L.synth_txome_text_len(tx.h)
-    buf = np.empty(tlen + ntxp, dtype=np.uint8)
-    starts = np.empty(ntxp, dtype=np.int64)
-    clens = np.empty(ntxp, dtype=np.uint32)
-    n = L.synth_txome_concat(tx.h, buf.ctypes.data, starts.ctypes.data, clens.ctypes.data)
-    assert n > 0 and n + 1 < 2**31, "text too long for a 32-bit index"
-    text_np = buf[:n]
-    namebuf = C.create_string_buffer(ntxp * 24 + 16)
-    L.synth_txome_name(seed, genes, repeats, namebuf, len(namebuf))
-    names = namebuf.value.decode().split("\n")[:-1]
-    assert len(names) == ntxp
+    L.synth_write_perfect_hash.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_char_p]
+    return L
 
+
+def write_index(out_dir: str, text_np: np.ndarray, starts: np.ndarray, clens: np.ndarray, names: list, k: int = 31, device: str | None = None,
+                perfect_dir: str | None = None) -> dict:
+    """The index files for a concatenated transcript text (upper-case ACGT.. with '$' after every transcript, laid out as
+    src/RapMapSAIndexer.cpp:536-635 does).  Dense flavour to out_dir; with perfect_dir also the `-p` flavour of the SAME index
+    (hash_info.bph / hash_info.val from tools/synth.cpp's BooPHF + FrugalBooMap writer; sa.bin, txpInfo.bin and rsd.bin are
+    links to out_dir's)."""
+    L = _synth_lib()
+    n, ntxp = int(text_np.size), len(names)
+    assert n > 0 and n + 1 < 2**31, "text too long for a 32-bit index"
     dev = device or ("cuda" if torch.cuda.is_available() else "cpu")
     text = torch.from_numpy(text_np).to(dev)
     t1 = time.time()
@@ -156,21 +159,77 @@ def build_synth_index(out_dir: str, seed: int, genes: int, repeats: int = 0, k: 
         f.write(struct.pack("<Q", n))
         text_np.tofile(f)
         f.write(struct.pack("<Q", ntxp))
-        clens.tofile(f)
+        clens.astype(np.uint32).tofile(f)
     with open(os.path.join(out_dir, "rsd.bin"), "wb") as f:
         f.write(struct.pack("<Q", n))
         np.packbits(text_np == ord("$"), bitorder="little").tofile(f)
     rc = L.synth_write_dense_hash(keys_np.ctypes.data, b_np.ctypes.data, e_np.ctypes.data, len(keys_np), os.fsencode(os.path.join(out_dir, "hash.bin")))
     assert rc == 0, rc
-    hdr = {"value0": {"IndexType": 1, "IndexVersion": "q5", "UsesKmers": True, "KmerLen": k, "BigSA": False, "PerfectHash": False,
-                      "SeqHash": "", "NameHash": "", "SeqHash512": "", "NameHash512": ""}}
     with open(os.path.join(out_dir, "header.json"), "w") as f:
-        json.dump(hdr, f, indent=4)
+        json.dump(_header(False, k), f, indent=4)
     t4 = time.time()
-    info = {"n": int(n), "ntxp": int(ntxp), "kmers": int(len(keys_np)), "device": dev, "s_text": t1 - t0, "s_sa": t2 - t1, "s_kmers": t3 - t2, "s_write": t4 - t3}
+    if perfect_dir:
+        os.makedirs(perfect_dir, exist_ok=True)
+        rc = L.synth_write_perfect_hash(keys_np.ctypes.data, b_np.ctypes.data, e_np.ctypes.data, len(keys_np), os.fsencode(os.path.join(perfect_dir, "hash_info")))
+        assert rc == 0, rc
+        for name in ("sa.bin", "txpInfo.bin", "rsd.bin"):
+            dst = os.path.join(perfect_dir, name)
+            if os.path.lexists(dst):
+                os.remove(dst)
+            os.symlink(os.path.relpath(os.path.join(out_dir, name), perfect_dir), dst)
+        with open(os.path.join(perfect_dir, "header.json"), "w") as f:
+            json.dump(_header(True, k), f, indent=4)
+    t5 = time.time()
+    return {"n": n, "ntxp": ntxp, "kmers": int(len(keys_np)), "device": dev, "s_sa": t2 - t1, "s_kmers": t3 - t2, "s_write": t4 - t3, "s_perfect": t5 - t4}
+
+
+def build_synth_index(out_dir: str, seed: int, genes: int, repeats: int = 0, k: int = 31, device: str | None = None, verbose: bool = True,
+                      perfect_dir: str | None = None) -> dict:
+    """Index of the synthetic transcriptome (tools/synth.cpp) `seed, genes, repeats`."""
+    from helpers import SynthTxome
+
+    t0 = time.time()
+    L = _synth_lib()
+    tx = SynthTxome(seed, genes, repeats)
+    ntxp = tx.ntxp
+    tlen = L.synth_txome_text_len(tx.h)
+    buf = np.empty(tlen + ntxp, dtype=np.uint8)
+    starts = np.empty(ntxp, dtype=np.int64)
+    clens = np.empty(ntxp, dtype=np.uint32)
+    n = L.synth_txome_concat(tx.h, buf.ctypes.data, starts.ctypes.data, clens.ctypes.data)
+    namebuf = C.create_string_buffer(ntxp * 24 + 16)
+    L.synth_txome_name(seed, genes, repeats, namebuf, len(namebuf))
+    names = namebuf.value.decode().split("\n")[:-1]
+    assert len(names) == ntxp
+    info = write_index(out_dir, buf[:n], starts, clens, names, k, device, perfect_dir)
+    info["s_total"] = time.time() - t0
     if verbose:
         print("[build_index]", json.dumps(info), file=sys.stderr)
     return info
+
+
+def build_fasta_index(fasta: str, out_dir: str, k: int = 31, device: str | None = None, perfect_dir: str | None = None) -> dict:
+    """Index of a plain FASTA whose records need none of the indexer's clean-ups: upper-case ACGT only, no poly-A tail of >= 10
+    bases, names without spaces, every transcript longer than k (src/RapMapSAIndexer.cpp:536-635 would otherwise replace Ns,
+    clip tails, cut names and drop short records - this tool refuses such input instead of approximating)."""
+    names, seqs = [], []
+    with open(fasta) as f:
+        for line in f:
+            line = line.rstrip("\n")
+            if line.startswith(">"):
+                names.append(line[1:])
+                seqs.append([])
+            elif line:
+                seqs[-1].append(line)
+    seqs = ["".join(x) for x in seqs]
+    for nm, sq in zip(names, seqs):
+        if " " in nm or "\t" in nm or set(sq) - set("ACGT") or len(sq) <= k or sq.endswith("A" * 10):
+            raise ValueError(f"record {nm!r} needs the reference indexer's clean-up rules; use rapmap quasiindex")
+    text = ("$".join(seqs) + "$").encode()
+    starts = np.zeros(len(seqs), dtype=np.int64)
+    starts[1:] = np.cumsum([len(sq) + 1 for sq in seqs])[:-1]
+    clens = np.array([len(sq) for sq in seqs], dtype=np.uint32)
+    return write_index(out_dir, np.frombuffer(text, dtype=np.uint8).copy(), starts, clens, names, k, device, perfect_dir)
 
 
 if __name__ == "__main__":
@@ -181,5 +240,6 @@ if __name__ == "__main__":
     ap.add_argument("--genes", type=int, default=37000)
     ap.add_argument("--seed", type=int, default=12345)
     ap.add_argument("--repeats", type=int, default=0)
+    ap.add_argument("--perfect-out", default=None, help="also write the -p (BooPHF) flavour of the index to this directory")
     a = ap.parse_args()
-    build_synth_index(a.out, a.seed, a.genes, a.repeats)
+    build_synth_index(a.out, a.seed, a.genes, a.repeats, perfect_dir=a.perfect_out)

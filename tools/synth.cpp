@@ -12,6 +12,7 @@
 // extern "C" entry points fill caller-provided buffers (used by bench.py / tests via ctypes).
 // This is data tooling, not part of the mapping path.
 #include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -407,4 +408,204 @@ extern "C" void synth_txome_name(uint64_t seed, int64_t genes, int repeat_famili
     out[w++] = '\n';
   }
   out[w] = 0;
+}
+
+// =================================================================================================
+// hash_info.bph / hash_info.val writer: the perfect-hash flavour of the index (`quasiindex -p`).
+//   .bph = boomphf::mphf::save (reference include/BooPHF.hpp:1172-1197): gamma, #levels, last rank, #keys, then per level
+//          {bits, words, bitset words, #rank samples, rank samples}, then the (here normally empty) final hash.
+//   .val = FrugalBooMap::save (include/FrugalBooMap.hpp:185-213): data_ (interval start per MPHF slot, cereal vector<int32>),
+//          lens_ (interval length, 255 => overflow_), overflow_ as a sparsepp table (spp_mix_32 placement, triangular probing).
+// The MPHF is the published BBHash cascade as the reference builds it (BooPHF.hpp:885-968, :1233-1300, :1318-1366): level i
+// has a bitset of ((ceil(gamma n) p^i) rounded up to 64) bits, p = 1 - ((gamma n - 1) / (gamma n))^(n - 1); every key that
+// no earlier level placed hashes into it (xorshift128* sequence seeded by two hash64 values, fastrange64), positions hit
+// exactly once stay set, the others are cleared and their keys go on; what reaches level 24 goes to an exact map.  The
+// bitsets depend on the key SET only, so this writer's .bph equals the reference's own byte for byte whenever the final
+// map is empty (tests/test_index_builder.py checks that, and that the unmodified reference maps with the files).
+// =================================================================================================
+namespace {
+inline uint64_t boo_hash64(uint64_t key, uint64_t seed) {  // HashFunctors::hash64, BooPHF.hpp:394-407
+  uint64_t hash = seed;
+  hash ^= (hash << 7) ^ key * (hash >> 3) ^ (~((hash << 11) + (key ^ (hash >> 5))));
+  hash = (~hash) + (hash << 21);
+  hash = hash ^ (hash >> 24);
+  hash = (hash + (hash << 3)) + (hash << 8);
+  hash = hash ^ (hash >> 14);
+  hash = (hash + (hash << 2)) + (hash << 4);
+  hash = hash ^ (hash >> 28);
+  hash = hash + (hash << 31);
+  return hash;
+}
+// hash of `key` for level `lv`: h0, h1, then the xorshift128* sequence (XorshiftHashFunctors, BooPHF.hpp:460-499)
+inline uint64_t boo_level_hash(uint64_t key, int lv) {
+  uint64_t s0 = boo_hash64(key, 0xAAAAAAAA55555555ULL);
+  if (lv == 0) return s0;
+  uint64_t s1 = boo_hash64(key, 0x33333333CCCCCCCCULL);
+  uint64_t h = s1;
+  for (int i = 2; i <= lv; ++i) {
+    uint64_t a = s0;
+    const uint64_t b = s1;
+    s0 = b;
+    a ^= a << 23;
+    s1 = a ^ b ^ (a >> 17) ^ (b >> 26);
+    h = s1 + b;
+  }
+  return h;
+}
+inline uint64_t fastrange64(uint64_t word, uint64_t p) { return static_cast<uint64_t>((static_cast<__uint128_t>(word) * static_cast<__uint128_t>(p)) >> 64); }
+inline uint32_t spp_mix_32(uint32_t a) {
+  a = a ^ (a >> 4);
+  a = (a ^ 0xdeadbeef) + (a << 5);
+  a = a ^ (a >> 11);
+  return a;
+}
+} // namespace
+
+extern "C" int synth_write_perfect_hash(const uint64_t* keys, const int32_t* begin, const int32_t* end, uint64_t n, const char* base) {
+  if (n == 0) return -3;
+  const double gamma = 2.0;
+  const int nbLevels = 25;
+  const double nD = static_cast<double>(n);
+  const double proba = 1.0 - std::pow(((gamma * nD - 1) / (gamma * nD)), static_cast<double>(n - 1));
+  const uint64_t hashDomain = static_cast<uint64_t>(std::ceil(nD * gamma));
+  struct Level { uint64_t domain; std::vector<uint64_t> bits; std::vector<uint64_t> ranks; };
+  std::vector<Level> lv(nbLevels);
+  for (int i = 0; i < nbLevels; ++i) {
+    uint64_t d = ((static_cast<uint64_t>(static_cast<double>(hashDomain) * std::pow(proba, i)) + 63) / 64) * 64;
+    if (d == 0) d = 64;
+    lv[i].domain = d;
+    lv[i].bits.assign(1 + d / 64, 0);
+  }
+  // ---- the cascade
+  std::vector<uint64_t> cur(keys, keys + n), nxt;
+  std::vector<std::pair<uint64_t, uint64_t>> finalHash;
+  for (int i = 0; i < nbLevels; ++i) {
+    if (i == nbLevels - 1) {  // exact map for what is left (BooPHF.hpp:1098-1107)
+      for (uint64_t j = 0; j < cur.size(); ++j) finalHash.emplace_back(cur[j], j);
+      break;
+    }
+    Level& L = lv[i];
+    std::vector<uint64_t> coll(L.bits.size(), 0);
+    const int64_t m = static_cast<int64_t>(cur.size());
+#pragma omp parallel for schedule(static)
+    for (int64_t j = 0; j < m; ++j) {
+      const uint64_t pos = fastrange64(boo_level_hash(cur[j], i), L.domain);
+      const uint64_t bit = 1ULL << (pos & 63);
+      const uint64_t old = __sync_fetch_and_or(&L.bits[pos >> 6], bit);
+      if (old & bit) __sync_fetch_and_or(&coll[pos >> 6], bit);
+    }
+    for (size_t w = 0; w < L.bits.size(); ++w) L.bits[w] &= ~coll[w];
+    // keys whose position was cleared go on to the next level
+    nxt.clear();
+#pragma omp parallel
+    {
+      std::vector<uint64_t> mine;
+#pragma omp for schedule(static) nowait
+      for (int64_t j = 0; j < m; ++j) {
+        const uint64_t pos = fastrange64(boo_level_hash(cur[j], i), L.domain);
+        if (!((L.bits[pos >> 6] >> (pos & 63)) & 1ULL)) mine.push_back(cur[j]);
+      }
+#pragma omp critical
+      nxt.insert(nxt.end(), mine.begin(), mine.end());
+    }
+    cur.swap(nxt);
+  }
+  // ---- rank samples every 512 bits, offset by the keys of the earlier levels (bitVector::build_ranks, :739-753)
+  uint64_t offset = 0;
+  for (auto& L : lv) {
+    for (size_t w = 0; w < L.bits.size(); ++w) {
+      if ((w * 64) % 512 == 0) L.ranks.push_back(offset);
+      offset += static_cast<uint64_t>(__builtin_popcountll(L.bits[w]));
+    }
+  }
+  const uint64_t lastRank = offset;
+  if (lastRank + finalHash.size() != n) return -4;  // duplicate keys in the input
+  std::sort(finalHash.begin(), finalHash.end());
+  // ---- slot of every key (mphf::lookup, :971-1009) -> data_ / lens_ in slot order
+  std::vector<int32_t> data(n);
+  std::vector<uint8_t> lens(n);
+  std::vector<std::pair<int32_t, int32_t>> overflow;
+  int bad = 0;
+#pragma omp parallel for schedule(static)
+  for (int64_t j = 0; j < static_cast<int64_t>(n); ++j) {
+    const uint64_t key = keys[j];
+    uint64_t slot = ~0ULL;
+    int level = 0;
+    uint64_t pos = 0;
+    for (; level < nbLevels - 1; ++level) {
+      pos = fastrange64(boo_level_hash(key, level), lv[level].domain);
+      if ((lv[level].bits[pos >> 6] >> (pos & 63)) & 1ULL) break;
+    }
+    if (level == nbLevels - 1) {
+      auto it = std::lower_bound(finalHash.begin(), finalHash.end(), std::make_pair(key, static_cast<uint64_t>(0)));
+      if (it != finalHash.end() && it->first == key) slot = it->second + lastRank;
+    } else {
+      const Level& L = lv[level];
+      const uint64_t wi = pos >> 6, block = pos >> 9;
+      uint64_t r = L.ranks[block];
+      for (uint64_t w = block * 8; w < wi; ++w) r += static_cast<uint64_t>(__builtin_popcountll(L.bits[w]));
+      r += static_cast<uint64_t>(__builtin_popcountll(L.bits[wi] & ((1ULL << (pos & 63)) - 1ULL)));
+      slot = r;
+    }
+    if (slot >= n) {
+#pragma omp atomic write
+      bad = 1;
+      continue;
+    }
+    data[slot] = begin[j];
+    const int32_t l = end[j] - begin[j];
+    lens[slot] = l >= 255 ? 255 : static_cast<uint8_t>(l);
+  }
+  if (bad) return -5;
+  for (uint64_t j = 0; j < n; ++j)
+    if (end[j] - begin[j] >= 255) overflow.emplace_back(begin[j], end[j] - begin[j]);
+  // ---- files
+  {
+    FILE* f = fopen((std::string(base) + ".bph").c_str(), "wb");
+    if (!f) return -1;
+    const int32_t nl = nbLevels;
+    fwrite(&gamma, 8, 1, f); fwrite(&nl, 4, 1, f); fwrite(&lastRank, 8, 1, f); fwrite(&n, 8, 1, f);
+    for (const auto& L : lv) {
+      const uint64_t nchar = L.bits.size(), nr = L.ranks.size();
+      fwrite(&L.domain, 8, 1, f); fwrite(&nchar, 8, 1, f); fwrite(L.bits.data(), 8, nchar, f);
+      fwrite(&nr, 8, 1, f); fwrite(L.ranks.data(), 8, nr, f);
+    }
+    const uint64_t nf = finalHash.size();
+    fwrite(&nf, 8, 1, f);
+    for (const auto& kv : finalHash) { fwrite(&kv.first, 8, 1, f); fwrite(&kv.second, 8, 1, f); }
+    fclose(f);
+  }
+  {
+    FILE* f = fopen((std::string(base) + ".val").c_str(), "wb");
+    if (!f) return -1;
+    fwrite(&n, 8, 1, f); fwrite(data.data(), 4, n, f);
+    fwrite(&n, 8, 1, f); fwrite(lens.data(), 1, n, f);
+    // overflow_: sparse_hash_map<int32, int32>, hash spp_mix_32 (include/sparsepp/spp_utils.h:178-184)
+    const uint64_t no = overflow.size();
+    uint64_t table = 32;
+    while (table * 4 < no * 5 + 4) table <<= 1;  // below sparsepp's 80 % occupancy
+    const uint64_t mask = table - 1;
+    std::vector<uint32_t> bitmap(table / 32, 0);
+    std::vector<uint32_t> slotOf(no);
+    for (uint64_t i = 0; i < no; ++i) {
+      uint64_t b = spp_mix_32(static_cast<uint32_t>(overflow[i].first)) & mask, probes = 0;
+      while (bitmap[b >> 5] >> (b & 31) & 1u) { ++probes; b = (b + probes) & mask; }
+      bitmap[b >> 5] |= 1u << (b & 31);
+      slotOf[i] = static_cast<uint32_t>(b);
+    }
+    std::vector<uint32_t> groupBase(table / 32 + 1, 0);
+    for (uint64_t g = 0; g < table / 32; ++g) groupBase[g + 1] = groupBase[g] + static_cast<uint32_t>(__builtin_popcount(bitmap[g]));
+    std::vector<std::pair<int32_t, int32_t>> recs(no);
+    for (uint64_t i = 0; i < no; ++i) {
+      const uint32_t s = slotOf[i];
+      recs[groupBase[s >> 5] + static_cast<uint32_t>(__builtin_popcount(bitmap[s >> 5] & ((1u << (s & 31)) - 1u)))] = overflow[i];
+    }
+    put_be32(f, 0x24687531u);
+    put_be32(f, static_cast<uint32_t>(table));
+    put_be32(f, static_cast<uint32_t>(no));
+    fwrite(bitmap.data(), 4, bitmap.size(), f);
+    for (const auto& r : recs) { fwrite(&r.first, 4, 1, f); fwrite(&r.second, 4, 1, f); }
+    fclose(f);
+  }
+  return 0;
 }
