@@ -2,8 +2,8 @@
 # the driver's bench invocation (both arms), as the round-end run does it
 mkdir -p gpurun_out
 timeout 900 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.log; echo "ref exit $?"
-/usr/bin/time -v timeout 1800 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.log; echo "bench exit $?"
-grep -E "\[bench\]|Elapsed|Maximum resident" gpurun_out/bench_n1.log | tail -20
+SECONDS=0; timeout 1800 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.log; echo "bench exit $?"
+echo "bench wall ${SECONDS}s"; grep -E "\[bench\]" gpurun_out/bench_n1.log | tail -20
 python - <<'PY'
 import json
 try:
