@@ -192,11 +192,15 @@ struct rapmap_cuda_mapper {
   uint32_t ivCap{0};
   uint64_t scratchSlotsK1{0};
   uint4* dPacked{nullptr};
+  uint4* dKmask{nullptr};
+  uint32_t* dOrder{nullptr};
+  uint32_t* dClassCtl{nullptr};
   IntervalRec* dIvScratch{nullptr};
   uint32_t ivStride{0};
   uint32_t* dVoteScratch{nullptr};
   uint32_t voteWords{0}, laneWords{0}, laneSmem{0}, pmax{0};
   int gridLane{0};
+  void (*laneKernel)(LaneParams){nullptr};   // sa_collect_lane_kernel instantiation for this index flavour / flag set
   // stage 2: hit resolution
   QASummary* dQSumm{nullptr};
   QARec* dQaArena{nullptr};
@@ -571,7 +575,7 @@ static void freeMapperBuffers(rapmap_cuda_mapper* m) {
   cudaFree(m->dSumm); cudaFree(m->dIvArena); cudaFree(m->dQSumm); cudaFree(m->dQaArena); cudaFree(m->dPosPool);
   cudaFree(m->dScratch); cudaFree(m->dPairCount); cudaFree(m->dPairOff); cudaFree(m->dHits); cudaFree(m->dCubTemp);
   cudaFree(m->dCtl); cudaFree(m->dCounters);
-  cudaFree(m->dPacked); cudaFree(m->dIvScratch); cudaFree(m->dVoteScratch);
+  cudaFree(m->dPacked); cudaFree(m->dKmask); cudaFree(m->dOrder); cudaFree(m->dClassCtl); cudaFree(m->dIvScratch); cudaFree(m->dVoteScratch);
   selAlnFree(m->selaln);
   if (m->hStage) cudaFreeHost(m->hStage);
   for (auto& e : m->ev) if (e) cudaEventDestroy(e);
@@ -640,14 +644,21 @@ static int mapperCreateImpl(const rapmap_cuda_index_t* idx, const rapmap_cuda_op
   // maximum shared-memory carve-out shrank L1 and cost 20 %.
   {  // SA-lookup kernel: one thread per read
     m->laneWords = (max_read_len + 31) / 32;
-    m->laneSmem = m->laneWords * 16u * kLaneThreads;
+    m->laneSmem = 2u * m->laneWords * 16u * kLaneThreads;  // packed read words + k-mer mask words
     if (m->laneSmem > 227 * 1024) return bail("max_read_len too large for the shared-memory read words");
-    M_TRY(cudaFuncSetAttribute(sa_collect_lane_kernel<kLaneThreads, kLaneMinBlocks>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(m->laneSmem)));
-    M_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sa_collect_lane_kernel<kLaneThreads, kLaneMinBlocks>, kLaneThreads, m->laneSmem));
+    const bool general = !(d.disableNIP && d.strictCheck);
+    m->laneKernel = idx->hdr.hashKind ? (general ? &sa_collect_lane_kernel<kLaneThreads, kLaneMinBlocks, true, true> : &sa_collect_lane_kernel<kLaneThreads, kLaneMinBlocks, true, false>)
+                                      : (general ? &sa_collect_lane_kernel<kLaneThreads, kLaneMinBlocks, false, true> : &sa_collect_lane_kernel<kLaneThreads, kLaneMinBlocks, false, false>);
+    M_TRY(cudaFuncSetAttribute(m->laneKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(m->laneSmem)));
+    M_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, m->laneKernel, kLaneThreads, m->laneSmem));
     if (occ < 1) return bail("sa_collect_lane_kernel does not fit on an SM");
     m->gridLane = m->numSMs * occ;
     m->scratchSlotsK1 = static_cast<uint64_t>(m->gridLane) * kLaneThreads;
     M_TRY(cudaMalloc(&m->dPacked, R * m->laneWords * sizeof(uint4)));
+    M_TRY(cudaMalloc(&m->dKmask, R * m->laneWords * sizeof(uint4)));
+    M_TRY(cudaMemset(m->dKmask, 0, R * m->laneWords * sizeof(uint4)));
+    M_TRY(cudaMalloc(&m->dOrder, R * 4));
+    M_TRY(cudaMalloc(&m->dClassCtl, 2 * kWorkClasses * 4));
     // interval arena: 4 (10 with chaining) records per read, plus the unused tails of the RAPMAP_LANE_CHUNK-record slices
     // every resident warp reserves
     const uint64_t want = R * (needPos ? 10 : 4) + 1024 + static_cast<uint64_t>(m->gridLane) * (kLaneThreads / 32) * RAPMAP_LANE_CHUNK;
@@ -726,14 +737,21 @@ static int enqueueAttempt(rapmap_cuda_mapper* m) {
   CU_TRY(cudaMemsetAsync(m->dCounters, 0, sizeof(Counters5), st));
   // ---- kernel 1: SA lookup
   LaneParams lp{};
-  lp.ix = m->idx->view; lp.reads = bv; lp.opts = m->dopts; lp.maxReadLen = m->maxReadLen; lp.nw = m->laneWords; lp.packed = m->dPacked;
+  lp.ix = m->idx->view; lp.reads = bv; lp.opts = m->dopts; lp.maxReadLen = m->maxReadLen; lp.nw = m->laneWords; lp.packed = m->dPacked; lp.kmask = m->dKmask; lp.maskChunks = (m->pmax + 7) / 8; lp.classCtl = m->dClassCtl; lp.order = m->dOrder;
   lp.summ = m->dSumm; lp.arena = m->dIvArena; lp.arenaCap = m->ivCap; lp.arenaCursor = m->dCtl + 0; lp.status = m->dCtl + 3;
   lp.ivScratch = m->dIvScratch; lp.ivStride = m->ivStride; lp.voteScratch = m->dVoteScratch; lp.voteWords = m->voteWords; lp.readCursor = m->dCtl + 4;
   const int g0 = static_cast<int>(std::min<uint64_t>(static_cast<uint64_t>(m->numSMs) * 8, (bv.numReads * m->laneWords + 255) / 256));
   pack_reads_kernel<<<g0, 256, 0, st>>>(lp);
+  const int g0b = static_cast<int>(std::min<uint64_t>(static_cast<uint64_t>(m->numSMs) * 8, (bv.numReads * lp.maskChunks + 255) / 256));
+  kmer_mask_kernel<<<g0b, 256, 0, st>>>(lp);
+  CU_TRY(cudaMemsetAsync(m->dClassCtl, 0, 2 * kWorkClasses * 4, st));
+  const int g0c = static_cast<int>(std::min<uint64_t>(static_cast<uint64_t>(m->numSMs) * 8, (bv.numReads + 255) / 256));
+  work_class_hist_kernel<<<g0c, 256, 0, st>>>(lp);
+  work_class_scatter_kernel<<<g0c, 256, 0, st>>>(lp);
+  m->launches += 3;
   CU_TRY(cudaEventRecord(m->ev[8], st));
   const int g1 = static_cast<int>(std::min<uint64_t>(m->gridLane, (bv.numReads + kLaneThreads - 1) / kLaneThreads));
-  sa_collect_lane_kernel<kLaneThreads, kLaneMinBlocks><<<g1, kLaneThreads, m->laneSmem, st>>>(lp);
+  m->laneKernel<<<g1, kLaneThreads, m->laneSmem, st>>>(lp);
   m->launches += 2;
   CU_TRY(cudaEventRecord(m->ev[2], st));
   // ---- kernel 2: hit resolution

@@ -100,10 +100,12 @@ __host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
   return x;
 }
 
-// Filter word / bit mask of a k-mer from its table hash h = mix64(key).
+// Filter word / bit mask of a k-mer from its table hash h = mix64(key): the word index comes from the top bits, the three
+// bit positions from bits 25..39 (disjoint from the word index for every filter size up to 2^24 words; no second multiply:
+// the mask kernel evaluates this twice per k-mer window of every read).
 __host__ __device__ __forceinline__ void filterSlot(uint64_t h, uint32_t shift, uint64_t& word, uint32_t& mask) {
-  const uint64_t g = (h ^ (h >> 29)) * 0x9E3779B97F4A7C15ULL;
-  word = g >> shift;
+  word = h >> shift;
+  const uint32_t g = static_cast<uint32_t>(h >> 25);
   mask = (1u << (g & 31)) | (1u << ((g >> 5) & 31)) | (1u << ((g >> 10) & 31));
 }
 

@@ -36,6 +36,7 @@ struct LaneParams {
   uint32_t maxReadLen;
   uint32_t nw;             // 32-base words per read (ceil(maxReadLen / 32))
   uint4* packed;           // [numReads][nw] {codes_lo, codes_hi, invalid mask, N mask}
+  uint4* kmask;            // [numReads][nw] per 32 k-mer start positions {absent fwd, absent rc, window valid, homopolymer} (kmer_mask_kernel)
   ReadSummary* summ;
   IntervalRec* arena;
   uint32_t arenaCap;
@@ -46,6 +47,9 @@ struct LaneParams {
   uint32_t* voteScratch;   // per resident thread: 3 x voteWords (tested, fwd present, rc present); k-mer vote mode only
   uint32_t voteWords;
   uint32_t* readCursor;
+  uint32_t maskChunks;     // 8-window chunks per read the mask kernel fills: ceil((maxReadLen - k + 1) / 8)
+  uint32_t* classCtl;      // [0, 8) class histogram, [8, 16) scatter cursors (zeroed per batch)
+  uint32_t* order;         // [numReads] read indices grouped by work class; the walk kernel takes reads in this order
 };
 
 // ---- K0: pack reads.  One thread per 32-base word of a read (a warp covers 8 reads x 4 words = 800 contiguous bytes).
@@ -84,6 +88,147 @@ __global__ void __launch_bounds__(256) pack_reads_kernel(LaneParams P) {
       if (uc == 'N') nn |= 1u << b;
     }
     P.packed[g] = make_uint4(static_cast<uint32_t>(codes), static_cast<uint32_t>(codes >> 32), inv, nn);
+  }
+}
+
+// ---- K0b: k-mer masks.  The walk of a noisy read spends most of its steps on k-mers that are not in the index (the ~31
+// windows covering a sequencing error, both orientations): each such step is "advance one base" with no other effect
+// (include/SACollector.hpp:520-546,:671-673).  Whether a window is such a dead position is a pure function of the window,
+// so it is computed here for EVERY window of every read, fully convergent (a thread owns 8 consecutive windows; the four
+// threads of a 32-window word combine their bytes with shuffles), and the walk kernel skips runs of dead positions with a
+// bit scan instead of a ~200-instruction loop trip with two dependent L2 loads each.
+// Per forward window q (bit q & 31 of word q >> 5): V = the window holds only ACGT; for V windows H = homopolymer,
+// AF / AR = the k-mer filter proves the k-mer / its reverse complement absent.  Windows with a non-ACGT base (V = 0) keep
+// taking the walk kernel's exact path (partial words of Kmer::fromChars, the N skips, 'U' on the reverse-complement strand).
+__global__ void __launch_bounds__(256) kmer_mask_kernel(LaneParams P) {
+  // task = (read, chunk of 8 windows); chunks beyond the longest possible read are never touched (the mask array is zeroed
+  // once when the mapper is created) and never read (a walk only looks at windows q <= L - k)
+  const uint32_t cpr = P.maskChunks;  // ceil((maxReadLen - k + 1) / 8)
+  const uint64_t nTasks = P.reads.numReads * cpr;
+  const int k = static_cast<int>(P.ix.k);
+  const uint32_t kbits = (k >= 32) ? 0xffffffffu : ((1u << k) - 1u);
+  const uint64_t kmask = (k >= 32) ? ~0ULL : ((1ULL << (2 * k)) - 1ULL);
+  uint8_t* out = reinterpret_cast<uint8_t*>(P.kmask);
+  for (uint64_t g = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; g < nTasks; g += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    const uint64_t r = g / cpr;
+    const int c = static_cast<int>(g - r * cpr);
+    const int wi = c >> 2, sh = (c & 3) * 8;
+    const uint64_t wordIdx = r * P.nw + wi;
+    const int mate = r >= P.reads.n ? 1 : 0;
+    const uint64_t ri = r - static_cast<uint64_t>(mate) * P.reads.n;
+    uint32_t len = P.reads.fixedLen;
+    if (P.reads.off[mate]) len = static_cast<uint32_t>(P.reads.off[mate][ri + 1] - P.reads.off[mate][ri]);
+    if (len > P.maxReadLen) len = 0;
+    const int L = static_cast<int>(len);
+    const int q0 = c * 8;
+    uint32_t af = 0, ar = 0, vv = 0, hh = 0;
+    if (q0 + k <= L) {
+      const uint4 a = __ldg(P.packed + wordIdx);
+      uint4 b = make_uint4(0u, 0u, 0u, 0u);
+      if (wi + 1 < static_cast<int>(P.nw)) b = __ldg(P.packed + wordIdx + 1);
+      const uint64_t ca = (static_cast<uint64_t>(a.y) << 32) | a.x, cb = (static_cast<uint64_t>(b.y) << 32) | b.x;
+      const uint64_t hi = sh ? ((ca << (2 * sh)) | (cb >> (64 - 2 * sh))) : ca;  // bases q0 .. q0+31
+      uint64_t lo = cb << (2 * sh);                                              // bases q0+32 .. (k + 7 <= 38 bases are needed)
+      const uint64_t inv = ((static_cast<uint64_t>(b.z) << 32) | a.z) >> sh;     // bit i: base q0+i is not ACGT
+      // rolling k-mer and reverse complement (Kmer::shiftFw / getRC, include/Kmer.hpp:92-100); `same` counts the equal
+      // neighbours inside the window: k - 1 of them = homopolymer (:484-487)
+      uint64_t w = hi >> (64 - 2 * k);
+      uint64_t wr = kmerRC(w, k);
+      int same = 0;
+      for (int j = 1; j < k; ++j) same += (((w >> (2 * j)) ^ (w >> (2 * j - 2))) & 3ULL) == 0ULL;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (q0 + i + k > L) break;
+        if (i > 0) {  // window q0+i: drop base q0+i-1, take base q0+i+k-1 (bit 63:62 of the remaining stream)
+          const int kk = i + k - 1;  // base index relative to q0
+          const uint64_t nb = kk < 32 ? ((hi >> (62 - 2 * kk)) & 3ULL) : ((lo >> 62) & 3ULL);
+          if (kk >= 32) lo <<= 2;
+          same -= (((w >> (2 * k - 2)) ^ (w >> (2 * k - 4))) & 3ULL) == 0ULL;  // pair (first, second) leaves
+          same += ((w ^ nb) & 3ULL) == 0ULL;                                     // pair (last, new) enters
+          w = ((w << 2) | nb) & kmask;
+          wr = (wr >> 2) | ((3ULL - nb) << (2 * k - 2));
+        }
+        if ((static_cast<uint32_t>(inv >> i) & kbits) != 0u) continue;
+        const uint32_t bit = 1u << i;
+        vv |= bit;
+        if (same == k - 1) hh |= bit;
+        if (P.ix.filter != nullptr) {
+          uint64_t wa, wb;
+          uint32_t ma, mb;
+          filterSlot(mix64(w), P.ix.filterShift, wa, ma);
+          filterSlot(mix64(wr), P.ix.filterShift, wb, mb);
+          const uint32_t fa = ldgKeep(P.ix.filter + wa), fb = ldgKeep(P.ix.filter + wb);
+          if ((fa & ma) != ma) af |= bit;
+          if ((fb & mb) != mb) ar |= bit;
+        }
+      }
+    }
+    uint8_t* o = out + wordIdx * 16 + (c & 3);
+    o[0] = static_cast<uint8_t>(af); o[4] = static_cast<uint8_t>(ar); o[8] = static_cast<uint8_t>(vv); o[12] = static_cast<uint8_t>(hh);
+  }
+}
+
+// ---- K0c: work-class ordering.  The cost of a read's walk is set by the number of places where it stops matching (each
+// costs a fresh round of lookups and binary searches); lanes of a warp that walk reads of different cost finish at different
+// times and the warp's instructions run with most lanes masked off.  The reads are therefore handed to the walk kernel
+// grouped by a cheap cost class read off the k-mer masks: the number of maximal runs of dead windows (0 = every window
+// may hit ... 6+), reads with a non-ACGT window last.  Counting sort: histogram, then scatter (order within a class is
+// arbitrary; results do not depend on it).
+static constexpr int kWorkClasses = 8;
+__device__ __forceinline__ int workClass(const LaneParams& P, uint64_t r) {
+  const int mate = r >= P.reads.n ? 1 : 0;
+  const uint64_t ri = r - static_cast<uint64_t>(mate) * P.reads.n;
+  uint32_t len = P.reads.fixedLen;
+  if (P.reads.off[mate]) len = static_cast<uint32_t>(P.reads.off[mate][ri + 1] - P.reads.off[mate][ri]);
+  const int k = static_cast<int>(P.ix.k);
+  if (len > P.maxReadLen || static_cast<int>(len) < k) return 0;
+  const int np = static_cast<int>(len) - k + 1;
+  int runs = 0;
+  bool bad = false;
+  uint32_t carry = 0;  // dead bit of the previous window
+  for (int j = 0; j * 32 < np; ++j) {
+    const uint4 mk = __ldg(P.kmask + r * P.nw + j);
+    const int nb = np - j * 32 < 32 ? np - j * 32 : 32;
+    const uint32_t rng = nb >= 32 ? 0xffffffffu : ((1u << nb) - 1u);
+    const uint32_t dead = (mk.z & (mk.w | (mk.x & mk.y))) & rng;
+    bad |= ((~mk.z) & rng) != 0u;
+    runs += __popc(dead & ~((dead << 1) | carry));
+    carry = dead >> 31;
+  }
+  if (bad) return kWorkClasses - 1;
+  return runs < kWorkClasses - 2 ? runs : kWorkClasses - 2;
+}
+
+__global__ void __launch_bounds__(256) work_class_hist_kernel(LaneParams P) {
+  __shared__ uint32_t h[kWorkClasses];
+  if (threadIdx.x < kWorkClasses) h[threadIdx.x] = 0;
+  __syncthreads();
+  for (uint64_t r = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r < P.reads.numReads; r += static_cast<uint64_t>(gridDim.x) * blockDim.x)
+    atomicAdd(&h[workClass(P, r)], 1u);
+  __syncthreads();
+  if (threadIdx.x < kWorkClasses && h[threadIdx.x]) atomicAdd(P.classCtl + threadIdx.x, h[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(256) work_class_scatter_kernel(LaneParams P) {
+  __shared__ uint32_t cnt[kWorkClasses], base[kWorkClasses];
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  const uint64_t rounds = (P.reads.numReads + stride - 1) / stride;
+  for (uint64_t it = 0; it < rounds; ++it) {
+    const uint64_t r = it * stride + static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (threadIdx.x < kWorkClasses) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    int c = 0;
+    uint32_t rank = 0;
+    if (r < P.reads.numReads) { c = workClass(P, r); rank = atomicAdd(&cnt[c], 1u); }
+    __syncthreads();
+    if (threadIdx.x < kWorkClasses) {
+      uint32_t off = 0;  // exclusive scan of the histogram
+      for (int j = 0; j < static_cast<int>(threadIdx.x); ++j) off += P.classCtl[j];
+      base[threadIdx.x] = off + (cnt[threadIdx.x] ? atomicAdd(P.classCtl + kWorkClasses + threadIdx.x, cnt[threadIdx.x]) : 0u);
+    }
+    __syncthreads();
+    if (r < P.reads.numReads) P.order[base[c] + rank] = static_cast<uint32_t>(r);
+    __syncthreads();
   }
 }
 
@@ -298,8 +443,9 @@ __device__ __forceinline__ int cmpSuffix(const LaneParams& P, const uint4* sm, u
 
 // k-mer and its reverse complement -> SA intervals; both table probes are in flight together.
 // knownA / knownB: the filter already proved that key absent.
+template <bool PHF>
 __device__ __forceinline__ void hashFind2(const DeviceIndex& ix, uint64_t ka, uint64_t kb, bool knownA, bool knownB, int2& ra, int2& rb) {
-  if (ix.hashKind) {  // -p index: the two BooPHF walks run one after the other (one inlined copy of the walk)
+  if (PHF) {  // -p index: the two BooPHF walks run one after the other (one inlined copy of the walk)
 #pragma unroll 1
     for (int which = 0; which < 2; ++which) {
       const int2 res = (which ? knownB : knownA) ? make_int2(-1, -1) : phfFindImpl(ix, which ? kb : ka);
@@ -377,7 +523,11 @@ enum : uint32_t {
 #define RAPMAP_LANE_CHUNK 256  // interval-arena records a warp reserves per atomic
 #endif
 
-template <int NT, int MINB>
+// PHF: -p index (BooPHF walk instead of the dense table).  GENERAL: any strand-decision / skip mode; false = the default flags'
+// coverage mode (disableNIP && strictCheck, include/SACollector.hpp:138) with the k-mer vote and NIP code compiled out: the
+// walk is bound by instruction fetch (profiles/r02b: 6.2 of 15 stall cycles per issue are `no instruction`), so code the
+// default configuration never runs is kept out of its kernel.
+template <int NT, int MINB, bool PHF, bool GENERAL>
 __global__ void __launch_bounds__(NT, MINB) sa_collect_lane_kernel(LaneParams P) {
   extern __shared__ __align__(16) uint8_t smemRaw[];
   uint4* smw = reinterpret_cast<uint4*>(smemRaw) + threadIdx.x;
@@ -386,8 +536,10 @@ __global__ void __launch_bounds__(NT, MINB) sa_collect_lane_kernel(LaneParams P)
   const int k = static_cast<int>(P.ix.k);
   const int nw = static_cast<int>(P.nw);
   const DevOpts& o = P.opts;
-  const bool useCov = o.disableNIP && o.strictCheck;  // include/SACollector.hpp:138
-  const bool voteMode = o.strictCheck && !useCov;
+  const bool disableNIP = GENERAL ? (o.disableNIP != 0) : true;
+  const bool strictCheck = GENERAL ? (o.strictCheck != 0) : true;
+  const bool useCov = disableNIP && strictCheck;  // include/SACollector.hpp:138
+  const bool voteMode = strictCheck && !useCov;
   const uint32_t slot = blockIdx.x * NT + threadIdx.x;
   IntervalRec* scr = P.ivScratch + static_cast<size_t>(slot) * 2 * P.ivStride;
   uint32_t* votes = voteMode ? P.voteScratch + static_cast<size_t>(slot) * 3 * P.voteWords : nullptr;
@@ -404,20 +556,95 @@ __global__ void __launch_bounds__(NT, MINB) sa_collect_lane_kernel(LaneParams P)
   int lookPos = 0;
 
   for (;;) {
-    // ---------------- refill: idle lanes take the next reads of the batch
+    // ---------------- publish + refill: lanes whose read is finished wait (LST_FINAL) until enough lanes of the warp are
+    // finished or idle, then all of them publish their interval lists in one go and the idle lanes take the next reads of
+    // the batch.  (Publishing each read the moment it finishes ran this whole block once per read with one active lane:
+    // a third of the kernel's instructions, profiles/r02b.)
     {
-      const unsigned idle = __ballot_sync(0xffffffffu, st == LST_IDLE);
-      if (idle) {
-        const unsigned busy = __ballot_sync(0xffffffffu, st != LST_IDLE && st != LST_EXIT);
-        if (__popc(idle) >= RAPMAP_LANE_REFILL || busy == 0u) {
+      const unsigned waiting = __ballot_sync(0xffffffffu, st == LST_IDLE || st == LST_FINAL);
+      if (waiting) {
+        const unsigned busy = __ballot_sync(0xffffffffu, st != LST_IDLE && st != LST_EXIT && st != LST_FINAL);
+        if (__popc(waiting) >= RAPMAP_LANE_REFILL || busy == 0u) {
+          const bool fin = st == LST_FINAL;
+          int tot = 0;
+          if (fin) {
+            if (flags & LF_FOUND) {
+              if (useCov) {  // strand decision by coverage (:283-288)
+                if (fwdCov > rcCov + static_cast<uint32_t>(o.strictCheckSlack)) nR = 0;
+                else if (rcCov > fwdCov + static_cast<uint32_t>(o.strictCheckSlack)) nF = 0;
+              } else if (strictCheck) {  // k-mer "spot check" vote (:289-337)
+                if (fwdHit > 0u && rcHit == 0u) nR = 0;
+                else if (rcHit > 0u && fwdHit == 0u) nF = 0;
+                else {
+                  int fs = 0, rs = 0;
+                  for (uint32_t j = 0; j < P.voteWords; ++j) {
+                    const int tested = __popc(votes[j]);
+                    fs += 2 * __popc(votes[P.voteWords + j]) - tested;
+                    rs += 2 * __popc(votes[2 * P.voteWords + j]) - tested;
+                  }
+                  if (fs > rs) nR = 0;
+                  else if (rs > fs) nF = 0;
+                }
+              }
+              if (o.covReq > 0.0 && disableNIP) {  // :343-358
+                if (nF > 0 && (static_cast<double>(fwdCov) / static_cast<double>(L)) < o.covReq) nF = 0;
+                if (nR > 0 && (static_cast<double>(rcCov) / static_cast<double>(L)) < o.covReq) nR = 0;
+              }
+            } else { nF = 0; nR = 0; }
+            tot = nF + nR;
+          }
+          const unsigned pm = __ballot_sync(0xffffffffu, fin && tot > 0);
+          uint32_t off = 0;
+          if (pm) {  // warp-aggregated reservation out of the warp's arena slice
+            int incl = fin ? tot : 0;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+              const int v = __shfl_up_sync(0xffffffffu, incl, d);
+              if (lane >= d) incl += v;
+            }
+            const uint32_t total = static_cast<uint32_t>(__shfl_sync(0xffffffffu, incl, 31));
+            if (total > chunkLeft) {
+              const uint32_t grab = total > RAPMAP_LANE_CHUNK ? total : RAPMAP_LANE_CHUNK;
+              uint32_t base = 0;
+              if (lane == 0) base = atomicAdd(P.arenaCursor, grab);
+              chunkBase = __shfl_sync(0xffffffffu, base, 0);
+              chunkLeft = grab;
+            }
+            off = chunkBase + static_cast<uint32_t>(incl - tot);
+            chunkBase += total;
+            chunkLeft -= total;
+          }
+          if (fin) {
+            if (tot > 0) {
+              // A read whose records cannot be stored publishes an EMPTY summary (the later kernels of this attempt must not
+              // follow ivOff into unwritten or out-of-range arena memory); the status bit makes the host grow and re-run.
+              bool stored = false;
+              if (flags & LF_OVF) atomicOr(P.status, kStatIvScratchFull);
+              else if (static_cast<uint64_t>(off) + static_cast<uint64_t>(tot) > P.arenaCap) atomicOr(P.status, kStatIntervalArenaFull);
+              else {
+                for (int i = 0; i < nF; ++i) P.arena[off + i] = scr[i];
+                for (int i = 0; i < nR; ++i) P.arena[off + nF + i] = scr[P.ivStride + i];
+                stored = true;
+              }
+              if (!stored) { nF = 0; nR = 0; off = 0; }
+            }
+            ReadSummary s;
+            s.ivOff = off; s.nFwd = static_cast<uint16_t>(nF); s.nRc = static_cast<uint16_t>(nR);
+            s.readLen = static_cast<uint16_t>(L); s.found = (flags & LF_FOUND) ? 1 : 0; s.pad = 0;
+            P.summ[r] = s;
+            st = LST_IDLE;
+          }
+
+          const unsigned idle = __ballot_sync(0xffffffffu, st == LST_IDLE);
           const int leader = __ffs(idle) - 1;
           uint32_t base = 0;
           if (lane == leader) base = atomicAdd(P.readCursor, static_cast<uint32_t>(__popc(idle)));
           base = __shfl_sync(0xffffffffu, base, leader);
           if (st == LST_IDLE) {
-            const uint64_t nr = static_cast<uint64_t>(base) + __popc(idle & ((1u << lane) - 1u));
-            if (nr >= P.reads.numReads) st = LST_EXIT;
+            const uint64_t slotNr = static_cast<uint64_t>(base) + __popc(idle & ((1u << lane) - 1u));
+            if (slotNr >= P.reads.numReads) st = LST_EXIT;
             else {
+              const uint64_t nr = __ldg(P.order + slotNr);
               r = static_cast<uint32_t>(nr);
               const int mate = nr >= P.reads.n ? 1 : 0;
               const uint64_t ri = nr - static_cast<uint64_t>(mate) * P.reads.n;
@@ -431,6 +658,10 @@ __global__ void __launch_bounds__(NT, MINB) sa_collect_lane_kernel(LaneParams P)
               } else {
                 const uint4* src = P.packed + static_cast<size_t>(nr) * P.nw;
                 for (int j = 0; j < nw; ++j) smw[j * NT] = __ldg(src + j);
+                {
+                  const uint4* msrc = P.kmask + static_cast<size_t>(nr) * P.nw;
+                  for (int j = 0; j < nw; ++j) smw[(nw + j) * NT] = __ldg(msrc + j);
+                }
                 if (voteMode) for (uint32_t j = 0; j < 3 * P.voteWords; ++j) votes[j] = 0u;
                 L = static_cast<int>(len);
                 rb = 0; flags = 0; nF = 0; nR = 0; fwdHit = 0; rcHit = 0; fwdCov = 0; rcCov = 0; ready = false;
@@ -450,6 +681,47 @@ __global__ void __launch_bounds__(NT, MINB) sa_collect_lane_kernel(LaneParams P)
     for (int spin = 0; spin < RAPMAP_LANE_SPIN; ++spin) {
       if (ready || !(st == LST_SCAN || st == LST_WSTART || st == LST_MM)) break;
       const bool rc = (flags & LF_RC) != 0u;
+      // ---- dead positions (kmer_mask_kernel): a run of windows that are valid and either homopolymers or absent from the
+      // index in both orientations is stepped over with a bit scan - exactly what the loop below would do one base at a time
+      // (++rb, no counter moves; with the k-mer vote the double misses are marked tested).  In the first-hit scan a window
+      // followed directly by an N is left to the loop (the "<=" of SACollector.hpp:178).
+      if (st != LST_MM) {
+        while (rb + k <= L) {
+          const int q = rc ? L - k - rb : rb;
+          const int wq = q >> 5, bq = q & 31;
+          const uint4 mk = sm[(nw + wq) * NT];
+          const uint32_t miss = mk.x & mk.y & mk.z;          // valid, absent in both orientations
+          uint32_t dead = miss | (mk.w & mk.z);              // ... or a homopolymer
+          if (st == LST_SCAN) {
+            const uint32_t n0 = sm[wq * NT].w, n1 = (wq + 1 < nw) ? sm[(wq + 1) * NT].w : 0u;
+            dead &= ~__funnelshift_r(n0, n1, static_cast<uint32_t>(k));  // N at q + k
+          }
+          int n;
+          uint32_t run;
+          if (!rc) {
+            const uint32_t live = ~dead >> bq;
+            n = live ? (__ffs(live) - 1) : (32 - bq);
+            run = (n >= 32 ? 0xffffffffu : ((1u << n) - 1u)) << bq;
+          } else {
+            const uint32_t live = ~dead << (31 - bq);
+            n = live ? __clz(live) : (bq + 1);
+            run = (n >= 32 ? 0xffffffffu : ((1u << n) - 1u)) << (bq + 1 - n);
+          }
+          if (n == 0) break;
+          if (voteMode && st != LST_SCAN) votes[wq] |= run & miss;
+          rb += n;
+          if (!rc ? (bq + n < 32) : (n <= bq)) break;  // the run ended inside this word
+        }
+      } else {
+        const int lp = rb + mlen - (k - 1);
+        const int q = rc ? L - k - lp : lp;
+        const uint4 mk = sm[(nw + (q >> 5)) * NT];
+        if ((mk.x & mk.y & mk.z) >> (q & 31) & 1u) {  // the k-mer after the interval is a double miss (:599-616, :671)
+          if (voteMode) voteLane(votes, P.voteWords, rc, lp, L, k, false, false);
+          st = LST_POSTMM;
+          break;
+        }
+      }
       for (;;) {
         if (st == LST_MM) lookPos = rb + mlen - (k - 1);  // mismatching k-mer after an interval, :599-616
         else {
@@ -476,6 +748,16 @@ __global__ void __launch_bounds__(NT, MINB) sa_collect_lane_kernel(LaneParams P)
       }
       if (!ready || P.ix.filter == nullptr) break;
       {
+        const int q = rc ? L - k - lookPos : lookPos;
+        const uint4 mk = sm[(nw + (q >> 5)) * NT];
+        if ((mk.z >> (q & 31)) & 1u) {  // valid window: the filter verdicts are in the masks (and it is not a double miss)
+          const bool aF = (mk.x >> (q & 31)) & 1u, aR = (mk.y >> (q & 31)) & 1u;
+          knownM = rc ? aR : aF;
+          knownC = rc ? aF : aR;
+          if (!(knownM && knownC)) break;
+        }
+      }
+      if (!(knownM && knownC)) {
         uint64_t wa, wb;
         uint32_t ma, mb;
         filterSlot(mix64(w), P.ix.filterShift, wa, ma);
@@ -496,7 +778,7 @@ __global__ void __launch_bounds__(NT, MINB) sa_collect_lane_kernel(LaneParams P)
     if (ready) {
       ready = false;
       int2 fm, fc;
-      hashFind2(P.ix, w, kmerRC(w, k), knownM, knownC, fm, fc);
+      hashFind2<PHF>(P.ix, w, kmerRC(w, k), knownM, knownC, fm, fc);
       const bool hm = fm.x >= 0, hc = fc.x >= 0;
       const bool rc = (flags & LF_RC) != 0u;
       if (st == LST_SCAN) {
@@ -605,10 +887,10 @@ __global__ void __launch_bounds__(NT, MINB) sa_collect_lane_kernel(LaneParams P)
       if ((flags & LF_LAST) || rb + mlen >= L) st = LST_WALKEND;  // :623, :630
       else {  // :634-657 next start: MMP skip, or the NIP skip when --noSensitive
         const int mismatchPos = rb + mlen;
-        const int lce = o.disableNIP ? mlen : lceLane(P.ix.SA, P.ix.text, P.ix.n, lbIn, static_cast<int64_t>(ubIn) - 1, mlen, L - mismatchPos);
+        const int lce = disableNIP ? mlen : lceLane(P.ix.SA, P.ix.text, P.ix.n, lbIn, static_cast<int64_t>(ubIn) - 1, mlen, L - mismatchPos);
         const int skipMatch = mismatchPos - (k - 1), skipLCE = rb + lce - (k - 1);
         rb = skipMatch > skipLCE ? skipMatch : skipLCE;
-        if (!o.disableNIP && lce > mlen && L > k) rb = rb < L - k ? rb : L - k;
+        if (!disableNIP && lce > mlen && L > k) rb = rb < L - k ? rb : L - k;
         if (rb + k == L) flags |= LF_LAST;  // :663
         st = LST_WSTART;
       }
@@ -637,78 +919,6 @@ __global__ void __launch_bounds__(NT, MINB) sa_collect_lane_kernel(LaneParams P)
       flags = (flags & ~LF_STAGE_MASK) | (stage << LF_STAGE_SHIFT);
     }
 
-    // ---------------- publish finished reads
-    {
-      const bool fin = st == LST_FINAL;
-      int tot = 0;
-      if (fin) {
-        if (flags & LF_FOUND) {
-          if (useCov) {  // strand decision by coverage (:283-288)
-            if (fwdCov > rcCov + static_cast<uint32_t>(o.strictCheckSlack)) nR = 0;
-            else if (rcCov > fwdCov + static_cast<uint32_t>(o.strictCheckSlack)) nF = 0;
-          } else if (o.strictCheck) {  // k-mer "spot check" vote (:289-337)
-            if (fwdHit > 0u && rcHit == 0u) nR = 0;
-            else if (rcHit > 0u && fwdHit == 0u) nF = 0;
-            else {
-              int fs = 0, rs = 0;
-              for (uint32_t j = 0; j < P.voteWords; ++j) {
-                const int tested = __popc(votes[j]);
-                fs += 2 * __popc(votes[P.voteWords + j]) - tested;
-                rs += 2 * __popc(votes[2 * P.voteWords + j]) - tested;
-              }
-              if (fs > rs) nR = 0;
-              else if (rs > fs) nF = 0;
-            }
-          }
-          if (o.covReq > 0.0 && o.disableNIP) {  // :343-358
-            if (nF > 0 && (static_cast<double>(fwdCov) / static_cast<double>(L)) < o.covReq) nF = 0;
-            if (nR > 0 && (static_cast<double>(rcCov) / static_cast<double>(L)) < o.covReq) nR = 0;
-          }
-        } else { nF = 0; nR = 0; }
-        tot = nF + nR;
-      }
-      const unsigned pm = __ballot_sync(0xffffffffu, fin && tot > 0);
-      uint32_t off = 0;
-      if (pm) {  // warp-aggregated reservation out of the warp's arena slice
-        int incl = fin ? tot : 0;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          const int v = __shfl_up_sync(0xffffffffu, incl, d);
-          if (lane >= d) incl += v;
-        }
-        const uint32_t total = static_cast<uint32_t>(__shfl_sync(0xffffffffu, incl, 31));
-        if (total > chunkLeft) {
-          const uint32_t grab = total > RAPMAP_LANE_CHUNK ? total : RAPMAP_LANE_CHUNK;
-          uint32_t base = 0;
-          if (lane == 0) base = atomicAdd(P.arenaCursor, grab);
-          chunkBase = __shfl_sync(0xffffffffu, base, 0);
-          chunkLeft = grab;
-        }
-        off = chunkBase + static_cast<uint32_t>(incl - tot);
-        chunkBase += total;
-        chunkLeft -= total;
-      }
-      if (fin) {
-        if (tot > 0) {
-          // A read whose records cannot be stored publishes an EMPTY summary (the later kernels of this attempt must not
-          // follow ivOff into unwritten or out-of-range arena memory); the status bit makes the host grow and re-run.
-          bool stored = false;
-          if (flags & LF_OVF) atomicOr(P.status, kStatIvScratchFull);
-          else if (static_cast<uint64_t>(off) + static_cast<uint64_t>(tot) > P.arenaCap) atomicOr(P.status, kStatIntervalArenaFull);
-          else {
-            for (int i = 0; i < nF; ++i) P.arena[off + i] = scr[i];
-            for (int i = 0; i < nR; ++i) P.arena[off + nF + i] = scr[P.ivStride + i];
-            stored = true;
-          }
-          if (!stored) { nF = 0; nR = 0; off = 0; }
-        }
-        ReadSummary s;
-        s.ivOff = off; s.nFwd = static_cast<uint16_t>(nF); s.nRc = static_cast<uint16_t>(nR);
-        s.readLen = static_cast<uint16_t>(L); s.found = (flags & LF_FOUND) ? 1 : 0; s.pad = 0;
-        P.summ[r] = s;
-        st = LST_IDLE;
-      }
-    }
   }
 }
 

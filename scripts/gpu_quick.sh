@@ -1,12 +1,15 @@
 #!/bin/bash
+# the edit-measure loop: GPU parity tests, then a short bench (all legs, no CPU baseline)
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1; tail -15 gpurun_out/pytest_gpu.log
-timeout 600 python bench.py --steps 6 --warmup 3 --no-cpu-baseline > gpurun_out/bench_nosel.json 2> gpurun_out/bench_nosel.log
-timeout 600 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --selaln > gpurun_out/bench_sel.json 2> gpurun_out/bench_sel.log
+timeout 1500 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider ${PYTEST_ARGS:-} > gpurun_out/pytest_gpu.log 2>&1; tail -15 gpurun_out/pytest_gpu.log
+timeout 900 python bench.py --steps ${STEPS:-5} --warmup 2 --no-cpu-baseline ${EXTRA:-} > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.log
 python - <<'PY'
 import json
-for f in ("bench_nosel","bench_sel"):
-    try:
-        d=json.load(open(f"gpurun_out/{f}.json")); print(f, round(d["value"]/1e6,2),"M pairs/s e2e", round(d["e2e"]["value"]/1e6,2), {k:round(v,2) for k,v in d["roofline"]["stage_ms_per_step"].items()}, d["parity_checked_vs_oracle"])
-    except Exception as e: print(f, "ERR", e, open(f"gpurun_out/{f}.log").read()[-600:])
+try:
+    d=json.load(open("gpurun_out/bench_quick.json"))
+    print("headline", round(d["value"]/1e6,2), "e2e", round(d["e2e"]["value"]/1e6,2), "frac", round(d["roofline"]["frac"],4), {k:round(v,2) for k,v in d["roofline"]["stage_ms_per_chunk"].items()}, d["parity_checked_vs_oracle"])
+    for k,v in d["legs"].items():
+        print(k, round(v["value"]/1e6,2), "e2e", round(v["e2e"]["value"]/1e6,2), v.get("parity"), {a:round(b,2) for a,b in (v.get("stage_ms_per_chunk") or v["roofline"]["stage_ms_per_chunk"]).items()})
+except Exception as e:
+    print("ERR", e); print(open("gpurun_out/bench_quick.log").read()[-3000:])
 PY
