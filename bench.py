@@ -234,7 +234,9 @@ def main():
     ap.add_argument("--oracle-sample", type=int, default=20000, help="pairs checked against / counted by the CPU oracle at N=1")
     ap.add_argument("--cpu-baseline-pairs", type=int, default=1000000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-mappers", type=int, default=3, help="mappers (CUDA streams) the ONE host thread of the end-to-end leg keeps busy")
+    ap.add_argument("--e2e-in", default="host", choices=["host", "device"], help="diagnosis only: where the end-to-end leg's inputs live")
+    ap.add_argument("--e2e-out", default="host", choices=["host", "device"], help="diagnosis only: where the end-to-end leg's outputs go")
+    ap.add_argument("--e2e-depth", type=int, default=2, choices=[1, 2], help="chunks the end-to-end leg keeps in flight on its ONE mapper (the mapper pipelines two)")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -306,17 +308,18 @@ def main():
     cap = B * 8
     d_hits = torch.empty(cap * 28, dtype=torch.uint8, device="cuda")
     d_off = torch.empty(B + 1, dtype=torch.int64, device="cuda")
-    nm = max(1, args.e2e_mappers)
+    nm = args.e2e_depth
     h_out = [(torch.empty(cap * 28, dtype=torch.uint8).pin_memory(), torch.empty(B + 1, dtype=torch.int64).pin_memory()) for _ in range(nm)]
+    d_outs = [(torch.empty(cap * 28, dtype=torch.uint8, device="cuda"), torch.empty(B + 1, dtype=torch.int64, device="cuda")) for _ in range(nm)] if args.e2e_out == "device" else None
     dev = torch.device("cuda", local)
 
     STAGES = ("pack", "sa", "map", "merge", "selaln", "ksw", "h2d", "d2h")
 
     def run_leg(ix, opts, steps, warmup, sample_clocks=False):
         """Resident leg (device buffers in and out, one mapper, CUDA events on its stream) and end-to-end leg (pinned host buffers
-        in and out through rapmap_cuda_map_batch_async / _wait: ONE host thread keeps `nm` mappers busy, so one chunk's PCIe
-        copies overlap another chunk's kernels) over the same chunk sequence; the two legs must produce the same hits."""
-        mappers = [rb.Mapper(ix, opts, max_batch=B, max_read_len=READ_LEN) for _ in range(nm)]
+        in and out through rapmap_cuda_map_batch_async / _wait: ONE host thread, ONE mapper, two chunks in flight, so one chunk's
+        PCIe copies overlap another chunk's kernels) over the same chunk sequence; the two legs must produce the same hits."""
+        mappers = [rb.Mapper(ix, opts, max_batch=B, max_read_len=READ_LEN)]
         mapper = mappers[0]
         stream = torch.cuda.ExternalStream(mapper.stream_ptr, device=dev)
 
@@ -348,26 +351,38 @@ def main():
         ms_res = max_over_ranks(e0.elapsed_time(e1))
 
         # ---- end to end
+        e2e_st = {"h2d": 0.0, "d2h": 0.0, "total": 0.0, "sa": 0.0, "pack": 0.0, "map": 0.0, "merge": 0.0, "n": 0}
+
         def e2e(first, count):
-            pending = [None] * nm
+            """ONE host thread, ONE mapper: chunk c+1 is enqueued (rapmap_cuda_map_batch_async) before chunk c is collected
+            (rapmap_cuda_mapper_wait), so the mapper's three streams overlap copy-in, kernels and copy-out of consecutive chunks."""
             hits = 0
-            for c in range(first, first + count + nm):
-                k = c % nm
-                if pending[k]:
-                    hits += mappers[k].wait().num_hits
-                    pending[k] = False
-                if c < first + count:
-                    a, b = host[c % nd]
-                    mappers[k].map_batch_async(a, b, n=B, fixed_len=READ_LEN, location=rb.LOC_HOST, hits_out=h_out[k][0], offsets_out=h_out[k][1],
-                                               out_location=rb.LOC_HOST, capacity=cap)
-                    pending[k] = True
+
+            def collect():
+                nonlocal hits
+                hits += mapper.wait().num_hits
+                t = mapper.timing()
+                e2e_st["h2d"] += t.ms_h2d; e2e_st["d2h"] += t.ms_d2h; e2e_st["total"] += t.ms_total; e2e_st["sa"] += t.ms_sa_collect; e2e_st["n"] += 1
+                e2e_st["pack"] += t.ms_pack_reads; e2e_st["map"] += t.ms_hits_to_mappings; e2e_st["merge"] += t.ms_merge
+
+            for c in range(first, first + count):
+                if mapper.in_flight == nm:
+                    collect()
+                a, b = host[c % nd] if args.e2e_in == "host" else devb[c % nd]
+                ho, oo = h_out[c % nm] if args.e2e_out == "host" else d_outs[c % nm]
+                mapper.map_batch_async(a, b, n=B, fixed_len=READ_LEN, location=rb.LOC_HOST if args.e2e_in == "host" else rb.LOC_DEVICE, hits_out=ho, offsets_out=oo,
+                                       out_location=rb.LOC_HOST if args.e2e_out == "host" else rb.LOC_DEVICE, capacity=cap)
+            while mapper.in_flight:
+                collect()
             return hits
 
-        e2e(0, max(warmup * CH, 2 * nm))
+        e2e(0, max(warmup * CH, 4))
         torch.cuda.synchronize()
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record(stream)
+        for kk in e2e_st:
+            e2e_st[kk] = 0
         e2e_hits = e2e(warmup * CH, steps * CH)
         f1.record(stream)  # every chunk has been waited for: the event marks the end of the host-visible work
         torch.cuda.synchronize()
@@ -375,7 +390,8 @@ def main():
         ms_e2e = max_over_ranks(f0.elapsed_time(f1))
         if e2e_hits != st["hits"]:
             raise SystemExit(f"end-to-end leg produced {e2e_hits} hits, resident leg {st['hits']} over the same chunks; refusing to report a number")
-        return {"ms_res": ms_res, "ms_e2e": ms_e2e, "st": st, "clocks": clocks, "mapper": mapper, "mappers": mappers, "steps": steps}
+        e2e_chunk = {kk: (e2e_st[kk] / max(1, e2e_st["n"])) for kk in ("h2d", "pack", "sa", "map", "merge", "d2h", "total")}
+        return {"ms_res": ms_res, "ms_e2e": ms_e2e, "st": st, "e2e_chunk": e2e_chunk, "clocks": clocks, "mapper": mapper, "mappers": mappers, "steps": steps}
 
     def oracle_check(o_idx_dir, opts, mapper, ns):
         """Parity + operation counts on the first `ns` pairs of chunk 0 (CPU oracle; N == 1 only)."""
@@ -426,7 +442,7 @@ def main():
     opts = rb.default_opts(sel_aln=args.selaln)
     H = run_leg(index, opts, args.steps, args.warmup, sample_clocks=True)
     value, e2e_value = leg_numbers(H, pairs_per_step)
-    log(f"rank {rank}: headline: resident {H['ms_res'] / args.steps:.2f} ms/step, end to end {H['ms_e2e'] / args.steps:.2f} ms/step ({nm} mappers, one host thread)")
+    log(f"rank {rank}: headline: resident {H['ms_res'] / args.steps:.2f} ms/step, end to end {H['ms_e2e'] / args.steps:.2f} ms/step (one mapper, one host thread, {nm} chunks in flight)")
     parity, ops, ops_per_pair, ns = None, None, None, 0
     if rank == 0 and world == 1 and args.oracle_sample > 0:
         ns = min(args.oracle_sample, B)
@@ -451,7 +467,8 @@ def main():
                        "index": "replicated per GPU (one NCCL broadcast of the packed image)", "sharding": "contiguous read ranges per rank, no data-path collective"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * B * READ_LEN * CH, "d2h_bytes_per_step": int(H["st"]["hits"] / args.steps * 28 + (B + 1) * 8 * CH),
                     "ms_per_step": H["ms_e2e"] / args.steps, "api": "rapmap_cuda_map_batch_async + rapmap_cuda_mapper_wait with pinned HOST buffers (ASCII bases in, rapmap_hit_t records + offsets out)",
-                    "host_threads": 1, "mappers": nm, "hits_equal_resident_leg": True},
+                    "host_threads": 1, "mappers": 1, "chunks_in_flight": nm, "hits_equal_resident_leg": True,
+                    "per_chunk_ms_on_its_streams": H["e2e_chunk"]},
             "gpu_launches": int(H["st"]["launch"]),
             "clocks": H["clocks"],
             "roofline": roofline(H, ops, ns, args.selaln),
@@ -486,7 +503,7 @@ def main():
                 line["legs"]["selaln"] = {
                     "config": "configs[2]" + (" / configs[4] (scaling)" if world > 1 else "") + ": same index and reads, quasimap -s (ksw2 selective alignment on)",
                     "value": v, "unit": UNIT, "ms_per_step": L["ms_res"] / leg_steps, "steps": leg_steps, "n_gpus": world,
-                    "e2e": {"value": e, "unit": UNIT, "ms_per_step": L["ms_e2e"] / leg_steps, "host_threads": 1, "mappers": nm, "hits_equal_resident_leg": True},
+                    "e2e": {"value": e, "unit": UNIT, "ms_per_step": L["ms_e2e"] / leg_steps, "host_threads": 1, "mappers": 1, "chunks_in_flight": nm, "hits_equal_resident_leg": True},
                     "roofline": roofline(L, lops, lns, True),
                     "ksw": {"dp_jobs_per_pair": L["st"]["dp_jobs"] / (B * nchunks), "dp_jobs_per_s": L["st"]["dp_jobs"] / ksw_s if ksw_s > 0 else None,
                             "general_kernel_share": L["st"]["dp_jobs_general"] / max(1, L["st"]["dp_jobs"]),
@@ -517,7 +534,7 @@ def main():
                 line["legs"]["perfect_hash"] = {
                     "config": f"configs[3]: the same {index.num_transcripts}-transcript transcriptome indexed with -p (BooPHF minimum perfect hash + FrugalBooMap), same reads, quasimap default flags",
                     "value": v, "unit": UNIT, "ms_per_step": L["ms_res"] / leg_steps, "steps": leg_steps, "n_gpus": world,
-                    "e2e": {"value": e, "unit": UNIT, "ms_per_step": L["ms_e2e"] / leg_steps, "host_threads": 1, "mappers": nm, "hits_equal_resident_leg": True},
+                    "e2e": {"value": e, "unit": UNIT, "ms_per_step": L["ms_e2e"] / leg_steps, "host_threads": 1, "mappers": 1, "chunks_in_flight": nm, "hits_equal_resident_leg": True},
                     "sa_lookup_ms_per_launch": L["st"]["sa"] / nchunks,
                     "stage_ms_per_chunk": {k: L["st"][k] / nchunks for k in STAGES},
                     "index_image_bytes": pindex.device_bytes, "dense_index_image_bytes": index.device_bytes,

@@ -13,6 +13,7 @@ There is no CPU fallback: if the CUDA library is missing or no device is present
 """
 from __future__ import annotations
 
+import collections
 import ctypes as C
 import os
 from dataclasses import dataclass
@@ -276,7 +277,7 @@ class Mapper:
         _check(lib().rapmap_cuda_mapper_create(index._h, C.byref(self.opts), max_batch, max_read_len, C.byref(self._h)))
         self._hits_buf = None
         self._off_buf = None
-        self._pending = None
+        self._pending = collections.deque()
 
     def _read_batch(self, seq1, seq2, n, fixed_len, off1, off2, location) -> ReadBatch:
         rb = ReadBatch()
@@ -294,26 +295,31 @@ class Mapper:
         """Maps one chunk. ``seq*``: uint8 numpy arrays (host) or torch CUDA tensors (location=LOC_DEVICE).
         Fixed-length reads: row-major ``n x fixed_len``; otherwise pass uint64 offset arrays of n+1 entries.
         Without ``hits_out`` the result arrays are views of buffers the mapper reuses: copy them before the next call."""
+        if self._pending:
+            raise RapMapCudaError(ERR_ARG, "map_batch with batches in flight: collect them with wait() first")
         self.map_batch_async(seq1, seq2, n, fixed_len, off1, off2, location, hits_out, offsets_out, out_location, capacity)
         try:
             return self.wait()
         except RapMapCudaError as e:
             if e.code == ERR_CAPACITY and hits_out is None:
-                self._hits_buf = np.empty(int(self._pending[1].num_hits) + 1024, dtype=HIT_DTYPE)
-                self._pending = None
+                self._hits_buf = np.empty(int(self._last_hb.num_hits) + 1024, dtype=HIT_DTYPE)
                 return self.map_batch(seq1, seq2, n, fixed_len, off1, off2, location, None, None, out_location, None)
             raise
 
     def map_batch_async(self, seq1, seq2=None, n: Optional[int] = None, fixed_len: int = 0, off1=None, off2=None,
                         location: int = LOC_HOST, hits_out=None, offsets_out=None, out_location: int = LOC_HOST, capacity: Optional[int] = None) -> None:
-        """rapmap_cuda_map_batch_async: enqueues the chunk on the mapper's stream and returns; :meth:`wait` collects it.
-        The input and output buffers must stay alive and untouched until then (the mapper keeps references)."""
+        """rapmap_cuda_map_batch_async: enqueues the chunk and returns; :meth:`wait` collects the OLDEST chunk in flight (a
+        mapper keeps up to two: one computes while the next one's reads come in and the previous one's results go out).
+        The input and output buffers must stay alive and untouched until then (the mapper keeps references); with chunks in
+        flight pass your own ``hits_out`` / ``offsets_out`` per chunk."""
         if n is None:
             n = (len(off1) - 1) if off1 is not None else int(np.prod(seq1.shape)) // fixed_len
         rb = self._read_batch(seq1, seq2, n, fixed_len, off1, off2, location)
         hb = HitBatch()
         hb.location = out_location
         if hits_out is None:
+            if self._pending:
+                raise RapMapCudaError(ERR_ARG, "chunks in flight need caller-provided output buffers")
             cap = capacity if capacity is not None else max(1024, 8 * n)
             if self._hits_buf is None or len(self._hits_buf) < cap:
                 self._hits_buf = np.empty(cap, dtype=HIT_DTYPE)
@@ -323,19 +329,20 @@ class Mapper:
         hb.hits = _as_ptr(hits_out)
         hb.hits_capacity = capacity if capacity is not None else (len(hits_out) if isinstance(hits_out, np.ndarray) else hits_out.numel() // 28)
         hb.pair_offsets = _as_ptr(offsets_out)
-        self._pending = (rb, hb, hits_out, offsets_out, n, (seq1, seq2, off1, off2))
-        rc = lib().rapmap_cuda_map_batch_async(self._h, C.byref(rb), C.byref(hb))
-        if rc != OK:
-            self._pending = None
-        _check(rc)
+        _check(lib().rapmap_cuda_map_batch_async(self._h, C.byref(rb), C.byref(hb)))
+        self._pending.append((rb, hb, hits_out, offsets_out, n, (seq1, seq2, off1, off2)))
+
+    @property
+    def in_flight(self) -> int:
+        return len(self._pending)
 
     def wait(self) -> BatchResult:
-        """rapmap_cuda_mapper_wait: blocks until the chunk in flight is mapped and its result is in the output buffers."""
-        if self._pending is None:
+        """rapmap_cuda_mapper_wait: blocks until the oldest chunk in flight is mapped and its result is in its output buffers."""
+        if not self._pending:
             raise RapMapCudaError(ERR_ARG, "no batch in flight")
-        rb, hb, hits_out, offsets_out, n, _keep = self._pending
+        rb, hb, hits_out, offsets_out, n, _keep = self._pending.popleft()
+        self._last_hb = hb
         _check(lib().rapmap_cuda_mapper_wait(self._h))
-        self._pending = None
         nh = int(hb.num_hits)
         if isinstance(hits_out, np.ndarray):
             return BatchResult(hits_out[:nh], offsets_out[: n + 1], np.array(list(hb.counters), dtype=np.uint64), nh)

@@ -134,6 +134,43 @@ __global__ void build_text2_kernel(const uint8_t* text, uint64_t n, TextRec* rec
   }
 }
 
+// Result copy-out without a host round trip: the number of records is only known on the device, so a kernel moves them -
+// to the caller's device buffer, or straight into its pinned host buffer over PCIe (16-byte stores, coalesced).  Nothing is
+// written when the records do not fit `cap` (the host reports RAPMAP_ERR_CAPACITY with the count).
+__global__ void __launch_bounds__(256) copy_out_kernel(const rapmap_hit_t* __restrict__ src, rapmap_hit_t* __restrict__ dst, uint64_t cap,
+                                                       const uint64_t* __restrict__ totalPtr, const uint64_t* __restrict__ offSrc, uint64_t* __restrict__ offDst,
+                                                       uint64_t nOff) {
+  const uint64_t tid = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x, stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  for (uint64_t i = tid; i < nOff; i += stride) offDst[i] = offSrc[i];
+  const uint64_t total = *totalPtr;
+  if (total > cap || dst == nullptr) return;
+  const uint64_t words = total * (sizeof(rapmap_hit_t) / 4);
+  if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    const uint64_t n4 = words / 4;
+    for (uint64_t i = tid; i < n4; i += stride) d4[i] = s4[i];
+    const uint32_t* s1 = reinterpret_cast<const uint32_t*>(src);
+    uint32_t* d1 = reinterpret_cast<uint32_t*>(dst);
+    for (uint64_t i = n4 * 4 + tid; i < words; i += stride) d1[i] = s1[i];
+  } else {
+    const uint32_t* s1 = reinterpret_cast<const uint32_t*>(src);
+    uint32_t* d1 = reinterpret_cast<uint32_t*>(dst);
+    for (uint64_t i = tid; i < words; i += stride) d1[i] = s1[i];
+  }
+}
+
+// Device-visible alias of a caller buffer: device memory as it is, pinned / registered host memory through its mapped
+// address; nullptr for pageable host memory (then the copy needs cudaMemcpyAsync and a host round trip for the size).
+void* deviceAlias(const void* p, int location) {
+  if (!p) return nullptr;
+  if (location == RAPMAP_LOC_DEVICE) return const_cast<void*>(p);
+  cudaPointerAttributes a{};
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (a.type == cudaMemoryTypeHost && a.devicePointer) return a.devicePointer;
+  return nullptr;
+}
+
 DeviceIndex viewOf(const uint8_t* blob, const ImageHeader& h) {
   DeviceIndex d;
   d.SA = reinterpret_cast<const int32_t*>(blob + h.offSA);
@@ -174,18 +211,49 @@ struct rapmap_cuda_index {
   std::vector<int32_t> lens;
 };
 
+// Batches a mapper keeps in flight: while batch c computes, batch c+1's reads come in over PCIe and batch c-1's results go
+// out - on three streams of ONE mapper, so the kernels of consecutive batches never compete for the SMs (three mappers on
+// three streams lost a quarter of the device-resident rate to that, profiles/r02d_e2e_diag.txt).
+static constexpr int kDepth = 2;
+
+// pinned block the compute stream writes at the end of an attempt; the host reads it after the batch's synchronisation
+struct StageBlock { uint32_t ctl[4]; uint64_t mergeTotal; uint64_t selTotal; uint32_t dpJobs[2]; Counters5 counters; };
+
+struct BatchSlot {
+  // reads staged from the host
+  uint8_t* dSeq[2]{nullptr, nullptr};
+  uint64_t* dOff[2]{nullptr, nullptr};
+  // results (per slot: batch c+1 computes while batch c goes out)
+  uint64_t* dPairOff{nullptr};
+  rapmap_hit_t* dHits{nullptr};
+  rapmap_hit_t* dSelOut{nullptr};   // survivors of the selective-alignment filter
+  StageBlock* hStage{nullptr};
+  cudaEvent_t ev[12]{};             // stage boundaries (timing)
+  cudaEvent_t evIn{nullptr}, evCompute{nullptr};
+  cudaEvent_t evOut{nullptr};       // cudaEventBlockingSync: a waiting host thread sleeps instead of spinning
+  BatchView view{};
+  bool paired{false};
+  bool inFlight{false};
+  bool rerun{false};                // an arena was re-allocated under this batch: its attempt has to be repeated
+  rapmap_hit_batch_t* out{nullptr};
+  bool directOut{false};            // results leave by copy_out_kernel (device or pinned host buffers)
+  void* outHitsDev{nullptr};
+  void* outOffDev{nullptr};
+  uint32_t launches{0};
+};
+
 struct rapmap_cuda_mapper {
   const rapmap_cuda_index* idx{nullptr};
   rapmap_cuda_opts_t opts{};
   DevOpts dopts{};
   uint64_t maxBatch{0};
   uint32_t maxReadLen{0};
-  cudaStream_t stream{nullptr};
+  cudaStream_t stream{nullptr};      // compute
+  cudaStream_t sIn{nullptr}, sOut{nullptr};
   int numSMs{0};
-  // staging of host reads
-  uint8_t* dSeq[2]{nullptr, nullptr};
-  uint64_t* dOff[2]{nullptr, nullptr};
   uint64_t seqCap{0};
+  BatchSlot slots[kDepth];
+  uint64_t submitted{0}, collected{0};  // batch sequence numbers: slot = seq % kDepth
   // stage 1: SA lookup (lane per read)
   ReadSummary* dSumm{nullptr};
   IntervalRec* dIvArena{nullptr};
@@ -218,8 +286,6 @@ struct rapmap_cuda_mapper {
   int gridLaneMap{0};
   // stage 3: mate merge
   uint32_t* dPairCount{nullptr};
-  uint64_t* dPairOff{nullptr};
-  rapmap_hit_t* dHits{nullptr};
   uint64_t hitsCap{0};
   // stage 4: selective alignment
   SelAlnWork selaln{};
@@ -229,18 +295,8 @@ struct rapmap_cuda_mapper {
   // control words: [0] interval cursor, [1] qa cursor, [2] pos cursor, [3] status, [4] read cursor of the lane kernel
   uint32_t* dCtl{nullptr};
   Counters5* dCounters{nullptr};
-  // pinned block the stream writes at the end of an attempt; the host reads it after ONE synchronisation
-  struct Stage { uint32_t ctl[4]; uint64_t mergeTotal; uint64_t selTotal; uint32_t dpJobs[2]; Counters5 counters; }* hStage{nullptr};
-  cudaEvent_t ev[11]{};
-  cudaEvent_t evDone{nullptr};   // cudaEventBlockingSync: a waiting host thread sleeps instead of spinning
   rapmap_cuda_timing_t timing{};
-  BatchView lastView{};
   uint64_t lastReads{0};
-  // the batch in flight between map_batch_async and mapper_wait
-  bool inFlight{false};
-  bool paired{false};
-  rapmap_hit_batch_t* pendingOut{nullptr};
-  uint32_t launches{0};
 };
 
 static constexpr int kWarps = 8;
@@ -571,16 +627,23 @@ static int deriveOpts(const rapmap_cuda_opts_t& o, DevOpts& d) {
 }
 
 static void freeMapperBuffers(rapmap_cuda_mapper* m) {
-  for (int i = 0; i < 2; ++i) { cudaFree(m->dSeq[i]); cudaFree(m->dOff[i]); }
+  for (auto& sl : m->slots) {
+    for (int i = 0; i < 2; ++i) { cudaFree(sl.dSeq[i]); cudaFree(sl.dOff[i]); }
+    cudaFree(sl.dPairOff); cudaFree(sl.dHits); cudaFree(sl.dSelOut);
+    if (sl.hStage) cudaFreeHost(sl.hStage);
+    for (auto& e : sl.ev) if (e) cudaEventDestroy(e);
+    if (sl.evIn) cudaEventDestroy(sl.evIn);
+    if (sl.evCompute) cudaEventDestroy(sl.evCompute);
+    if (sl.evOut) cudaEventDestroy(sl.evOut);
+  }
   cudaFree(m->dSumm); cudaFree(m->dIvArena); cudaFree(m->dQSumm); cudaFree(m->dQaArena); cudaFree(m->dPosPool);
-  cudaFree(m->dScratch); cudaFree(m->dPairCount); cudaFree(m->dPairOff); cudaFree(m->dHits); cudaFree(m->dCubTemp);
+  cudaFree(m->dScratch); cudaFree(m->dPairCount); cudaFree(m->dCubTemp);
   cudaFree(m->dCtl); cudaFree(m->dCounters);
   cudaFree(m->dPacked); cudaFree(m->dKmask); cudaFree(m->dOrder); cudaFree(m->dClassCtl); cudaFree(m->dIvScratch); cudaFree(m->dVoteScratch);
   selAlnFree(m->selaln);
-  if (m->hStage) cudaFreeHost(m->hStage);
-  for (auto& e : m->ev) if (e) cudaEventDestroy(e);
-  if (m->evDone) cudaEventDestroy(m->evDone);
   if (m->stream) cudaStreamDestroy(m->stream);
+  if (m->sIn) cudaStreamDestroy(m->sIn);
+  if (m->sOut) cudaStreamDestroy(m->sOut);
 }
 
 // RAPMAP_B200_TINY_ARENAS=1 (tests only): every growable device work area starts far too small, so that the first batch
@@ -610,13 +673,24 @@ static int mapperCreateImpl(const rapmap_cuda_index_t* idx, const rapmap_cuda_op
   M_TRY(cudaGetDeviceProperties(&prop, idx->device));
   m->numSMs = prop.multiProcessorCount;
   M_TRY(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
-  for (auto& e : m->ev) M_TRY(cudaEventCreate(&e));
-  M_TRY(cudaEventCreateWithFlags(&m->evDone, cudaEventBlockingSync | cudaEventDisableTiming));
+  M_TRY(cudaStreamCreateWithFlags(&m->sIn, cudaStreamNonBlocking));
+  M_TRY(cudaStreamCreateWithFlags(&m->sOut, cudaStreamNonBlocking));
   const uint64_t R = 2 * max_batch;
   m->seqCap = max_batch * max_read_len;
-  for (int i = 0; i < 2; ++i) {
-    M_TRY(cudaMalloc(&m->dSeq[i], m->seqCap + 16));
-    M_TRY(cudaMalloc(&m->dOff[i], (max_batch + 1) * 8));
+  m->hitsCap = tiny ? 8 : max_batch * 6 + 1024;
+  for (auto& sl : m->slots) {
+    for (auto& e : sl.ev) M_TRY(cudaEventCreate(&e));
+    M_TRY(cudaEventCreateWithFlags(&sl.evIn, cudaEventDisableTiming));
+    M_TRY(cudaEventCreateWithFlags(&sl.evCompute, cudaEventDisableTiming));
+    M_TRY(cudaEventCreateWithFlags(&sl.evOut, cudaEventBlockingSync | cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) {
+      M_TRY(cudaMalloc(&sl.dSeq[i], m->seqCap + 16));
+      M_TRY(cudaMalloc(&sl.dOff[i], (max_batch + 1) * 8));
+    }
+    M_TRY(cudaMalloc(&sl.dPairOff, (max_batch + 1) * 8));
+    M_TRY(cudaMalloc(&sl.dHits, m->hitsCap * sizeof(rapmap_hit_t)));
+    if (opts->sel_aln) M_TRY(cudaMalloc(&sl.dSelOut, m->hitsCap * sizeof(rapmap_hit_t)));
+    M_TRY(cudaMallocHost(&sl.hStage, sizeof(StageBlock)));
   }
   M_TRY(cudaMalloc(&m->dSumm, R * sizeof(ReadSummary)));
   M_TRY(cudaMalloc(&m->dQSumm, R * sizeof(QASummary)));
@@ -626,15 +700,11 @@ static int mapperCreateImpl(const rapmap_cuda_index_t* idx, const rapmap_cuda_op
   m->posCap = (needPos && !tiny) ? static_cast<uint32_t>(std::min<uint64_t>(R * 12 + 1024, 0xFFFFFFF0ull)) : 16;
   M_TRY(cudaMalloc(&m->dPosPool, static_cast<uint64_t>(m->posCap) * 4));
   M_TRY(cudaMalloc(&m->dPairCount, (max_batch + 1) * 4));
-  M_TRY(cudaMalloc(&m->dPairOff, (max_batch + 1) * 8));
-  m->hitsCap = tiny ? 8 : max_batch * 6 + 1024;
-  M_TRY(cudaMalloc(&m->dHits, m->hitsCap * sizeof(rapmap_hit_t)));
   M_TRY(cudaMalloc(&m->dCtl, 8 * 4));
   M_TRY(cudaMalloc(&m->dCounters, sizeof(Counters5)));
-  M_TRY(cudaMallocHost(&m->hStage, sizeof(*m->hStage)));
   {
     cub::TransformInputIterator<uint64_t, CastU64, uint32_t*> it(m->dPairCount, CastU64());
-    M_TRY(cub::DeviceScan::ExclusiveSum(nullptr, m->cubTempBytes, it, m->dPairOff, static_cast<int>(max_batch + 1)));
+    M_TRY(cub::DeviceScan::ExclusiveSum(nullptr, m->cubTempBytes, it, m->slots[0].dPairOff, static_cast<int>(max_batch + 1)));
     M_TRY(cudaMalloc(&m->dCubTemp, m->cubTempBytes + 16));
   }
   // ---- launch geometry: persistent grids, whole multiples of the SM count
@@ -724,20 +794,24 @@ static int growU32(void** p, uint32_t& cap, uint64_t need, size_t elem) {
   return RAPMAP_OK;
 }
 
-// Enqueues one attempt at the batch on the mapper's stream: K0 pack, K1 SA lookup, K2 hit resolution, K3 merge
-// (count -> scan -> write), K4 selective alignment, then the copy of the control block to pinned host memory.  Nothing
-// here waits for the device: every kernel launches against the CURRENT capacities and raises a status bit instead of
-// writing past them (finishBatch grows what overflowed and calls this again).
-static int enqueueAttempt(rapmap_cuda_mapper* m) {
+// Enqueues one attempt at a batch: K0 pack / k-mer masks / work classes, K1 SA lookup, K2 hit resolution, K3 merge
+// (count -> scan -> write), K4 selective alignment and the copy of the control block to pinned host memory on the compute
+// stream, then the result copy-out on the output stream.  Nothing here waits for the device: every kernel launches
+// against the CURRENT capacities and raises a status bit instead of writing past them (finishBatch grows what overflowed
+// and calls this again).
+static int enqueueAttempt(rapmap_cuda_mapper* m, BatchSlot& sl) {
   cudaStream_t st = m->stream;
-  const BatchView& bv = m->lastView;
+  const BatchView& bv = sl.view;
   const uint64_t n = bv.n;
-  const bool paired = m->paired;
+  const bool paired = sl.paired;
+  CU_TRY(cudaStreamWaitEvent(st, sl.evIn, 0));
   CU_TRY(cudaMemsetAsync(m->dCtl, 0, 32, st));
   CU_TRY(cudaMemsetAsync(m->dCounters, 0, sizeof(Counters5), st));
+  CU_TRY(cudaEventRecord(sl.ev[11], st));
   // ---- kernel 1: SA lookup
   LaneParams lp{};
-  lp.ix = m->idx->view; lp.reads = bv; lp.opts = m->dopts; lp.maxReadLen = m->maxReadLen; lp.nw = m->laneWords; lp.packed = m->dPacked; lp.kmask = m->dKmask; lp.maskChunks = (m->pmax + 7) / 8; lp.classCtl = m->dClassCtl; lp.order = m->dOrder;
+  lp.ix = m->idx->view; lp.reads = bv; lp.opts = m->dopts; lp.maxReadLen = m->maxReadLen; lp.nw = m->laneWords; lp.packed = m->dPacked;
+  lp.kmask = m->dKmask; lp.maskChunks = (m->pmax + 7) / 8; lp.classCtl = m->dClassCtl; lp.order = m->dOrder;
   lp.summ = m->dSumm; lp.arena = m->dIvArena; lp.arenaCap = m->ivCap; lp.arenaCursor = m->dCtl + 0; lp.status = m->dCtl + 3;
   lp.ivScratch = m->dIvScratch; lp.ivStride = m->ivStride; lp.voteScratch = m->dVoteScratch; lp.voteWords = m->voteWords; lp.readCursor = m->dCtl + 4;
   const int g0 = static_cast<int>(std::min<uint64_t>(static_cast<uint64_t>(m->numSMs) * 8, (bv.numReads * m->laneWords + 255) / 256));
@@ -748,12 +822,11 @@ static int enqueueAttempt(rapmap_cuda_mapper* m) {
   const int g0c = static_cast<int>(std::min<uint64_t>(static_cast<uint64_t>(m->numSMs) * 8, (bv.numReads + 255) / 256));
   work_class_hist_kernel<<<g0c, 256, 0, st>>>(lp);
   work_class_scatter_kernel<<<g0c, 256, 0, st>>>(lp);
-  m->launches += 3;
-  CU_TRY(cudaEventRecord(m->ev[8], st));
+  CU_TRY(cudaEventRecord(sl.ev[8], st));
   const int g1 = static_cast<int>(std::min<uint64_t>(m->gridLane, (bv.numReads + kLaneThreads - 1) / kLaneThreads));
   m->laneKernel<<<g1, kLaneThreads, m->laneSmem, st>>>(lp);
-  m->launches += 2;
-  CU_TRY(cudaEventRecord(m->ev[2], st));
+  sl.launches += 5;
+  CU_TRY(cudaEventRecord(sl.ev[2], st));
   // ---- kernel 2: hit resolution
   MapParams mp{};
   mp.ix = m->idx->view; mp.opts = m->dopts; mp.numReads = bv.numReads; mp.numPairs = n; mp.pairedInput = paired ? 1 : 0;
@@ -764,23 +837,23 @@ static int enqueueAttempt(rapmap_cuda_mapper* m) {
   if (m->chainLaneMap) {  // -s / -f: thread-per-read with chaining and position lists; the marked rest below
     const int gl = static_cast<int>(std::min<uint64_t>(m->gridLaneMap, (bv.numReads + kChainLaneThreads - 1) / kChainLaneThreads));
     hits_to_mappings_chain_lane_kernel<kChainLaneThreads, kChainLaneCap><<<gl, kChainLaneThreads, chainLaneStride(kChainLaneCap) * kChainLaneThreads, st>>>(mp);
-    ++m->launches;
+    ++sl.launches;
     mp.skipDone = 1;
   }
   if (m->laneMap) {  // small reads thread-per-read; the rest (marked) by the warp-per-read kernel below
     const int gl = static_cast<int>(std::min<uint64_t>(m->gridLaneMap, (bv.numReads + kMapLaneThreads - 1) / kMapLaneThreads));
     hits_to_mappings_lane_kernel<kMapLaneThreads, kMapLaneCap><<<gl, kMapLaneThreads, kMapLaneSmem, st>>>(mp);
-    ++m->launches;
+    ++sl.launches;
     mp.skipDone = 1;
   }
   const int g2 = static_cast<int>(std::min<uint64_t>(m->gridMap, (bv.numReads + kWarps - 1) / kWarps));
   hits_to_mappings_kernel<kWarps><<<g2, kWarps * 32, m->mapSmem, st>>>(mp);
-  ++m->launches;
-  CU_TRY(cudaEventRecord(m->ev[3], st));
+  ++sl.launches;
+  CU_TRY(cudaEventRecord(sl.ev[3], st));
   // ---- kernel 3: mate merge: count -> exclusive scan -> write at the final, input-ordered offsets
   MergeParams gp{};
   gp.opts = m->dopts; gp.numPairs = n; gp.pairedInput = paired ? 1 : 0; gp.qsumm = m->dQSumm; gp.qaArena = m->dQaArena; gp.summ = m->dSumm;
-  gp.pairCount = m->dPairCount; gp.pairOffset = m->dPairOff; gp.hits = m->dHits; gp.hitsCap = m->hitsCap; gp.counters = m->dCounters;
+  gp.pairCount = m->dPairCount; gp.pairOffset = sl.dPairOff; gp.hits = sl.dHits; gp.hitsCap = m->hitsCap; gp.counters = m->dCounters;
   gp.posPool = m->dPosPool;
   gp.reads = bv; gp.text = m->idx->view.text; gp.txpOffsets = m->idx->view.txpOffsets; gp.txpLens = m->idx->view.txpLens;
   const int g3 = static_cast<int>(std::min<uint64_t>(static_cast<uint64_t>(m->numSMs) * 8, (n + 255) / 256));
@@ -788,49 +861,65 @@ static int enqueueAttempt(rapmap_cuda_mapper* m) {
   CU_TRY(cudaMemsetAsync(m->dPairCount + n, 0, 4, st));
   if (fuzzy) merge_count_kernel<true><<<g3, 256, 0, st>>>(gp);
   else merge_count_kernel<false><<<g3, 256, 0, st>>>(gp);
-  ++m->launches;
+  ++sl.launches;
   {
     cub::TransformInputIterator<uint64_t, CastU64, uint32_t*> it(m->dPairCount, CastU64());
     size_t tb = m->cubTempBytes;
-    CU_TRY(cub::DeviceScan::ExclusiveSum(m->dCubTemp, tb, it, m->dPairOff, static_cast<int>(n + 1), st));
+    CU_TRY(cub::DeviceScan::ExclusiveSum(m->dCubTemp, tb, it, sl.dPairOff, static_cast<int>(n + 1), st));
   }
-  CU_TRY(cudaMemcpyAsync(&m->hStage->mergeTotal, m->dPairOff + n, 8, cudaMemcpyDeviceToHost, st));
-  CU_TRY(cudaEventRecord(m->ev[4], st));
+  CU_TRY(cudaMemcpyAsync(&sl.hStage->mergeTotal, sl.dPairOff + n, 8, cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaEventRecord(sl.ev[4], st));
   // optimistic: written against hitsCap (a pair whose slice would pass it is skipped; the host sees mergeTotal > hitsCap)
   if (fuzzy) merge_write_kernel<true><<<g3, 256, 0, st>>>(gp);
   else merge_write_kernel<false><<<g3, 256, 0, st>>>(gp);
-  ++m->launches;
-  CU_TRY(cudaEventRecord(m->ev[5], st));
-  // ---- selective alignment (ksw2 scoring + score filter): survivors to selaln.outHits, dPairOff rewritten in place
-  m->hStage->selTotal = 0; m->hStage->dpJobs[0] = 0; m->hStage->dpJobs[1] = 0;
+  ++sl.launches;
+  CU_TRY(cudaEventRecord(sl.ev[5], st));
+  // ---- selective alignment (ksw2 scoring + score filter): survivors to the slot's dSelOut, dPairOff rewritten in place
+  sl.hStage->selTotal = 0; sl.hStage->dpJobs[0] = 0; sl.hStage->dpJobs[1] = 0;
   if (m->dopts.selAln) {
-    int rc = selAlnEnqueue(m->selaln, m->selLaunch, m->idx->view, m->dopts, bv, n, paired, m->dHits, m->dPairOff, m->hitsCap, m->dCubTemp, m->cubTempBytes,
-                           m->numSMs, st, &m->launches, &m->hStage->selTotal, m->hStage->dpJobs, m->ev[9], m->ev[10], g_err);
+    int rc = selAlnEnqueue(m->selaln, m->selLaunch, m->idx->view, m->dopts, bv, n, paired, sl.dHits, sl.dSelOut, sl.dPairOff, m->hitsCap, m->dCubTemp,
+                           m->cubTempBytes, m->numSMs, st, &sl.launches, &sl.hStage->selTotal, sl.hStage->dpJobs, sl.ev[9], sl.ev[10], g_err);
     if (rc) return rc;
   }
-  CU_TRY(cudaEventRecord(m->ev[6], st));
-  CU_TRY(cudaMemcpyAsync(m->hStage->ctl, m->dCtl, 16, cudaMemcpyDeviceToHost, st));
-  CU_TRY(cudaMemcpyAsync(&m->hStage->counters, m->dCounters, sizeof(Counters5), cudaMemcpyDeviceToHost, st));
-  CU_TRY(cudaEventRecord(m->evDone, st));
+  CU_TRY(cudaEventRecord(sl.ev[6], st));
+  CU_TRY(cudaMemcpyAsync(sl.hStage->ctl, m->dCtl, 16, cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaMemcpyAsync(&sl.hStage->counters, m->dCounters, sizeof(Counters5), cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaEventRecord(sl.evCompute, st));
+  // ---- results out, on their own stream: the next batch computes meanwhile
+  CU_TRY(cudaStreamWaitEvent(m->sOut, sl.evCompute, 0));
+  if (sl.directOut) {
+    const rapmap_hit_t* src = m->dopts.selAln ? sl.dSelOut : sl.dHits;
+    // a small grid for PCIe: ~16k threads with a 16-byte store each cover the link's bandwidth-delay product and leave the
+    // SMs to the next batch's kernels
+    const int gco = sl.out->location == RAPMAP_LOC_DEVICE ? m->numSMs * 4 : 64;
+    copy_out_kernel<<<gco, 256, 0, m->sOut>>>(src, static_cast<rapmap_hit_t*>(sl.outHitsDev), sl.out->hits_capacity, sl.dPairOff + n, sl.dPairOff,
+                                               static_cast<uint64_t*>(sl.outOffDev), n + 1);
+    ++sl.launches;
+  }
+  CU_TRY(cudaEventRecord(sl.ev[7], m->sOut));
+  CU_TRY(cudaEventRecord(sl.evOut, m->sOut));
   return RAPMAP_OK;
 }
 
-// Host threads sleep on the blocking event for big batches (several mappers per process: spinning threads fight the
-// launching ones for cores); small batches spin, the wake-up latency would show.
-static cudaError_t waitAttempt(rapmap_cuda_mapper* m) {
-  if (m->lastView.n >= 32768) return cudaEventSynchronize(m->evDone);
-  return cudaStreamSynchronize(m->stream);
+// Host threads sleep on the blocking event for big batches (several ranks per box: spinning threads fight the launching
+// ones for cores); small batches spin, the wake-up latency would show.
+static cudaError_t waitSlot(rapmap_cuda_mapper* m, BatchSlot& sl) {
+  if (sl.view.n >= 32768) return cudaEventSynchronize(sl.evOut);
+  return cudaStreamSynchronize(m->sOut);
 }
 
 static int mapBatchAsyncImpl(rapmap_cuda_mapper_t* m, const rapmap_read_batch_t* reads, rapmap_hit_batch_t* out) {
   if (!m || !reads || !out) return fail(RAPMAP_ERR_ARG, "null argument");
-  if (m->inFlight) return fail(RAPMAP_ERR_ARG, "the mapper already has a batch in flight (call rapmap_cuda_mapper_wait first)");
-  m->pendingOut = out;
-  std::memset(&m->timing, 0, sizeof(m->timing));
+  if (m->submitted - m->collected >= static_cast<uint64_t>(kDepth))
+    return fail(RAPMAP_ERR_ARG, "the mapper already has 2 batches in flight (call rapmap_cuda_mapper_wait first)");
+  BatchSlot& sl = m->slots[m->submitted % kDepth];
+  sl.out = out;
+  sl.rerun = false;
+  sl.launches = 0;
   if (reads->n == 0) {
-    m->lastView = BatchView{};
-    m->lastReads = 0;
-    m->inFlight = true;
+    sl.view = BatchView{};
+    sl.inFlight = true;
+    ++m->submitted;
     return RAPMAP_OK;
   }
   if (reads->n > m->maxBatch) return fail(RAPMAP_ERR_ARG, "batch larger than the mapper's max_batch");
@@ -839,15 +928,14 @@ static int mapBatchAsyncImpl(rapmap_cuda_mapper_t* m, const rapmap_read_batch_t*
   if (reads->seq2 && ((reads->off1 == nullptr) != (reads->off2 == nullptr))) return fail(RAPMAP_ERR_ARG, "off1/off2 must both be set or both be null");
   if (!out->pair_offsets) return fail(RAPMAP_ERR_ARG, "pair_offsets is null");
   CU_TRY(cudaSetDevice(m->idx->device));
-  cudaStream_t st = m->stream;
   const uint64_t n = reads->n;
-  m->paired = reads->seq2 != nullptr;
+  sl.paired = reads->seq2 != nullptr;
 
-  // ---- reads to the device
-  CU_TRY(cudaEventRecord(m->ev[0], st));
+  // ---- reads to the device, on the input stream
+  CU_TRY(cudaEventRecord(sl.ev[0], m->sIn));
   BatchView bv{};
-  bv.n = n; bv.numReads = m->paired ? 2 * n : n; bv.fixedLen = reads->fixed_len;
-  for (int mate = 0; mate < (m->paired ? 2 : 1); ++mate) {
+  bv.n = n; bv.numReads = sl.paired ? 2 * n : n; bv.fixedLen = reads->fixed_len;
+  for (int mate = 0; mate < (sl.paired ? 2 : 1); ++mate) {
     const uint8_t* seq = mate ? reads->seq2 : reads->seq1;
     const uint64_t* off = mate ? reads->off2 : reads->off1;
     if (reads->location == RAPMAP_LOC_DEVICE) {
@@ -856,31 +944,39 @@ static int mapBatchAsyncImpl(rapmap_cuda_mapper_t* m, const rapmap_read_batch_t*
       uint64_t bytes = off ? off[n] - off[0] : n * reads->fixed_len;
       if (off && off[0] != 0) return fail(RAPMAP_ERR_ARG, "offsets must start at 0");
       if (bytes > m->seqCap) return fail(RAPMAP_ERR_ARG, "read bases exceed max_batch * max_read_len");
-      CU_TRY(cudaMemcpyAsync(m->dSeq[mate], seq, bytes, cudaMemcpyHostToDevice, st));
-      bv.seq[mate] = m->dSeq[mate];
-      if (off) { CU_TRY(cudaMemcpyAsync(m->dOff[mate], off, (n + 1) * 8, cudaMemcpyHostToDevice, st)); bv.off[mate] = m->dOff[mate]; }
+      CU_TRY(cudaMemcpyAsync(sl.dSeq[mate], seq, bytes, cudaMemcpyHostToDevice, m->sIn));
+      bv.seq[mate] = sl.dSeq[mate];
+      if (off) { CU_TRY(cudaMemcpyAsync(sl.dOff[mate], off, (n + 1) * 8, cudaMemcpyHostToDevice, m->sIn)); bv.off[mate] = sl.dOff[mate]; }
       else bv.off[mate] = nullptr;
     }
   }
-  m->lastView = bv;
-  m->lastReads = bv.numReads;
-  CU_TRY(cudaEventRecord(m->ev[1], st));
-  m->launches = 0;
-  int rc = enqueueAttempt(m);
+  sl.view = bv;
+  CU_TRY(cudaEventRecord(sl.ev[1], m->sIn));
+  CU_TRY(cudaEventRecord(sl.evIn, m->sIn));
+  sl.outHitsDev = deviceAlias(out->hits, out->location);
+  sl.outOffDev = deviceAlias(out->pair_offsets, out->location);
+  sl.directOut = sl.outOffDev != nullptr && (sl.outHitsDev != nullptr || out->hits == nullptr || out->hits_capacity == 0) &&
+                 (reinterpret_cast<uintptr_t>(sl.outOffDev) & 7) == 0 && (reinterpret_cast<uintptr_t>(sl.outHitsDev) & 3) == 0;
+  int rc = enqueueAttempt(m, sl);
   if (rc) return rc;
-  m->inFlight = true;
+  sl.inFlight = true;
+  ++m->submitted;
   return RAPMAP_OK;
 }
 
-// Waits for the attempt in flight; grows what overflowed and re-runs (deterministic: same batch, bigger arenas); then copies
-// the result to the caller's buffers.  Two host synchronisations in the common case: one for the control block, one for
-// the result copy whose size the control block gives.
+// Waits for the OLDEST batch in flight; grows what overflowed and re-runs (deterministic: same batch, bigger arenas).  With
+// device or pinned host output buffers the attempt has already moved the result out (copy_out_kernel): ONE host
+// synchronisation per batch.  Pageable host buffers take a cudaMemcpyAsync of the now known size and a second one.
 static int mapperWaitImpl(rapmap_cuda_mapper_t* m) {
   if (!m) return fail(RAPMAP_ERR_ARG, "null argument");
-  if (!m->inFlight) return fail(RAPMAP_ERR_ARG, "no batch in flight");
-  m->inFlight = false;
-  rapmap_hit_batch_t* out = m->pendingOut;
-  const uint64_t n = m->lastView.n;
+  if (m->submitted == m->collected) return fail(RAPMAP_ERR_ARG, "no batch in flight");
+  BatchSlot& sl = m->slots[m->collected % kDepth];
+  ++m->collected;
+  sl.inFlight = false;
+  rapmap_hit_batch_t* out = sl.out;
+  std::memset(&m->timing, 0, sizeof(m->timing));
+  const uint64_t n = sl.view.n;
+  m->lastReads = sl.view.numReads;
   if (n == 0) {
     out->num_hits = 0;
     std::memset(out->counters, 0, sizeof(out->counters));
@@ -888,26 +984,36 @@ static int mapperWaitImpl(rapmap_cuda_mapper_t* m) {
     return RAPMAP_OK;
   }
   CU_TRY(cudaSetDevice(m->idx->device));
-  cudaStream_t st = m->stream;
   uint32_t retries = 0;
   uint64_t total = 0;
   for (;; ++retries) {
-    CU_TRY(waitAttempt(m));
+    CU_TRY(waitSlot(m, sl));
     CU_TRY(cudaGetLastError());
-    if (retries > 8) return fail(RAPMAP_ERR_CAPACITY, "device work arenas kept overflowing");
-    const uint32_t status = m->hStage->ctl[3];
+    if (retries > 10) return fail(RAPMAP_ERR_CAPACITY, "device work arenas kept overflowing");
+    if (sl.rerun) {  // an earlier batch's overflow re-allocated arenas while this one was queued behind it
+      sl.rerun = false;
+      int rc = enqueueAttempt(m, sl);
+      if (rc) return rc;
+      continue;
+    }
+    const uint32_t status = sl.hStage->ctl[3];
     if (status & kStatReadTooLong) return fail(RAPMAP_ERR_ARG, "a read is longer than the mapper's max_read_len");
-    bool again = false;
-    if (status & kStatIntervalArenaFull) { int rc = growU32(reinterpret_cast<void**>(&m->dIvArena), m->ivCap, m->hStage->ctl[0], sizeof(IntervalRec)); if (rc) return rc; again = true; }
+    const bool hitsFull = sl.hStage->mergeTotal > m->hitsCap;
+    if ((status & (kStatIntervalArenaFull | kStatIvScratchFull | kStatQAArenaFull | kStatPosPoolFull | kStatScratchFull)) == 0 && !hitsFull) break;
+    // ---- something overflowed: drain the device (a later batch may be running on the arenas), grow, repeat the attempt
+    CU_TRY(cudaStreamSynchronize(m->stream));
+    CU_TRY(cudaStreamSynchronize(m->sOut));
+    for (auto& other : m->slots)
+      if (&other != &sl && other.inFlight) other.rerun = true;
+    if (status & kStatIntervalArenaFull) { int rc = growU32(reinterpret_cast<void**>(&m->dIvArena), m->ivCap, sl.hStage->ctl[0], sizeof(IntervalRec)); if (rc) return rc; }
     if (status & kStatIvScratchFull) {  // a read produced more intervals per strand than the per-thread list holds: size it for the worst case
       if (m->ivStride >= m->pmax) return fail(RAPMAP_ERR_CAPACITY, "interval scratch overflow at worst-case size");
       cudaFree(m->dIvScratch); m->dIvScratch = nullptr;
       m->ivStride = m->pmax;
       CU_TRY(cudaMalloc(&m->dIvScratch, m->scratchSlotsK1 * 2 * m->ivStride * sizeof(IntervalRec)));
-      again = true;
     }
-    if (status & kStatQAArenaFull) { int rc = growU32(reinterpret_cast<void**>(&m->dQaArena), m->qaCap, m->hStage->ctl[1], sizeof(QARec)); if (rc) return rc; again = true; }
-    if (status & kStatPosPoolFull) { int rc = growU32(reinterpret_cast<void**>(&m->dPosPool), m->posCap, m->hStage->ctl[2], 4); if (rc) return rc; again = true; }
+    if (status & kStatQAArenaFull) { int rc = growU32(reinterpret_cast<void**>(&m->dQaArena), m->qaCap, sl.hStage->ctl[1], sizeof(QARec)); if (rc) return rc; }
+    if (status & kStatPosPoolFull) { int rc = growU32(reinterpret_cast<void**>(&m->dPosPool), m->posCap, sl.hStage->ctl[2], 4); if (rc) return rc; }
     if (status & kStatScratchFull) {
       // worst case of a strand: pmax intervals of < maxInterval entries, padded to a power of two
       uint64_t worst = 1;
@@ -920,57 +1026,60 @@ static int mapperWaitImpl(rapmap_cuda_mapper_t* m) {
       // fewer resident warps when the strips get large
       while (m->gridMap > m->numSMs && m->scratchStride * static_cast<uint64_t>(m->gridMap) * kWarps > (8ull << 30)) m->gridMap -= m->numSMs;
       CU_TRY(cudaMalloc(&m->dScratch, m->scratchStride * static_cast<uint64_t>(m->gridMap) * kWarps));
-      again = true;
     }
-    if (!again && m->hStage->mergeTotal > m->hitsCap) {  // the merge produced more records than the hit array holds
-      cudaFree(m->dHits); m->dHits = nullptr;
-      m->hitsCap = m->hStage->mergeTotal + m->hStage->mergeTotal / 4 + 1024;
-      CU_TRY(cudaMalloc(&m->dHits, m->hitsCap * sizeof(rapmap_hit_t)));
+    if (status == 0 && hitsFull) {  // the merge produced more records than the hit arrays hold
+      m->hitsCap = sl.hStage->mergeTotal + sl.hStage->mergeTotal / 4 + 1024;
+      for (auto& any : m->slots) {
+        cudaFree(any.dHits); any.dHits = nullptr;
+        CU_TRY(cudaMalloc(&any.dHits, m->hitsCap * sizeof(rapmap_hit_t)));
+        if (m->dopts.selAln) {
+          cudaFree(any.dSelOut); any.dSelOut = nullptr;
+          CU_TRY(cudaMalloc(&any.dSelOut, m->hitsCap * sizeof(rapmap_hit_t)));
+        }
+      }
       if (m->dopts.selAln) {
         cudaError_t e2 = selAlnReserve(m->selaln, m->hitsCap);
         if (e2 != cudaSuccess) return fail(RAPMAP_ERR_CUDA, std::string("selAlnReserve: ") + cudaGetErrorString(e2));
       }
-      again = true;
     }
-    if (!again) break;
-    int rc = enqueueAttempt(m);
+    int rc = enqueueAttempt(m, sl);
     if (rc) return rc;
   }
-  total = m->dopts.selAln ? m->hStage->selTotal : m->hStage->mergeTotal;
+  total = m->dopts.selAln ? sl.hStage->selTotal : sl.hStage->mergeTotal;
   // ---- results out
   out->num_hits = total;
   int rcOut = RAPMAP_OK;
   if (total > out->hits_capacity || (total > 0 && !out->hits)) {
     rcOut = fail(RAPMAP_ERR_CAPACITY, "hits_capacity too small for this batch (see num_hits)");
-  } else {
+  } else if (!sl.directOut) {  // pageable host buffers: the size is known now, the copy takes a second synchronisation
     cudaMemcpyKind kind = out->location == RAPMAP_LOC_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
-    const rapmap_hit_t* src = m->dopts.selAln ? m->selaln.outHits : m->dHits;
-    if (total > 0) CU_TRY(cudaMemcpyAsync(out->hits, src, total * sizeof(rapmap_hit_t), kind, st));
-    CU_TRY(cudaMemcpyAsync(out->pair_offsets, m->dPairOff, (n + 1) * 8, kind, st));
+    const rapmap_hit_t* src = m->dopts.selAln ? sl.dSelOut : sl.dHits;
+    if (total > 0) CU_TRY(cudaMemcpyAsync(out->hits, src, total * sizeof(rapmap_hit_t), kind, m->sOut));
+    CU_TRY(cudaMemcpyAsync(out->pair_offsets, sl.dPairOff, (n + 1) * 8, kind, m->sOut));
+    CU_TRY(cudaEventRecord(sl.ev[7], m->sOut));
+    CU_TRY(cudaEventRecord(sl.evOut, m->sOut));
+    CU_TRY(waitSlot(m, sl));
   }
-  CU_TRY(cudaEventRecord(m->ev[7], st));
-  CU_TRY(cudaEventRecord(m->evDone, st));
-  CU_TRY(waitAttempt(m));
-  for (int c = 0; c < 5; ++c) out->counters[c] = m->hStage->counters.v[c];
+  for (int c = 0; c < 5; ++c) out->counters[c] = sl.hStage->counters.v[c];
   // paired reads: totHits is taken after the score filter (reference src/RapMapSAMapper.cpp:702); unmated: before (:241-246)
-  if (m->dopts.selAln && m->paired) out->counters[3] = total;
-  auto ms = [&](int a, int b) { float t = 0; cudaEventElapsedTime(&t, m->ev[a], m->ev[b]); return t; };
-  m->timing.ms_h2d = ms(0, 1);
-  if (retries == 0) {  // the events of a re-run attempt do not line up with ev[0]/ev[1]: stage times are reported for clean batches only
-    m->timing.ms_pack_reads = ms(1, 8);
+  if (m->dopts.selAln && sl.paired) out->counters[3] = total;
+  auto ms = [&](int a, int b) { float t = 0; if (cudaEventElapsedTime(&t, sl.ev[a], sl.ev[b]) != cudaSuccess) { cudaGetLastError(); t = 0; } return t; };
+  if (retries == 0) {  // the events of a repeated attempt do not line up: stage times are reported for clean batches only
+    m->timing.ms_h2d = ms(0, 1);
+    m->timing.ms_pack_reads = ms(11, 8);
     m->timing.ms_sa_collect = ms(8, 2);
     m->timing.ms_hits_to_mappings = ms(2, 3);
     m->timing.ms_merge = ms(3, 5);
     m->timing.ms_sel_aln = ms(5, 6);
     m->timing.ms_ksw = m->dopts.selAln ? ms(9, 10) : 0.0f;
     m->timing.ms_d2h = ms(6, 7);
+    m->timing.ms_total = ms(0, 7);
   }
-  m->timing.ms_total = ms(0, 7);
-  m->timing.launches = m->launches;
+  m->timing.launches = sl.launches;
   m->timing.retries = retries;
-  m->timing.sa_intervals = m->hStage->ctl[0];
-  m->timing.dp_jobs = m->hStage->dpJobs[0];
-  m->timing.dp_jobs_general = m->hStage->dpJobs[1];
+  m->timing.sa_intervals = sl.hStage->ctl[0];
+  m->timing.dp_jobs = sl.hStage->dpJobs[0];
+  m->timing.dp_jobs_general = sl.hStage->dpJobs[1];
   return rcOut;
 }
 
@@ -982,7 +1091,7 @@ int rapmap_cuda_mapper_create(const rapmap_cuda_index_t* idx, const rapmap_cuda_
 void rapmap_cuda_mapper_free(rapmap_cuda_mapper_t* m) {
   if (!m) return;
   cudaSetDevice(m->idx->device);
-  if (m->inFlight) cudaStreamSynchronize(m->stream);
+  cudaStreamSynchronize(m->sIn); cudaStreamSynchronize(m->stream); cudaStreamSynchronize(m->sOut);
   freeMapperBuffers(m);
   delete m;
 }
@@ -1014,7 +1123,7 @@ void* rapmap_cuda_mapper_stream(const rapmap_cuda_mapper_t* m) { return m ? stat
 static int debugIntervalsImpl(rapmap_cuda_mapper_t* m, uint64_t read_index, rapmap_sa_interval_t* out, uint32_t cap, uint32_t* n_fwd,
                               uint32_t* n_rc, uint8_t* found_hit) {
   if (!m || !n_fwd || !n_rc || !found_hit) return fail(RAPMAP_ERR_ARG, "null argument");
-  if (m->inFlight) return fail(RAPMAP_ERR_ARG, "a batch is in flight");
+  if (m->submitted != m->collected) return fail(RAPMAP_ERR_ARG, "a batch is in flight");
   if (read_index >= m->lastReads) return fail(RAPMAP_ERR_ARG, "read index out of range of the last batch");
   CU_TRY(cudaSetDevice(m->idx->device));
   ReadSummary s;

@@ -55,7 +55,6 @@ struct SelAlnWork {
   int32_t* pairBest{nullptr};    // [maxBatch]
   uint32_t* outCount{nullptr};   // [maxBatch + 1]
   uint64_t* outOff{nullptr};     // [maxBatch + 1]
-  rapmap_hit_t* outHits{nullptr};
   uint64_t hitsCap{0};
   uint64_t maxBatch{0};
   uint32_t maxReadLen{0};
@@ -63,14 +62,14 @@ struct SelAlnWork {
 
 inline void selAlnFree(SelAlnWork& w) {
   cudaFree(w.taskScore); cudaFree(w.taskRef); cudaFree(w.taskHash); cudaFree(w.jobs); cudaFree(w.slowList); cudaFree(w.jobCursor); cudaFree(w.hitScore);
-  cudaFree(w.pairBest); cudaFree(w.outCount); cudaFree(w.outOff); cudaFree(w.outHits);
+  cudaFree(w.pairBest); cudaFree(w.outCount); cudaFree(w.outOff);
   w = SelAlnWork();
 }
 
 inline cudaError_t selAlnReserve(SelAlnWork& w, uint64_t hits) {
   if (hits <= w.hitsCap) return cudaSuccess;
-  cudaFree(w.taskScore); cudaFree(w.taskRef); cudaFree(w.taskHash); cudaFree(w.jobs); cudaFree(w.slowList); cudaFree(w.hitScore); cudaFree(w.outHits);
-  w.slowList = nullptr; w.taskScore = nullptr; w.taskRef = nullptr; w.taskHash = nullptr; w.jobs = nullptr; w.hitScore = nullptr; w.outHits = nullptr;
+  cudaFree(w.taskScore); cudaFree(w.taskRef); cudaFree(w.taskHash); cudaFree(w.jobs); cudaFree(w.slowList); cudaFree(w.hitScore);
+  w.slowList = nullptr; w.taskScore = nullptr; w.taskRef = nullptr; w.taskHash = nullptr; w.jobs = nullptr; w.hitScore = nullptr;
   uint64_t cap = hits;
   cudaError_t e;
   if ((e = cudaMalloc(&w.taskScore, cap * 2 * 4)) != cudaSuccess) return e;
@@ -79,7 +78,6 @@ inline cudaError_t selAlnReserve(SelAlnWork& w, uint64_t hits) {
   if ((e = cudaMalloc(&w.jobs, cap * 2 * sizeof(DPJob))) != cudaSuccess) return e;
   if ((e = cudaMalloc(&w.slowList, cap * 2 * 4)) != cudaSuccess) return e;
   if ((e = cudaMalloc(&w.hitScore, cap * 4)) != cudaSuccess) return e;
-  if ((e = cudaMalloc(&w.outHits, cap * sizeof(rapmap_hit_t))) != cudaSuccess) return e;
   w.hitsCap = cap;
   return cudaSuccess;
 }
@@ -849,18 +847,18 @@ inline int selAlnSetup(const SelAlnWork& w, SelAlnLaunch& L, std::string& err) {
 }
 
 // Enqueues the four stages on `st` (no host synchronisation): afterwards dPairOff holds the post-filter offsets,
-// w.outHits the surviving hits, *hTotal (pinned) their number and hJobs[0..1] the DP job counts (all / left to the
+// dOutHits the surviving hits, *hTotal (pinned) their number and hJobs[0..1] the DP job counts (all / left to the
 // general kernel).  The work arrays must hold hitsCap records (selAlnReserve); a batch whose merge produced more is
 // skipped by the kernels and re-run by the caller after growing.
 inline int selAlnEnqueue(SelAlnWork& w, const SelAlnLaunch& L, const DeviceIndex& ix, const DevOpts& opts, const BatchView& bv, uint64_t n, bool paired,
-                         rapmap_hit_t* dHits, uint64_t* dPairOff, uint64_t hitsCap, void* dCubTemp, size_t cubTempBytes, int numSMs, cudaStream_t st,
+                         rapmap_hit_t* dHits, rapmap_hit_t* dOutHits, uint64_t* dPairOff, uint64_t hitsCap, void* dCubTemp, size_t cubTempBytes, int numSMs, cudaStream_t st,
                          uint32_t* launches, uint64_t* hTotal, uint32_t* hJobs, cudaEvent_t evKsw0, cudaEvent_t evKsw1, std::string& err) {
   auto cuFail = [&](const char* what, cudaError_t e) { err = std::string(what) + ": " + cudaGetErrorString(e); return RAPMAP_ERR_CUDA; };
   cudaError_t e;
   SelAlnParams sp{};
   sp.ix = ix; sp.opts = opts; sp.reads = bv; sp.numPairs = n; sp.pairedInput = paired ? 1 : 0; sp.hits = dHits; sp.pairOff = dPairOff;
   sp.taskScore = w.taskScore; sp.taskRef = w.taskRef; sp.taskHash = w.taskHash; sp.jobs = w.jobs; sp.jobCursor = w.jobCursor; sp.hitScore = w.hitScore;
-  sp.pairBest = w.pairBest; sp.outCount = w.outCount; sp.outOff = w.outOff; sp.outHits = w.outHits; sp.maxReadLen = w.maxReadLen;
+  sp.pairBest = w.pairBest; sp.outCount = w.outCount; sp.outOff = w.outOff; sp.outHits = dOutHits; sp.maxReadLen = w.maxReadLen;
   sp.hitsCap = hitsCap < w.hitsCap ? hitsCap : w.hitsCap;
   if ((e = cudaMemsetAsync(w.jobCursor, 0, 8, st)) != cudaSuccess) return cuFail("memset", e);
   constexpr int W = 8;

@@ -446,34 +446,85 @@ def test_every_arena_overflow_retry_path(monkeypatch, flags):
 
 
 @pytest.mark.skipif(not have_ref(), reason="needs oracle/_ref to build the mid-size index")
-@pytest.mark.parametrize("sel", [False, True])
-def test_async_calls_one_thread_four_mappers(sel):
-    """rapmap_cuda_map_batch_async / rapmap_cuda_mapper_wait: one host thread keeps four mappers (streams) busy on one shared
-    index; every chunk equals the oracle's result for that chunk."""
+@pytest.mark.parametrize("sel,pinned", [(False, False), (True, False), (False, True), (True, True)])
+def test_async_pipeline_two_chunks_in_flight(sel, pinned):
+    """rapmap_cuda_map_batch_async / rapmap_cuda_mapper_wait: one host thread, two mappers on one shared index, each with two
+    chunks in flight (copy-in, kernels and copy-out of consecutive chunks overlap on the mapper's three streams); every
+    chunk equals the oracle's result for that chunk.  Pageable and pinned output buffers; a third chunk is refused."""
+    import torch
+
     idx_dir, tx = synth_index(2500)
     index = rb.Index(idx_dir, 0)
     opts = rb.default_opts(sel_aln=sel)
-    n, chunks = 5000, 12
+    n, chunks = 5000, 14
     data = [tx.reads(n, rseed=1000 + c) for c in range(chunks)]
     om = OracleMapper(idx_dir, opts)
     refs = [om.map(a, b, 100) for a, b in data]
-    mappers = [make_mapper(index, opts, n, 100) for _ in range(4)]
-    outs = [(np.empty(16 * n, dtype=rb.HIT_DTYPE), np.empty(n + 1, dtype=np.uint64)) for _ in range(4)]
-    pending = [None] * 4
+    mappers = [make_mapper(index, opts, n, 100) for _ in range(2)]
+
+    def buffers():
+        if pinned:
+            return torch.empty(16 * n * 28, dtype=torch.uint8).pin_memory(), torch.empty(n + 1, dtype=torch.int64).pin_memory()
+        return np.empty(16 * n, dtype=rb.HIT_DTYPE), np.empty(n + 1, dtype=np.uint64)
+
+    outs = [[buffers() for _ in range(2)] for _ in range(2)]
     done = {}
-    for c in range(chunks + 4):
-        k = c % 4
-        if pending[k] is not None:
-            r = mappers[k].wait()
-            done[pending[k]] = rb.BatchResult(r.hits.copy(), r.pair_offsets.copy(), r.counters, r.num_hits)
-            pending[k] = None
-        if c < chunks:
-            mappers[k].map_batch_async(data[c][0], data[c][1], n=n, fixed_len=100, hits_out=outs[k][0], offsets_out=outs[k][1])
-            pending[k] = c
+    order = [[], []]
+
+    def collect(k):
+        c = order[k].pop(0)
+        r = mappers[k].wait()
+        if pinned:
+            hits = r.hits.numpy()[: r.num_hits * 28].copy().view(rb.HIT_DTYPE)
+            offs = r.pair_offsets.numpy().copy().view(np.uint64)
+        else:
+            hits, offs = r.hits.copy(), r.pair_offsets.copy()
+        done[c] = rb.BatchResult(hits, offs, r.counters, r.num_hits)
+
+    for c in range(chunks):
+        k = c % 2
+        if mappers[k].in_flight == 2:
+            collect(k)
+        ho, oo = outs[k][(c // 2) % 2]
+        mappers[k].map_batch_async(data[c][0], data[c][1], n=n, fixed_len=100, hits_out=ho, offsets_out=oo, capacity=16 * n)
+        order[k].append(c)
+    with pytest.raises(rb.RapMapCudaError):  # a third chunk in flight is refused
+        ho, oo = buffers()
+        mappers[0].map_batch_async(data[0][0], data[0][1], n=n, fixed_len=100, hits_out=ho, offsets_out=oo, capacity=16 * n)
+    for k in range(2):
+        while mappers[k].in_flight:
+            collect(k)
     for c in range(chunks):
         assert_same(done[c], refs[c], f"chunk {c}")
     with pytest.raises(rb.RapMapCudaError):
         mappers[0].wait()  # nothing in flight
+
+
+@pytest.mark.skipif(not have_ref(), reason="needs oracle/_ref to build the mid-size index")
+def test_overflow_with_two_chunks_in_flight(monkeypatch):
+    """Tiny arenas AND two chunks in flight: the first chunk's overflow re-allocates the work areas under the second chunk,
+    whose attempt is then repeated; both must equal the oracle."""
+    monkeypatch.setenv("RAPMAP_B200_TINY_ARENAS", "1")
+    idx_dir, tx = synth_index(2500)
+    index = rb.Index(idx_dir, 0)
+    opts = rb.default_opts(sel_aln=True)
+    n = 6000
+    data = [tx.reads(n, rseed=77 + c) for c in range(3)]
+    mapper = make_mapper(index, opts, n, 100)
+    monkeypatch.delenv("RAPMAP_B200_TINY_ARENAS")
+    om = OracleMapper(idx_dir, opts)
+    outs = [(np.empty(16 * n, dtype=rb.HIT_DTYPE), np.empty(n + 1, dtype=np.uint64)) for _ in range(2)]
+    got = []
+    for c in range(3):
+        if mapper.in_flight == 2:
+            r = mapper.wait()
+            got.append(rb.BatchResult(r.hits.copy(), r.pair_offsets.copy(), r.counters, r.num_hits))
+        mapper.map_batch_async(data[c][0], data[c][1], n=n, fixed_len=100, hits_out=outs[c % 2][0], offsets_out=outs[c % 2][1], capacity=16 * n)
+    while mapper.in_flight:
+        r = mapper.wait()
+        got.append(rb.BatchResult(r.hits.copy(), r.pair_offsets.copy(), r.counters, r.num_hits))
+    for c in range(3):
+        assert_same(got[c], om.map(data[c][0], data[c][1], 100), f"chunk {c}")
 
 
 @pytest.mark.skipif(not have_ref(), reason="needs oracle/_ref to build the mid-size index")
@@ -538,3 +589,33 @@ def test_index_replica_from_image_carries_names(synth_small):
     with pytest.raises(rb.RapMapCudaError):
         rb.Index.from_image(0, blob.data_ptr() + 32, nbytes - 32)  # misaligned / not an image
     del src
+
+
+@pytest.mark.parametrize("sel", [False, True])
+def test_direct_copy_out_to_pinned_and_device_buffers(synth_small, sel):
+    """Results leave the device by a kernel when the caller's buffers are device memory or pinned host memory (one host
+    synchronisation per batch); pageable numpy buffers take the cudaMemcpyAsync path.  All three must hold the same bytes;
+    a too small pinned buffer reports RAPMAP_ERR_CAPACITY with the needed count."""
+    import torch
+
+    idx_dir, index, s1, s2, L, tx = synth_small
+    opts = rb.default_opts(sel_aln=sel)
+    n = s1.shape[0]
+    mapper = make_mapper(index, opts, n, L)
+    ref = mapper.map_batch(s1, s2, n=n, fixed_len=L)
+    ref_hits, ref_off, nh = ref.hits.copy().view(np.uint8).reshape(-1), ref.pair_offsets.copy(), ref.num_hits
+    cap = nh + 7
+    for where in ("pinned", "device"):
+        hits = torch.zeros(cap * 28, dtype=torch.uint8)
+        offs = torch.zeros(n + 1, dtype=torch.int64)
+        hits, offs = (hits.pin_memory(), offs.pin_memory()) if where == "pinned" else (hits.cuda(), offs.cuda())
+        r = mapper.map_batch(s1, s2, n=n, fixed_len=L, hits_out=hits, offsets_out=offs, out_location=rb.LOC_HOST if where == "pinned" else rb.LOC_DEVICE, capacity=cap)
+        torch.cuda.synchronize()
+        assert r.num_hits == nh and mapper.timing().retries == 0
+        assert np.array_equal(hits.cpu().numpy()[: nh * 28], ref_hits), where
+        assert np.array_equal(offs.cpu().numpy().view(np.uint64), ref_off), where
+    small = torch.zeros(10 * 28, dtype=torch.uint8).pin_memory()
+    offs = torch.zeros(n + 1, dtype=torch.int64).pin_memory()
+    with pytest.raises(rb.RapMapCudaError) as e:
+        mapper.map_batch(s1, s2, n=n, fixed_len=L, hits_out=small, offsets_out=offs, capacity=10)
+    assert e.value.code == rb.ERR_CAPACITY
