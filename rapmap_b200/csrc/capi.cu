@@ -268,6 +268,7 @@ struct rapmap_cuda_mapper {
   uint32_t* dVoteScratch{nullptr};
   uint32_t voteWords{0}, laneWords{0}, laneSmem{0}, pmax{0};
   int gridLane{0};
+  bool masksInGlobal{false};
   void (*laneKernel)(LaneParams){nullptr};   // sa_collect_lane_kernel instantiation for this index flavour / flag set
   // stage 2: hit resolution
   QASummary* dQSumm{nullptr};
@@ -715,6 +716,7 @@ static int mapperCreateImpl(const rapmap_cuda_index_t* idx, const rapmap_cuda_op
   {  // SA-lookup kernel: one thread per read
     m->laneWords = (max_read_len + 31) / 32;
     m->laneSmem = 2u * m->laneWords * 16u * kLaneThreads;  // packed read words + k-mer mask words
+    if (m->laneSmem > 227 * 1024) { m->laneSmem /= 2; m->masksInGlobal = true; }  // very long reads: masks stay in global memory
     if (m->laneSmem > 227 * 1024) return bail("max_read_len too large for the shared-memory read words");
     const bool general = !(d.disableNIP && d.strictCheck);
     m->laneKernel = idx->hdr.hashKind ? (general ? &sa_collect_lane_kernel<kLaneThreads, kLaneMinBlocks, true, true> : &sa_collect_lane_kernel<kLaneThreads, kLaneMinBlocks, true, false>)
@@ -811,7 +813,7 @@ static int enqueueAttempt(rapmap_cuda_mapper* m, BatchSlot& sl) {
   // ---- kernel 1: SA lookup
   LaneParams lp{};
   lp.ix = m->idx->view; lp.reads = bv; lp.opts = m->dopts; lp.maxReadLen = m->maxReadLen; lp.nw = m->laneWords; lp.packed = m->dPacked;
-  lp.kmask = m->dKmask; lp.maskChunks = (m->pmax + 7) / 8; lp.classCtl = m->dClassCtl; lp.order = m->dOrder;
+  lp.kmask = m->dKmask; lp.maskChunks = (m->pmax + 7) / 8; lp.classCtl = m->dClassCtl; lp.order = m->dOrder; lp.masksInGlobal = m->masksInGlobal ? 1u : 0u;
   lp.summ = m->dSumm; lp.arena = m->dIvArena; lp.arenaCap = m->ivCap; lp.arenaCursor = m->dCtl + 0; lp.status = m->dCtl + 3;
   lp.ivScratch = m->dIvScratch; lp.ivStride = m->ivStride; lp.voteScratch = m->dVoteScratch; lp.voteWords = m->voteWords; lp.readCursor = m->dCtl + 4;
   const int g0 = static_cast<int>(std::min<uint64_t>(static_cast<uint64_t>(m->numSMs) * 8, (bv.numReads * m->laneWords + 255) / 256));

@@ -50,6 +50,7 @@ struct LaneParams {
   uint32_t maskChunks;     // 8-window chunks per read the mask kernel fills: ceil((maxReadLen - k + 1) / 8)
   uint32_t* classCtl;      // [0, 8) class histogram, [8, 16) scatter cursors (zeroed per batch)
   uint32_t* order;         // [numReads] read indices grouped by work class; the walk kernel takes reads in this order
+  uint32_t masksInGlobal;  // 1: reads so long that packed words + masks exceed the shared memory of a block: the masks are read from kmask
 };
 
 // ---- K0: pack reads.  One thread per 32-base word of a read (a warp covers 8 reads x 4 words = 800 contiguous bytes).
@@ -552,6 +553,8 @@ __global__ void __launch_bounds__(NT, MINB) sa_collect_lane_kernel(LaneParams P)
   int mlen = 0, b0 = 0, b1 = 0, mQ = 0, pass = 0, guard = 0, prevMMPEnd = 0, nF = 0, nR = 0;
   uint32_t fwdHit = 0, rcHit = 0, fwdCov = 0, rcCov = 0;
   bool ready = false;   // a k-mer (w, at lookPos) is waiting for its lookups
+  const bool mglob = P.masksInGlobal != 0u;
+  auto maskWord = [&](int wq) -> uint4 { return mglob ? __ldg(P.kmask + static_cast<size_t>(r) * P.nw + wq) : sm[(nw + wq) * NT]; };
   uint64_t w = 0;
   int lookPos = 0;
 
@@ -658,7 +661,7 @@ __global__ void __launch_bounds__(NT, MINB) sa_collect_lane_kernel(LaneParams P)
               } else {
                 const uint4* src = P.packed + static_cast<size_t>(nr) * P.nw;
                 for (int j = 0; j < nw; ++j) smw[j * NT] = __ldg(src + j);
-                {
+                if (!mglob) {
                   const uint4* msrc = P.kmask + static_cast<size_t>(nr) * P.nw;
                   for (int j = 0; j < nw; ++j) smw[(nw + j) * NT] = __ldg(msrc + j);
                 }
@@ -689,7 +692,7 @@ __global__ void __launch_bounds__(NT, MINB) sa_collect_lane_kernel(LaneParams P)
         while (rb + k <= L) {
           const int q = rc ? L - k - rb : rb;
           const int wq = q >> 5, bq = q & 31;
-          const uint4 mk = sm[(nw + wq) * NT];
+          const uint4 mk = maskWord(wq);
           const uint32_t miss = mk.x & mk.y & mk.z;          // valid, absent in both orientations
           uint32_t dead = miss | (mk.w & mk.z);              // ... or a homopolymer
           if (st == LST_SCAN) {
@@ -715,7 +718,7 @@ __global__ void __launch_bounds__(NT, MINB) sa_collect_lane_kernel(LaneParams P)
       } else {
         const int lp = rb + mlen - (k - 1);
         const int q = rc ? L - k - lp : lp;
-        const uint4 mk = sm[(nw + (q >> 5)) * NT];
+        const uint4 mk = maskWord(q >> 5);
         if ((mk.x & mk.y & mk.z) >> (q & 31) & 1u) {  // the k-mer after the interval is a double miss (:599-616, :671)
           if (voteMode) voteLane(votes, P.voteWords, rc, lp, L, k, false, false);
           st = LST_POSTMM;
@@ -749,7 +752,7 @@ __global__ void __launch_bounds__(NT, MINB) sa_collect_lane_kernel(LaneParams P)
       if (!ready || P.ix.filter == nullptr) break;
       {
         const int q = rc ? L - k - lookPos : lookPos;
-        const uint4 mk = sm[(nw + (q >> 5)) * NT];
+        const uint4 mk = maskWord(q >> 5);
         if ((mk.z >> (q & 31)) & 1u) {  // valid window: the filter verdicts are in the masks (and it is not a double miss)
           const bool aF = (mk.x >> (q & 31)) & 1u, aR = (mk.y >> (q & 31)) & 1u;
           knownM = rc ? aR : aF;

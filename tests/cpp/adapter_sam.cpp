@@ -18,6 +18,9 @@
 #include "RapMapUtils.hpp"
 #include "SingleAlignmentFormatter.hpp"
 #include "rapmap_b200/adapter.hpp"
+#include "spdlog/sinks/ostream_sink.h"
+#include "spdlog/sinks/stdout_sinks.h"
+#include "spdlog/spdlog.h"
 
 using SAIndex32BitDense = RapMapSAIndex<int32_t, RegHashT<uint64_t, rapmap::utils::SAInterval<int32_t>, rapmap::utils::KmerKeyHasher>>;
 
@@ -36,6 +39,9 @@ int main(int argc, char** argv) {
     else if (a == "--chunk" && i + 1 < argc) chunk = std::stoul(argv[++i]);
     else { std::cerr << "unknown argument " << a << "\n"; return 2; }
   }
+  // the reference's loaders log through a registered spdlog logger (src/RapMapSAMapper.cpp:1178-1180)
+  auto consoleSink = std::make_shared<spdlog::sinks::stderr_sink_mt>();
+  auto consoleLog = spdlog::create("stderrLog", {consoleSink});
   // the reference's index object: transcript names / lengths for its SAM writers
   SAIndex32BitDense rmi;
   if (!rmi.load(indexDir)) { std::cerr << "reference index load failed\n"; return 1; }
@@ -44,8 +50,18 @@ int main(int argc, char** argv) {
   rapmap_cuda_opts_t o;
   if (selAln) rapmap_cuda_opts_selaln(&o); else rapmap_cuda_opts_default(&o);
 
+  // output exactly as mapReads sets it up (src/RapMapSAMapper.cpp:842-846): a "%v" spdlog logger over the file stream; the
+  // logger overload of writeSAMHeader prints rapmap::version (the std::ostream overload carries a stale literal)
   std::ofstream out(outName, std::ios::binary);
-  rapmap::utils::writeSAMHeader(rmi, out);
+  auto outputSink = std::make_shared<spdlog::sinks::ostream_sink_mt>(out);
+  auto outLog = std::make_shared<spdlog::logger>("rapmap::outLog", outputSink);
+  outLog->set_pattern("%v");
+  rapmap::utils::writeSAMHeader(rmi, outLog);
+  auto flushChunk = [&](fmt::MemoryWriter& ss) {  // src/RapMapSAMapper.cpp:350-363: drop the trailing newline, the logger adds one
+    std::string outStr(ss.str());
+    if (!outStr.empty()) { outStr.pop_back(); outLog->info(std::move(outStr)); }
+    ss.clear();
+  };
   rapmap::utils::HitCounters hctr;
   std::vector<std::vector<rapmap::utils::QuasiAlignment>> hits;
   fmt::MemoryWriter sstream;
@@ -64,8 +80,7 @@ int main(int argc, char** argv) {
           if (!jointHits.empty()) rapmap::utils::writeAlignmentsToStream(rp, formatter, hctr, jointHits, sstream);
           else rapmap::utils::writeUnalignedPairToStream(rp, sstream);
         }
-        out.write(sstream.data(), static_cast<std::streamsize>(sstream.size()));
-        sstream.clear();
+        flushChunk(sstream);
       }
       parser.stop();
     } else {
@@ -81,8 +96,7 @@ int main(int argc, char** argv) {
           if (!h.empty()) rapmap::utils::writeAlignmentsToStream(r, formatter, hctr, h, sstream);
           else rapmap::utils::writeUnalignedSingleToStream(r, sstream);
         }
-        out.write(sstream.data(), static_cast<std::streamsize>(sstream.size()));
-        sstream.clear();
+        flushChunk(sstream);
       }
       parser.stop();
     }
@@ -90,6 +104,7 @@ int main(int argc, char** argv) {
     std::cerr << "adapter_sam: " << e.what() << "\n";
     return 1;
   }
+  outLog->flush();
   out.close();
   std::cerr << "adapter_sam: reads " << hctr.numReads << " totHits " << hctr.totHits << "\n";
   rapmap_cuda_index_free(gidx);

@@ -339,8 +339,8 @@ def test_repeat_families_exercise_big_intervals_and_spill():
     assert_same(res, OracleMapper(idx_dir, opts).map(s1, s2, 100), "repeats")
 
 
-@pytest.mark.parametrize("read_len,sel", [(150, False), (150, True), (250, True), (300, False)])
-def test_longer_reads_match_oracle(read_len, sel):
+@pytest.mark.parametrize("read_len,sel,max_len", [(150, False, 0), (150, True, 0), (250, True, 0), (300, False, 0), (300, True, 1000), (700, False, 1000)])
+def test_longer_reads_match_oracle(read_len, sel, max_len):
     """Reads longer than the benchmark's 100 bases: 5..10 packed words per read in the SA-lookup kernel, ksw2 windows
     beyond the thread-per-job kernel's strip (general warp kernel), more intervals / SA entries per read in hit resolution."""
     idx_dir, tx = synth_index(2500)
@@ -348,7 +348,8 @@ def test_longer_reads_match_oracle(read_len, sel):
     s1, s2 = tx.reads(n, rseed=4242, read_len=read_len)
     opts = rb.default_opts(sel_aln=sel)
     index = rb.Index(idx_dir, 0)
-    mapper = make_mapper(index, opts, n, read_len)
+    # max_read_len = 1000: packed words + k-mer masks no longer fit a block's shared memory, the masks are read from global memory
+    mapper = make_mapper(index, opts, n, max_len or read_len)
     res = mapper.map_batch(s1, s2, n=n, fixed_len=read_len)
     assert_same(res, OracleMapper(idx_dir, opts).map(s1, s2, read_len), f"L={read_len} sel={sel}")
 
