@@ -285,6 +285,9 @@ struct rapmap_cuda_mapper {
   bool laneMap{false};
   bool chainLaneMap{false};
   int gridLaneMap{0};
+  int gridChain[3]{0, 0, 0};
+  uint32_t* dOrder2{nullptr};    // reads grouped by SA-entry count (hit resolution with chaining)
+  uint32_t* dK2Class{nullptr};
   // stage 3: mate merge
   uint32_t* dPairCount{nullptr};
   uint64_t hitsCap{0};
@@ -318,6 +321,8 @@ static constexpr int kWarps = 8;
 #endif
 static constexpr int kChainLaneThreads = RAPMAP_CHAINLANE_THREADS;  // lane-per-read hit resolution with chaining (-s / -f)
 static constexpr int kChainLaneCap = RAPMAP_CHAINLANE_CAP;
+// the three size ranges of the chaining lane kernel: (threads per block, strip entries); ~68 KB of shared memory per block each
+#define RAPMAP_CHAIN_CLASSES(X) X(128, 16) X(64, 32) X(32, 64)
 static constexpr int kMapLaneThreads = 128;                // lane-per-read hit resolution
 static constexpr int kMapLaneCap = RAPMAP_MAPLANE_CAP;     // SA entries per read it takes
 static constexpr uint32_t kMapLaneSmem = 2u * kMapLaneCap * kMapLaneThreads * 8u;
@@ -640,7 +645,7 @@ static void freeMapperBuffers(rapmap_cuda_mapper* m) {
   cudaFree(m->dSumm); cudaFree(m->dIvArena); cudaFree(m->dQSumm); cudaFree(m->dQaArena); cudaFree(m->dPosPool);
   cudaFree(m->dScratch); cudaFree(m->dPairCount); cudaFree(m->dCubTemp);
   cudaFree(m->dCtl); cudaFree(m->dCounters);
-  cudaFree(m->dPacked); cudaFree(m->dKmask); cudaFree(m->dOrder); cudaFree(m->dClassCtl); cudaFree(m->dIvScratch); cudaFree(m->dVoteScratch);
+  cudaFree(m->dPacked); cudaFree(m->dKmask); cudaFree(m->dOrder); cudaFree(m->dClassCtl); cudaFree(m->dOrder2); cudaFree(m->dK2Class); cudaFree(m->dIvScratch); cudaFree(m->dVoteScratch);
   selAlnFree(m->selaln);
   if (m->stream) cudaStreamDestroy(m->stream);
   if (m->sIn) cudaStreamDestroy(m->sIn);
@@ -750,11 +755,19 @@ static int mapperCreateImpl(const rapmap_cuda_index_t* idx, const rapmap_cuda_op
     m->laneMap = !d.selAln && !d.fuzzy && !d.doChaining && !off;
     m->chainLaneMap = !m->laneMap && !off;
     if (m->chainLaneMap) {
-      const uint32_t smemC = chainLaneStride(kChainLaneCap) * kChainLaneThreads;
-      M_TRY(cudaFuncSetAttribute(hits_to_mappings_chain_lane_kernel<kChainLaneThreads, kChainLaneCap>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smemC)));
-      M_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hits_to_mappings_chain_lane_kernel<kChainLaneThreads, kChainLaneCap>, kChainLaneThreads, smemC));
-      if (occ < 1) return bail("hits_to_mappings_chain_lane_kernel does not fit on an SM");
-      m->gridLaneMap = m->numSMs * occ;
+      int ci = 0;
+#define SETUP_CHAIN(NT_, CAP_)                                                                                                                       \
+      {                                                                                                                                              \
+        const uint32_t smemC = chainLaneStride(CAP_) * NT_;                                                                                          \
+        M_TRY(cudaFuncSetAttribute(hits_to_mappings_chain_lane_kernel<NT_, CAP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smemC))); \
+        M_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hits_to_mappings_chain_lane_kernel<NT_, CAP_>, NT_, smemC));                         \
+        if (occ < 1) return bail("hits_to_mappings_chain_lane_kernel does not fit on an SM");                                                         \
+        m->gridChain[ci++] = m->numSMs * occ;                                                                                                          \
+      }
+      RAPMAP_CHAIN_CLASSES(SETUP_CHAIN)
+#undef SETUP_CHAIN
+      M_TRY(cudaMalloc(&m->dOrder2, R * 4));
+      M_TRY(cudaMalloc(&m->dK2Class, 2 * kK2Buckets * 4));
     }
     if (m->laneMap) {
       M_TRY(cudaFuncSetAttribute(hits_to_mappings_lane_kernel<kMapLaneThreads, kMapLaneCap>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMapLaneSmem)));
@@ -836,11 +849,28 @@ static int enqueueAttempt(rapmap_cuda_mapper* m, BatchSlot& sl) {
   mp.posPool = m->dPosPool; mp.posCap = m->posCap; mp.posCursor = m->dCtl + 2;
   mp.scratch = m->dScratch; mp.scratchEntries = m->scratchEntries; mp.scratchStride = m->scratchStride; mp.smemEntries = m->smemEntries;
   mp.status = m->dCtl + 3;
-  if (m->chainLaneMap) {  // -s / -f: thread-per-read with chaining and position lists; the marked rest below
-    const int gl = static_cast<int>(std::min<uint64_t>(m->gridLaneMap, (bv.numReads + kChainLaneThreads - 1) / kChainLaneThreads));
-    hits_to_mappings_chain_lane_kernel<kChainLaneThreads, kChainLaneCap><<<gl, kChainLaneThreads, chainLaneStride(kChainLaneCap) * kChainLaneThreads, st>>>(mp);
-    ++sl.launches;
-    mp.skipDone = 1;
+  if (m->chainLaneMap) {
+    // -s / -f: reads grouped by their number of SA entries, then thread-per-read with chaining and position lists, one launch
+    // per size range (strip and block size to match); what is bigger than the biggest strip goes to the warp-per-read kernel
+    CU_TRY(cudaMemsetAsync(m->dK2Class, 0, 2 * kK2Buckets * 4, st));
+    const int gc = static_cast<int>(std::min<uint64_t>(static_cast<uint64_t>(m->numSMs) * 8, (bv.numReads + 255) / 256));
+    mp.classHist = m->dK2Class;
+    k2_class_hist_kernel<<<gc, 256, 0, st>>>(mp, kChainLaneMaxIv);
+    k2_class_scatter_kernel<<<gc, 256, 0, st>>>(mp, kChainLaneMaxIv, m->dOrder2);
+    sl.launches += 2;
+    mp.order = m->dOrder2;
+    int ci = 0;
+    uint32_t lo = 1;
+#define LAUNCH_CHAIN(NT_, CAP_)                                                                                                              \
+    {                                                                                                                                        \
+      mp.bLo = lo; mp.bHi = CAP_; lo = CAP_ + 1;                                                                                             \
+      const int gl = static_cast<int>(std::min<uint64_t>(m->gridChain[ci++], (bv.numReads + NT_ - 1) / NT_));                                  \
+      hits_to_mappings_chain_lane_kernel<NT_, CAP_><<<gl, NT_, chainLaneStride(CAP_) * NT_, st>>>(mp);                                         \
+      ++sl.launches;                                                                                                                         \
+    }
+    RAPMAP_CHAIN_CLASSES(LAUNCH_CHAIN)
+#undef LAUNCH_CHAIN
+    mp.bLo = kK2MaxEntries + 1; mp.bHi = kK2MaxEntries + 1;  // the warp-per-read kernel below takes the last bucket
   }
   if (m->laneMap) {  // small reads thread-per-read; the rest (marked) by the warp-per-read kernel below
     const int gl = static_cast<int>(std::min<uint64_t>(m->gridLaneMap, (bv.numReads + kMapLaneThreads - 1) / kMapLaneThreads));
@@ -1000,6 +1030,7 @@ static int mapperWaitImpl(rapmap_cuda_mapper_t* m) {
     }
     const uint32_t status = sl.hStage->ctl[3];
     if (status & kStatReadTooLong) return fail(RAPMAP_ERR_ARG, "a read is longer than the mapper's max_read_len");
+    if (status & kStatInternal) return fail(RAPMAP_ERR_CUDA, "internal error: a kernel met a case its launch configuration excludes");
     const bool hitsFull = sl.hStage->mergeTotal > m->hitsCap;
     if ((status & (kStatIntervalArenaFull | kStatIvScratchFull | kStatQAArenaFull | kStatPosPoolFull | kStatScratchFull)) == 0 && !hitsFull) break;
     // ---- something overflowed: drain the device (a later batch may be running on the arenas), grow, repeat the attempt

@@ -37,7 +37,26 @@ struct MapParams {
   uint32_t smemEntries;
   uint32_t* status;
   uint8_t skipDone;          // 1: reads already resolved by hits_to_mappings_lane_kernel are skipped (nQA != kTodoMark)
+  // size-class ordering (k2_class_* kernels): reads grouped by the number of expanded SA entries
+  const uint32_t* order;     // nullptr: reads in batch order
+  uint32_t* classHist;       // [kK2Buckets] reads per bucket, [kK2Buckets, 2 kK2Buckets) scatter cursors
+  uint32_t bLo, bHi;         // buckets this launch works on (inclusive)
 };
+
+// bucket = number of expanded SA entries of a read (both strands), 1 .. kK2MaxEntries; 0 = no interval at all;
+// kK2MaxEntries + 1 = more entries, or more intervals than a lane kernel takes (warp-per-read kernel)
+static constexpr int kK2MaxEntries = 64;
+static constexpr int kK2Buckets = kK2MaxEntries + 2;
+
+// [lo, hi) of the positions in P.order that hold the reads of buckets bLo .. bHi (prefix sums of the histogram)
+__device__ __forceinline__ void classRange(const MapParams& P, uint32_t& lo, uint32_t& hi) {
+  lo = 0; hi = 0;
+  for (uint32_t b = 0; b <= P.bHi; ++b) {
+    const uint32_t c = P.classHist[b];
+    if (b < P.bLo) lo += c;
+    hi += c;
+  }
+}
 
 static constexpr uint32_t kTodoMark = 0xFFFFFFFFu;
 
@@ -405,7 +424,10 @@ __global__ void __launch_bounds__(WARPS * 32) hits_to_mappings_kernel(MapParams 
   uint8_t* globBase = P.scratch + gw * P.scratchStride;
   const bool needPos = P.opts.selAln || P.opts.fuzzy;
 
-  for (uint64_t r = gw; r < P.numReads; r += static_cast<uint64_t>(gridDim.x) * WARPS) {
+  uint32_t pLo = 0, pHi = static_cast<uint32_t>(P.numReads);
+  if (P.order) classRange(P, pLo, pHi);
+  for (uint64_t p = pLo + gw; p < pHi; p += static_cast<uint64_t>(gridDim.x) * WARPS) {
+    const uint64_t r = P.order ? P.order[p] : p;
     if (P.skipDone && P.qsumm[r].nQA != kTodoMark) continue;
     ReadSummary s = P.summ[r];
     QASummary out;
@@ -751,9 +773,11 @@ __global__ void __launch_bounds__(NT) hits_to_mappings_chain_lane_kernel(MapPara
   const DevOpts& o = P.opts;
   const bool needPos = o.selAln || o.fuzzy;
   const uint64_t stride = static_cast<uint64_t>(gridDim.x) * NT;
-  for (uint64_t rbase = static_cast<uint64_t>(blockIdx.x) * NT + (threadIdx.x & ~31); rbase < P.numReads; rbase += stride) {
-    const uint64_t r = rbase + lane;
-    const bool valid = r < P.numReads;
+  uint32_t pLo = 0, pHi = static_cast<uint32_t>(P.numReads);
+  if (P.order) classRange(P, pLo, pHi);  // the reads of this launch's size range, contiguous in P.order
+  for (uint64_t rbase = pLo + static_cast<uint64_t>(blockIdx.x) * NT + (threadIdx.x & ~31); rbase < pHi; rbase += stride) {
+    const bool valid = rbase + lane < pHi;
+    const uint64_t r = valid ? (P.order ? P.order[rbase + lane] : rbase + lane) : 0;
     int nF = 0, nR = 0;
     uint32_t ivOff = 0, readLen = 0;
     if (valid) {
@@ -772,6 +796,7 @@ __global__ void __launch_bounds__(NT) hits_to_mappings_chain_lane_kernel(MapPara
       }
       if (totF + totR > static_cast<uint32_t>(CAP)) todo = true;
     }
+    if (todo && P.order) atomicOr(P.status, kStatInternal);  // the size classes promise reads that fit the strip
     const uint32_t total = todo ? 0u : totF + totR;
     // ---- stage 1: one key/value per SA entry (forward strand first); the value carries the SA index for now
     if (total > 0) {
@@ -993,6 +1018,62 @@ __global__ void __launch_bounds__(NT) hits_to_mappings_chain_lane_kernel(MapPara
       out.qaOff = off; out.nQA = todo ? kTodoMark : nFinal;
       P.qsumm[r] = out;
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Size classes.  Under -s / -f a read's intervals expand to ~20 SA entries on average and to 64 and more for a few per cent
+// (profiles/r02e): a lane kernel with one fixed strip either leaves half of the reads to the warp-per-read kernel (strip of
+// 16: 9.7 of 11.7 ms were spent there) or pays the big strip and the longest read of every warp for all reads.  So the
+// reads are grouped by their entry count (counting sort: histogram, then scatter) and the lane kernel is launched per
+// size range with a strip and block size to match; consecutive reads of a warp then have (nearly) the same amount of work.
+__device__ __forceinline__ int k2Bucket(const MapParams& P, uint64_t r, int maxIv) {
+  const ReadSummary s = P.summ[r];
+  const int nIv = s.nFwd + s.nRc;
+  if (nIv == 0) return 0;
+  if (nIv > maxIv) return kK2MaxEntries + 1;
+  const IntervalRec* ivs = P.arena + s.ivOff;
+  uint32_t tot = 0;
+  for (int j = 0; j < nIv; ++j) tot += static_cast<uint32_t>(ivs[j].end - ivs[j].begin);
+  if (tot == 0) return 1;
+  return tot <= static_cast<uint32_t>(kK2MaxEntries) ? static_cast<int>(tot) : kK2MaxEntries + 1;
+}
+
+__global__ void __launch_bounds__(256) k2_class_hist_kernel(MapParams P, int maxIv) {
+  __shared__ uint32_t h[kK2Buckets];
+  for (int i = threadIdx.x; i < kK2Buckets; i += blockDim.x) h[i] = 0;
+  __syncthreads();
+  for (uint64_t r = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r < P.numReads; r += static_cast<uint64_t>(gridDim.x) * blockDim.x)
+    atomicAdd(&h[k2Bucket(P, r, maxIv)], 1u);
+  __syncthreads();
+  for (int i = threadIdx.x; i < kK2Buckets; i += blockDim.x)
+    if (h[i]) atomicAdd(P.classHist + i, h[i]);
+}
+
+__global__ void __launch_bounds__(256) k2_class_scatter_kernel(MapParams P, int maxIv, uint32_t* order) {
+  __shared__ uint32_t cnt[kK2Buckets], base[kK2Buckets];
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  const uint64_t rounds = (P.numReads + stride - 1) / stride;
+  for (uint64_t it = 0; it < rounds; ++it) {
+    const uint64_t r = it * stride + static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    for (int i = threadIdx.x; i < kK2Buckets; i += blockDim.x) cnt[i] = 0;
+    __syncthreads();
+    int c = 0;
+    uint32_t rank = 0;
+    if (r < P.numReads) {
+      c = k2Bucket(P, r, maxIv);
+      rank = atomicAdd(&cnt[c], 1u);
+      if (c == 0) { QASummary z; z.qaOff = 0; z.nQA = 0; P.qsumm[r] = z; }  // nothing to resolve
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kK2Buckets; i += blockDim.x) {
+      uint32_t off = 0;  // exclusive scan of the histogram
+      for (int j = 0; j < i; ++j) off += P.classHist[j];
+      base[i] = off + (cnt[i] ? atomicAdd(P.classHist + kK2Buckets + i, cnt[i]) : 0u);
+    }
+    __syncthreads();
+    if (r < P.numReads) order[base[c] + rank] = static_cast<uint32_t>(r);
+    __syncthreads();
   }
 }
 

@@ -75,6 +75,7 @@ enum : uint32_t {
   kStatReadTooLong = 8u,
   kStatPosPoolFull = 16u,
   kStatIvScratchFull = 32u,
+  kStatInternal = 64u,        // a kernel met a case its launch configuration excludes (a bug, never a capacity matter)
 };
 
 } // namespace rapmap_b200
