@@ -285,7 +285,7 @@ struct rapmap_cuda_mapper {
   bool laneMap{false};
   bool chainLaneMap{false};
   int gridLaneMap{0};
-  int gridChain[3]{0, 0, 0};
+  int gridChain[2]{0, 0};
   uint32_t* dOrder2{nullptr};    // reads grouped by SA-entry count (hit resolution with chaining)
   uint32_t* dK2Class{nullptr};
   // stage 3: mate merge
@@ -321,8 +321,10 @@ static constexpr int kWarps = 8;
 #endif
 static constexpr int kChainLaneThreads = RAPMAP_CHAINLANE_THREADS;  // lane-per-read hit resolution with chaining (-s / -f)
 static constexpr int kChainLaneCap = RAPMAP_CHAINLANE_CAP;
-// the three size ranges of the chaining lane kernel: (threads per block, strip entries); ~68 KB of shared memory per block each
-#define RAPMAP_CHAIN_CLASSES(X) X(128, 16) X(64, 32) X(32, 64)
+// the size ranges of the chaining lane kernel: (threads per block, strip entries); ~68 KB of shared memory per block each.
+// A third range (32 threads, 64 entries) ran at 3 warps per SM: 6.4 ms for the 22 % of reads with 33-64 entries, which the
+// warp-per-read kernel resolves in ~2.5 ms (profiles/r02f_launches_selaln.csv)
+#define RAPMAP_CHAIN_CLASSES(X) X(128, 16) X(64, 32)
 static constexpr int kMapLaneThreads = 128;                // lane-per-read hit resolution
 static constexpr int kMapLaneCap = RAPMAP_MAPLANE_CAP;     // SA entries per read it takes
 static constexpr uint32_t kMapLaneSmem = 2u * kMapLaneCap * kMapLaneThreads * 8u;

@@ -45,7 +45,7 @@ struct MapParams {
 
 // bucket = number of expanded SA entries of a read (both strands), 1 .. kK2MaxEntries; 0 = no interval at all;
 // kK2MaxEntries + 1 = more entries, or more intervals than a lane kernel takes (warp-per-read kernel)
-static constexpr int kK2MaxEntries = 64;
+static constexpr int kK2MaxEntries = 32;
 static constexpr int kK2Buckets = kK2MaxEntries + 2;
 
 // [lo, hi) of the positions in P.order that hold the reads of buckets bLo .. bHi (prefix sums of the histogram)

@@ -1,12 +1,12 @@
 #!/bin/bash
 # per-kernel time of a bench step from an ncu launch list; EXTRA="--selaln" (default) or EXTRA=""
 mkdir -p gpurun_out
-python bench.py --steps 1 --warmup 0 --no-cpu-baseline --oracle-sample 0 > /dev/null 2>&1
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"sa_collect|pack_reads|hits_to_mappings|merge_|selaln|ksw" -c 200 --csv --log-file gpurun_out/launches_sel.csv \
-   python bench.py --steps 2 --warmup 1 --no-cpu-baseline --oracle-sample 0 ${EXTRA---selaln} > gpurun_out/ncu_launch_sel.json 2> gpurun_out/ncu_launch_sel.log
-python - <<'PY'
+python bench.py --steps 1 --warmup 0 --no-cpu-baseline --oracle-sample 0 --legs none > /dev/null 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"sa_collect|pack_reads|kmer_mask|work_class|k2_class|hits_to_mappings|merge_|selaln|ksw|copy_out" -c 400 --csv --log-file gpurun_out/launches${TAG:-_sel}.csv \
+   python bench.py --steps 1 --warmup 1 --chunks 4 --e2e-depth 1 --legs none --no-cpu-baseline --oracle-sample 0 ${EXTRA---selaln} > gpurun_out/ncu_launch_sel.json 2> gpurun_out/ncu_launch_sel.log
+python - <<PY
 import csv, collections
-rows=list(csv.reader(l for l in open("gpurun_out/launches_sel.csv") if not l.startswith("==")))
+rows=list(csv.reader(l for l in open("gpurun_out/launches${TAG:-_sel}.csv") if not l.startswith("==")))
 h=rows[0]; ki=h.index("Kernel Name"); vi=h.index("Metric Value")
 agg=collections.OrderedDict()
 for r in rows[1:]:
