@@ -191,6 +191,11 @@ int rapmap_cuda_format_sam_mt(const rapmap_cuda_index_t* idx, const rapmap_cuda_
 int rapmap_cuda_sam_header(const rapmap_cuda_index_t* idx, char** sam, uint64_t* sam_len);
 void rapmap_cuda_free(void* p);
 
+/* Page-locked host memory for read / result buffers (callers that do not link the CUDA runtime themselves).  With pinned
+ * buffers the copies of rapmap_cuda_map_batch_async overlap the kernels and a chunk costs one host synchronisation. */
+void* rapmap_cuda_host_alloc(uint64_t bytes);
+void rapmap_cuda_host_free(void* p);
+
 #ifdef __cplusplus
 }
 #endif

@@ -121,7 +121,7 @@ SYMBOLS = [
     "rapmap_cuda_index_device_bytes", "rapmap_cuda_index_image_bytes", "rapmap_cuda_index_image_ptr", "rapmap_cuda_index_from_image",
     "rapmap_cuda_mapper_create", "rapmap_cuda_mapper_free", "rapmap_cuda_map_batch", "rapmap_cuda_map_batch_async", "rapmap_cuda_mapper_wait",
     "rapmap_cuda_last_timing", "rapmap_cuda_mapper_stream", "rapmap_cuda_debug_intervals",
-    "rapmap_cuda_format_sam", "rapmap_cuda_format_sam_mt", "rapmap_cuda_sam_header", "rapmap_cuda_free",
+    "rapmap_cuda_format_sam", "rapmap_cuda_format_sam_mt", "rapmap_cuda_sam_header", "rapmap_cuda_free", "rapmap_cuda_host_alloc", "rapmap_cuda_host_free",
 ]
 
 _lib = None

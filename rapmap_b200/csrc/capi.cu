@@ -1269,4 +1269,14 @@ int rapmap_cuda_format_sam_mt(const rapmap_cuda_index_t* idx, const rapmap_cuda_
 
 void rapmap_cuda_free(void* p) { std::free(p); }
 
+void* rapmap_cuda_host_alloc(uint64_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); fail(RAPMAP_ERR_CUDA, "cudaMallocHost failed"); return nullptr; }
+  return p;
+}
+
+void rapmap_cuda_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
 } // extern "C"
