@@ -92,22 +92,37 @@ bool HostIndex::load(const std::string& dirIn, std::string& err) {
     }
   }
   if (k == 0 || k > 31) { err = "unsupported k-mer length"; return false; }
-  if (bigSA) {
-    // 64-bit suffix arrays (text > 2^31) are row f4 of SURVEY.md §8; refuse loudly rather than truncate.
-    err = "BigSA (64-bit suffix array) indexes are not supported by the device path yet";
+  // BigSA indexes (IndexT = int64_t: src/RapMapSAIndexer.cpp:86-220, instantiations src/RapMapSAIndex.cpp:178-185) store 8-byte
+  // suffix-array entries, transcript offsets, hash intervals and FrugalBooMap starts.  The device image keeps 32-bit positions,
+  // so such an index is read and NARROWED when its text has fewer than 2^31 positions; a longer text is refused, never truncated.
+  auto tooBig = [&]() {
+    err = "BigSA index with a text of 2^31 or more positions: the device index holds 32-bit positions (SURVEY.md section 8 f4)";
     unsupported = true;
     return false;
-  }
+  };
 
   {
     File f(dir + "sa.bin");
     if (!f.ok()) { err = "cannot open sa.bin"; return false; }
     uint64_t n = 0;
     if (!f.get(n)) { err = "sa.bin: truncated"; return false; }
-    if (n > (f.size() - 8) / sizeof(int32_t)) { err = "sa.bin: element count exceeds the file size"; return false; }
-    if (n >= (1ull << 31)) { err = "sa.bin: more than 2^31 suffixes in a 32-bit index"; return false; }
+    const uint64_t esz = bigSA ? 8 : 4;
+    if (n > (f.size() - 8) / esz) { err = "sa.bin: element count exceeds the file size"; return false; }
+    if (n >= (1ull << 31)) { if (bigSA) return tooBig(); err = "sa.bin: more than 2^31 suffixes in a 32-bit index"; return false; }
     SA.resize(n);
-    if (!f.read(SA.data(), n * sizeof(int32_t))) { err = "sa.bin: truncated"; return false; }
+    if (!bigSA) {
+      if (!f.read(SA.data(), n * sizeof(int32_t))) { err = "sa.bin: truncated"; return false; }
+    } else {
+      std::vector<int64_t> wide(std::min<uint64_t>(n, 1 << 20));
+      for (uint64_t at = 0; at < n; at += wide.size()) {
+        const uint64_t cnt = std::min<uint64_t>(wide.size(), n - at);
+        if (!f.read(wide.data(), cnt * 8)) { err = "sa.bin: truncated"; return false; }
+        for (uint64_t i = 0; i < cnt; ++i) {
+          if (wide[i] < 0 || wide[i] >= static_cast<int64_t>(n)) { err = "sa.bin: suffix array entry outside the text"; return false; }
+          SA[at + i] = static_cast<int32_t>(wide[i]);
+        }
+      }
+    }
   }
   {
     File f(dir + "txpInfo.bin");
@@ -125,9 +140,18 @@ bool HostIndex::load(const std::string& dirIn, std::string& err) {
       if (!f.read(&s[0], l)) { err = "txpInfo.bin: truncated"; return false; }
     }
     if (!f.get(n)) { err = "txpInfo.bin: truncated"; return false; }
-    if (n > fsz / 4) { err = "txpInfo.bin: offset count exceeds the file size"; return false; }
+    if (n > fsz / (bigSA ? 8 : 4)) { err = "txpInfo.bin: offset count exceeds the file size"; return false; }
     txpOffsets.resize(n);
-    if (!f.read(txpOffsets.data(), n * sizeof(int32_t))) { err = "txpInfo.bin: truncated"; return false; }
+    if (!bigSA) {
+      if (!f.read(txpOffsets.data(), n * sizeof(int32_t))) { err = "txpInfo.bin: truncated"; return false; }
+    } else {
+      std::vector<int64_t> wide(n);
+      if (!f.read(wide.data(), n * 8)) { err = "txpInfo.bin: truncated"; return false; }
+      for (uint64_t i = 0; i < n; ++i) {
+        if (wide[i] < 0 || wide[i] >= (1ll << 31)) return tooBig();
+        txpOffsets[i] = static_cast<int32_t>(wide[i]);
+      }
+    }
     if (!f.get(n)) { err = "txpInfo.bin: truncated"; return false; }
     if (n > fsz) { err = "txpInfo.bin: text length exceeds the file size"; return false; }
     text.resize(n);
@@ -167,15 +191,28 @@ bool HostIndex::load(const std::string& dirIn, std::string& err) {
     uint64_t fsz = f.size(), hdr = 0, magic = 0, tableSize = 0, numBuckets = 0;
     if (!read32or64(f, magic, hdr) || !read32or64(f, tableSize, hdr) || !read32or64(f, numBuckets, hdr)) { err = "hash.bin: truncated"; return false; }
     if (magic != 0x24687531ULL) { err = "hash.bin: not a sparsepp table (bad magic)"; return false; }
-    const uint64_t rec = sizeof(KmerRecord);
-    if (fsz < hdr + numBuckets * rec) { err = "hash.bin: truncated"; return false; }
+    const uint64_t rec = bigSA ? 24 : sizeof(KmerRecord);  // {u64 k-mer, IndexT begin, IndexT end}
+    if (numBuckets > fsz / rec || fsz < hdr + numBuckets * rec) { err = "hash.bin: truncated"; return false; }
     // Group occupancy bitmaps (one word per 32 or 64 buckets) sit between header and records; their size is
     // whatever is left.  Only the records matter for a re-laid-out device table.
     uint64_t meta = fsz - hdr - numBuckets * rec;
     if (meta != (tableSize + 31) / 32 * 4 && meta != (tableSize + 63) / 64 * 8) { err = "hash.bin: unexpected group-bitmap size"; return false; }
     std::fseek(f.f, static_cast<long>(hdr + meta), SEEK_SET);
     kmers.resize(numBuckets);
-    if (!f.read(kmers.data(), numBuckets * rec)) { err = "hash.bin: truncated"; return false; }
+    if (!bigSA) {
+      if (!f.read(kmers.data(), numBuckets * rec)) { err = "hash.bin: truncated"; return false; }
+    } else {
+      struct Wide { uint64_t kmer; int64_t begin, end; };
+      std::vector<Wide> wide(std::min<uint64_t>(numBuckets, 1 << 20));
+      for (uint64_t at = 0; at < numBuckets; at += wide.size()) {
+        const uint64_t cnt = std::min<uint64_t>(wide.size(), numBuckets - at);
+        if (!f.read(wide.data(), cnt * rec)) { err = "hash.bin: truncated"; return false; }
+        for (uint64_t i = 0; i < cnt; ++i) {
+          if (wide[i].begin < 0 || wide[i].end < wide[i].begin || wide[i].end > static_cast<int64_t>(SA.size())) { err = "hash.bin: k-mer interval outside the suffix array"; return false; }
+          kmers[at + i] = KmerRecord{wide[i].kmer, static_cast<int32_t>(wide[i].begin), static_cast<int32_t>(wide[i].end)};
+        }
+      }
+    }
     {
       const int64_t n = static_cast<int64_t>(SA.size());
       uint32_t bad = 0;
@@ -222,9 +259,19 @@ bool HostIndex::load(const std::string& dirIn, std::string& err) {
     if (!v.ok()) { err = "cannot open hash_info.val"; return false; }
     uint64_t n = 0;
     if (!v.get(n)) { err = "hash_info.val: truncated"; return false; }
-    if (n > v.size() / 4) { err = "hash_info.val: element count exceeds the file size"; return false; }
+    if (n > v.size() / (bigSA ? 8 : 4)) { err = "hash_info.val: element count exceeds the file size"; return false; }
     phf.data.resize(n);
-    if (!v.read(phf.data.data(), n * 4) || !v.get(n)) { err = "hash_info.val: truncated"; return false; }
+    if (!bigSA) {
+      if (!v.read(phf.data.data(), n * 4)) { err = "hash_info.val: truncated"; return false; }
+    } else {
+      std::vector<int64_t> wide(n);
+      if (!v.read(wide.data(), n * 8)) { err = "hash_info.val: truncated"; return false; }
+      for (uint64_t i = 0; i < n; ++i) {
+        if (wide[i] < 0 || wide[i] >= static_cast<int64_t>(SA.size())) { err = "hash_info.val: interval start outside the suffix array"; return false; }
+        phf.data[i] = static_cast<int32_t>(wide[i]);
+      }
+    }
+    if (!v.get(n)) { err = "hash_info.val: truncated"; return false; }
     if (n > v.size()) { err = "hash_info.val: element count exceeds the file size"; return false; }
     phf.lens.resize(n);
     if (!v.read(phf.lens.data(), n)) { err = "hash_info.val: truncated"; return false; }
@@ -236,11 +283,20 @@ bool HostIndex::load(const std::string& dirIn, std::string& err) {
     }
     long here = std::ftell(v.f);
     uint64_t remaining = v.size() - static_cast<uint64_t>(here);
-    if (remaining < numBuckets * 8) { err = "hash_info.val: truncated overflow table"; return false; }
-    std::fseek(v.f, static_cast<long>(static_cast<uint64_t>(here) + (remaining - numBuckets * 8)), SEEK_SET);
+    const uint64_t orec = bigSA ? 16 : 8;  // {IndexT start, IndexT length}
+    if (numBuckets > remaining / orec) { err = "hash_info.val: truncated overflow table"; return false; }
+    std::fseek(v.f, static_cast<long>(static_cast<uint64_t>(here) + (remaining - numBuckets * orec)), SEEK_SET);
     phf.overflow.resize(numBuckets);
-    for (auto& kv : phf.overflow)
-      if (!v.get(kv.first) || !v.get(kv.second)) { err = "hash_info.val: truncated"; return false; }
+    for (auto& kv : phf.overflow) {
+      if (!bigSA) {
+        if (!v.get(kv.first) || !v.get(kv.second)) { err = "hash_info.val: truncated"; return false; }
+      } else {
+        int64_t a = 0, b = 0;
+        if (!v.get(a) || !v.get(b)) { err = "hash_info.val: truncated"; return false; }
+        if (a < 0 || b < 0 || a >= (1ll << 31) || b >= (1ll << 31)) return tooBig();
+        kv.first = static_cast<int32_t>(a); kv.second = static_cast<int32_t>(b);
+      }
+    }
     std::sort(phf.overflow.begin(), phf.overflow.end());
     {
       const int64_t n = static_cast<int64_t>(SA.size());

@@ -255,6 +255,76 @@ def antisense_index() -> tuple[str, SynthTxome, str]:
     return os.path.join(d, "idx") + "/", tx, fa2
 
 
+def make_bigsa_copy(src: str, dst: str) -> str:
+    """Rewrites a 32-bit index directory as the BigSA flavour the reference writes for texts beyond 2^31 (IndexT = int64_t,
+    src/RapMapSAIndexer.cpp:86-220): 8-byte suffix-array entries, transcript offsets, hash intervals ({u64, i64, i64} records)
+    and FrugalBooMap starts / overflow pairs; header.json says BigSA.  The reference takes its int64 code path on the result
+    (src/RapMapSAMapper.cpp:1210-1240); tests/test_oracle_golden.py checks that it prints the same SAM as on the original."""
+    import json
+    import shutil
+    import struct
+
+    os.makedirs(dst, exist_ok=True)
+    with open(os.path.join(src, "header.json")) as f:
+        hdr = json.load(f)
+    hdr["value0"]["BigSA"] = True
+    with open(os.path.join(dst, "header.json"), "w") as f:
+        json.dump(hdr, f, indent=4)
+    shutil.copy(os.path.join(src, "rsd.bin"), os.path.join(dst, "rsd.bin"))
+    b = open(os.path.join(src, "sa.bin"), "rb").read()
+    n = struct.unpack_from("<Q", b, 0)[0]
+    with open(os.path.join(dst, "sa.bin"), "wb") as f:
+        f.write(struct.pack("<Q", n))
+        np.frombuffer(b, dtype="<i4", offset=8, count=n).astype("<i8").tofile(f)
+    b = open(os.path.join(src, "txpInfo.bin"), "rb").read()
+    nt = struct.unpack_from("<Q", b, 0)[0]
+    p = 8
+    for _ in range(nt):
+        p += 8 + struct.unpack_from("<Q", b, p)[0]
+    no = struct.unpack_from("<Q", b, p)[0]
+    offs = np.frombuffer(b, dtype="<i4", offset=p + 8, count=no)
+    with open(os.path.join(dst, "txpInfo.bin"), "wb") as f:
+        f.write(b[: p + 8])
+        offs.astype("<i8").tofile(f)
+        f.write(b[p + 8 + 4 * no:])
+
+    def widen_table(blob: bytes, at: int, key_bytes: int) -> bytes:
+        """sparsepp table at blob[at:]: be32 magic / table size / #records (no 64-bit escape at these sizes), group bitmaps, records
+        {key, i32, i32} -> {key, i64, i64}."""
+        magic, table, cnt = struct.unpack_from(">III", blob, at)
+        assert magic == 0x24687531 and table != 0xFFFFFFFF and cnt != 0xFFFFFFFF
+        rec = key_bytes + 8
+        recs_at = len(blob) - cnt * rec
+        recs = np.frombuffer(blob, dtype=np.dtype([("k", f"V{key_bytes}"), ("a", "<i4"), ("b", "<i4")]), offset=recs_at, count=cnt)
+        wide = np.zeros(cnt, dtype=np.dtype([("k", f"V{key_bytes}"), ("a", "<i8"), ("b", "<i8")]))
+        wide["k"], wide["a"], wide["b"] = recs["k"], recs["a"], recs["b"]
+        return blob[at:recs_at] + wide.tobytes()
+
+    if os.path.exists(os.path.join(src, "hash.bin")):
+        blob = open(os.path.join(src, "hash.bin"), "rb").read()
+        with open(os.path.join(dst, "hash.bin"), "wb") as f:
+            f.write(widen_table(blob, 0, 8))
+    else:
+        shutil.copy(os.path.join(src, "hash_info.bph"), os.path.join(dst, "hash_info.bph"))
+        blob = open(os.path.join(src, "hash_info.val"), "rb").read()
+        nd = struct.unpack_from("<Q", blob, 0)[0]
+        data = np.frombuffer(blob, dtype="<i4", offset=8, count=nd)
+        lens_at = 8 + 4 * nd
+        nl = struct.unpack_from("<Q", blob, lens_at)[0]
+        table_at = lens_at + 8 + nl
+        # overflow_: keys are IndexT too -> {i32, i32} records become {i64, i64}
+        magic, table, cnt = struct.unpack_from(">III", blob, table_at)
+        recs_at = len(blob) - cnt * 8
+        recs = np.frombuffer(blob, dtype="<i4", offset=recs_at, count=2 * cnt)
+        with open(os.path.join(dst, "hash_info.val"), "wb") as f:
+            f.write(struct.pack("<Q", nd))
+            data.astype("<i8").tofile(f)
+            f.write(blob[lens_at:table_at])
+            f.write(blob[table_at:recs_at])
+            recs.astype("<i8").tofile(f)
+    return dst if dst.endswith("/") else dst + "/"
+
+
 # ----------------------------------------------------------------------------------------------
 # golden fixtures
 # ----------------------------------------------------------------------------------------------

@@ -99,3 +99,30 @@ def test_malformed_index_is_an_io_error_not_a_crash(tmp_path, what):
     with pytest.raises(rb.RapMapCudaError) as e:
         rb.Index(_corrupt_copy(tmp_path, what, mutate), 0)
     assert e.value.code == rb.ERR_IO, str(e.value)
+
+
+def test_bigsa_index_parses_and_oversized_is_refused(tmp_path):
+    """A BigSA (int64) index directory is parsed and narrowed (no GPU here: the call then stops at the device check with
+    RAPMAP_ERR_CUDA, not at the files); one whose transcript offsets pass 2^31 is refused with RAPMAP_ERR_UNSUPPORTED."""
+    import struct
+
+    import torch
+
+    from helpers import make_bigsa_copy
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by the GPU tests")
+    big = make_bigsa_copy(os.path.join(GOLD, "synth_idx"), str(tmp_path / "big"))
+    with pytest.raises(rb.RapMapCudaError) as e:
+        rb.Index(big, 0)
+    assert e.value.code == rb.ERR_CUDA, str(e.value)
+    b = bytearray(open(os.path.join(big, "txpInfo.bin"), "rb").read())
+    n = struct.unpack_from("<Q", b, 0)[0]
+    p = 8
+    for _ in range(n):
+        p += 8 + struct.unpack_from("<Q", b, p)[0]
+    struct.pack_into("<q", b, p + 8 + 8 * (n - 1), 1 << 33)  # last transcript starts beyond 2^31
+    open(os.path.join(big, "txpInfo.bin"), "wb").write(bytes(b))
+    with pytest.raises(rb.RapMapCudaError) as e:
+        rb.Index(big, 0)
+    assert e.value.code == rb.ERR_UNSUPPORTED, str(e.value)

@@ -620,3 +620,20 @@ def test_direct_copy_out_to_pinned_and_device_buffers(synth_small, sel):
     with pytest.raises(rb.RapMapCudaError) as e:
         mapper.map_batch(s1, s2, n=n, fixed_len=L, hits_out=small, offsets_out=offs, capacity=10)
     assert e.value.code == rb.ERR_CAPACITY
+
+
+@pytest.mark.parametrize("idx,case", [("synth_idx", "synth/default"), ("synth_idx", "synth/selaln"), ("synth_idx_p", "synth_p/selaln")])
+def test_bigsa_index_flavour(synth_small, tmp_path, idx, case):
+    """BigSA (int64) index files (helpers.make_bigsa_copy; accepted by the unmodified reference, tests/test_oracle_golden.py):
+    read, narrowed to the device's 32-bit positions, and the SAM is the golden SAM of the 32-bit index."""
+    from helpers import make_bigsa_copy
+
+    idx_dir, index, s1, s2, L, tx = synth_small
+    big = rb.Index(make_bigsa_copy(os.path.join(GOLD, idx), str(tmp_path / "big")), 0)
+    opts = opts_from_flags(GOLDEN[case]["flags"])
+    n = s1.shape[0]
+    mapper = make_mapper(big, opts, n, L)
+    res = mapper.map_batch(s1, s2, n=n, fixed_len=L)
+    n1, n2 = synth_names(tx, n)
+    sam = big.sam_header() + mapper.format_sam(s1, s2, n1, n2, res, n, fixed_len=L)
+    assert md5(sam) == GOLDEN[case]["md5"]

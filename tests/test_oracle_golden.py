@@ -112,3 +112,17 @@ def test_oracle_matches_live_reference_on_antisense_transcriptome(tmp_path):
         subprocess.run([REF_BIN, "quasimap", "-i", idx, "-r", str(d / "a1.fastq"), "-t", "1", "-o", str(d / "ref.sam")] + flags, check=True, capture_output=True)
         subprocess.run([ORACLE_CLI, "-i", idx, "-r", str(d / "a1.fastq"), "-o", str(d / "ora.sam")] + flags, check=True, capture_output=True)
         assert (d / "ref.sam").read_bytes() == (d / "ora.sam").read_bytes(), ["-r"] + flags
+
+
+@pytest.mark.skipif(not have_ref(), reason="compiled reference (oracle/_ref) not present")
+@pytest.mark.parametrize("idx,case", [("synth_idx", "synth/default"), ("synth_idx", "synth/selaln"), ("synth_idx_p", "synth_p/default")])
+def test_bigsa_rewrite_is_accepted_by_the_reference(fastqs, tmp_path, idx, case):
+    """helpers.make_bigsa_copy turns a 32-bit index into the BigSA (int64) flavour: the unmodified reference dispatches on
+    header.json (src/RapMapSAMapper.cpp:1210-1240), maps with its int64 instantiation and prints the golden SAM."""
+    from helpers import make_bigsa_copy
+
+    big = make_bigsa_copy(os.path.join(GOLD, idx), str(tmp_path / "big"))
+    r1, r2 = fastqs["synth"]
+    out = tmp_path / "o.sam"
+    subprocess.run([REF_BIN, "quasimap", "-i", big, "-1", r1, "-2", r2, "-t", "1", "-o", str(out)] + GOLDEN[case]["flags"], check=True, capture_output=True)
+    assert md5(out.read_bytes()) == GOLDEN[case]["md5"]
