@@ -236,7 +236,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-in", default="host", choices=["host", "device"], help="diagnosis only: where the end-to-end leg's inputs live")
     ap.add_argument("--e2e-out", default="host", choices=["host", "device"], help="diagnosis only: where the end-to-end leg's outputs go")
-    ap.add_argument("--e2e-depth", type=int, default=2, choices=[1, 2], help="chunks the end-to-end leg keeps in flight on its ONE mapper (the mapper pipelines two)")
+    ap.add_argument("--e2e-depth", type=int, default=3, choices=[1, 2, 3], help="chunks the end-to-end leg keeps in flight on its ONE mapper (the mapper pipelines two)")
     args = ap.parse_args()
 
     if args.impl == "reference":

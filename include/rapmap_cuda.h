@@ -155,12 +155,13 @@ int rapmap_cuda_map_batch(rapmap_cuda_mapper_t* m, const rapmap_read_batch_t* re
 /* The same call split in two, so that ONE host thread keeps the device busy - the reference gets its overlap from N worker
  * threads around a shared parser queue (src/RapMapSAMapper.cpp:853-909); here a mapper pipelines consecutive chunks on three
  * CUDA streams: while chunk i computes, the reads of chunk i+1 come in over PCIe and the results of chunk i-1 go out.
- * _async validates, enqueues the copies and every kernel of the chunk and returns without waiting; up to TWO chunks may be
- * in flight per mapper (a third _async fails with RAPMAP_ERR_ARG).  `reads`, its buffers, `out` and its buffers must stay
+ * _async validates, enqueues the copies and every kernel of the chunk and returns without waiting; up to
+ * rapmap_cuda_max_in_flight() chunks (3) may be in flight per mapper (one more _async fails with RAPMAP_ERR_ARG).  `reads`, its buffers, `out` and its buffers must stay
  * valid and untouched until the rapmap_cuda_mapper_wait(m) that collects the chunk returns; _wait collects the OLDEST chunk
  * in flight and fills its out->num_hits / counters and the caller's buffers.  With pinned (or device) output buffers a chunk
  * costs one host synchronisation; pageable output buffers cost a second one.  rapmap_cuda_map_batch == _async + _wait. */
 int rapmap_cuda_map_batch_async(rapmap_cuda_mapper_t* m, const rapmap_read_batch_t* reads, rapmap_hit_batch_t* out);
+uint32_t rapmap_cuda_max_in_flight(void);
 int rapmap_cuda_mapper_wait(rapmap_cuda_mapper_t* m);
 int rapmap_cuda_last_timing(const rapmap_cuda_mapper_t* m, rapmap_cuda_timing_t* t);
 /* The mapper's CUDA stream (cudaStream_t as void*): every kernel and copy of map_batch is issued on it, so a caller

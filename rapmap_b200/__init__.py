@@ -119,7 +119,7 @@ SYMBOLS = [
     "rapmap_cuda_last_error", "rapmap_cuda_opts_default", "rapmap_cuda_opts_selaln", "rapmap_cuda_index_load", "rapmap_cuda_index_free",
     "rapmap_cuda_index_num_transcripts", "rapmap_cuda_index_transcript_name", "rapmap_cuda_index_transcript_len", "rapmap_cuda_index_k",
     "rapmap_cuda_index_device_bytes", "rapmap_cuda_index_image_bytes", "rapmap_cuda_index_image_ptr", "rapmap_cuda_index_from_image",
-    "rapmap_cuda_mapper_create", "rapmap_cuda_mapper_free", "rapmap_cuda_map_batch", "rapmap_cuda_map_batch_async", "rapmap_cuda_mapper_wait",
+    "rapmap_cuda_mapper_create", "rapmap_cuda_mapper_free", "rapmap_cuda_map_batch", "rapmap_cuda_map_batch_async", "rapmap_cuda_mapper_wait", "rapmap_cuda_max_in_flight",
     "rapmap_cuda_last_timing", "rapmap_cuda_mapper_stream", "rapmap_cuda_debug_intervals",
     "rapmap_cuda_format_sam", "rapmap_cuda_format_sam_mt", "rapmap_cuda_sam_header", "rapmap_cuda_free", "rapmap_cuda_host_alloc", "rapmap_cuda_host_free",
 ]
@@ -158,6 +158,7 @@ def lib() -> C.CDLL:
     L.rapmap_cuda_map_batch.argtypes = [C.c_void_p, C.POINTER(ReadBatch), C.POINTER(HitBatch)]
     L.rapmap_cuda_map_batch_async.argtypes = [C.c_void_p, C.POINTER(ReadBatch), C.POINTER(HitBatch)]
     L.rapmap_cuda_mapper_wait.argtypes = [C.c_void_p]
+    L.rapmap_cuda_max_in_flight.restype = C.c_uint32
     L.rapmap_cuda_last_timing.argtypes = [C.c_void_p, C.POINTER(Timing)]
     L.rapmap_cuda_mapper_stream.argtypes = [C.c_void_p]
     L.rapmap_cuda_mapper_stream.restype = C.c_void_p
@@ -169,6 +170,11 @@ def lib() -> C.CDLL:
     L.rapmap_cuda_free.argtypes = [C.c_void_p]
     _lib = L
     return L
+
+
+def max_in_flight() -> int:
+    """Chunks a mapper pipelines (rapmap_cuda_max_in_flight)."""
+    return int(lib().rapmap_cuda_max_in_flight())
 
 
 def _check(rc: int) -> None:
@@ -309,7 +315,7 @@ class Mapper:
     def map_batch_async(self, seq1, seq2=None, n: Optional[int] = None, fixed_len: int = 0, off1=None, off2=None,
                         location: int = LOC_HOST, hits_out=None, offsets_out=None, out_location: int = LOC_HOST, capacity: Optional[int] = None) -> None:
         """rapmap_cuda_map_batch_async: enqueues the chunk and returns; :meth:`wait` collects the OLDEST chunk in flight (a
-        mapper keeps up to two: one computes while the next one's reads come in and the previous one's results go out).
+        mapper keeps up to max_in_flight(): one computes while the next one's reads come in and the previous one's results go out).
         The input and output buffers must stay alive and untouched until then (the mapper keeps references); with chunks in
         flight pass your own ``hits_out`` / ``offsets_out`` per chunk."""
         if n is None:

@@ -78,11 +78,11 @@ __global__ void build_table_kernel(const KmerRecord* recs, uint64_t n, uint4* ta
   }
 }
 
-__global__ void build_filter_kernel(const KmerRecord* recs, uint64_t n, uint32_t* filter, uint32_t shift) {
+__global__ void build_filter_kernel(const KmerRecord* recs, uint64_t n, uint32_t k, uint32_t* filter, uint32_t shift) {
   for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
     uint64_t word;
     uint32_t mask;
-    filterSlot(mix64(recs[i].kmer), shift, word, mask);
+    filterInsertBits(recs[i].kmer, k, shift, word, mask);
     atomicOr(filter + word, mask);
   }
 }
@@ -100,7 +100,7 @@ __global__ void build_filter_from_text_kernel(const uint8_t* text, uint64_t n, u
     if (!ok) continue;
     uint64_t word;
     uint32_t mask;
-    filterSlot(mix64(w), shift, word, mask);
+    filterInsertBits(w, k, shift, word, mask);
     atomicOr(filter + word, mask);
   }
 }
@@ -211,10 +211,13 @@ struct rapmap_cuda_index {
   std::vector<int32_t> lens;
 };
 
-// Batches a mapper keeps in flight: while batch c computes, batch c+1's reads come in over PCIe and batch c-1's results go
-// out - on three streams of ONE mapper, so the kernels of consecutive batches never compete for the SMs (three mappers on
+// Batches a mapper keeps in flight (kDepth slots): while batch c computes, batch c+1's reads come in over PCIe and batch
+// c-1's results go out - on three streams of ONE mapper, so the kernels of consecutive batches never compete for the SMs (three mappers on
 // three streams lost a quarter of the device-resident rate to that, profiles/r02d_e2e_diag.txt).
-static constexpr int kDepth = 2;
+#ifndef RAPMAP_DEPTH
+#define RAPMAP_DEPTH 3  // with 2 the copy-in of chunk c+2 could only start after the copy-out of chunk c: copy-out + copy-in ~ one chunk of compute, no slack
+#endif
+static constexpr int kDepth = RAPMAP_DEPTH;
 
 // pinned block the compute stream writes at the end of an attempt; the host reads it after the batch's synchronisation
 struct StageBlock { uint32_t ctl[4]; uint64_t mergeTotal; uint64_t selTotal; uint32_t dpJobs[2]; Counters5 counters; };
@@ -499,7 +502,7 @@ static int indexLoadImpl(const char* index_dir, int device, rapmap_cuda_index_t*
         uint32_t shift = 64;
         for (uint64_t w = hdr.filterWords; w > 1; w >>= 1) --shift;
         e3 = cudaMemset(idx->blob + hdr.offFilter, 0, hdr.filterWords * 4);
-        if (e3 == cudaSuccess) build_filter_kernel<<<2048, 256>>>(dRecs, h.kmers.size(), reinterpret_cast<uint32_t*>(idx->blob + hdr.offFilter), shift);
+        if (e3 == cudaSuccess) build_filter_kernel<<<2048, 256>>>(dRecs, h.kmers.size(), hdr.k, reinterpret_cast<uint32_t*>(idx->blob + hdr.offFilter), shift);
       }
       e3 = cudaDeviceSynchronize();
     }
@@ -945,7 +948,7 @@ static cudaError_t waitSlot(rapmap_cuda_mapper* m, BatchSlot& sl) {
 static int mapBatchAsyncImpl(rapmap_cuda_mapper_t* m, const rapmap_read_batch_t* reads, rapmap_hit_batch_t* out) {
   if (!m || !reads || !out) return fail(RAPMAP_ERR_ARG, "null argument");
   if (m->submitted - m->collected >= static_cast<uint64_t>(kDepth))
-    return fail(RAPMAP_ERR_ARG, "the mapper already has 2 batches in flight (call rapmap_cuda_mapper_wait first)");
+    return fail(RAPMAP_ERR_ARG, "the mapper already has its maximum of batches in flight (call rapmap_cuda_mapper_wait first)");
   BatchSlot& sl = m->slots[m->submitted % kDepth];
   sl.out = out;
   sl.rerun = false;
@@ -1130,6 +1133,8 @@ void rapmap_cuda_mapper_free(rapmap_cuda_mapper_t* m) {
   freeMapperBuffers(m);
   delete m;
 }
+
+uint32_t rapmap_cuda_max_in_flight(void) { return static_cast<uint32_t>(kDepth); }
 
 int rapmap_cuda_map_batch_async(rapmap_cuda_mapper_t* m, const rapmap_read_batch_t* reads, rapmap_hit_batch_t* out) {
   return guarded([&] { return mapBatchAsyncImpl(m, reads, out); });

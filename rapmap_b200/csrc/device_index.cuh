@@ -4,7 +4,8 @@
 // ncclBroadcast / cudaMemcpy):
 //   ImageHeader | SA int32[n] | text u8[n + pad] | rank uint4[ceil(n/64)+1] | txpOffsets int32[T] |
 //   txpLens int32[T] | hash table uint4[slots] | packed text TextRec[ceil(n/32)+1] | k-mer filter u32[F]
-// * k-mer filter: a word-blocked Bloom filter over the indexed k-mers (3 bits inside one 32-bit word, ~6 bits per key,
+// * k-mer filter: a word-blocked Bloom filter over the indexed k-mers, keyed by the canonical k-mer with an orientation
+//   marker (4 bits inside one 32-bit word, ~6 bits per key,
 //   at most 64 MB so that it stays resident in the 126 MB L2, loads carry an L2 evict_last policy).  ~90 % of the
 //   lookups of a read with sequencing errors are for k-mers that are not in the index (the 31 windows covering a
 //   mismatch, both orientations); the filter answers ~92 % of those from L2 without touching the table in HBM.
@@ -100,13 +101,45 @@ __host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
   return x;
 }
 
-// Filter word / bit mask of a k-mer from its table hash h = mix64(key): the word index comes from the top bits, the three
-// bit positions from bits 25..39 (disjoint from the word index for every filter size up to 2^24 words; no second multiply:
-// the mask kernel evaluates this twice per k-mer window of every read).
-__host__ __device__ __forceinline__ void filterSlot(uint64_t h, uint32_t shift, uint64_t& word, uint32_t& mask) {
+// k-mer filter, keyed by the CANONICAL k-mer c = min(w, rc(w)): a read window asks about w and rc(w) at once, so one
+// probe answers both.  From h = mix64(c): the word index comes from the top bits, three presence bits from bits 25..39, and
+// an orientation marker from bits 40..44 (indexed k-mer equals its canonical form) or 45..49 (it is the reverse complement
+// of it).  All five fields are disjoint from the word index for every filter size up to 2^14 ... 2^24 words.
+//   w may be in the index   <=> the three presence bits and the marker of w's orientation are set
+__host__ __device__ __forceinline__ void filterSlot(uint64_t h, uint32_t shift, uint64_t& word, uint32_t& presence, uint32_t& markCanon, uint32_t& markRc) {
   word = h >> shift;
   const uint32_t g = static_cast<uint32_t>(h >> 25);
-  mask = (1u << (g & 31)) | (1u << ((g >> 5) & 31)) | (1u << ((g >> 10) & 31));
+  presence = (1u << (g & 31)) | (1u << ((g >> 5) & 31)) | (1u << ((g >> 10) & 31));
+  markCanon = 1u << ((g >> 15) & 31);
+  markRc = 1u << ((g >> 20) & 31);
+}
+
+// Reverse complement of a k-mer word (Kmer::getRC, reference include/Kmer.hpp:92-100), host and device.
+__host__ __device__ __forceinline__ uint64_t kmerRevComp(uint64_t w, uint32_t k) {
+  uint64_t x = ~w;  // complement: A<->T, C<->G is 3 - code
+  x = ((x >> 2) & 0x3333333333333333ULL) | ((x & 0x3333333333333333ULL) << 2);
+  x = ((x >> 4) & 0x0F0F0F0F0F0F0F0FULL) | ((x & 0x0F0F0F0F0F0F0F0FULL) << 4);
+  x = ((x >> 8) & 0x00FF00FF00FF00FFULL) | ((x & 0x00FF00FF00FF00FFULL) << 8);
+  x = ((x >> 16) & 0x0000FFFF0000FFFFULL) | ((x & 0x0000FFFF0000FFFFULL) << 16);
+  x = (x >> 32) | (x << 32);
+  return x >> (2 * (32 - k));
+}
+
+// Filter insertion of an indexed k-mer / query of a read k-mer w with reverse complement wr: the word and the two masks
+// "w may be present" / "wr may be present" (a mask is satisfied when all its bits are set in the word).
+__host__ __device__ __forceinline__ void filterInsertBits(uint64_t x, uint32_t k, uint32_t shift, uint64_t& word, uint32_t& bits) {
+  const uint64_t r = kmerRevComp(x, k);
+  const bool canon = x <= r;
+  uint32_t p, mc, mr;
+  filterSlot(mix64(canon ? x : r), shift, word, p, mc, mr);
+  bits = p | (canon ? mc : mr);
+}
+__host__ __device__ __forceinline__ void filterQuery(uint64_t w, uint64_t wr, uint32_t shift, uint64_t& word, uint32_t& maskW, uint32_t& maskWr) {
+  const bool canon = w <= wr;
+  uint32_t p, mc, mr;
+  filterSlot(mix64(canon ? w : wr), shift, word, p, mc, mr);
+  maskW = p | (canon ? mc : mr);
+  maskWr = p | (canon ? (w == wr ? mc : mr) : mc);  // a palindrome (even k only) is its own reverse complement
 }
 
 #ifdef __CUDACC__

@@ -154,13 +154,12 @@ __global__ void __launch_bounds__(256) kmer_mask_kernel(LaneParams P) {
         vv |= bit;
         if (same == k - 1) hh |= bit;
         if (P.ix.filter != nullptr) {
-          uint64_t wa, wb;
+          uint64_t fw;
           uint32_t ma, mb;
-          filterSlot(mix64(w), P.ix.filterShift, wa, ma);
-          filterSlot(mix64(wr), P.ix.filterShift, wb, mb);
-          const uint32_t fa = ldgKeep(P.ix.filter + wa), fb = ldgKeep(P.ix.filter + wb);
-          if ((fa & ma) != ma) af |= bit;
-          if ((fb & mb) != mb) ar |= bit;
+          filterQuery(w, wr, P.ix.filterShift, fw, ma, mb);  // ONE probe answers both orientations (canonical key)
+          const uint32_t fv = ldgKeep(P.ix.filter + fw);
+          if ((fv & ma) != ma) af |= bit;
+          if ((fv & mb) != mb) ar |= bit;
         }
       }
     }
@@ -761,13 +760,12 @@ __global__ void __launch_bounds__(NT, MINB) sa_collect_lane_kernel(LaneParams P)
         }
       }
       if (!(knownM && knownC)) {
-        uint64_t wa, wb;
+        uint64_t fw;
         uint32_t ma, mb;
-        filterSlot(mix64(w), P.ix.filterShift, wa, ma);
-        filterSlot(mix64(kmerRC(w, k)), P.ix.filterShift, wb, mb);
-        const uint32_t fa = ldgKeep(P.ix.filter + wa), fb = ldgKeep(P.ix.filter + wb);
-        knownM = (fa & ma) != ma;
-        knownC = (fb & mb) != mb;
+        filterQuery(w, kmerRC(w, k), P.ix.filterShift, fw, ma, mb);
+        const uint32_t fv = ldgKeep(P.ix.filter + fw);
+        knownM = (fv & ma) != ma;
+        knownC = (fv & mb) != mb;
       }
       if (!(knownM && knownC)) break;
       // double miss: no counter moves (strandHits / otherStrandHits, :541-546,:671); the walk steps one base (:673)

@@ -448,8 +448,8 @@ def test_every_arena_overflow_retry_path(monkeypatch, flags):
 
 @pytest.mark.skipif(not have_ref(), reason="needs oracle/_ref to build the mid-size index")
 @pytest.mark.parametrize("sel,pinned", [(False, False), (True, False), (False, True), (True, True)])
-def test_async_pipeline_two_chunks_in_flight(sel, pinned):
-    """rapmap_cuda_map_batch_async / rapmap_cuda_mapper_wait: one host thread, two mappers on one shared index, each with two
+def test_async_pipeline_chunks_in_flight(sel, pinned):
+    """rapmap_cuda_map_batch_async / rapmap_cuda_mapper_wait: one host thread, two mappers on one shared index, each with several
     chunks in flight (copy-in, kernels and copy-out of consecutive chunks overlap on the mapper's three streams); every
     chunk equals the oracle's result for that chunk.  Pageable and pinned output buffers; a third chunk is refused."""
     import torch
@@ -468,7 +468,8 @@ def test_async_pipeline_two_chunks_in_flight(sel, pinned):
             return torch.empty(16 * n * 28, dtype=torch.uint8).pin_memory(), torch.empty(n + 1, dtype=torch.int64).pin_memory()
         return np.empty(16 * n, dtype=rb.HIT_DTYPE), np.empty(n + 1, dtype=np.uint64)
 
-    outs = [[buffers() for _ in range(2)] for _ in range(2)]
+    D = rb.max_in_flight()
+    outs = [[buffers() for _ in range(D)] for _ in range(2)]
     done = {}
     order = [[], []]
 
@@ -484,12 +485,17 @@ def test_async_pipeline_two_chunks_in_flight(sel, pinned):
 
     for c in range(chunks):
         k = c % 2
-        if mappers[k].in_flight == 2:
+        if mappers[k].in_flight == D:
             collect(k)
-        ho, oo = outs[k][(c // 2) % 2]
+        ho, oo = outs[k][(c // 2) % D]
         mappers[k].map_batch_async(data[c][0], data[c][1], n=n, fixed_len=100, hits_out=ho, offsets_out=oo, capacity=16 * n)
         order[k].append(c)
-    with pytest.raises(rb.RapMapCudaError):  # a third chunk in flight is refused
+    while mappers[0].in_flight < D:  # fill the pipeline, then one chunk more is refused
+        c = chunks - 1
+        ho, oo = buffers()
+        mappers[0].map_batch_async(data[c][0], data[c][1], n=n, fixed_len=100, hits_out=ho, offsets_out=oo, capacity=16 * n)
+        order[0].append(c)
+    with pytest.raises(rb.RapMapCudaError):
         ho, oo = buffers()
         mappers[0].map_batch_async(data[0][0], data[0][1], n=n, fixed_len=100, hits_out=ho, offsets_out=oo, capacity=16 * n)
     for k in range(2):
@@ -503,7 +509,7 @@ def test_async_pipeline_two_chunks_in_flight(sel, pinned):
 
 @pytest.mark.skipif(not have_ref(), reason="needs oracle/_ref to build the mid-size index")
 def test_overflow_with_two_chunks_in_flight(monkeypatch):
-    """Tiny arenas AND two chunks in flight: the first chunk's overflow re-allocates the work areas under the second chunk,
+    """Tiny arenas AND several chunks in flight: the first chunk's overflow re-allocates the work areas under the second chunk,
     whose attempt is then repeated; both must equal the oracle."""
     monkeypatch.setenv("RAPMAP_B200_TINY_ARENAS", "1")
     idx_dir, tx = synth_index(2500)
@@ -514,13 +520,13 @@ def test_overflow_with_two_chunks_in_flight(monkeypatch):
     mapper = make_mapper(index, opts, n, 100)
     monkeypatch.delenv("RAPMAP_B200_TINY_ARENAS")
     om = OracleMapper(idx_dir, opts)
-    outs = [(np.empty(16 * n, dtype=rb.HIT_DTYPE), np.empty(n + 1, dtype=np.uint64)) for _ in range(2)]
+    outs = [(np.empty(16 * n, dtype=rb.HIT_DTYPE), np.empty(n + 1, dtype=np.uint64)) for _ in range(3)]
     got = []
     for c in range(3):
-        if mapper.in_flight == 2:
+        if mapper.in_flight == rb.max_in_flight():
             r = mapper.wait()
             got.append(rb.BatchResult(r.hits.copy(), r.pair_offsets.copy(), r.counters, r.num_hits))
-        mapper.map_batch_async(data[c][0], data[c][1], n=n, fixed_len=100, hits_out=outs[c % 2][0], offsets_out=outs[c % 2][1], capacity=16 * n)
+        mapper.map_batch_async(data[c][0], data[c][1], n=n, fixed_len=100, hits_out=outs[c][0], offsets_out=outs[c][1], capacity=16 * n)
     while mapper.in_flight:
         r = mapper.wait()
         got.append(rb.BatchResult(r.hits.copy(), r.pair_offsets.copy(), r.counters, r.num_hits))

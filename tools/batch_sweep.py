@@ -2,7 +2,7 @@
 """Chunk-size sweep of the C-ABI call (the reference's own chunk is 10,000 pairs, src/RapMapSAMapper.cpp:853).
 
 For each chunk size: pairs/s with device-resident buffers (one call at a time) and end to end with pinned host buffers through
-rapmap_cuda_map_batch_async / _wait (one host thread, one mapper, two chunks in flight), default flags and -s, on the
+rapmap_cuda_map_batch_async / _wait (one host thread, one mapper, three chunks in flight), default flags and -s, on the
 benchmark index.  Output: one JSON document on stdout (kept under profiles/)."""
 import json
 import os
@@ -39,7 +39,7 @@ def main():
             mapper = rb.Mapper(index, opts, max_batch=n, max_read_len=100)
             cap = 8 * n
             dh, do = torch.empty(cap * 28, dtype=torch.uint8, device="cuda"), torch.empty(n + 1, dtype=torch.int64, device="cuda")
-            hh = [(torch.empty(cap * 28, dtype=torch.uint8).pin_memory(), torch.empty(n + 1, dtype=torch.int64).pin_memory()) for _ in range(2)]
+            hh = [(torch.empty(cap * 28, dtype=torch.uint8).pin_memory(), torch.empty(n + 1, dtype=torch.int64).pin_memory()) for _ in range(3)]
             calls = max(8, min(400, (4 << 20) // n))
             chunks = max(1, nmax // n)
 
@@ -58,10 +58,10 @@ def main():
 
             def e2e(count):
                 for c in range(count):
-                    if mapper.in_flight == 2:
+                    if mapper.in_flight == 3:
                         mapper.wait()
                     o = (c % chunks) * n
-                    mapper.map_batch_async(h1[o:o + n], h2[o:o + n], n=n, fixed_len=100, hits_out=hh[c % 2][0], offsets_out=hh[c % 2][1], capacity=cap)
+                    mapper.map_batch_async(h1[o:o + n], h2[o:o + n], n=n, fixed_len=100, hits_out=hh[c % 3][0], offsets_out=hh[c % 3][1], capacity=cap)
                 while mapper.in_flight:
                     mapper.wait()
 

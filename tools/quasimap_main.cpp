@@ -3,7 +3,7 @@
 // (src/RapMapSAMapper.cpp:801-909, src/FastxParser.cpp:229-328); here the stages are a pipeline around ONE mapper:
 //
 //   parser threads (one per mate file: gz inflate / line splitting into pinned chunk buffers)
-//     -> main thread: rapmap_cuda_map_batch_async / rapmap_cuda_mapper_wait, two chunks in flight (copy-in, kernels, copy-out overlap)
+//     -> main thread: rapmap_cuda_map_batch_async / rapmap_cuda_mapper_wait, up to rapmap_cuda_max_in_flight() chunks in flight (copy-in, kernels, copy-out overlap)
 //     -> formatter: rapmap_cuda_format_sam_mt over -t host threads, written in input order
 //
 // Output is byte-identical to `rapmap quasimap -t 1` (paired reads, and unmated reads with -r).
@@ -232,7 +232,7 @@ int main(int argc, char** argv) {
   if (!fx[0].open(paired ? r1 : ru) || (paired && !fx[1].open(r2))) { std::fprintf(stderr, "cannot open read files\n"); return 1; }
 
   // ---- chunk pool and queues
-  constexpr int kChunks = 4;
+  constexpr int kChunks = 6;
   std::vector<Chunk> pool(kChunks);
   Queue<Chunk*> freeQ, parsedQ, mappedQ;
   for (auto& c : pool) {
@@ -300,7 +300,7 @@ int main(int argc, char** argv) {
     }
   });
 
-  // ---- mapping: two chunks in flight on one mapper
+  // ---- mapping: several chunks in flight on one mapper
   rapmap_cuda_mapper_t* mapper = nullptr;
   uint32_t mapperMaxLen = 0;
   std::deque<Chunk*> inFlight;
@@ -343,7 +343,7 @@ int main(int argc, char** argv) {
       for (int k = 0; k < (paired ? 2 : 1); ++k) growSeq(c->m[k], 16);
       c->rb = rapmap_read_batch_t{c->m[0].seq, c->m[0].off.data(), paired ? c->m[1].seq : nullptr, paired ? c->m[1].off.data() : nullptr, c->n, 0, RAPMAP_LOC_HOST};
       c->hb = rapmap_hit_batch_t{c->hits, c->hitsCap, c->offs, 0, {0, 0, 0, 0, 0}, RAPMAP_LOC_HOST};
-      if (inFlight.size() == 2) collect();
+      if (inFlight.size() == rapmap_cuda_max_in_flight()) collect();
       if (rapmap_cuda_map_batch_async(mapper, &c->rb, &c->hb) != RAPMAP_OK) die("map_batch_async");
       inFlight.push_back(c);
     } else {
