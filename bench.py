@@ -306,29 +306,42 @@ def main():
         devb.append((h1.cuda(), h2.cuda()))
     log(f"rank {rank}: generated {nd} x {B} pairs in {time.time() - t0:.1f}s")
     cap = B * 8
-    d_hits = torch.empty(cap * 28, dtype=torch.uint8, device="cuda")
-    d_off = torch.empty(B + 1, dtype=torch.int64, device="cuda")
     nm = args.e2e_depth
+    d_res = [(torch.empty(cap * 28, dtype=torch.uint8, device="cuda"), torch.empty(B + 1, dtype=torch.int64, device="cuda")) for _ in range(nm)]
     h_out = [(torch.empty(cap * 28, dtype=torch.uint8).pin_memory(), torch.empty(B + 1, dtype=torch.int64).pin_memory()) for _ in range(nm)]
-    d_outs = [(torch.empty(cap * 28, dtype=torch.uint8, device="cuda"), torch.empty(B + 1, dtype=torch.int64, device="cuda")) for _ in range(nm)] if args.e2e_out == "device" else None
+    d_outs = d_res
     dev = torch.device("cuda", local)
 
     STAGES = ("pack", "sa", "map", "merge", "selaln", "ksw", "h2d", "d2h")
 
     def run_leg(ix, opts, steps, warmup, sample_clocks=False):
-        """Resident leg (device buffers in and out, one mapper, CUDA events on its stream) and end-to-end leg (pinned host buffers
+        """Resident leg (device buffers in and out, one mapper, CUDA events on its compute stream) and end-to-end leg (pinned host buffers
         in and out through rapmap_cuda_map_batch_async / _wait: ONE host thread, ONE mapper, two chunks in flight, so one chunk's
         PCIe copies overlap another chunk's kernels) over the same chunk sequence; the two legs must produce the same hits."""
         mappers = [rb.Mapper(ix, opts, max_batch=B, max_read_len=READ_LEN)]
         mapper = mappers[0]
         stream = torch.cuda.ExternalStream(mapper.stream_ptr, device=dev)
 
-        def resident(c):
-            a, b = devb[c % nd]
-            return mapper.map_batch(a, b, n=B, fixed_len=READ_LEN, location=rb.LOC_DEVICE, hits_out=d_hits, offsets_out=d_off, out_location=rb.LOC_DEVICE, capacity=cap)
+        def resident_run(first, count, st=None):
+            """Device buffers in and out; chunks go through the same asynchronous pipeline (no host gap between chunks)."""
+            def collect():
+                r = mapper.wait()
+                if st is not None:
+                    t = mapper.timing()
+                    st["pack"] += t.ms_pack_reads; st["sa"] += t.ms_sa_collect; st["map"] += t.ms_hits_to_mappings; st["merge"] += t.ms_merge
+                    st["selaln"] += t.ms_sel_aln; st["ksw"] += t.ms_ksw; st["h2d"] += t.ms_h2d; st["d2h"] += t.ms_d2h
+                    st["launch"] += t.launches; st["hits"] += r.num_hits; st["retries"] += t.retries; st["dp_jobs"] += t.dp_jobs; st["dp_jobs_general"] += t.dp_jobs_general
 
-        for c in range(warmup * CH):
-            resident(c)
+            for c in range(first, first + count):
+                if mapper.in_flight == nm:
+                    collect()
+                a, b = devb[c % nd]
+                mapper.map_batch_async(a, b, n=B, fixed_len=READ_LEN, location=rb.LOC_DEVICE, hits_out=d_res[c % nm][0], offsets_out=d_res[c % nm][1],
+                                       out_location=rb.LOC_DEVICE, capacity=cap)
+            while mapper.in_flight:
+                collect()
+
+        resident_run(0, warmup * CH)
         torch.cuda.synchronize()
         barrier()
         sampler = ClockSampler(local) if sample_clocks else None
@@ -338,12 +351,7 @@ def main():
         st = {k: 0.0 for k in STAGES}
         st.update({"launch": 0, "hits": 0, "retries": 0, "dp_jobs": 0, "dp_jobs_general": 0})
         e0.record(stream)
-        for c in range(steps * CH):
-            r = resident(warmup * CH + c)
-            t = mapper.timing()
-            st["pack"] += t.ms_pack_reads; st["sa"] += t.ms_sa_collect; st["map"] += t.ms_hits_to_mappings; st["merge"] += t.ms_merge
-            st["selaln"] += t.ms_sel_aln; st["ksw"] += t.ms_ksw; st["h2d"] += t.ms_h2d; st["d2h"] += t.ms_d2h
-            st["launch"] += t.launches; st["hits"] += r.num_hits; st["retries"] += t.retries; st["dp_jobs"] += t.dp_jobs; st["dp_jobs_general"] += t.dp_jobs_general
+        resident_run(warmup * CH, steps * CH, st)
         e1.record(stream)
         torch.cuda.synchronize()
         barrier()

@@ -114,6 +114,7 @@ typedef struct {
   float ms_ksw;             /* the ksw2 DP kernels alone (part of ms_sel_aln) */
   uint32_t dp_jobs;         /* ksw_extz2 DP problems of the batch (getAlnScore calls that reach the aligner) */
   uint32_t dp_jobs_general; /* of those, the ones the thread-per-job kernel left to the general warp-per-job kernel */
+  uint32_t dp_jobs_exact_lane; /* of those, the ones the two-jobs-per-thread kernel handed to the byte-exact thread-per-job kernel */
 } rapmap_cuda_timing_t;
 
 /* Thread-local message for the last non-zero status. */

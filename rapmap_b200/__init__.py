@@ -106,7 +106,7 @@ class Timing(C.Structure):
         ("ms_h2d", C.c_float), ("ms_sa_collect", C.c_float), ("ms_hits_to_mappings", C.c_float), ("ms_merge", C.c_float),
         ("ms_sel_aln", C.c_float), ("ms_pack_reads", C.c_float), ("ms_d2h", C.c_float), ("ms_total", C.c_float),
         ("launches", C.c_uint32), ("retries", C.c_uint32), ("sa_intervals", C.c_uint64),
-        ("ms_ksw", C.c_float), ("dp_jobs", C.c_uint32), ("dp_jobs_general", C.c_uint32),
+        ("ms_ksw", C.c_float), ("dp_jobs", C.c_uint32), ("dp_jobs_general", C.c_uint32), ("dp_jobs_exact_lane", C.c_uint32),
     ]
 
 

@@ -220,7 +220,7 @@ struct rapmap_cuda_index {
 static constexpr int kDepth = RAPMAP_DEPTH;
 
 // pinned block the compute stream writes at the end of an attempt; the host reads it after the batch's synchronisation
-struct StageBlock { uint32_t ctl[4]; uint64_t mergeTotal; uint64_t selTotal; uint32_t dpJobs[2]; Counters5 counters; };
+struct StageBlock { uint32_t ctl[4]; uint64_t mergeTotal; uint64_t selTotal; uint32_t dpJobs[4]; Counters5 counters; };
 
 struct BatchSlot {
   // reads staged from the host
@@ -912,7 +912,7 @@ static int enqueueAttempt(rapmap_cuda_mapper* m, BatchSlot& sl) {
   ++sl.launches;
   CU_TRY(cudaEventRecord(sl.ev[5], st));
   // ---- selective alignment (ksw2 scoring + score filter): survivors to the slot's dSelOut, dPairOff rewritten in place
-  sl.hStage->selTotal = 0; sl.hStage->dpJobs[0] = 0; sl.hStage->dpJobs[1] = 0;
+  sl.hStage->selTotal = 0; sl.hStage->dpJobs[0] = 0; sl.hStage->dpJobs[1] = 0; sl.hStage->dpJobs[2] = 0; sl.hStage->dpJobs[3] = 0;
   if (m->dopts.selAln) {
     int rc = selAlnEnqueue(m->selaln, m->selLaunch, m->idx->view, m->dopts, bv, n, paired, sl.dHits, sl.dSelOut, sl.dPairOff, m->hitsCap, m->dCubTemp,
                            m->cubTempBytes, m->numSMs, st, &sl.launches, &sl.hStage->selTotal, sl.hStage->dpJobs, sl.ev[9], sl.ev[10], g_err);
@@ -1118,6 +1118,7 @@ static int mapperWaitImpl(rapmap_cuda_mapper_t* m) {
   m->timing.sa_intervals = sl.hStage->ctl[0];
   m->timing.dp_jobs = sl.hStage->dpJobs[0];
   m->timing.dp_jobs_general = sl.hStage->dpJobs[1];
+  m->timing.dp_jobs_exact_lane = sl.hStage->dpJobs[3];
   return rcOut;
 }
 

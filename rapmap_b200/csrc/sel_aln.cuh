@@ -23,10 +23,12 @@
 #pragma once
 #include <string>
 
+#include <cub/block/block_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include "kernels.cuh"
 #include "kmer_utils.cuh"
+#include "ksw_pair.cuh"
 
 namespace rapmap_b200 {
 
@@ -50,7 +52,9 @@ struct SelAlnWork {
   uint64_t* taskHash{nullptr};   // window hash, 0 = task never reaches the cache stage
   DPJob* jobs{nullptr};
   uint32_t* slowList{nullptr};   // DP jobs the thread-per-job kernel leaves to the general warp kernel
-  uint32_t* jobCursor{nullptr};  // [0] job count, [1] slow-list count
+  uint32_t* pairLeft{nullptr};   // DP jobs without a partner of their geometry in their tile (pair kernel, second pass)
+  uint32_t* exactList{nullptr};  // DP jobs the pair kernel hands to the byte-exact thread-per-job kernel
+  uint32_t* jobCursor{nullptr};  // [0] job count, [1] slow-list count, [2] pairLeft count, [3] exactList count
   int32_t* hitScore{nullptr};    // [hitsCap] final per-hit score (INT_MIN = dropped)
   int32_t* pairBest{nullptr};    // [maxBatch]
   uint32_t* outCount{nullptr};   // [maxBatch + 1]
@@ -61,15 +65,15 @@ struct SelAlnWork {
 };
 
 inline void selAlnFree(SelAlnWork& w) {
-  cudaFree(w.taskScore); cudaFree(w.taskRef); cudaFree(w.taskHash); cudaFree(w.jobs); cudaFree(w.slowList); cudaFree(w.jobCursor); cudaFree(w.hitScore);
+  cudaFree(w.taskScore); cudaFree(w.taskRef); cudaFree(w.taskHash); cudaFree(w.jobs); cudaFree(w.slowList); cudaFree(w.pairLeft); cudaFree(w.exactList); cudaFree(w.jobCursor); cudaFree(w.hitScore);
   cudaFree(w.pairBest); cudaFree(w.outCount); cudaFree(w.outOff);
   w = SelAlnWork();
 }
 
 inline cudaError_t selAlnReserve(SelAlnWork& w, uint64_t hits) {
   if (hits <= w.hitsCap) return cudaSuccess;
-  cudaFree(w.taskScore); cudaFree(w.taskRef); cudaFree(w.taskHash); cudaFree(w.jobs); cudaFree(w.slowList); cudaFree(w.hitScore);
-  w.slowList = nullptr; w.taskScore = nullptr; w.taskRef = nullptr; w.taskHash = nullptr; w.jobs = nullptr; w.hitScore = nullptr;
+  cudaFree(w.taskScore); cudaFree(w.taskRef); cudaFree(w.taskHash); cudaFree(w.jobs); cudaFree(w.slowList); cudaFree(w.pairLeft); cudaFree(w.exactList); cudaFree(w.hitScore);
+  w.pairLeft = nullptr; w.exactList = nullptr; w.slowList = nullptr; w.taskScore = nullptr; w.taskRef = nullptr; w.taskHash = nullptr; w.jobs = nullptr; w.hitScore = nullptr;
   uint64_t cap = hits;
   cudaError_t e;
   if ((e = cudaMalloc(&w.taskScore, cap * 2 * 4)) != cudaSuccess) return e;
@@ -77,6 +81,8 @@ inline cudaError_t selAlnReserve(SelAlnWork& w, uint64_t hits) {
   if ((e = cudaMalloc(&w.taskHash, cap * 2 * 8)) != cudaSuccess) return e;
   if ((e = cudaMalloc(&w.jobs, cap * 2 * sizeof(DPJob))) != cudaSuccess) return e;
   if ((e = cudaMalloc(&w.slowList, cap * 2 * 4)) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&w.pairLeft, cap * 2 * 4)) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&w.exactList, cap * 2 * 4)) != cudaSuccess) return e;
   if ((e = cudaMalloc(&w.hitScore, cap * 4)) != cudaSuccess) return e;
   w.hitsCap = cap;
   return cudaSuccess;
@@ -86,7 +92,7 @@ inline cudaError_t selAlnAlloc(SelAlnWork& w, uint64_t maxBatch, uint32_t maxRea
   w.maxBatch = maxBatch;
   w.maxReadLen = maxReadLen;
   cudaError_t e;
-  if ((e = cudaMalloc(&w.jobCursor, 8)) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&w.jobCursor, 32)) != cudaSuccess) return e;
   if ((e = cudaMalloc(&w.pairBest, maxBatch * 4)) != cudaSuccess) return e;
   if ((e = cudaMalloc(&w.outCount, (maxBatch + 1) * 4)) != cudaSuccess) return e;
   if ((e = cudaMalloc(&w.outOff, (maxBatch + 1) * 8)) != cudaSuccess) return e;
@@ -306,6 +312,15 @@ struct KswParams {
   const uint32_t* jobIdx;   // nullptr: jobs[0 .. *jobCount); else the jobs listed here (the ones the lane kernel left)
   uint32_t* slowList;       // lane kernel: jobs it does not take
   uint32_t* slowCount;
+  // pair kernel (two jobs of one geometry per thread): its input list (nullptr = all jobs), the jobs that found no partner
+  // of their geometry in their tile (second pass), and the jobs it hands to the byte-exact thread-per-job kernel
+  const uint32_t* pairSrc;
+  const uint32_t* pairSrcCount;
+  uint32_t* pairLeft;
+  uint32_t* pairLeftCount;
+  uint32_t* exactList;
+  uint32_t* exactCount;
+  uint32_t pairPass;
 };
 
 // General path: every geometry (any bandwidth, short windows).  State in shared memory, laid out as the reference's
@@ -590,7 +605,8 @@ __global__ void __launch_bounds__(NT, RAPMAP_KSW_MINB) ksw_extz_lane_kernel(KswP
   int minSc = P.mat1 < P.matN ? P.mat1 : P.matN;
   minSc = minSc < P.mat0 ? minSc : P.mat0;
   const int w = P.w;
-  for (uint32_t j = blockIdx.x * NT + threadIdx.x; j < nJobs; j += gridDim.x * NT) {
+  for (uint32_t jj = blockIdx.x * NT + threadIdx.x; jj < nJobs; jj += gridDim.x * NT) {
+    const uint32_t j = P.jobIdx ? P.jobIdx[jj] : jj;
     const DPJob jb = P.jobs[j];
     const int qlen = jb.rlen, tlen = jb.tlen1;
     const int tl16 = (tlen + 15) / 16 * 16, ql16 = (qlen + 15) / 16 * 16 + 16;
@@ -731,6 +747,75 @@ __global__ void __launch_bounds__(NT, RAPMAP_KSW_MINB) ksw_extz_lane_kernel(KswP
   }
 }
 
+// Pair kernel: TWO DP jobs of one geometry (qlen, tlen) per thread, 16-bit halves of one register per band column
+// (ksw_pair.cuh has the DP and the argument why it is exact).  A tile of 2 * NT jobs is sorted by geometry in shared
+// memory (cub::BlockRadixSort, blocked: thread i gets sorted items 2i and 2i + 1); equal neighbours run as a pair, an
+// item without a partner runs alone (both halves hold the same job) and its unequal neighbour goes to the `pairLeft`
+// list, which a second launch (pairPass = 1) pairs up across tiles.  Jobs outside the pair kernel's geometry, and pairs
+// whose x-side left the int8 range, go to the byte-exact thread-per-job kernel through `exactList`.
+template <int NT, int CELLS>
+__global__ void __launch_bounds__(NT, 2) ksw_extz_pair_kernel(KswParams P) {
+  extern __shared__ __align__(16) uint8_t pairStrip[];
+  using Sort = cub::BlockRadixSort<uint32_t, NT, 2, uint32_t>;
+  __shared__ typename Sort::TempStorage sortTmp;
+  uint32_t* myW = reinterpret_cast<uint32_t*>(pairStrip) + threadIdx.x;
+  uint8_t* myB = pairStrip + static_cast<size_t>(threadIdx.x) * 4;
+  // cell p (two bytes: job 0, job 1) of this thread's strip
+  auto cellByte = [&](int p, int half) -> uint8_t& { return myB[(static_cast<size_t>(p >> 1) * NT) * 4 + (p & 1) * 2 + half]; };
+  const kswpair::Consts C = kswpair::makeConsts(P.mat0, P.mat1, P.matN, P.q, P.e, P.w);
+  const uint32_t nSrc = *P.pairSrcCount;
+  constexpr uint32_t kNoJob = 0xFFFFFFu;
+  for (uint32_t base = blockIdx.x * 2u * NT; base < nSrc; base += gridDim.x * 2u * NT) {
+    uint32_t keys[2], vals[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const uint32_t i = base + 2u * threadIdx.x + k;
+      keys[k] = kNoJob; vals[k] = 0u;
+      if (i < nSrc) {
+        const uint32_t j = P.pairSrc ? P.pairSrc[i] : i;
+        const int qlen = P.jobs[j].rlen, tlen = P.jobs[j].tlen1;
+        if (kswpair::geomOk(C, qlen, tlen, CELLS)) { keys[k] = (static_cast<uint32_t>(qlen) << 11) | static_cast<uint32_t>(tlen); vals[k] = j; }
+        else P.exactList[atomicAdd(P.exactCount, 1u)] = j;
+      }
+    }
+    __syncthreads();
+    Sort(sortTmp).Sort(keys, vals, 0, 24);
+    int nrep = 0;
+    if (keys[0] != kNoJob) {
+      nrep = 1;
+      if (keys[1] != keys[0] && keys[1] != kNoJob) {
+        if (P.pairPass == 0) P.pairLeft[atomicAdd(P.pairLeftCount, 1u)] = vals[1];
+        else nrep = 2;   // second pass: run the two one after the other
+      }
+    }
+    for (int rep = 0; rep < nrep; ++rep) {
+      const bool both = rep == 0 && keys[1] == keys[0];
+      const uint32_t j0 = rep ? vals[1] : vals[0], j1 = both ? vals[1] : j0;
+      const DPJob ja = P.jobs[j0], jb = P.jobs[j1];
+      const int qlen = ja.rlen, tlen = ja.tlen1;
+      const int TL = kswpair::stripTL(tlen), words = (kswpair::stripCells(qlen, tlen) + 1) / 2;
+      for (int i = 0; i < words; ++i) myW[static_cast<size_t>(i) * NT] = 0u;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const DPJob& jx = half ? jb : ja;
+        const uint8_t* read;
+        uint32_t rl;
+        readSpan(P.reads, jx.read, read, rl);
+        for (int i = 0; i < qlen; ++i) cellByte(TL + i, half) = nt4(queryChar(read, rl, jx.rc != 0, jx.rskip + (qlen - 1 - i)));
+        for (int t = 0; t < tlen; ++t) cellByte(t, half) = nt4(__ldg(P.ix.text + jx.tpos + t));
+      }
+      int32_t sc0, sc1;
+      if (kswpair::pairDP<NT>(myW, qlen, tlen, C, sc0, sc1)) {
+        P.taskScore[ja.slot] = sc0;
+        if (both) P.taskScore[jb.slot] = sc1;
+      } else {
+        P.exactList[atomicAdd(P.exactCount, 1u)] = j0;
+        if (both) P.exactList[atomicAdd(P.exactCount, 1u)] = j1;
+      }
+    }
+  }
+}
+
 __device__ __forceinline__ int32_t taskValue(const SelAlnParams& P, uint64_t slot) {
   const int32_t ref = P.taskRef[slot];
   return ref >= 0 ? P.taskScore[ref] : P.taskScore[slot];
@@ -813,11 +898,12 @@ struct CastU64b {
 struct SelAlnLaunch {
   uint32_t warpSmemBytes{0};
   int32_t tl16max{0};
-  uint32_t smemK{0}, smemL{0};
-  int occK{1}, occL{1};
-  bool laneKsw{true};
+  uint32_t smemK{0}, smemL{0}, smemP{0};
+  int occK{1}, occL{1}, occP{1};
+  bool laneKsw{true}, pairKsw{true};
 };
 static constexpr int kKswWarps = 4, kKswLaneThreads = 128, kKswLaneSeq = 352;
+static constexpr int kKswPairThreads = 128, kKswPairCells = 384;   // strip cells per thread: reads up to ~155 bases
 
 inline int selAlnSetup(const SelAlnWork& w, SelAlnLaunch& L, std::string& err) {
   auto cuFail = [&](const char* what, cudaError_t e) { err = std::string(what) + ": " + cudaGetErrorString(e); return RAPMAP_ERR_CUDA; };
@@ -843,6 +929,14 @@ inline int selAlnSetup(const SelAlnWork& w, SelAlnLaunch& L, std::string& err) {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&L.occL, ksw_extz_lane_kernel<kKswLaneThreads, kKswLaneSeq>, kKswLaneThreads, L.smemL);
     if (L.occL < 1) L.occL = 1;
   }
+  L.pairKsw = L.laneKsw && !(sel && std::string(sel) == "lane");
+  if (L.pairKsw) {
+    L.smemP = kKswPairThreads * kKswPairCells * 2;
+    if ((e = cudaFuncSetAttribute(ksw_extz_pair_kernel<kKswPairThreads, kKswPairCells>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L.smemP))) != cudaSuccess)
+      return cuFail("cudaFuncSetAttribute(ksw pair)", e);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&L.occP, ksw_extz_pair_kernel<kKswPairThreads, kKswPairCells>, kKswPairThreads, L.smemP);
+    if (L.occP < 1) L.occP = 1;
+  }
   return RAPMAP_OK;
 }
 
@@ -860,7 +954,7 @@ inline int selAlnEnqueue(SelAlnWork& w, const SelAlnLaunch& L, const DeviceIndex
   sp.taskScore = w.taskScore; sp.taskRef = w.taskRef; sp.taskHash = w.taskHash; sp.jobs = w.jobs; sp.jobCursor = w.jobCursor; sp.hitScore = w.hitScore;
   sp.pairBest = w.pairBest; sp.outCount = w.outCount; sp.outOff = w.outOff; sp.outHits = dOutHits; sp.maxReadLen = w.maxReadLen;
   sp.hitsCap = hitsCap < w.hitsCap ? hitsCap : w.hitsCap;
-  if ((e = cudaMemsetAsync(w.jobCursor, 0, 8, st)) != cudaSuccess) return cuFail("memset", e);
+  if ((e = cudaMemsetAsync(w.jobCursor, 0, 32, st)) != cudaSuccess) return cuFail("memset", e);
   constexpr int W = 8;
   int g = static_cast<int>(std::min<uint64_t>(static_cast<uint64_t>(numSMs) * 8, (n + W * 32 - 1) / (W * 32)));
   selaln_prepare_kernel<W><<<g, W * 32, 0, st>>>(sp);
@@ -877,7 +971,16 @@ inline int selAlnEnqueue(SelAlnWork& w, const SelAlnLaunch& L, const DeviceIndex
   }
   kp.q = static_cast<int8_t>(opts.go); kp.e = static_cast<int8_t>(opts.ge); kp.w = opts.dpBandwidth;
   if (evKsw0 && (e = cudaEventRecord(evKsw0, st)) != cudaSuccess) return cuFail("event", e);
-  if (L.laneKsw) {  // thread-per-job kernel first; what it leaves (short windows, wide bands, long reads) goes to the warp kernel
+  if (L.pairKsw) {  // two jobs of one geometry per thread; second pass over the jobs that found no partner in their tile
+    kp.pairSrc = nullptr; kp.pairSrcCount = w.jobCursor; kp.pairLeft = w.pairLeft; kp.pairLeftCount = w.jobCursor + 2;
+    kp.exactList = w.exactList; kp.exactCount = w.jobCursor + 3; kp.pairPass = 0;
+    ksw_extz_pair_kernel<kKswPairThreads, kKswPairCells><<<numSMs * L.occP, kKswPairThreads, L.smemP, st>>>(kp);
+    kp.pairSrc = w.pairLeft; kp.pairSrcCount = w.jobCursor + 2; kp.pairPass = 1;
+    ksw_extz_pair_kernel<kKswPairThreads, kKswPairCells><<<numSMs * L.occP, kKswPairThreads, L.smemP, st>>>(kp);
+    *launches += 2;
+    kp.jobIdx = w.exactList; kp.jobCount = w.jobCursor + 3;   // the byte-exact kernel below takes what they handed over
+  }
+  if (L.laneKsw) {  // thread-per-job kernel; what it leaves (short windows, wide bands, long reads) goes to the warp kernel
     kp.slowList = w.slowList; kp.slowCount = w.jobCursor + 1;
     ksw_extz_lane_kernel<kKswLaneThreads, kKswLaneSeq><<<numSMs * L.occL, kKswLaneThreads, L.smemL, st>>>(kp);
     ++*launches;
@@ -898,7 +1001,7 @@ inline int selAlnEnqueue(SelAlnWork& w, const SelAlnLaunch& L, const DeviceIndex
   selaln_write_kernel<<<g3, 256, 0, st>>>(sp);
   ++*launches;
   if ((e = cudaMemcpyAsync(hTotal, w.outOff + n, 8, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuFail("memcpy", e);
-  if ((e = cudaMemcpyAsync(hJobs, w.jobCursor, 8, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuFail("memcpy", e);
+  if ((e = cudaMemcpyAsync(hJobs, w.jobCursor, 16, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuFail("memcpy", e);
   if ((e = cudaMemcpyAsync(dPairOff, w.outOff, (n + 1) * 8, cudaMemcpyDeviceToDevice, st)) != cudaSuccess) return cuFail("memcpy", e);
   return RAPMAP_OK;
 }
