@@ -137,26 +137,29 @@ __global__ void build_text2_kernel(const uint8_t* text, uint64_t n, TextRec* rec
 // Result copy-out without a host round trip: the number of records is only known on the device, so a kernel moves them -
 // to the caller's device buffer, or straight into its pinned host buffer over PCIe (16-byte stores, coalesced).  Nothing is
 // written when the records do not fit `cap` (the host reports RAPMAP_ERR_CAPACITY with the count).
+// `skip` (a multiple of 4 records): the leading records a copy engine has already been asked to move (pinned host buffers,
+// see enqueueAttempt); offSrc == nullptr: the offsets went the same way.
 __global__ void __launch_bounds__(256) copy_out_kernel(const rapmap_hit_t* __restrict__ src, rapmap_hit_t* __restrict__ dst, uint64_t cap,
                                                        const uint64_t* __restrict__ totalPtr, const uint64_t* __restrict__ offSrc, uint64_t* __restrict__ offDst,
-                                                       uint64_t nOff) {
+                                                       uint64_t nOff, uint64_t skip) {
   const uint64_t tid = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x, stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
-  for (uint64_t i = tid; i < nOff; i += stride) offDst[i] = offSrc[i];
+  if (offSrc != nullptr)
+    for (uint64_t i = tid; i < nOff; i += stride) offDst[i] = offSrc[i];
   const uint64_t total = *totalPtr;
-  if (total > cap || dst == nullptr) return;
-  const uint64_t words = total * (sizeof(rapmap_hit_t) / 4);
+  if (total > cap || dst == nullptr || total <= skip) return;
+  const uint64_t words = total * (sizeof(rapmap_hit_t) / 4), w0 = skip * (sizeof(rapmap_hit_t) / 4);  // w0 is a multiple of 4 words
   if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
     const uint4* s4 = reinterpret_cast<const uint4*>(src);
     uint4* d4 = reinterpret_cast<uint4*>(dst);
     const uint64_t n4 = words / 4;
-    for (uint64_t i = tid; i < n4; i += stride) d4[i] = s4[i];
+    for (uint64_t i = w0 / 4 + tid; i < n4; i += stride) d4[i] = s4[i];
     const uint32_t* s1 = reinterpret_cast<const uint32_t*>(src);
     uint32_t* d1 = reinterpret_cast<uint32_t*>(dst);
     for (uint64_t i = n4 * 4 + tid; i < words; i += stride) d1[i] = s1[i];
   } else {
     const uint32_t* s1 = reinterpret_cast<const uint32_t*>(src);
     uint32_t* d1 = reinterpret_cast<uint32_t*>(dst);
-    for (uint64_t i = tid; i < words; i += stride) d1[i] = s1[i];
+    for (uint64_t i = w0 + tid; i < words; i += stride) d1[i] = s1[i];
   }
 }
 
@@ -304,6 +307,7 @@ struct rapmap_cuda_mapper {
   Counters5* dCounters{nullptr};
   rapmap_cuda_timing_t timing{};
   uint64_t lastReads{0};
+  double hitsPerPair{0.0};          // records per pair of the last collected batch (sizes the copy-engine part of the next copy-outs)
 };
 
 static constexpr int kWarps = 8;
@@ -659,6 +663,12 @@ static void freeMapperBuffers(rapmap_cuda_mapper* m) {
 
 // RAPMAP_B200_TINY_ARENAS=1 (tests only): every growable device work area starts far too small, so that the first batch
 // of a mapper walks through each overflow -> grow -> re-run path of finishBatch().
+// RAPMAP_B200_COPYOUT=kernel (A/B and tests): the copy-out kernel moves everything, no copy-engine part.
+static bool noSpeculativeCopy() {
+  static const bool v = [] { const char* t = std::getenv("RAPMAP_B200_COPYOUT"); return t && std::string(t) == "kernel"; }();
+  return v;
+}
+
 static bool tinyArenas() {
   const char* t = std::getenv("RAPMAP_B200_TINY_ARENAS");
   return t && t[0] == '1';
@@ -929,8 +939,24 @@ static int enqueueAttempt(rapmap_cuda_mapper* m, BatchSlot& sl) {
     // a small grid for PCIe: ~16k threads with a 16-byte store each cover the link's bandwidth-delay product and leave the
     // SMs to the next batch's kernels
     const int gco = sl.out->location == RAPMAP_LOC_DEVICE ? m->numSMs * 4 : 64;
-    copy_out_kernel<<<gco, 256, 0, m->sOut>>>(src, static_cast<rapmap_hit_t*>(sl.outHitsDev), sl.out->hits_capacity, sl.dPairOff + n, sl.dPairOff,
-                                               static_cast<uint64_t*>(sl.outOffDev), n + 1);
+    // Pinned host buffers: the copy engines move the offsets (fixed size) and the part of the records the previous batches
+    // make certain enough (98 % of their records-per-pair rate), the kernel only the tail whose length is known on the
+    // device alone.  A kernel that pushes the whole 100+ MB over PCIe keeps its SMs' memory pipes full of posted writes for
+    // 2 ms and doubled the time of the next batch's first kernels (profiles/r02j_e2e_diag.txt); records past num_hits that
+    // the speculative copy may bring along lie inside hits_capacity and are unspecified anyway.
+    uint64_t skip = 0;
+    const uint64_t* offSrc = sl.dPairOff;
+    if (sl.out->location == RAPMAP_LOC_HOST && !noSpeculativeCopy()) {
+      CU_TRY(cudaMemcpyAsync(sl.out->pair_offsets, sl.dPairOff, (n + 1) * 8, cudaMemcpyDeviceToHost, m->sOut));
+      offSrc = nullptr;
+      if (sl.outHitsDev != nullptr && m->hitsPerPair > 0.0) {
+        skip = static_cast<uint64_t>(m->hitsPerPair * 0.98 * static_cast<double>(n));
+        skip = std::min<uint64_t>(skip, std::min<uint64_t>(sl.out->hits_capacity, m->hitsCap)) & ~3ULL;
+        if (skip > 0) CU_TRY(cudaMemcpyAsync(sl.out->hits, src, skip * sizeof(rapmap_hit_t), cudaMemcpyDeviceToHost, m->sOut));
+      }
+    }
+    copy_out_kernel<<<gco, 256, 0, m->sOut>>>(src, static_cast<rapmap_hit_t*>(sl.outHitsDev), sl.out->hits_capacity, sl.dPairOff + n, offSrc,
+                                               static_cast<uint64_t*>(sl.outOffDev), n + 1, skip);
     ++sl.launches;
   }
   CU_TRY(cudaEventRecord(sl.ev[7], m->sOut));
@@ -1084,6 +1110,7 @@ static int mapperWaitImpl(rapmap_cuda_mapper_t* m) {
     if (rc) return rc;
   }
   total = m->dopts.selAln ? sl.hStage->selTotal : sl.hStage->mergeTotal;
+  m->hitsPerPair = static_cast<double>(total) / static_cast<double>(n);
   // ---- results out
   out->num_hits = total;
   int rcOut = RAPMAP_OK;

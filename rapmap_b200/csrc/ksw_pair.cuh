@@ -83,7 +83,9 @@ RAPMAP_HD inline uint32_t addRelu(uint32_t a, uint32_t b) {  // max(a + b, 0) pe
 }
 RAPMAP_HD inline uint32_t perm(uint32_t a, uint32_t b, uint32_t sel) {
 #ifdef __CUDA_ARCH__
-  return __byte_perm(a, b, sel);
+  uint32_t d;   // PTX prmt in its generic form: bit 3 of a selector nibble replicates the sign of the selected byte (__byte_perm masks that bit off)
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
 #else
   const uint64_t v = (static_cast<uint64_t>(b) << 32) | a;
   uint32_t r = 0;
@@ -181,27 +183,26 @@ RAPMAP_HD inline bool pairDP(const uint32_t* myW, int qlen, int tlen, const Cons
 #pragma unroll
   for (int c = 0; c < 32; ++c) { U[c] = 0u; V[c] = 0u; X[c] = 0u; Y[c] = 0u; S[c] = C.qe2x2; }
   uint32_t A = 0u, B = 0u, mqe = kNeg16x2, mte = kNeg16x2, ovf = 0u;
-  bool exact = true;
-  int curSt = 0, pst0 = 0, pen0 = 0;
-  for (int r = 0; r < qlen + tlen - 1; ++r) {
+  bool exact = true, moved = false, done = false;
+  int curSt = 0, pst0 = 0, pen0 = 0, r = 0;
+  const int R = qlen + tlen - 1;
+  uint32_t xIn = 0u, vIn = 0u;   // OLD x / v of column st - 1 on the first anti-diagonal after the window moved
+  // Outer loop: one pass per position of the 16-aligned window start; the state moves down 16 slots BETWEEN the inner loops
+  // (a conditional move inside the anti-diagonal loop made the compiler re-copy all 160 state registers every iteration).
+  while (!done) {
+  for (; r < R; ++r) {
     int st0 = 0, en0 = tlen - 1;
     if (st0 < r - qlen + 1) st0 = r - qlen + 1;
     if (en0 > r) en0 = r;
     if (st0 < ((r - w + 1) >> 1)) st0 = (r - w + 1) >> 1;
     if (en0 > ((r + w) >> 1)) en0 = (r + w) >> 1;
-    if (st0 > en0) break;
+    if (st0 > en0) { done = true; break; }
     const int st = st0 & ~15, en = ((en0 + 16) & ~15) - 1;
-    uint32_t xPrev, vPrev;  // OLD x / v of column st - 1
-    if (st != curSt) {      // the 16-aligned window start moved one block: column st - 1 was slot 15
-      xPrev = X[15]; vPrev = V[15];
-#pragma unroll
-      for (int c = 0; c < 16; ++c) {
-        U[c] = U[c + 16]; V[c] = V[c + 16]; X[c] = X[c + 16]; Y[c] = Y[c + 16]; S[c] = S[c + 16];
-        U[c + 16] = 0u; V[c + 16] = 0u; X[c + 16] = 0u; Y[c + 16] = 0u; S[c + 16] = C.qe2x2;
-      }
-      curSt = st;
-    } else if (st > 0) { xPrev = 0u; vPrev = 0u; }       // "not calculated; set to zeros" (:121)
-    else { xPrev = 0u; vPrev = r ? C.qx2 : 0u; }          // :122
+    if (st != curSt) break;   // the window start moves one block: shift below, then this anti-diagonal again
+    uint32_t xPrev, vPrev;    // OLD x / v of column st - 1
+    if (moved) { xPrev = xIn; vPrev = vIn; moved = false; }   // it was slot 15 before the move
+    else if (st > 0) { xPrev = 0u; vPrev = 0u; }              // "not calculated; set to zeros" (:121)
+    else { xPrev = 0u; vPrev = r ? C.qx2 : 0u; }              // :122
     const int cSt0 = st0 - st, cEn = en - st, cEn0 = en0 - st;
     if (en >= r) {  // the diagonal's first-row cell (:123), only during the first anti-diagonals
       const int cR = r - st;
@@ -262,6 +263,16 @@ RAPMAP_HD inline bool pairDP(const uint32_t* myW, int qlen, int tlen, const Cons
     if (en0 == tlen - 1) mte = maxs(mte, B);
     if (r - st0 == qlen - 1) mqe = maxs(mqe, A);
     pst0 = st0; pen0 = en0;
+  }
+  if (done || r >= R) break;
+  xIn = X[15]; vIn = V[15];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    U[c] = U[c + 16]; V[c] = V[c + 16]; X[c] = X[c + 16]; Y[c] = Y[c + 16]; S[c] = S[c + 16];
+    U[c + 16] = 0u; V[c + 16] = 0u; X[c + 16] = 0u; Y[c + 16] = 0u; S[c + 16] = C.qe2x2;
+  }
+  curSt += 16;
+  moved = true;
   }
   const uint32_t best = maxs(mqe, mte);
   const int16_t b0 = static_cast<int16_t>(best & 0xffffu), b1 = static_cast<int16_t>(best >> 16);

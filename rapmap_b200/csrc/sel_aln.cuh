@@ -747,6 +747,31 @@ __global__ void __launch_bounds__(NT, RAPMAP_KSW_MINB) ksw_extz_lane_kernel(KswP
   }
 }
 
+// nt4 codes (seq_nt4_table_loc) of `len` bytes at p, eight bytes per aligned 64-bit load (only words that hold a byte of
+// the range are touched), branch-free per byte; comp: the codes of rapmap::utils::reverseRead's output for these bytes
+// (A<->T, C<->G, U -> A, anything else N).  put(i, code) receives byte i of the range.
+template <typename Put>
+__device__ __forceinline__ void fillCodes8(const uint8_t* p, int len, bool comp, Put put) {
+  const uint64_t* a = reinterpret_cast<const uint64_t*>(reinterpret_cast<uintptr_t>(p) & ~static_cast<uintptr_t>(7));
+  const int off = static_cast<int>(reinterpret_cast<uintptr_t>(p) & 7);
+  for (int i0 = -off; i0 < len; i0 += 8, ++a) {
+    const uint64_t wd = __ldg(a);
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      const int i = i0 + b;
+      if (i < 0 || i >= len) continue;
+      const uint32_t ch = static_cast<uint32_t>(wd >> (8 * b)) & 0xffu;
+      const uint32_t d = (ch & 0xDFu) - 'A';                                  // A C G T -> 0 2 6 19
+      const bool acgt = d < 20u && ((0x80045u >> d) & 1u);
+      const uint32_t c2 = ((ch >> 1) ^ (ch >> 2)) & 3u;
+      uint32_t code;
+      if (!comp) code = acgt ? c2 : (ch < 4u ? ch : 4u);
+      else code = acgt ? 3u - c2 : ((ch & 0xDFu) == 'U' ? 0u : 4u);
+      put(i, code);
+    }
+  }
+}
+
 // Pair kernel: TWO DP jobs of one geometry (qlen, tlen) per thread, 16-bit halves of one register per band column
 // (ksw_pair.cuh has the DP and the argument why it is exact).  A tile of 2 * NT jobs is sorted by geometry in shared
 // memory (cub::BlockRadixSort, blocked: thread i gets sorted items 2i and 2i + 1); equal neighbours run as a pair, an
@@ -801,8 +826,12 @@ __global__ void __launch_bounds__(NT, 2) ksw_extz_pair_kernel(KswParams P) {
         const uint8_t* read;
         uint32_t rl;
         readSpan(P.reads, jx.read, read, rl);
-        for (int i = 0; i < qlen; ++i) cellByte(TL + i, half) = nt4(queryChar(read, rl, jx.rc != 0, jx.rskip + (qlen - 1 - i)));
-        for (int t = 0; t < tlen; ++t) cellByte(t, half) = nt4(__ldg(P.ix.text + jx.tpos + t));
+        // cell TL + i = code of query[qlen - 1 - i]: forward reads run backwards through the read, reverse-complemented ones
+        // forwards through it with the complement table (reverseRead)
+        const bool rc = jx.rc != 0;
+        const uint8_t* qsrc = rc ? read + (static_cast<int>(rl) - jx.rskip - qlen) : read + jx.rskip;
+        fillCodes8(qsrc, qlen, rc, [&](int i, uint32_t code) { cellByte(TL + (rc ? i : qlen - 1 - i), half) = static_cast<uint8_t>(code); });
+        fillCodes8(P.ix.text + jx.tpos, tlen, false, [&](int t, uint32_t code) { cellByte(t, half) = static_cast<uint8_t>(code); });
       }
       int32_t sc0, sc1;
       if (kswpair::pairDP<NT>(myW, qlen, tlen, C, sc0, sc1)) {
