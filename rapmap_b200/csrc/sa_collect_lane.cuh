@@ -398,25 +398,10 @@ __device__ __forceinline__ int cmpSuffix(const LaneParams& P, const uint4* sm, u
   if (!exact) {
     const int cmpLim = (sentIdx >= 0 && sentIdx < lim) ? sentIdx : lim;  // ordinary characters live below cmpLim
     while (i < cmpLim) {
-      const int64_t pos = static_cast<int64_t>(t) + i;
-      const Words8 rec = ldg256(P.ix.text2 + (pos >> 5));
-      const int s = static_cast<int>(pos & 31);
-      const uint64_t c0 = (static_cast<uint64_t>(rec.v[1]) << 32) | rec.v[0], c1 = (static_cast<uint64_t>(rec.v[3]) << 32) | rec.v[2];
-      const uint64_t tc = s ? ((c0 << (2 * s)) | (c1 >> (64 - 2 * s))) : c0;
-      const uint32_t tinv = __funnelshift_r(rec.v[4], rec.v[5], s);
-      const int qp = rb + i;
-      uint64_t qc;
-      uint32_t qinv;
-      if (!rc) loadWin<NT>(sm, nw, qp, qc, qinv);
-      else {  // strand positions qp .. qp+31 = forward positions q+31 .. q, complemented
-        const int q = L - 32 - qp;
-        uint64_t val;
-        uint32_t inv;
-        loadWin<NT>(sm, nw, q < 0 ? 0 : q, val, inv);
-        if (q < 0) { val >>= 2 * (-q); inv <<= -q; }
-        qc = kmerRC(val, 32);
-        qinv = __brev(inv);
-      }
+      uint64_t tc, qc;
+      uint32_t tinv, qinv;
+      textWin32(P.ix, static_cast<int64_t>(t) + i, tc, tinv);
+      queryWin32<NT>(sm, nw, L, rc, rb + i, qc, qinv);
       const int left = cmpLim - i;
       const int nv = left < 32 ? left : 32;
       uint64_t x = tc ^ qc;
@@ -439,6 +424,28 @@ __device__ __forceinline__ int cmpSuffix(const LaneParams& P, const uint4* sm, u
   const uint64_t ri = r - static_cast<uint64_t>(mate) * P.reads.n;
   const uint8_t* src = P.reads.off[mate] ? P.reads.seq[mate] + P.reads.off[mate][ri] : P.reads.seq[mate] + ri * P.reads.fixedLen;
   return cmpSuffixAscii<NT>(P.ix.text, P.ix.n, sm, nw, src, L, rc, rb, m, t, i, sentIdx, sent, rel);
+}
+
+// 32 text characters from `pos` as 2-bit codes (first character in bits 63:62) + their non-ACGT bits (first in bit 0).
+__device__ __forceinline__ void textWin32(const DeviceIndex& ix, int64_t pos, uint64_t& tc, uint32_t& tinv) {
+  const Words8 rec = ldg256(ix.text2 + (pos >> 5));
+  const int s = static_cast<int>(pos & 31);
+  const uint64_t c0 = (static_cast<uint64_t>(rec.v[1]) << 32) | rec.v[0], c1 = (static_cast<uint64_t>(rec.v[3]) << 32) | rec.v[2];
+  tc = s ? ((c0 << (2 * s)) | (c1 >> (64 - 2 * s))) : c0;
+  tinv = __funnelshift_r(rec.v[4], rec.v[5], s);
+}
+
+// 32 characters of a strand of the read from strand position qp, same format.
+template <int NT>
+__device__ __forceinline__ void queryWin32(const uint4* sm, int nw, int L, bool rc, int qp, uint64_t& qc, uint32_t& qinv) {
+  if (!rc) { loadWin<NT>(sm, nw, qp, qc, qinv); return; }
+  const int q = L - 32 - qp;  // strand positions qp .. qp+31 = forward positions q+31 .. q, complemented
+  uint64_t val;
+  uint32_t inv;
+  loadWin<NT>(sm, nw, q < 0 ? 0 : q, val, inv);
+  if (q < 0) { val >>= 2 * (-q); inv <<= -q; }
+  qc = kmerRC(val, 32);
+  qinv = __brev(inv);
 }
 
 // k-mer and its reverse complement -> SA intervals; both table probes are in flight together.
