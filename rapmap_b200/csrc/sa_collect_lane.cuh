@@ -343,6 +343,28 @@ __device__ __forceinline__ uint64_t query8(const uint4* sm, int nw, const uint8_
   return (static_cast<uint64_t>(hi) << 32) | lo;
 }
 
+// 32 text characters from `pos` as 2-bit codes (first character in bits 63:62) + their non-ACGT bits (first in bit 0).
+__device__ __forceinline__ void textWin32(const DeviceIndex& ix, int64_t pos, uint64_t& tc, uint32_t& tinv) {
+  const Words8 rec = ldg256(ix.text2 + (pos >> 5));
+  const int s = static_cast<int>(pos & 31);
+  const uint64_t c0 = (static_cast<uint64_t>(rec.v[1]) << 32) | rec.v[0], c1 = (static_cast<uint64_t>(rec.v[3]) << 32) | rec.v[2];
+  tc = s ? ((c0 << (2 * s)) | (c1 >> (64 - 2 * s))) : c0;
+  tinv = __funnelshift_r(rec.v[4], rec.v[5], s);
+}
+
+// 32 characters of a strand of the read from strand position qp, same format.
+template <int NT>
+__device__ __forceinline__ void queryWin32(const uint4* sm, int nw, int L, bool rc, int qp, uint64_t& qc, uint32_t& qinv) {
+  if (!rc) { loadWin<NT>(sm, nw, qp, qc, qinv); return; }
+  const int q = L - 32 - qp;  // strand positions qp .. qp+31 = forward positions q+31 .. q, complemented
+  uint64_t val;
+  uint32_t inv;
+  loadWin<NT>(sm, nw, q < 0 ? 0 : q, val, inv);
+  if (q < 0) { val >>= 2 * (-q); inv <<= -q; }
+  qc = kmerRC(val, 32);
+  qinv = __brev(inv);
+}
+
 // One suffix comparison of extendSearchNaive (include/SASearcher.hpp:160-176 and the two sentinel searches): query
 // q[i] vs text[t + i] for i >= i0 while i < m and t + i < n; q[sentIdx] reads `sent` when sentIdx >= 0.  Returns the
 // index at which the reference's inner loop stops; rel = -1 (query < text), +1 (query > text), 0 (ran off).
@@ -424,28 +446,6 @@ __device__ __forceinline__ int cmpSuffix(const LaneParams& P, const uint4* sm, u
   const uint64_t ri = r - static_cast<uint64_t>(mate) * P.reads.n;
   const uint8_t* src = P.reads.off[mate] ? P.reads.seq[mate] + P.reads.off[mate][ri] : P.reads.seq[mate] + ri * P.reads.fixedLen;
   return cmpSuffixAscii<NT>(P.ix.text, P.ix.n, sm, nw, src, L, rc, rb, m, t, i, sentIdx, sent, rel);
-}
-
-// 32 text characters from `pos` as 2-bit codes (first character in bits 63:62) + their non-ACGT bits (first in bit 0).
-__device__ __forceinline__ void textWin32(const DeviceIndex& ix, int64_t pos, uint64_t& tc, uint32_t& tinv) {
-  const Words8 rec = ldg256(ix.text2 + (pos >> 5));
-  const int s = static_cast<int>(pos & 31);
-  const uint64_t c0 = (static_cast<uint64_t>(rec.v[1]) << 32) | rec.v[0], c1 = (static_cast<uint64_t>(rec.v[3]) << 32) | rec.v[2];
-  tc = s ? ((c0 << (2 * s)) | (c1 >> (64 - 2 * s))) : c0;
-  tinv = __funnelshift_r(rec.v[4], rec.v[5], s);
-}
-
-// 32 characters of a strand of the read from strand position qp, same format.
-template <int NT>
-__device__ __forceinline__ void queryWin32(const uint4* sm, int nw, int L, bool rc, int qp, uint64_t& qc, uint32_t& qinv) {
-  if (!rc) { loadWin<NT>(sm, nw, qp, qc, qinv); return; }
-  const int q = L - 32 - qp;  // strand positions qp .. qp+31 = forward positions q+31 .. q, complemented
-  uint64_t val;
-  uint32_t inv;
-  loadWin<NT>(sm, nw, q < 0 ? 0 : q, val, inv);
-  if (q < 0) { val >>= 2 * (-q); inv <<= -q; }
-  qc = kmerRC(val, 32);
-  qinv = __brev(inv);
 }
 
 // k-mer and its reverse complement -> SA intervals; both table probes are in flight together.
@@ -803,7 +803,13 @@ __global__ void __launch_bounds__(NT, MINB) sa_collect_lane_kernel(LaneParams P)
         if (voteMode) voteLane(votes, P.voteWords, rc, lookPos, L, k, hm, hc);
         if (st == LST_WSTART) {
           if (!hm) ++rb;  // :673
-          else { lbIn = fm.x; ubIn = fm.y; st = LST_EXTINIT; }
+          else {
+            lbIn = fm.x; ubIn = fm.y; st = LST_EXTINIT;
+#ifdef RAPMAP_K1_PREFETCH_SA
+            // the interval's SA entries are probed from the next trip on: start them on their way now
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(P.ix.SA + fm.x));
+#endif
+          }
         } else st = LST_POSTMM;
       }
     }

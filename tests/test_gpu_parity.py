@@ -508,6 +508,33 @@ def test_async_pipeline_chunks_in_flight(sel, pinned):
 
 
 @pytest.mark.skipif(not have_ref(), reason="needs oracle/_ref to build the mid-size index")
+@pytest.mark.parametrize("sel", [False, True])
+def test_copy_engine_copy_out_with_uneven_chunks(sel):
+    """Pinned output buffers: the copy engines move the offsets and the part of the records the previous chunks predict,
+    copy_out_kernel only the tail.  Chunks of very different size and hit density (unmappable reads: the prediction is far
+    above the real count; a dense chunk after them: far below) must still arrive exactly."""
+    import torch
+
+    idx_dir, tx = synth_index(2500)
+    index = rb.Index(idx_dir, 0)
+    opts = rb.default_opts(sel_aln=sel)
+    rng = np.random.default_rng(5)
+    junk = lambda n: (np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, (n, 100))], np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, (n, 100))])
+    plan = [("reads", 4000), ("reads", 4000), ("junk", 4000), ("reads", 1500), ("junk", 300), ("reads", 4000), ("reads", 37)]
+    om = OracleMapper(idx_dir, opts)
+    mapper = make_mapper(index, opts, 4000, 100)
+    ho, oo = torch.empty(16 * 4000 * 28, dtype=torch.uint8).pin_memory(), torch.empty(4001, dtype=torch.int64).pin_memory()
+    for c, (kind, n) in enumerate(plan):
+        a, b = tx.reads(n, rseed=3000 + c) if kind == "reads" else junk(n)
+        a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+        ho.fill_(0xEE)
+        mapper.map_batch_async(a, b, n=n, fixed_len=100, hits_out=ho, offsets_out=oo, capacity=16 * 4000)
+        r = mapper.wait()
+        got = rb.BatchResult(r.hits.numpy()[: r.num_hits * 28].copy().view(rb.HIT_DTYPE), r.pair_offsets.numpy()[: n + 1].copy().view(np.uint64), r.counters, r.num_hits)
+        assert_same(got, om.map(a, b, 100), f"chunk {c} ({kind}, {n} pairs)")
+
+
+@pytest.mark.skipif(not have_ref(), reason="needs oracle/_ref to build the mid-size index")
 def test_overflow_with_two_chunks_in_flight(monkeypatch):
     """Tiny arenas AND several chunks in flight: the first chunk's overflow re-allocates the work areas under the second chunk,
     whose attempt is then repeated; both must equal the oracle."""
