@@ -737,9 +737,6 @@ static int mapperCreateImpl(const rapmap_cuda_index_t* idx, const rapmap_cuda_op
     m->laneWords = (max_read_len + 31) / 32;
     m->laneSmem = 2u * m->laneWords * 16u * kLaneThreads;  // packed read words + k-mer mask words
     if (m->laneSmem > 227 * 1024) { m->laneSmem /= 2; m->masksInGlobal = true; }  // very long reads: masks stay in global memory
-#ifdef RAPMAP_FORCE_MASKS_GLOBAL
-    if (!m->masksInGlobal) { m->laneSmem /= 2; m->masksInGlobal = true; }   // A/B: more L1 for the SA / text / table sectors
-#endif
     if (m->laneSmem > 227 * 1024) return bail("max_read_len too large for the shared-memory read words");
     const bool general = !(d.disableNIP && d.strictCheck);
     m->laneKernel = idx->hdr.hashKind ? (general ? &sa_collect_lane_kernel<kLaneThreads, kLaneMinBlocks, true, true> : &sa_collect_lane_kernel<kLaneThreads, kLaneMinBlocks, true, false>)

@@ -803,13 +803,7 @@ __global__ void __launch_bounds__(NT, MINB) sa_collect_lane_kernel(LaneParams P)
         if (voteMode) voteLane(votes, P.voteWords, rc, lookPos, L, k, hm, hc);
         if (st == LST_WSTART) {
           if (!hm) ++rb;  // :673
-          else {
-            lbIn = fm.x; ubIn = fm.y; st = LST_EXTINIT;
-#ifdef RAPMAP_K1_PREFETCH_SA
-            // the interval's SA entries are probed from the next trip on: start them on their way now
-            asm volatile("prefetch.global.L2 [%0];" :: "l"(P.ix.SA + fm.x));
-#endif
-          }
+          else { lbIn = fm.x; ubIn = fm.y; st = LST_EXTINIT; }
         } else st = LST_POSTMM;
       }
     }
