@@ -116,15 +116,25 @@ RAPMAP_HD inline uint32_t funnelR(uint32_t lo, uint32_t hi, uint32_t sh) {
 #endif
 }
 
-#define RAPMAP_PICK_CASES16(A) case 0: return A[0]; case 1: return A[1]; case 2: return A[2]; case 3: return A[3]; case 4: return A[4]; case 5: return A[5]; \
-  case 6: return A[6]; case 7: return A[7]; case 8: return A[8]; case 9: return A[9]; case 10: return A[10]; case 11: return A[11]; case 12: return A[12];       \
-  case 13: return A[13]; case 14: return A[14]; case 15: return A[15];
-#define RAPMAP_PICK_CASES32(A) RAPMAP_PICK_CASES16(A) case 16: return A[16]; case 17: return A[17]; case 18: return A[18]; case 19: return A[19];                \
-  case 20: return A[20]; case 21: return A[21]; case 22: return A[22]; case 23: return A[23]; case 24: return A[24]; case 25: return A[25]; case 26: return A[26]; \
-  case 27: return A[27]; case 28: return A[28]; case 29: return A[29]; case 30: return A[30]; case 31: return A[31];
-// statically indexed reads behind a switch: the arrays stay in registers
-RAPMAP_HD inline uint32_t pick16(const uint32_t (&A)[32], int c) { switch (c) { RAPMAP_PICK_CASES16(A) default: return 0u; } }
-RAPMAP_HD inline uint32_t pick32(const uint32_t (&A)[32], int c) { switch (c) { RAPMAP_PICK_CASES32(A) default: return 0u; } }
+// A[c] for a run-time c without moving the array to local memory: a uniform branch picks the group of eight registers,
+// three levels of selects the register (a 32-way branch tree cost a quarter of the kernel's time in branch latency).
+RAPMAP_HD inline uint32_t pick8(uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4, uint32_t a5, uint32_t a6, uint32_t a7, int c) {
+  const bool p0 = (c & 1) != 0, p1 = (c & 2) != 0, p2 = (c & 4) != 0;
+  const uint32_t t0 = p0 ? a1 : a0, t1 = p0 ? a3 : a2, t2 = p0 ? a5 : a4, t3 = p0 ? a7 : a6;
+  const uint32_t s0 = p1 ? t1 : t0, s1 = p1 ? t3 : t2;
+  return p2 ? s1 : s0;
+}
+RAPMAP_HD inline uint32_t pick16(const uint32_t (&A)[32], int c) {
+  return (c & 8) ? pick8(A[8], A[9], A[10], A[11], A[12], A[13], A[14], A[15], c) : pick8(A[0], A[1], A[2], A[3], A[4], A[5], A[6], A[7], c);
+}
+RAPMAP_HD inline uint32_t pick32(const uint32_t (&A)[32], int c) {
+  switch (c >> 3) {
+    case 0: return pick8(A[0], A[1], A[2], A[3], A[4], A[5], A[6], A[7], c);
+    case 1: return pick8(A[8], A[9], A[10], A[11], A[12], A[13], A[14], A[15], c);
+    case 2: return pick8(A[16], A[17], A[18], A[19], A[20], A[21], A[22], A[23], c);
+    default: return pick8(A[24], A[25], A[26], A[27], A[28], A[29], A[30], A[31], c);
+  }
+}
 
 // Scoring constants of a launch (KSW2Aligner's 5x5 matrix: match, mismatch, wildcard = 0; gap open q, gap extend e, band w).
 struct Consts {
@@ -216,6 +226,8 @@ RAPMAP_HD inline bool pairDP(const uint32_t* myW, int qlen, int tlen, const Cons
     const int qB = TL + (qlen - 1 - r) + st;
     const uint32_t* qW = myW + static_cast<size_t>(qB >> 1) * NT;
     const uint32_t qSh = static_cast<uint32_t>(qB & 1) * 16u;
+    // (all 16 words, although only the 8-9 that overlap the window are used: skipping the others with a branch per word
+    // was slower, 7.1 vs 6.6 ms - this kernel runs two warps per scheduler and pays for every branch)
     uint32_t qLo = qW[0];
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
@@ -237,8 +249,8 @@ RAPMAP_HD inline bool pairDP(const uint32_t* myW, int qlen, int tlen, const Cons
       if (c == 16 && cEn < 16) break;
       const uint32_t xOld = X[c], vOld = V[c], uOld = U[c];
       const uint32_t aa = xPrev + vPrev;                          // checked below: never beyond 127, so it never wraps
-      const uint32_t bb = sx8(Y[c] + uOld);                       // _mm_add_epi8: this one does wrap in the out-of-band lanes
-      uint32_t z = max3u(S[c], aa, bb);                           // max_epi8(z, a) on non-negative bytes, then max_epu8(z, b)
+      const uint32_t bb = Y[c] + uOld;                            // _mm_add_epi8: wraps in the out-of-band lanes (128 .. 127 + M), and the
+      uint32_t z = max3u(S[c], aa, bb);                           // wrapped byte read as unsigned IS this number: max_epu8(z, b) as it stands
       z = minu(z, C.Mx2);                                         // min_epu8: z in [0, M]
       U[c] = z - vPrev;                                           // in [0, M] (z >= vt1, see the header comment)
       V[c] = z - uOld;

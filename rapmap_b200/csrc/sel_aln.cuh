@@ -754,20 +754,25 @@ template <typename Put>
 __device__ __forceinline__ void fillCodes8(const uint8_t* p, int len, bool comp, Put put) {
   const uint64_t* a = reinterpret_cast<const uint64_t*>(reinterpret_cast<uintptr_t>(p) & ~static_cast<uintptr_t>(7));
   const int off = static_cast<int>(reinterpret_cast<uintptr_t>(p) & 7);
-  for (int i0 = -off; i0 < len; i0 += 8, ++a) {
-    const uint64_t wd = __ldg(a);
+  for (int i0 = -off; i0 < len; i0 += 32, a += 4) {
+    uint64_t wd[4];
 #pragma unroll
-    for (int b = 0; b < 8; ++b) {
-      const int i = i0 + b;
-      if (i < 0 || i >= len) continue;
-      const uint32_t ch = static_cast<uint32_t>(wd >> (8 * b)) & 0xffu;
-      const uint32_t d = (ch & 0xDFu) - 'A';                                  // A C G T -> 0 2 6 19
-      const bool acgt = d < 20u && ((0x80045u >> d) & 1u);
-      const uint32_t c2 = ((ch >> 1) ^ (ch >> 2)) & 3u;
-      uint32_t code;
-      if (!comp) code = acgt ? c2 : (ch < 4u ? ch : 4u);
-      else code = acgt ? 3u - c2 : ((ch & 0xDFu) == 'U' ? 0u : 4u);
-      put(i, code);
+    for (int j = 0; j < 4; ++j) wd[j] = (i0 + 8 * j < len) ? __ldg(a + j) : 0ULL;   // four loads in flight
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        const int i = i0 + 8 * j + b;
+        if (i < 0 || i >= len) continue;
+        const uint32_t ch = static_cast<uint32_t>(wd[j] >> (8 * b)) & 0xffu;
+        const uint32_t d = (ch & 0xDFu) - 'A';                                  // A C G T -> 0 2 6 19
+        const bool acgt = d < 20u && ((0x80045u >> d) & 1u);
+        const uint32_t c2 = ((ch >> 1) ^ (ch >> 2)) & 3u;
+        uint32_t code;
+        if (!comp) code = acgt ? c2 : (ch < 4u ? ch : 4u);
+        else code = acgt ? 3u - c2 : ((ch & 0xDFu) == 'U' ? 0u : 4u);
+        put(i, code);
+      }
     }
   }
 }
