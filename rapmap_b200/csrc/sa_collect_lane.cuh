@@ -79,29 +79,14 @@ __global__ void __launch_bounds__(256) pack_reads_kernel(LaneParams P) {
     uint64_t codes = 0;
     uint32_t inv = 0, nn = 0;
     const int n = L - i0 < 32 ? L - i0 : 32;
-    if (n > 0) {
-      // the 32 bytes through aligned 64-bit loads issued together (a byte loop is one dependent L1 round trip per base); only
-      // words that hold a byte of the read are touched
-      const uint8_t* p = src + i0;
-      const uint64_t* a = reinterpret_cast<const uint64_t*>(reinterpret_cast<uintptr_t>(p) & ~static_cast<uintptr_t>(7));
-      const int off = static_cast<int>(reinterpret_cast<uintptr_t>(p) & 7);
-      uint64_t w[5];
-#pragma unroll
-      for (int j = 0; j < 5; ++j) w[j] = (8 * j - off < n) ? __ldg(a + j) : 0ULL;
-      uint64_t v[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) v[j] = off ? ((w[j] >> (8 * off)) | (w[j + 1] << (64 - 8 * off))) : w[j];
-#pragma unroll
-      for (int b = 0; b < 32; ++b) {
-        const uint32_t ch = static_cast<uint32_t>(v[b >> 3] >> (8 * (b & 7))) & 0xffu;
-        const uint32_t uc = ch & 0xDFu;
-        const bool in = b < n;
-        const bool ok = uc == 'A' || uc == 'C' || uc == 'G' || uc == 'T';
-        const uint32_t code = ok ? (((ch >> 1) ^ (ch >> 2)) & 3u) : (uc == 'U' ? 3u : (uc == 'N' ? 1u : 0u));
-        codes |= static_cast<uint64_t>(in ? code : 0u) << (62 - 2 * b);
-        inv |= (in && !ok) ? 1u << b : 0u;
-        nn |= (in && uc == 'N') ? 1u << b : 0u;
-      }
+    for (int b = 0; b < n; ++b) {
+      const uint32_t ch = __ldg(src + i0 + b);
+      const uint32_t uc = ch & 0xDFu;
+      const bool ok = uc == 'A' || uc == 'C' || uc == 'G' || uc == 'T';
+      const uint32_t code = ok ? (((ch >> 1) ^ (ch >> 2)) & 3u) : (uc == 'U' ? 3u : (uc == 'N' ? 1u : 0u));
+      codes |= static_cast<uint64_t>(code) << (62 - 2 * b);
+      if (!ok) inv |= 1u << b;
+      if (uc == 'N') nn |= 1u << b;
     }
     P.packed[g] = make_uint4(static_cast<uint32_t>(codes), static_cast<uint32_t>(codes >> 32), inv, nn);
   }
