@@ -964,11 +964,26 @@ static int enqueueAttempt(rapmap_cuda_mapper* m, BatchSlot& sl) {
   return RAPMAP_OK;
 }
 
-// Host threads sleep on the blocking event for big batches (several ranks per box: spinning threads fight the launching
-// ones for cores); small batches spin, the wake-up latency would show.
+// Waiting for a batch.  Small batches spin (cudaStreamSynchronize: a wake-up latency would show).  Big batches poll
+// cudaEventQuery with 50 us naps: the thread uses next to no CPU (several ranks per box: spinning threads fight the launching
+// ones for cores) and there is no interrupt in the path - sleeping on a cudaEventBlockingSync event cost a quarter of
+// the resident rate with 8 ranks on one virtualised box (1041 vs 1450 M pairs/s, profiles/r02k_n8_diag.txt).
+// RAPMAP_B200_WAIT=block selects the blocking event.
+static int waitMode() {
+  static const int v = [] { const char* t = std::getenv("RAPMAP_B200_WAIT"); return (t && std::string(t) == "block") ? 0 : 1; }();
+  return v;
+}
+
 static cudaError_t waitSlot(rapmap_cuda_mapper* m, BatchSlot& sl) {
-  if (sl.view.n >= 32768) return cudaEventSynchronize(sl.evOut);
-  return cudaStreamSynchronize(m->sOut);
+  if (sl.view.n < 32768) return cudaStreamSynchronize(m->sOut);
+  if (waitMode() == 1) {
+    for (;;) {
+      const cudaError_t e = cudaEventQuery(sl.evOut);
+      if (e != cudaErrorNotReady) return e;
+      std::this_thread::sleep_for(std::chrono::microseconds(50));
+    }
+  }
+  return cudaEventSynchronize(sl.evOut);
 }
 
 static int mapBatchAsyncImpl(rapmap_cuda_mapper_t* m, const rapmap_read_batch_t* reads, rapmap_hit_batch_t* out) {

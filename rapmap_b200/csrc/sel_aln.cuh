@@ -781,7 +781,7 @@ __device__ __forceinline__ void fillCodes8(const uint8_t* p, int len, bool comp,
 // (ksw_pair.cuh has the DP and the argument why it is exact).  A tile of 2 * NT jobs is sorted by geometry in shared
 // memory (cub::BlockRadixSort, blocked: thread i gets sorted items 2i and 2i + 1); equal neighbours run as a pair, an
 // item without a partner runs alone (both halves hold the same job) and its unequal neighbour goes to the `pairLeft`
-// list, which a second launch (pairPass = 1) pairs up across tiles.  Jobs outside the pair kernel's geometry, and pairs
+// list, which a second launch (pairPass = 1) pairs up across tiles (what is still single there goes to the byte-exact kernel).  Jobs outside the pair kernel's geometry, and pairs
 // whose x-side left the int8 range, go to the byte-exact thread-per-job kernel through `exactList`.
 template <int NT, int CELLS>
 __global__ void __launch_bounds__(NT, 2) ksw_extz_pair_kernel(KswParams P) {
@@ -814,13 +814,15 @@ __global__ void __launch_bounds__(NT, 2) ksw_extz_pair_kernel(KswParams P) {
     if (keys[0] != kNoJob) {
       nrep = 1;
       if (keys[1] != keys[0] && keys[1] != kNoJob) {
+        // no partner in this tile: to the second pass; still none there (a handful of jobs per batch): to the thread-per-job
+        // kernel, which runs behind this one anyway (a second DP in this thread would double the tail of the launch)
         if (P.pairPass == 0) P.pairLeft[atomicAdd(P.pairLeftCount, 1u)] = vals[1];
-        else nrep = 2;   // second pass: run the two one after the other
+        else P.exactList[atomicAdd(P.exactCount, 1u)] = vals[1];
       }
     }
     for (int rep = 0; rep < nrep; ++rep) {
-      const bool both = rep == 0 && keys[1] == keys[0];
-      const uint32_t j0 = rep ? vals[1] : vals[0], j1 = both ? vals[1] : j0;
+      const bool both = keys[1] == keys[0];
+      const uint32_t j0 = vals[0], j1 = both ? vals[1] : j0;
       const DPJob ja = P.jobs[j0], jb = P.jobs[j1];
       const int qlen = ja.rlen, tlen = ja.tlen1;
       const int TL = kswpair::stripTL(tlen), words = (kswpair::stripCells(qlen, tlen) + 1) / 2;
