@@ -946,7 +946,7 @@ static int enqueueAttempt(rapmap_cuda_mapper* m, BatchSlot& sl) {
     // the speculative copy may bring along lie inside hits_capacity and are unspecified anyway.
     uint64_t skip = 0;
     const uint64_t* offSrc = sl.dPairOff;
-    if (sl.out->location == RAPMAP_LOC_HOST && !noSpeculativeCopy()) {
+    if (sl.out->location == RAPMAP_LOC_HOST && n >= 32768 && !noSpeculativeCopy()) {   // (small batches: two more DMA submissions cost more than the kernel's PCIe stores)
       CU_TRY(cudaMemcpyAsync(sl.out->pair_offsets, sl.dPairOff, (n + 1) * 8, cudaMemcpyDeviceToHost, m->sOut));
       offSrc = nullptr;
       if (sl.outHitsDev != nullptr && m->hitsPerPair > 0.0) {
