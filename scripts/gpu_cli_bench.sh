@@ -17,4 +17,12 @@ for mode in "-n" "-o /dev/null"; do
     echo "mode [$mode] flags [$fl]  rapmap_b200: $ours  |  rapmap_ref -t $NP: $ref"
   done
 done
+echo "second pass, engine only (files and index warm), default wait (poll) | RAPMAP_B200_WAIT=block"
+for mode in "-n" "-o /dev/null"; do
+  for fl in "" "-s"; do
+    build/bin/rapmap_b200 quasimap -i $IDX -1 $D/r1.fastq -2 $D/r2.fastq -t $NP $mode $fl 2> $D/ours.log; ours=$(grep -o "Elapsed time: [0-9.e+-]*" $D/ours.log | tail -1)
+    RAPMAP_B200_WAIT=block build/bin/rapmap_b200 quasimap -i $IDX -1 $D/r1.fastq -2 $D/r2.fastq -t $NP $mode $fl 2> $D/ours.log; blk=$(grep -o "Elapsed time: [0-9.e+-]*" $D/ours.log | tail -1)
+    echo "mode [$mode] flags [$fl]  rapmap_b200: $ours  |  blocking wait: $blk"
+  done
+done
 } | tee gpurun_out/cli_bench.txt
