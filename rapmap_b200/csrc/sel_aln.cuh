@@ -8,16 +8,20 @@
 // dovetail veto, the soft / hard filter and alnScore_.
 //
 // Stages (all on the mapper's stream):
-//   selaln_prepare_kernel  warp per pair: classifies every (hit, read end) task, emulates the alignment cache
+//   selaln_prepare_kernel  thread per pair: classifies every (hit, read end) task, emulates the alignment cache
 //                          ("first earlier hit of this read end with a byte-identical reference window wins", which
 //                          is what a MetroHash64-keyed map gives up to 2^-64 collisions), scores UNGAPPED tasks
 //                          inline and queues the remaining ones as DP jobs.
-//   ksw_extz_kernel        warp per DP job: lane-for-lane restatement of the SSE kernel — int8 wrapping lanes with
-//                          unsigned max/min clamps, the 16-lane block rounding that widens the band, stale
-//                          out-of-band lanes, the separate int32 H[] track — in shared memory laid out exactly as
+//   ksw_extz_pair_kernel   the main DP path (ksw_pair.cuh): two jobs of one geometry per thread, int8 lanes of the SSE
+//                          code as 16-bit halves of one register per band column, native 16x2 instructions; a second
+//                          launch pairs the jobs that found no partner of their geometry in their tile.
+//   ksw_extz_lane_kernel   thread per DP job, byte lanes of 32-bit registers, exact H[] sweep: takes what the pair kernel
+//                          hands over (odd geometries; pairs whose x side left the int8 range: never seen).
+//   ksw_extz_kernel        warp per DP job, any geometry: lane-for-lane restatement of the SSE kernel - int8 wrapping
+//                          lanes with unsigned max/min clamps, the 16-lane block rounding that widens the band, stale
+//                          out-of-band lanes, the separate int32 H[] track - in shared memory laid out exactly as
 //                          the reference's kcalloc block (u|v|x|y|s|sf|qr) because its 16-byte loads and stores run
-//                          past tlen/qlen into the neighbouring arrays.  Integer-ALU bound; no HBM traffic beyond
-//                          the <= 120-byte window.
+//                          past tlen/qlen into the neighbouring arrays.
 //   selaln_score_kernel    thread per pair: per-hit score, best score, survivor count.
 //   selaln_write_kernel    thread per pair: compacts the survivors (after an exclusive scan) with aln_score set.
 #pragma once
