@@ -13,7 +13,8 @@ BASELINE.json configs[1]: --chunks (10) chunks of --batch (2^20) pairs per GPU, 
   * the headline: configs[1], default `quasimap` flags (no -s): `value` with reads resident in HBM, `e2e` through the C-ABI
     with pinned HOST buffers (copies inside the timed region), the SA-lookup kernel's roofline, the reference CPU baseline;
   * `legs.selaln`       configs[2] (and, under torchrun, configs[4]): the same index and reads with `quasimap -s`;
-  * `legs.perfect_hash` configs[3]: the same transcriptome indexed with -p (BooPHF + FrugalBooMap walked on the device).
+  * `legs.perfect_hash` configs[3]: the same transcriptome indexed with -p (BooPHF + FrugalBooMap; lookups served by the dense
+    table the engine derives from FrugalBooMap::find when it loads the index; `walk`: the same leg with the BooPHF walked per lookup).
 
 Every leg is parity-checked before its number is printed (CPU oracle on a bounded sample; -p against the dense results).
 Index replicated per GPU (one NCCL broadcast of the packed image), read ranges sharded by rank, no data-path collective:
@@ -545,6 +546,7 @@ def main():
                     "e2e": {"value": e, "unit": UNIT, "ms_per_step": L["ms_e2e"] / leg_steps, "host_threads": 1, "mappers": 1, "chunks_in_flight": nm, "hits_equal_resident_leg": True},
                     "sa_lookup_ms_per_launch": L["st"]["sa"] / nchunks,
                     "stage_ms_per_chunk": {k: L["st"][k] / nchunks for k in STAGES},
+                    "lookup": "dense table derived at load time from FrugalBooMap::find over every MPHF slot (answers every query exactly as the walk; 4.3 GB of HBM)",
                     "index_image_bytes": pindex.device_bytes, "dense_index_image_bytes": index.device_bytes,
                     "index_files": "hash_info.bph / hash_info.val written by tools/build_index.py (byte-identical to `quasiindex -p` output on the test transcriptomes, tests/test_index_builder.py)",
                     "gpu_launches": int(L["st"]["launch"]),
@@ -553,6 +555,23 @@ def main():
             for mp in L["mappers"]:
                 mp.close()
             del L, pindex, _keep1
+            # the same leg with the BooPHF walked on the device for every lookup (RAPMAP_B200_PHF=walk: no derived table)
+            os.environ["RAPMAP_B200_PHF"] = "walk"
+            try:
+                _pd, windex, _keep2 = load_index(True)
+            finally:
+                del os.environ["RAPMAP_B200_PHF"]
+            wsteps = min(leg_steps, 3)
+            L = run_leg(windex, rb.default_opts(), wsteps, args.warmup)
+            v, e = leg_numbers(L, pairs_per_step)
+            log(f"rank {rank}: leg perfect_hash (walk): resident {L['ms_res'] / wsteps:.2f} ms/step, end to end {L['ms_e2e'] / wsteps:.2f} ms/step")
+            if rank == 0:
+                line["legs"]["perfect_hash"]["walk"] = {"value": v, "unit": UNIT, "e2e": {"value": e, "unit": UNIT}, "steps": wsteps,
+                                                        "sa_lookup_ms_per_launch": L["st"]["sa"] / (wsteps * CH), "index_image_bytes": windex.device_bytes,
+                                                        "lookup": "BooPHF level walk + FrugalBooMap verification per lookup on the device (RAPMAP_B200_PHF=walk)"}
+            for mp in L["mappers"]:
+                mp.close()
+            del L, windex, _keep2
         else:
             raise SystemExit(f"unknown leg {name}")
 

@@ -78,6 +78,31 @@ __global__ void build_table_kernel(const KmerRecord* recs, uint64_t n, uint4* ta
   }
 }
 
+// -p index: the dense table derived from the perfect hash.  FrugalBooMap::find(q) can only succeed when q is the k-mer the
+// text holds at SA[data_[lookup(q)]], i.e. when q is one of the keys key_i = textWord(SA[data_[i]]), i < |data_|.  So the
+// table gets (key_i -> find(key_i)) for every i whose find succeeds - found or not is decided by the SAME device function the
+// lookups used before - and answers every later query exactly as the walk would: a query that hits in the walk equals its
+// own key_i and was inserted; a query in the table hit in the walk by construction.
+__global__ void derive_table_from_phf_kernel(DeviceIndex ix, uint4* table, uint64_t mask) {
+  for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < ix.phfNumData; i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    const int32_t ind = ix.phfData[i];
+    const uint64_t key = phfTextWord(ix, ix.SA[ind]);
+    const int2 r = phfFindImpl(ix, key);
+    if (r.x < 0) continue;
+    uint64_t s = mix64(key) & mask & ~1ULL;
+    while (true) {
+      unsigned long long* keyp = reinterpret_cast<unsigned long long*>(table + s);
+      const unsigned long long old = atomicCAS(keyp, static_cast<unsigned long long>(kEmptyKey), static_cast<unsigned long long>(key));
+      if (old == kEmptyKey || old == key) {
+        reinterpret_cast<int32_t*>(table + s)[2] = r.x;
+        reinterpret_cast<int32_t*>(table + s)[3] = r.y;
+        break;
+      }
+      s = (s + 1) & mask;
+    }
+  }
+}
+
 __global__ void build_filter_kernel(const KmerRecord* recs, uint64_t n, uint32_t k, uint32_t* filter, uint32_t shift) {
   for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
     uint64_t word;
@@ -190,7 +215,8 @@ DeviceIndex viewOf(const uint8_t* blob, const ImageHeader& h) {
   d.n = static_cast<int64_t>(h.n);
   d.k = h.k;
   d.numTxp = static_cast<uint32_t>(h.numTxp);
-  d.hashKind = h.hashKind; d.phfLevels = h.phfLevels; d.phfNumFinal = static_cast<uint32_t>(h.phfNumFinal);
+  d.hashKind = (h.hashKind && !h.phfTableDerived) ? 1u : 0u;  // what the kernels walk: the BooPHF arrays only while no table answers for them
+  d.phfLevels = h.phfLevels; d.phfNumFinal = static_cast<uint32_t>(h.phfNumFinal);
   d.phfNumOverflow = static_cast<uint32_t>(h.phfNumOverflow); d.phfLastRank = h.phfLastRank; d.phfNumData = h.phfNumData;
   d.phfLv = reinterpret_cast<const PhfLevelDev*>(blob + h.offPhfLevels);
   d.phfBits = reinterpret_cast<const uint64_t*>(blob + h.offPhfBits);
@@ -363,6 +389,12 @@ void rapmap_cuda_opts_selaln(rapmap_cuda_opts_t* o) {
   o->sel_aln = 1;
 }
 
+// RAPMAP_B200_PHF=walk: -p indexes keep walking the BooPHF arrays on the device (no derived table; the smaller image).
+static bool phfWalkOnly() {
+  const char* t = std::getenv("RAPMAP_B200_PHF");
+  return t && std::string(t) == "walk";
+}
+
 static int indexLoadImpl(const char* index_dir, int device, rapmap_cuda_index_t** out) {
   if (!index_dir || !out) return fail(RAPMAP_ERR_ARG, "null argument");
   *out = nullptr;
@@ -380,7 +412,13 @@ static int indexLoadImpl(const char* index_dir, int device, rapmap_cuda_index_t*
   const uint64_t T = h.txpOffsets.size();
   uint64_t slots = 64;
   while (slots < 2 * h.kmers.size()) slots <<= 1;
-  if (h.perfectHash) slots = 16;  // -p index: no dense table, the BooPHF arrays are used as they are
+  // -p index: by default the lookups are served by a dense table DERIVED from the perfect hash once the image is up (180 GB of
+  // HBM: 4.3 GB buy back the 3.6x that the BooPHF walk costs the SA-lookup kernel); RAPMAP_B200_PHF=walk keeps the walk
+  const bool deriveTable = h.perfectHash && !phfWalkOnly();
+  if (h.perfectHash) {
+    slots = 16;
+    if (deriveTable) while (slots < 2 * h.phf.data.size()) slots <<= 1;
+  }
   const uint64_t rankWords = n / 64 + 1;
 
   ImageHeader hdr{};
@@ -471,6 +509,14 @@ static int indexLoadImpl(const char* index_dir, int device, rapmap_cuda_index_t*
     if (!h.phf.data.empty()) IDX_TRY(cudaMemcpy(idx->blob + hdr.offPhfData, h.phf.data.data(), h.phf.data.size() * 4, cudaMemcpyHostToDevice));
     if (!h.phf.lens.empty()) IDX_TRY(cudaMemcpy(idx->blob + hdr.offPhfLens, h.phf.lens.data(), h.phf.lens.size(), cudaMemcpyHostToDevice));
     if (!h.phf.overflow.empty()) IDX_TRY(cudaMemcpy(idx->blob + hdr.offPhfOverflow, h.phf.overflow.data(), h.phf.overflow.size() * 8, cudaMemcpyHostToDevice));
+  }
+  if (deriveTable) {
+    hdr.phfTableDerived = 0;   // the kernel below walks the BooPHF arrays
+    derive_table_from_phf_kernel<<<4096, 256>>>(viewOf(idx->blob, hdr), reinterpret_cast<uint4*>(idx->blob + hdr.offTable), slots - 1);
+    IDX_TRY(cudaDeviceSynchronize());
+    hdr.phfTableDerived = 1;
+    idx->hdr = hdr;
+    IDX_TRY(cudaMemcpy(idx->blob, &hdr, sizeof(hdr), cudaMemcpyHostToDevice));
   }
   if (h.perfectHash && hdr.offFilter) {
     // -p index: the k-mer records are not stored, so the filter is filled from the text.  Every key FrugalBooMap::find can
@@ -739,7 +785,7 @@ static int mapperCreateImpl(const rapmap_cuda_index_t* idx, const rapmap_cuda_op
     if (m->laneSmem > 227 * 1024) { m->laneSmem /= 2; m->masksInGlobal = true; }  // very long reads: masks stay in global memory
     if (m->laneSmem > 227 * 1024) return bail("max_read_len too large for the shared-memory read words");
     const bool general = !(d.disableNIP && d.strictCheck);
-    m->laneKernel = idx->hdr.hashKind ? (general ? &sa_collect_lane_kernel<kLaneThreads, kLaneMinBlocks, true, true> : &sa_collect_lane_kernel<kLaneThreads, kLaneMinBlocks, true, false>)
+    m->laneKernel = idx->view.hashKind ? (general ? &sa_collect_lane_kernel<kLaneThreads, kLaneMinBlocks, true, true> : &sa_collect_lane_kernel<kLaneThreads, kLaneMinBlocks, true, false>)
                                       : (general ? &sa_collect_lane_kernel<kLaneThreads, kLaneMinBlocks, false, true> : &sa_collect_lane_kernel<kLaneThreads, kLaneMinBlocks, false, false>);
     M_TRY(cudaFuncSetAttribute(m->laneKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(m->laneSmem)));
     M_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, m->laneKernel, kLaneThreads, m->laneSmem));

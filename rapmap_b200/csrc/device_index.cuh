@@ -41,7 +41,8 @@ struct ImageHeader {
   uint64_t filterWords;    // power of two
   uint64_t offText2;       // 0: the text holds characters the packed compare cannot order (outside '$'..'z'); ASCII path only
   // -p index only
-  uint32_t phfLevels, phfPad;
+  uint32_t phfLevels;
+  uint32_t phfTableDerived;  // 1: the hash-table section of this -p image answers every lookup (derived from FrugalBooMap::find at load time)
   uint64_t phfLastRank, phfNumData, phfNumFinal, phfNumOverflow;
   uint64_t offPhfLevels, offPhfBits, offPhfRanks, offPhfFinal, offPhfData, offPhfLens, offPhfOverflow;
   // host-readable trailer: transcript names, '\0'-terminated, in transcript order (a replica built from the image alone can
@@ -182,6 +183,18 @@ __device__ __forceinline__ uint64_t phfHash64(uint64_t key, uint64_t seed) {
   return hash;
 }
 
+// The k-mer word FrugalBooMap::find builds from the text at a suffix (Kmer::fromChars; the text holds upper-case ACGT and '$').
+__device__ __forceinline__ uint64_t phfTextWord(const DeviceIndex& ix, int64_t textInd) {
+  uint64_t w = 0;
+  for (uint32_t j = 0; j < ix.k; ++j) {
+    const uint8_t ch = __ldg(ix.text + textInd + j);
+    uint32_t cd;
+    if (ch == 'A') cd = 0; else if (ch == 'C') cd = 1; else if (ch == 'G') cd = 2; else if (ch == 'T') cd = 3; else break;
+    w |= static_cast<uint64_t>(cd) << (2 * (ix.k - 1 - j));
+  }
+  return w;
+}
+
 // FrugalBooMap::find (reference include/FrugalBooMap.hpp:149-167) over boomphf::mphf::lookup (include/BooPHF.hpp:971-1009,
 // getLevel :1318-1351, xorshift128* next :493-499, fastrange64 :815-820, bitVector::rank :756-769): level walk -> rank ->
 // data_[slot] -> SA -> verify the 31-mer in the text against the key -> length from lens_ / overflow_.
@@ -221,15 +234,7 @@ __device__ __forceinline__ int2 phfFindImpl(const DeviceIndex& ix, uint64_t key)
   }
   if (slot >= ix.phfNumData) return make_int2(-1, -1);
   const int32_t ind = __ldg(ix.phfData + slot);
-  const int64_t textInd = __ldg(ix.SA + ind);
-  uint64_t w = 0;
-  for (uint32_t j = 0; j < ix.k; ++j) {  // Kmer::fromChars on the text; the text holds upper-case ACGT and '$'
-    const uint8_t ch = __ldg(ix.text + textInd + j);
-    uint32_t cd;
-    if (ch == 'A') cd = 0; else if (ch == 'C') cd = 1; else if (ch == 'G') cd = 2; else if (ch == 'T') cd = 3; else break;
-    w |= static_cast<uint64_t>(cd) << (2 * (ix.k - 1 - j));
-  }
-  if (w != key) return make_int2(-1, -1);
+  if (phfTextWord(ix, __ldg(ix.SA + ind)) != key) return make_int2(-1, -1);
   int32_t len = __ldg(ix.phfLens + slot);
   if (len == 255) {
     uint32_t lo = 0, hi = ix.phfNumOverflow;

@@ -262,7 +262,19 @@ def test_device_resident_inputs_match_host_inputs(synth_small):
     assert np.array_equal(dev.hits, h_hits) and np.array_equal(dev.pair_offsets, h_off)
 
 
-def test_perfect_hash_index_gives_identical_hits(synth_small):
+PHF_MODES = ["derived_table", "walk"]   # -p lookups: dense table derived from FrugalBooMap::find at load (default) / BooPHF walked per lookup
+
+
+def _phf_mode(monkeypatch, mode):
+    if mode == "walk":
+        monkeypatch.setenv("RAPMAP_B200_PHF", "walk")
+    else:
+        monkeypatch.delenv("RAPMAP_B200_PHF", raising=False)
+
+
+@pytest.mark.parametrize("mode", PHF_MODES)
+def test_perfect_hash_index_gives_identical_hits(synth_small, monkeypatch, mode):
+    _phf_mode(monkeypatch, mode)
     idx_dir, index, s1, s2, L, tx = synth_small
     opts = rb.default_opts()
     n = s1.shape[0]
@@ -273,9 +285,12 @@ def test_perfect_hash_index_gives_identical_hits(synth_small):
     assert np.array_equal(a_hits, b.hits) and np.array_equal(a_off, b.pair_offsets)
 
 
+@pytest.mark.parametrize("mode", PHF_MODES)
 @pytest.mark.parametrize("sel", [False, True])
-def test_perfect_hash_index_matches_reference_golden_sam(synth_small, sel):
-    """-p index through the on-device BooPHF + FrugalBooMap lookup: SAM identical to `rapmap_ref quasimap` on its own -p index."""
+def test_perfect_hash_index_matches_reference_golden_sam(synth_small, sel, monkeypatch, mode):
+    """-p index (lookups through the table derived from FrugalBooMap::find, or through the on-device BooPHF walk): SAM identical to
+    `rapmap_ref quasimap` on its own -p index."""
+    _phf_mode(monkeypatch, mode)
     idx_dir, index, s1, s2, L, tx = synth_small
     n = s1.shape[0]
     opts = rb.default_opts(sel_aln=sel)
@@ -294,8 +309,10 @@ def test_perfect_hash_index_matches_reference_golden_sam(synth_small, sel):
 
 
 @pytest.mark.skipif(not have_ref(), reason="needs oracle/_ref to build the mid-size index")
-def test_mid_size_perfect_hash_index_matches_dense():
+@pytest.mark.parametrize("mode", PHF_MODES)
+def test_mid_size_perfect_hash_index_matches_dense(monkeypatch, mode):
     """13.9k-transcript -p index (6.1 M keys over 25 BooPHF levels) gives the hits of the dense index."""
+    _phf_mode(monkeypatch, mode)
     d_dir, tx = synth_index(2500)
     p_dir, _ = synth_index(2500, perfect=True)
     n = 30000
