@@ -103,6 +103,15 @@ __global__ void derive_table_from_phf_kernel(DeviceIndex ix, uint4* table, uint6
   }
 }
 
+// SA entry -> {transcript id, position in the transcript} (RapMapSAIndex::transcriptAtPosition + txpOffsets, once per entry)
+__global__ void build_sa_tidpos_kernel(DeviceIndex ix, uint2* out) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < ix.n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int32_t g = ix.SA[i];
+    const uint32_t tid = transcriptAt(ix, g);
+    out[i] = make_uint2(tid, static_cast<uint32_t>(g - ix.txpOffsets[tid]));
+  }
+}
+
 __global__ void build_filter_kernel(const KmerRecord* recs, uint64_t n, uint32_t k, uint32_t* filter, uint32_t shift) {
   for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
     uint64_t word;
@@ -210,6 +219,7 @@ DeviceIndex viewOf(const uint8_t* blob, const ImageHeader& h) {
   d.rank = reinterpret_cast<const uint4*>(blob + h.offRank);
   d.txpOffsets = reinterpret_cast<const int32_t*>(blob + h.offTxpOffsets);
   d.txpLens = reinterpret_cast<const int32_t*>(blob + h.offTxpLens);
+  d.saTidPos = reinterpret_cast<const uint2*>(blob + h.offSaTidPos);
   d.table = reinterpret_cast<const uint4*>(blob + h.offTable);
   d.tableMask = h.tableSlots - 1;
   d.n = static_cast<int64_t>(h.n);
@@ -465,6 +475,7 @@ static int indexLoadImpl(const char* index_dir, int device, rapmap_cuda_index_t*
   uint64_t namesBytes = 0;
   for (const auto& nm : h.txpNames) namesBytes += nm.size() + 1;
   hdr.offNames = off; hdr.namesBytes = namesBytes; off = align256(off + namesBytes + 1);
+  hdr.offSaTidPos = off; off = align256(off + n * 8);
   hdr.totalBytes = off;
 
   auto* idx = new rapmap_cuda_index();
@@ -498,7 +509,7 @@ static int indexLoadImpl(const char* index_dir, int device, rapmap_cuda_index_t*
   }
   IDX_TRY(cudaMemset(idx->blob + hdr.offTable, 0xFF, slots * 16));
   if (h.perfectHash) {
-    IDX_TRY(cudaMemset(idx->blob + hdr.offPhfLevels, 0, hdr.totalBytes - hdr.offPhfLevels));
+    IDX_TRY(cudaMemset(idx->blob + hdr.offPhfLevels, 0, hdr.offNames - hdr.offPhfLevels));   // the PHF sections only: the names behind them are in place
     IDX_TRY(cudaMemcpy(idx->blob + hdr.offPhfLevels, lvDev.data(), lvDev.size() * sizeof(PhfLevelDev), cudaMemcpyHostToDevice));
     for (size_t i = 0; i < lvDev.size(); ++i) {
       const auto& lv = h.phf.levels[i];
@@ -527,6 +538,9 @@ static int indexLoadImpl(const char* index_dir, int device, rapmap_cuda_index_t*
     build_filter_from_text_kernel<<<4096, 256>>>(idx->blob + hdr.offText, n, hdr.k, reinterpret_cast<uint32_t*>(idx->blob + hdr.offFilter), shift);
     IDX_TRY(cudaDeviceSynchronize());
   }
+  // per SA entry: transcript and position inside it (the rank records and txpOffsets are in place above)
+  build_sa_tidpos_kernel<<<4096, 256>>>(viewOf(idx->blob, hdr), reinterpret_cast<uint2*>(idx->blob + hdr.offSaTidPos));
+  IDX_TRY(cudaDeviceSynchronize());
   {  // packed text
     uint32_t* dBad = nullptr;
     IDX_TRY(cudaMalloc(&dBad, 4));
@@ -611,7 +625,7 @@ static int indexFromImageImpl(int device, void* blob, uint64_t bytes, rapmap_cud
     struct { uint64_t off, len; } sec[] = {
       {hdr.offSA, n * 4}, {hdr.offText, n + 256}, {hdr.offRank, (n / 64 + 1) * 16}, {hdr.offTxpOffsets, T * 4}, {hdr.offTxpLens, T * 4},
       {hdr.offTable, hdr.tableSlots * 16}, {hdr.offFilter, hdr.offFilter ? hdr.filterWords * 4 : 0}, {hdr.offText2, hdr.offText2 ? (n / 32 + 2) * sizeof(TextRec) : 0},
-      {hdr.offNames, hdr.namesBytes}};
+      {hdr.offNames, hdr.namesBytes}, {hdr.offSaTidPos, n * 8}};
     for (const auto& sc : sec)
       if (sc.off > bytes || sc.len > bytes - sc.off) return fail(RAPMAP_ERR_ARG, "index image: a section lies outside the blob");
     if (hdr.tableSlots == 0 || (hdr.tableSlots & (hdr.tableSlots - 1)) != 0) return fail(RAPMAP_ERR_ARG, "index image: table size is not a power of two");

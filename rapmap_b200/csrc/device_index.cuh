@@ -3,7 +3,7 @@
 // HBM layout (one contiguous blob, sections 256-byte aligned, so the whole index is a single
 // ncclBroadcast / cudaMemcpy):
 //   ImageHeader | SA int32[n] | text u8[n + pad] | rank uint4[ceil(n/64)+1] | txpOffsets int32[T] |
-//   txpLens int32[T] | hash table uint4[slots] | packed text TextRec[ceil(n/32)+1] | k-mer filter u32[F]
+//   txpLens int32[T] | hash table uint4[slots] | packed text TextRec[ceil(n/32)+1] | k-mer filter u32[F] | SA (tid, pos) uint2[n]
 // * k-mer filter: a word-blocked Bloom filter over the indexed k-mers, keyed by the canonical k-mer with an orientation
 //   marker (4 bits inside one 32-bit word, ~6 bits per key,
 //   at most 64 MB so that it stays resident in the 126 MB L2, loads carry an L2 evict_last policy).  ~90 % of the
@@ -15,6 +15,9 @@
 //   their non-ACGT mask, so the 32-base window at ANY position p lies inside record p/32: one aligned 256-bit load
 //   (one DRAM sector) feeds 32 character comparisons of extendSearchNaive.  The ASCII text stays for exact
 //   fall-backs ('$', IUPAC) and for the selective-alignment windows.
+// * SA (tid, pos): for every SA entry the transcript of the text position and the position inside it, precomputed at load
+//   (8 n bytes of HBM): hit resolution expands an SA interval with ONE load per entry instead of the dependent chain
+//   SA[i] -> rank record -> txpOffsets[tid].
 // * rank: one 16-byte record per 64 text positions {bits_lo, bits_hi, #'$' before this word, 0}: a
 //   transcript id is ONE 16-byte load + popcount (replaces rank9b::rank, reference src/rank9b.cpp:55-60,
 //   which needs three loads; same value: number of set bits strictly before p).
@@ -28,7 +31,7 @@
 namespace rapmap_b200 {
 
 struct ImageHeader {
-  uint64_t magic;          // 'RMB2IMG2'
+  uint64_t magic;          // 'RMB2IMG3'
   uint64_t totalBytes;
   uint64_t n;              // text / SA length
   uint64_t numTxp;
@@ -48,6 +51,7 @@ struct ImageHeader {
   // host-readable trailer: transcript names, '\0'-terminated, in transcript order (a replica built from the image alone can
   // print SAM headers and records; the lengths are the txpLens section)
   uint64_t offNames, namesBytes;
+  uint64_t offSaTidPos;    // uint2[n]: {transcript, position in it} of the text position SA[i] (hit resolution reads one record instead of SA -> rank -> txpOffsets)
 };
 
 // One level of the MPHF (boomphf::level, reference include/BooPHF.hpp:820-842): bitset of `domain` bits with a rank
@@ -58,7 +62,7 @@ struct PhfLevelDev {
   uint64_t ranksOff;   // first rank sample of this level
   uint64_t pad;
 };
-static constexpr uint64_t kImageMagic = 0x32474D4932424D52ULL;  // 'RMB2IMG2'
+static constexpr uint64_t kImageMagic = 0x33474D4932424D52ULL;  // 'RMB2IMG3'
 
 // 64 bases starting at text position 32 j: codes (first base in bits 63:62 of c0), non-ACGT mask (first base in bit 0 of inv0).
 struct __align__(32) TextRec {
@@ -74,6 +78,7 @@ struct DeviceIndex {
   const uint4* rank;
   const int32_t* txpOffsets;
   const int32_t* txpLens;
+  const uint2* saTidPos;   // per SA entry: {transcript id, position inside the transcript}
   const uint4* table;
   uint64_t tableMask;
   int64_t n;

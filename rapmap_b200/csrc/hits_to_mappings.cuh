@@ -274,9 +274,9 @@ __device__ RAPMAP_K2_STRAND_ATTR void resolveStrand(const MapParams& P, WorkArea
     uint32_t ord = (nIv == 1) ? 0u : (j == minIdx ? 0u : static_cast<uint32_t>(j < minIdx ? j + 1 : j));
     int span = iv.end - iv.begin;
     for (int e = lane; e < span; e += 32) {
-      int32_t g = __ldg(ix.SA + iv.begin + e);
-      uint32_t tid = transcriptAt(ix, g);
-      int32_t pos = g - __ldg(ix.txpOffsets + tid);
+      const uint2 tp = __ldg(ix.saTidPos + iv.begin + e);  // {transcript, position in it} of SA[begin + e]
+      const uint32_t tid = tp.x;
+      const int32_t pos = static_cast<int32_t>(tp.y);
       keys[base + e] = (static_cast<uint64_t>(tid) << 32) | (static_cast<uint64_t>(ord) << 16) | static_cast<uint64_t>(e);
       vals[base + e] = (static_cast<uint64_t>(static_cast<uint32_t>(pos)) << 32) | (static_cast<uint64_t>(iv.qpos) << 16) | iv.len;
     }
@@ -599,23 +599,14 @@ __global__ void __launch_bounds__(NT) hits_to_mappings_lane_kernel(MapParams P) 
         }
       }
     }
-    // ---- stages 2-4: SA entry -> text position -> transcript -> position in the transcript (loads of a stage are independent)
+    // ---- stage 2: SA entry -> {transcript, position in the transcript}: one independent load per entry (the image holds the
+    //      pair per SA entry; it used to be the dependent chain SA -> rank record -> txpOffsets)
 #pragma unroll 4
     for (uint32_t i = 0; i < total; ++i) {
       const uint64_t v = vals[i * NT];
-      const int32_t g = __ldg(ix.SA + (v >> 32));
-      vals[i * NT] = (static_cast<uint64_t>(static_cast<uint32_t>(g)) << 32) | (v & 0xffffffffULL);
-    }
-#pragma unroll 4
-    for (uint32_t i = 0; i < total; ++i) {
-      const uint32_t tid = transcriptAt(ix, static_cast<int32_t>(vals[i * NT] >> 32));
-      keys[i * NT] |= static_cast<uint64_t>(tid) << 32;
-    }
-#pragma unroll 4
-    for (uint32_t i = 0; i < total; ++i) {
-      const uint64_t v = vals[i * NT];
-      const int32_t pos = static_cast<int32_t>(v >> 32) - __ldg(ix.txpOffsets + (keys[i * NT] >> 32));
-      vals[i * NT] = (static_cast<uint64_t>(static_cast<uint32_t>(pos)) << 32) | (v & 0xffffffffULL);
+      const uint2 tp = __ldg(ix.saTidPos + (v >> 32));
+      keys[i * NT] |= static_cast<uint64_t>(tp.x) << 32;
+      vals[i * NT] = (static_cast<uint64_t>(tp.y) << 32) | (v & 0xffffffffULL);
     }
     // ---- per strand: sort by (tid, ord, entry), resolve the transcript segments, compact {tid, pos, chain} in place
     uint32_t nOutF = 0, nOutR = 0;
@@ -820,23 +811,13 @@ __global__ void __launch_bounds__(NT) hits_to_mappings_chain_lane_kernel(MapPara
         }
       }
     }
-    // ---- stages 2-4: SA entry -> text position -> transcript -> position in the transcript
+    // ---- stage 2: SA entry -> {transcript, position in the transcript}, one independent load per entry
 #pragma unroll 4
     for (uint32_t i = 0; i < total; ++i) {
       const uint64_t v = vals[i];
-      const int32_t g = __ldg(ix.SA + (v >> 32));
-      vals[i] = (static_cast<uint64_t>(static_cast<uint32_t>(g)) << 32) | (v & 0xffffffffULL);
-    }
-#pragma unroll 4
-    for (uint32_t i = 0; i < total; ++i) {
-      const uint32_t tid = transcriptAt(ix, static_cast<int32_t>(vals[i] >> 32));
-      keys[i] |= static_cast<uint64_t>(tid) << 32;
-    }
-#pragma unroll 4
-    for (uint32_t i = 0; i < total; ++i) {
-      const uint64_t v = vals[i];
-      const int32_t pos = static_cast<int32_t>(v >> 32) - __ldg(ix.txpOffsets + (keys[i] >> 32));
-      vals[i] = (static_cast<uint64_t>(static_cast<uint32_t>(pos)) << 32) | (v & 0xffffffffULL);
+      const uint2 tp = __ldg(ix.saTidPos + (v >> 32));
+      keys[i] |= static_cast<uint64_t>(tp.x) << 32;
+      vals[i] = (static_cast<uint64_t>(tp.y) << 32) | (v & 0xffffffffULL);
     }
     // ---- per strand: sort, resolve the transcript segments; hit o of a strand is compacted in place at [b0 + o]:
     //      keys = tid << 32 | pos, vals = chain score (double bits), outMeta = posOff << 16 | nAll << 8 | chain

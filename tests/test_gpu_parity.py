@@ -642,6 +642,31 @@ def test_index_replica_from_image_carries_names(synth_small):
     del src
 
 
+def test_perfect_hash_index_replica_from_image(synth_small):
+    """The image of a -p index (BooPHF arrays, the table derived from them, the transcript names behind them) as a replica:
+    same SAM header, same hits as the dense index."""
+    import torch
+
+    idx_dir, index, s1, s2, L, tx = synth_small
+    pidx = rb.Index(os.path.join(GOLD, "synth_idx_p"), 0)
+    ptr, nbytes = pidx.image()
+    blob = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    import ctypes as C
+    try:
+        rt = C.CDLL("libcudart.so.12")
+    except OSError:
+        rt = C.CDLL("/usr/local/cuda/lib64/libcudart.so.12")
+    assert rt.cudaMemcpy(C.c_void_p(blob.data_ptr()), C.c_void_p(ptr), C.c_size_t(nbytes), 3) == 0
+    replica = rb.Index.from_image(0, blob.data_ptr(), nbytes)
+    assert replica.sam_header() == pidx.sam_header()
+    opts = rb.default_opts()
+    n = s1.shape[0]
+    a = make_mapper(index, opts, n, L).map_batch(s1, s2, n=n, fixed_len=L)
+    a_hits, a_off = a.hits.copy(), a.pair_offsets.copy()
+    b = make_mapper(replica, opts, n, L).map_batch(s1, s2, n=n, fixed_len=L)
+    assert np.array_equal(a_hits, b.hits) and np.array_equal(a_off, b.pair_offsets)
+
+
 @pytest.mark.parametrize("sel", [False, True])
 def test_direct_copy_out_to_pinned_and_device_buffers(synth_small, sel):
     """Results leave the device by a kernel when the caller's buffers are device memory or pinned host memory (one host
