@@ -26,6 +26,7 @@
 #pragma once
 #include <climits>
 #include "kmer_utils.cuh"
+#include "pack_swar.cuh"
 
 namespace rapmap_b200 {
 
@@ -81,27 +82,13 @@ __global__ void __launch_bounds__(256) pack_reads_kernel(LaneParams P) {
     const int n = L - i0 < 32 ? L - i0 : 32;
     const uint8_t* p = src + i0;
     if (n == 32 && (reinterpret_cast<uintptr_t>(p) & 3) == 0) {
-      // full word, 4-byte aligned: four bases per 32-bit operation (the byte loop below costs ~33 instructions per base and
-      // made this kernel math-pipe bound, profiles/r02l).  zb(v): 0x80 in every byte of v that is zero.
-      auto zb = [](uint32_t v) { return ~(((v & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | v) & 0x80808080u; };
+      // full word, 4-byte aligned: four bases per 32-bit operation (pack_swar.cuh; the byte loop below costs ~33 instructions
+      // per base and made this kernel math-pipe bound, profiles/r02l)
       const uint32_t* p4 = reinterpret_cast<const uint32_t*>(p);
       uint32_t x[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) x[j] = __ldg(p4 + j);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const uint32_t u = x[j] & 0xDFDFDFDFu;
-        const uint32_t ok = zb(u ^ 0x41414141u) | zb(u ^ 0x43434343u) | zb(u ^ 0x47474747u) | zb(u ^ 0x54545454u);
-        uint32_t code = ((x[j] >> 1) ^ (x[j] >> 2)) & 0x03030303u;
-        if (ok != 0x80808080u) {  // a base that is not A/C/G/T: 'U' = 3, 'N' = 1, anything else 0, all with the invalid bit
-          const uint32_t isU = zb(u ^ 0x55555555u) >> 7, isN = zb(u ^ 0x4E4E4E4Eu) >> 7, bad = (~ok & 0x80808080u) >> 7;
-          code = (code & ((ok >> 7) * 3u)) | (isU * 3u) | isN;
-          inv |= (((bad * 0x00204081u) >> 21) & 0xFu) << (4 * j);   // byte i of the word -> bit i
-          nn |= (((isN * 0x00204081u) >> 21) & 0xFu) << (4 * j);
-        }
-        const uint32_t c8 = (code * 0x40100401u) >> 24;              // the four 2-bit codes, first base on top
-        codes |= static_cast<uint64_t>(c8) << (56 - 8 * j);
-      }
+      packBases32(x, codes, inv, nn);
     } else {
     for (int b = 0; b < n; ++b) {
       const uint32_t ch = __ldg(src + i0 + b);
