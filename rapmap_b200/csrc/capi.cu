@@ -356,14 +356,6 @@ static constexpr int kWarps = 8;
 #ifndef RAPMAP_MAPLANE_CAP
 #define RAPMAP_MAPLANE_CAP 16
 #endif
-#ifndef RAPMAP_CHAINLANE_CAP
-#define RAPMAP_CHAINLANE_CAP 16   // bigger strips lose more to tail divergence and occupancy than they save the warp kernel (sweep in DESIGN.md §5)
-#endif
-#ifndef RAPMAP_CHAINLANE_THREADS
-#define RAPMAP_CHAINLANE_THREADS 128
-#endif
-static constexpr int kChainLaneThreads = RAPMAP_CHAINLANE_THREADS;  // lane-per-read hit resolution with chaining (-s / -f)
-static constexpr int kChainLaneCap = RAPMAP_CHAINLANE_CAP;
 // the size ranges of the chaining lane kernel: (threads per block, strip entries); ~68 KB of shared memory per block each.
 // A third range (32 threads, 64 entries) ran at 3 warps per SM: 6.4 ms for the 22 % of reads with 33-64 entries, which the
 // warp-per-read kernel resolves in ~2.5 ms (profiles/r02f_launches_selaln.csv)
