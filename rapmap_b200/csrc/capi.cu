@@ -715,10 +715,14 @@ static void freeMapperBuffers(rapmap_cuda_mapper* m) {
 
 // RAPMAP_B200_TINY_ARENAS=1 (tests only): every growable device work area starts far too small, so that the first batch
 // of a mapper walks through each overflow -> grow -> re-run path of finishBatch().
-// RAPMAP_B200_COPYOUT=kernel (A/B and tests): the copy-out kernel moves everything, no copy-engine part.
-static bool noSpeculativeCopy() {
-  static const bool v = [] { const char* t = std::getenv("RAPMAP_B200_COPYOUT"); return t && std::string(t) == "kernel"; }();
-  return v;
+// Copy-engine part of the copy-out (enqueueAttempt): by default for batches of 32k pairs and more (below that two more DMA
+// submissions cost more than the kernel's PCIe stores).  RAPMAP_B200_COPYOUT=kernel: never (A/B); =engine: for every batch
+// (tests: small batches through the same path).  Read per batch, so a test can switch it.
+static bool speculativeCopy(uint64_t n) {
+  const char* t = std::getenv("RAPMAP_B200_COPYOUT");
+  if (t && std::string(t) == "kernel") return false;
+  if (t && std::string(t) == "engine") return true;
+  return n >= 32768;
 }
 
 static bool tinyArenas() {
@@ -998,7 +1002,7 @@ static int enqueueAttempt(rapmap_cuda_mapper* m, BatchSlot& sl) {
     // the speculative copy may bring along lie inside hits_capacity and are unspecified anyway.
     uint64_t skip = 0;
     const uint64_t* offSrc = sl.dPairOff;
-    if (sl.out->location == RAPMAP_LOC_HOST && n >= 32768 && !noSpeculativeCopy()) {   // (small batches: two more DMA submissions cost more than the kernel's PCIe stores)
+    if (sl.out->location == RAPMAP_LOC_HOST && speculativeCopy(n)) {
       CU_TRY(cudaMemcpyAsync(sl.out->pair_offsets, sl.dPairOff, (n + 1) * 8, cudaMemcpyDeviceToHost, m->sOut));
       offSrc = nullptr;
       if (sl.outHitsDev != nullptr && m->hitsPerPair > 0.0) {

@@ -526,12 +526,13 @@ def test_async_pipeline_chunks_in_flight(sel, pinned):
 
 @pytest.mark.skipif(not have_ref(), reason="needs oracle/_ref to build the mid-size index")
 @pytest.mark.parametrize("sel", [False, True])
-def test_copy_engine_copy_out_with_uneven_chunks(sel):
+def test_copy_engine_copy_out_with_uneven_chunks(sel, monkeypatch):
     """Pinned output buffers: the copy engines move the offsets and the part of the records the previous chunks predict,
     copy_out_kernel only the tail.  Chunks of very different size and hit density (unmappable reads: the prediction is far
     above the real count; a dense chunk after them: far below) must still arrive exactly."""
     import torch
 
+    monkeypatch.setenv("RAPMAP_B200_COPYOUT", "engine")  # the copy-engine part for these small chunks too (default: >= 32k pairs)
     idx_dir, tx = synth_index(2500)
     index = rb.Index(idx_dir, 0)
     opts = rb.default_opts(sel_aln=sel)
