@@ -5,8 +5,8 @@
 // collectHitsSimpleSA (:84-326, leftmost anchor or minimap2-style chain DP) and the fwd/rc merge (:834-881).
 //
 // B200 mapping: the reference walks SA entries one by one into a std::map<tid, ProcessedSAHit>.  Here the
-// warp expands all SA entries of a strand at once (lane = entry: SA[i] -> rank record -> txpOffsets, three
-// dependent loads per lane, 32 in flight), sorts the (tid, interval order, entry) keys with a warp bitonic
+// warp expands all SA entries of a strand at once (lane = entry: one load of the entry's {transcript, position} record,
+// 32 in flight), sorts the (tid, interval order, entry) keys with a warp bitonic
 // network (shared memory for the common <= 64 entries, an L2-resident global work strip otherwise) and
 // resolves each transcript segment with one lane (map iteration order == ascending tid == sorted order).
 // Chain scoring keeps the reference's double/float arithmetic with explicit round-to-nearest intrinsics so
@@ -538,9 +538,8 @@ __global__ void __launch_bounds__(WARPS * 32) hits_to_mappings_kernel(MapParams 
 
 // ---------------------------------------------------------------------------------------------------------------
 // Lane-per-read form for the common small case: no chaining / position lists (plain quasimap), at most LANE_MAXIV
-// intervals and CAP expanded SA entries per read.  One thread resolves one read: the three dependent loads per SA entry
-// (SA -> rank record -> txpOffsets) are issued for ALL entries of the read stage by stage, so a lane has up to CAP
-// loads in flight and a warp 32 reads; the (tid, interval order, entry) keys are insertion-sorted in the lane's
+// intervals and CAP expanded SA entries per read.  One thread resolves one read: the {transcript, position} records of ALL
+// its SA entries are loaded together, so a lane has up to CAP loads in flight and a warp 32 reads; the (tid, interval order, entry) keys are insertion-sorted in the lane's
 // shared-memory strip (interleaved across the block), segments are resolved with the same rules as resolveStrand
 // (strict / consensus intersection, leftmost anchor, PERFECT flag of a single read-spanning interval), the two strands
 // are merged by tid.  Anything bigger is marked kTodoMark and left to the warp-per-read kernel.
