@@ -36,4 +36,15 @@ RAPMAP_HD inline void packBases32(const uint32_t (&x)[8], uint64_t& codes, uint3
   }
 }
 
+// ksw2's code of one base (seq_nt4_table_loc, reference src/ksw2pp/KSW2Aligner.cpp:61-72: A C G T either case = 0..3, the raw
+// bytes 0..3 themselves, anything else 4) without a branch; comp: the code of rapmap::utils::reverseRead's output for this
+// byte (A<->T, C<->G, U -> A, anything else N = 4).  Used by the ksw2 pair kernel's strip fill.
+RAPMAP_HD inline uint32_t baseCode(uint32_t ch, bool comp) {
+  const uint32_t d = (ch & 0xDFu) - 'A';                                  // A C G T -> 0 2 6 19
+  const bool acgt = d < 20u && ((0x80045u >> d) & 1u);
+  const uint32_t c2 = ((ch >> 1) ^ (ch >> 2)) & 3u;
+  if (!comp) return acgt ? c2 : (ch < 4u ? ch : 4u);
+  return acgt ? 3u - c2 : ((ch & 0xDFu) == 'U' ? 0u : 4u);
+}
+
 } // namespace rapmap_b200

@@ -33,6 +33,7 @@
 #include "kernels.cuh"
 #include "kmer_utils.cuh"
 #include "ksw_pair.cuh"
+#include "pack_swar.cuh"
 
 namespace rapmap_b200 {
 
@@ -768,14 +769,7 @@ __device__ __forceinline__ void fillCodes8(const uint8_t* p, int len, bool comp,
       for (int b = 0; b < 8; ++b) {
         const int i = i0 + 8 * j + b;
         if (i < 0 || i >= len) continue;
-        const uint32_t ch = static_cast<uint32_t>(wd[j] >> (8 * b)) & 0xffu;
-        const uint32_t d = (ch & 0xDFu) - 'A';                                  // A C G T -> 0 2 6 19
-        const bool acgt = d < 20u && ((0x80045u >> d) & 1u);
-        const uint32_t c2 = ((ch >> 1) ^ (ch >> 2)) & 3u;
-        uint32_t code;
-        if (!comp) code = acgt ? c2 : (ch < 4u ? ch : 4u);
-        else code = acgt ? 3u - c2 : ((ch & 0xDFu) == 'U' ? 0u : 4u);
-        put(i, code);
+        put(i, baseCode(static_cast<uint32_t>(wd[j] >> (8 * b)) & 0xffu, comp));
       }
     }
   }

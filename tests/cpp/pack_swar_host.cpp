@@ -16,7 +16,26 @@ static void perBase(const uint8_t* s, uint64_t& codes, uint32_t& inv, uint32_t& 
     if (uc == 'N') nn |= 1u << b;
   }
 }
+// the switch-based originals (sel_aln.cuh nt4, kmer_utils.cuh rcChar)
+static uint8_t nt4Ref(uint8_t c) {
+  if (c < 4) return c;
+  switch (c | 0x20) { case 'a': return 0; case 'c': return 1; case 'g': return 2; case 't': return 3; default: return 4; }
+}
+static uint8_t rcCharRef(uint8_t c) {
+  switch (c | 0x20) {
+    case 'a': return 'T'; case 'c': return 'G'; case 'g': return 'C'; case 't': return 'A';
+    case 'u': return (c == 'U' || c == 'u') ? 'A' : 'N';
+    default: return 'N';
+  }
+}
 int main() {
+  long badCode = 0;
+  for (int v = 0; v < 256; ++v) {
+    if (baseCode(static_cast<uint32_t>(v), false) != nt4Ref(static_cast<uint8_t>(v))) ++badCode;
+    if (baseCode(static_cast<uint32_t>(v), true) != nt4Ref(rcCharRef(static_cast<uint8_t>(v)))) ++badCode;
+  }
+  std::printf("base codes: mismatches %ld\n", badCode);
+  if (badCode) return 1;
   std::mt19937_64 rng(99);
   const char alpha[] = "ACGTacgtNnUuRYKMSWBDHV$#-*";
   long bad = 0, n = 0;
